@@ -1,0 +1,51 @@
+"""Loader for the committed reference fixtures (tests/golden/*.npz)."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names(kind=None):
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    if kind is None:
+        return names
+    return [n for n in names if load_golden(n)["meta"]["kind"] == kind]
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {"meta": json.loads(str(d["meta"])), "inputs": {}, "grad_inputs": {}, "params": {}, "grads": {}}
+    for k in d.files:
+        if k == "meta":
+            continue
+        t = torch.from_numpy(d[k])
+        if k.startswith("in."):
+            out["inputs"][k[3:]] = t
+        elif k.startswith("grad_in."):
+            out["grad_inputs"][k[8:]] = t
+        elif k.startswith("param."):
+            out["params"][k[6:]] = t
+        elif k.startswith("grad."):
+            out["grads"][k[5:]] = t
+        else:
+            out[k] = t
+    m = out["meta"]["modes"]
+    out["meta"]["modes"] = tuple(m) if isinstance(m, list) else m
+    return out
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    if a.is_complex() != b.is_complex():
+        a = torch.view_as_real(a) if a.is_complex() else a
+        b = torch.view_as_real(b) if b.is_complex() else b
+    a = a.to(torch.complex128 if a.is_complex() else torch.float64)
+    b = b.to(a.dtype)
+    denom = torch.linalg.vector_norm(b).item()
+    num = torch.linalg.vector_norm(a - b).item()
+    return num / max(denom, 1e-300)
