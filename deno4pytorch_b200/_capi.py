@@ -1,0 +1,92 @@
+"""ctypes view of include/deno_spectral.h (no torch imports here).
+
+``bind(cdll)`` attaches argument / return types for every exported symbol and returns the
+library.  ``EXPORTED_SYMBOLS`` is the list the CPU test-suite checks the built ``.so`` against.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+ABI_VERSION = 1
+
+ACTIVATION_IDS = {"identity": 0, "gelu": 1, "silu": 2, "relu": 3, "tanh": 4, "leakyrelu": 5}
+
+STATUS_NAMES = {0: "DENO_OK", 1: "DENO_E_INVALID", 2: "DENO_E_UNSUPPORTED", 3: "DENO_E_WORKSPACE", 4: "DENO_E_CUDA"}
+
+
+class SpectralDesc(C.Structure):
+    """struct deno_spectral_desc"""
+    _fields_ = [
+        ("ndim", C.c_int32),
+        ("batch", C.c_int32),
+        ("cin", C.c_int32),
+        ("cout", C.c_int32),
+        ("spatial", C.c_int32 * 3),
+        ("modes", C.c_int32 * 3),
+        ("act", C.c_int32),
+        ("flags", C.c_int32),
+    ]
+
+
+def make_desc(batch, cin, cout, spatial, modes, act) -> SpectralDesc:
+    nd = len(spatial)
+    assert len(modes) == nd and 1 <= nd <= 3
+    d = SpectralDesc()
+    d.ndim, d.batch, d.cin, d.cout = nd, int(batch), int(cin), int(cout)
+    for a in range(3):
+        d.spatial[a] = int(spatial[a]) if a < nd else 0
+        d.modes[a] = int(modes[a]) if a < nd else 0
+    d.act = ACTIVATION_IDS[act] if isinstance(act, str) else int(act)
+    d.flags = 0
+    return d
+
+
+_DESC_P = C.POINTER(SpectralDesc)
+_PP = C.POINTER(C.c_void_p)
+
+_PROTOTYPES = {
+    "deno_spectral_abi_version": (C.c_int, []),
+    "deno_last_error": (C.c_char_p, []),
+    "deno_spectral_last_launch_count": (C.c_int, []),
+    "deno_spectral_num_modes": (C.c_size_t, [_DESC_P]),
+    "deno_spectral_twiddle_bytes": (C.c_size_t, [_DESC_P]),
+    "deno_spectral_twiddle_fill": (C.c_int, [_DESC_P, C.c_void_p, C.c_size_t]),
+    "deno_spectral_workspace_bytes": (C.c_size_t, [_DESC_P, C.c_int]),
+    "deno_spectral_xhat_bytes": (C.c_size_t, [_DESC_P]),
+    "deno_spectral_fwd": (C.c_int, [_DESC_P, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "deno_spectral_bwd": (C.c_int, [_DESC_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.deno_spectral_abi_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"libdeno_spectral ABI version {got}, expected {ABI_VERSION}")
+    return lib
+
+
+def pointer_array(ptrs):
+    """HOST array of device pointers (w_blocks / gw_blocks)."""
+    arr = (C.c_void_p * 4)()
+    for j in range(4):
+        arr[j] = ptrs[j] if j < len(ptrs) else None
+    return arr
+
+
+class DenoError(RuntimeError):
+    pass
+
+
+def check(lib: C.CDLL, rc: int, what: str):
+    if rc != 0:
+        msg = lib.deno_last_error().decode("utf-8", "replace")
+        raise DenoError(f"{what} failed with {STATUS_NAMES.get(rc, rc)}: {msg}")

@@ -1,0 +1,596 @@
+// capi.cu - the extern "C" boundary of libdeno_spectral.so (see include/deno_spectral.h).
+//
+// Host-side orchestration only: validates the descriptor, carves the caller's workspace,
+// picks launch geometry and enqueues the kernels of spectral_simt.cuh (and, for the shapes it
+// covers, the tcgen05 path of spectral_tc.cuh) on the caller's stream.  No allocation, no
+// synchronisation, no global mutable state.
+#include "../../include/deno_spectral.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "spectral_simt.cuh"
+#ifndef DENO_EMULATE
+#include "spectral_tc.cuh"
+#endif
+
+namespace {
+
+using namespace deno;
+
+thread_local std::string g_error;
+thread_local int g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+
+constexpr size_t kAlign = 256;
+constexpr int kMaxSmemBytes = 227 * 1024;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+// ------------------------------------------------------------------------------------------
+// Descriptor-derived shape bookkeeping
+// ------------------------------------------------------------------------------------------
+struct Shape {
+  int ndim, B, CI, CO;
+  int X, H, W;        // outer (3-D only, else 1), plane rows (1 for 1-D), plane cols
+  int mX, mH, mW;     // modes on those axes (unused = 0)
+  int KX, KH, MW;     // packed modes per axis (1 when the axis is absent)
+  int KX4, KH4, MWp;
+  long long S;        // points per channel
+  int Q;              // KH * MW: packed modes of one plane
+  int M;              // total packed modes
+  int act;
+};
+
+int parse_desc(const deno_spectral_desc* d, Shape& s) {
+  if (d == nullptr) return fail(DENO_E_INVALID, "null descriptor");
+  if (d->ndim < 1 || d->ndim > 3) return fail(DENO_E_INVALID, "ndim must be 1, 2 or 3");
+  if (d->batch < 1 || d->cin < 1 || d->cout < 1) return fail(DENO_E_INVALID, "batch/cin/cout must be positive");
+  if (d->flags != 0) return fail(DENO_E_INVALID, "flags must be 0");
+  if (d->act < DENO_ACT_IDENTITY || d->act > DENO_ACT_LEAKYRELU) return fail(DENO_E_INVALID, "unknown activation id");
+  for (int a = 0; a < d->ndim; ++a) {
+    if (d->spatial[a] < 1 || d->modes[a] < 1) return fail(DENO_E_INVALID, "spatial sizes and modes must be positive");
+  }
+  const int nd = d->ndim;
+  s.ndim = nd;
+  s.B = d->batch;
+  s.CI = d->cin;
+  s.CO = d->cout;
+  s.act = d->act;
+  s.W = d->spatial[nd - 1];
+  s.mW = d->modes[nd - 1];
+  s.H = nd >= 2 ? d->spatial[nd - 2] : 1;
+  s.mH = nd >= 2 ? d->modes[nd - 2] : 0;
+  s.X = nd == 3 ? d->spatial[0] : 1;
+  s.mX = nd == 3 ? d->modes[0] : 0;
+  if (s.mW > s.W / 2 + 1)
+    return fail(DENO_E_INVALID, "modes on the last axis exceed the rfft length N/2+1 (the reference fails in einsum)");
+  if (nd == 1 && (s.W % 2) != 0)
+    return fail(DENO_E_INVALID, "SpectralConv1d needs an even length (the reference's irfft has no n=, spectral_layers.py:106)");
+  if ((nd >= 2 && 2 * s.mH > s.H) || (nd == 3 && 2 * s.mX > s.X))
+    return fail(DENO_E_UNSUPPORTED, "2*modes exceeds the grid on a leading axis (overlapping corner blocks)");
+  s.KH = nd >= 2 ? 2 * s.mH : 1;
+  s.KX = nd == 3 ? 2 * s.mX : 1;
+  s.MW = s.mW;
+  s.KH4 = round_up(s.KH, 4);
+  s.KX4 = round_up(s.KX, 4);
+  s.MWp = round_up(s.MW, 4);
+  s.S = (long long)s.X * s.H * s.W;
+  s.Q = s.KH * s.MW;
+  s.M = s.KX * s.Q;
+  return DENO_OK;
+}
+
+PlaneGeom make_geom(const Shape& s, int channels) {
+  PlaneGeom g;
+  g.H = s.H;
+  g.W = s.W;
+  g.KH = s.KH;
+  g.MW = s.MW;
+  g.C = channels;
+  g.NBO = s.B;
+  g.NBI = s.X;
+  g.sbo = (long long)channels * s.S;
+  g.sbi = (long long)s.H * s.W;
+  g.sc = s.S;
+  return g;
+}
+
+ModeDecode make_decode(const Shape& s) {
+  ModeDecode md;
+  md.ndim = s.ndim;
+  if (s.ndim == 1) {
+    md.m1 = s.mW; md.m2 = 1; md.m3 = 1;
+    md.Mblk = s.mW;
+  } else if (s.ndim == 2) {
+    md.m1 = s.mH; md.m2 = s.mW; md.m3 = 1;
+    md.Mblk = s.mH * s.mW;
+  } else {
+    md.m1 = s.mX; md.m2 = s.mH; md.m3 = s.mW;
+    md.Mblk = s.mX * s.mH * s.mW;
+  }
+  md.M = s.M;
+  return md;
+}
+
+// ------------------------------------------------------------------------------------------
+// Twiddle tables (host, fp64 -> fp32)
+// ------------------------------------------------------------------------------------------
+struct TwLayout {
+  size_t last, mid, outer, cl, total;  // float offsets
+};
+
+TwLayout tw_layout(const Shape& s) {
+  TwLayout t;
+  size_t off = 0;
+  t.last = off;  off += (size_t)s.W * s.MWp * 2;
+  t.mid = off;   off += (size_t)s.H * s.KH4 * 2;
+  t.outer = off; off += (s.ndim == 3) ? (size_t)s.X * s.KX4 * 2 : 0;
+  t.cl = off;    off += (size_t)s.MWp;
+  t.total = off;
+  return t;
+}
+
+void fill_axis(float* dst, int n, int nfreq, int pitch, int m, bool half) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int x = 0; x < n; ++x) {
+    for (int k = 0; k < pitch; ++k) {
+      float c = 0.f, sn = 0.f;
+      if (k < nfreq) {
+        long long f = half ? k : (k < m ? k : (long long)n - 2 * m + k);
+        if (n == 1) f = 0;
+        long long r = (f * x) % n;
+        double ang = two_pi * (double)r / (double)n;
+        c = (float)cos(ang);
+        sn = (float)sin(ang);
+      }
+      dst[((size_t)x * pitch + k) * 2 + 0] = c;
+      dst[((size_t)x * pitch + k) * 2 + 1] = sn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launch-geometry heuristics (pure functions of the shape so that workspace sizing agrees)
+// ------------------------------------------------------------------------------------------
+struct AnalysisCfg { int G, RT, RTP, YC, RS, threads; size_t smem; };
+
+int analysis_cfg(const PlaneGeom& g, AnalysisCfg& c) {
+  const int MWp = round_up(g.MW, 4), NLG = MWp / 4, KQ = round_up(g.KH, 4) / 4;
+  c.G = (g.H >= 32) ? 1 : (g.H == 1 ? 8 : (32 + g.H - 1) / g.H);
+  const int rows = c.G * g.H;
+  int rtcap = (512 / NLG) & ~31;
+  if (rtcap < 32) rtcap = 32;
+  const int ntiles = (rows + rtcap - 1) / rtcap;
+  c.RT = (rows + ntiles - 1) / ntiles;
+  c.RTP = c.RT < 32 ? c.RT : round_up(c.RT, 32);
+  c.threads = round_up(c.RTP * NLG, 32);
+  if (c.threads < 64) c.threads = 64;
+  if (c.threads > 1024) return fail(DENO_E_UNSUPPORTED, "too many retained modes on the last axis for plane_analysis");
+  const int nchunks = (g.W + 127) / 128;
+  c.YC = (g.W + nchunks - 1) / nchunks;
+  const int ntask2 = c.G * KQ * g.MW;
+  c.RS = c.threads / ntask2;
+  if (c.RS < 1) c.RS = 1;
+  if (c.RS > 8) c.RS = 8;
+  AnalysisParams p;
+  p.g = g; p.G = c.G; p.RT = c.RT; p.YC = c.YC; p.RS = c.RS;
+  c.smem = (size_t)analysis_smem(p).total * sizeof(float);
+  if (c.smem > (size_t)kMaxSmemBytes) return fail(DENO_E_UNSUPPORTED, "plane_analysis tile does not fit shared memory");
+  return DENO_OK;
+}
+
+struct SynthCfg { int R, PTS, tiles, threads; size_t smem; };
+
+int synth_cfg(const PlaneGeom& g, int CO, SynthCfg& c) {
+  SynthParams p;
+  p.g = g;
+  p.CO = CO;
+  if (g.H == 1) {
+    const int nt = (g.W + 255) / 256;
+    c.R = 1;
+    c.PTS = round_up((g.W + nt - 1) / nt, 4);
+    c.tiles = (g.W + c.PTS - 1) / c.PTS;
+    p.R = c.R; p.PTS = c.PTS;
+    c.smem = (size_t)synth_smem(p).total * sizeof(float);
+  } else {
+    int best = 0;
+    for (int R = kSynthMaxRows; R >= 1; --R) {
+      if (R > g.H) continue;
+      p.R = R; p.PTS = R * g.W;
+      const size_t bytes = (size_t)synth_smem(p).total * sizeof(float);
+      if (bytes <= 72 * 1024) { best = R; break; }
+    }
+    if (best == 0) best = 1;
+    c.R = best;
+    c.PTS = best * g.W;
+    c.tiles = (g.H + best - 1) / best;
+    p.R = c.R; p.PTS = c.PTS;
+    c.smem = (size_t)synth_smem(p).total * sizeof(float);
+  }
+  if (c.smem > (size_t)kMaxSmemBytes) return fail(DENO_E_UNSUPPORTED, "plane_synthesis tile does not fit shared memory (too many channels)");
+  c.threads = 256;
+  return DENO_OK;
+}
+
+struct WgradCfg { int PTS, tiles, ncta, threads; size_t smem; };
+
+int wgrad_cfg(const Shape& s, WgradCfg& c) {
+  const int rowsum = s.CO + round_up(s.CI, 4);
+  int pts = (96 * 1024 / 4) / rowsum - 4;
+  pts &= ~3;
+  if (pts > 512) pts = 512;
+  if (pts < 4) return fail(DENO_E_UNSUPPORTED, "too many channels for bypass_wgrad");
+  const int plane = s.H * s.W;
+  if (pts > round_up(plane, 4)) pts = round_up(plane, 4);
+  c.PTS = pts;
+  c.tiles = (plane + pts - 1) / pts;
+  c.ncta = s.B * s.X * c.tiles;
+  c.threads = 256;
+  c.smem = (size_t)rowsum * (pts + 4) * sizeof(float);
+  return DENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Workspace carving
+// ------------------------------------------------------------------------------------------
+struct FwdWs { size_t xhat, yhat, t2, v, total; };
+struct BwdWs { size_t gz, ghat, gxhat, t2, v, partial, total; };
+
+FwdWs fwd_ws(const Shape& s) {
+  FwdWs w;
+  size_t off = 0;
+  w.xhat = off; off += align_up((size_t)s.B * s.CI * s.M * 8);
+  w.yhat = off; off += align_up((size_t)s.B * s.CO * s.M * 8);
+  w.t2 = off;   off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.v = off;    off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
+  w.total = off;
+  return w;
+}
+
+int bwd_ws(const Shape& s, BwdWs& w) {
+  WgradCfg wc;
+  int rc = wgrad_cfg(s, wc);
+  if (rc != DENO_OK) return rc;
+  size_t off = 0;
+  w.gz = off;      off += align_up((size_t)s.B * s.CO * s.S * 4);
+  w.ghat = off;    off += align_up((size_t)s.B * s.CO * s.M * 8);
+  w.gxhat = off;   off += align_up((size_t)s.B * s.CI * s.M * 8);
+  w.t2 = off;      off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
+  w.v = off;       off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.partial = off; off += align_up((size_t)wc.ncta * ((size_t)s.CO * s.CI + s.CO) * 4);
+  w.total = off;
+  return DENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Launch helpers
+// ------------------------------------------------------------------------------------------
+int check_launch(const char* what) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DENO_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return DENO_OK;
+}
+
+template <typename K>
+int allow_smem(K kernel, size_t bytes, const char* what) {
+#ifndef DENO_EMULATE
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(DENO_E_CUDA, std::string(what) + " smem opt-in: " + cudaGetErrorString(e));
+  }
+#else
+  (void)kernel; (void)bytes; (void)what;
+#endif
+  return DENO_OK;
+}
+
+struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; };
+
+TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
+  const float* base = static_cast<const float*>(twiddles);
+  const TwLayout t = tw_layout(s);
+  TwPtrs p;
+  p.last = reinterpret_cast<const float2*>(base + t.last);
+  p.mid = reinterpret_cast<const float2*>(base + t.mid);
+  p.outer = reinterpret_cast<const float2*>(base + t.outer);
+  p.cl = base + t.cl;
+  return p;
+}
+
+// x / (gy, z) -> packed plane spectra [B*X][C][KH][MW]
+int launch_analysis(const Shape& s, int channels, const float* u, const float* z, float* gz_out, float2* out,
+                    const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
+  AnalysisParams p;
+  p.g = make_geom(s, channels);
+  AnalysisCfg c;
+  int rc = analysis_cfg(p.g, c);
+  if (rc != DENO_OK) return rc;
+  p.u = u; p.z = z; p.gz_out = gz_out; p.out = out;
+  p.twW = tw.last; p.twH = tw.mid; p.cl = tw.cl;
+  p.scale = scale; p.herm = herm; p.act = s.act;
+  p.nplanes = s.B * s.X * channels;
+  p.G = c.G; p.RT = c.RT; p.RTP = c.RTP; p.YC = c.YC; p.RS = c.RS;
+  const int grid = (p.nplanes + c.G - 1) / c.G;
+  if (z != nullptr) {
+    rc = allow_smem(plane_analysis_kernel<true>, c.smem, "plane_analysis");
+    if (rc != DENO_OK) return rc;
+    DENO_LAUNCH(plane_analysis_kernel<true>, dim3(grid), dim3(c.threads), c.smem, st, p);
+  } else {
+    rc = allow_smem(plane_analysis_kernel<false>, c.smem, "plane_analysis");
+    if (rc != DENO_OK) return rc;
+    DENO_LAUNCH(plane_analysis_kernel<false>, dim3(grid), dim3(c.threads), c.smem, st, p);
+  }
+  return check_launch("plane_analysis");
+}
+
+int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, float2* out, const TwPtrs& tw,
+                 cudaStream_t st) {
+  OuterParams p;
+  p.in = in; p.out = out; p.twX = tw.outer;
+  p.B = s.B; p.C = channels; p.X = s.X; p.KX = s.KX; p.Q = s.Q;
+  const long long units = analysis ? (long long)s.B * channels * (s.KX4 / 4) * s.Q
+                                   : (long long)s.B * channels * ((s.X + 3) / 4) * s.Q;
+  long long blocks = (units + 255) / 256;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (analysis) {
+    DENO_LAUNCH(outer_analysis_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p);
+  } else {
+    DENO_LAUNCH(outer_synthesis_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p);
+  }
+  return check_launch(analysis ? "outer_analysis" : "outer_synthesis");
+}
+
+int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks,
+               cudaStream_t st) {
+  MixParams p;
+  p.in = in; p.out = out;
+  p.md = make_decode(s);
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < 4; ++j) p.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
+  p.B = s.B;
+  if (!backward) {
+    p.CI = s.CI; p.CO = s.CO;
+    p.w_sci = (long long)s.CO * p.md.Mblk; p.w_sco = p.md.Mblk;
+    p.conj_w = 0;
+  } else {
+    p.CI = s.CO; p.CO = s.CI;
+    p.w_sci = p.md.Mblk; p.w_sco = (long long)s.CO * p.md.Mblk;
+    p.conj_w = 1;
+  }
+  dim3 block(32, 8);
+  dim3 grid((s.M + 31) / 32, (p.CO + 7) / 8, (s.B + kMixBatchTile - 1) / kMixBatchTile);
+  DENO_LAUNCH(mode_mix_kernel, grid, block, 0, st, p);
+  return check_launch("mode_mix");
+}
+
+int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, void* const* gw_blocks, cudaStream_t st) {
+  MixWgradParams p;
+  p.xhat = xhat; p.ghat = ghat;
+  p.md = make_decode(s);
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < 4; ++j) p.gw[j] = static_cast<float2*>(gw_blocks[j < nblk ? j : 0]);
+  p.B = s.B; p.CI = s.CI; p.CO = s.CO;
+  dim3 block(32, 8);
+  dim3 grid((s.M + 31) / 32, ((s.CO + 3) / 4 + 7) / 8, s.CI);
+  DENO_LAUNCH(mode_mix_wgrad_kernel, grid, block, 0, st, p);
+  return check_launch("mode_mix_wgrad");
+}
+
+// spec [B*X][CO][KH][MW] + bypass(u) -> y (, z)
+int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, const float* u, const float* lw,
+                     long long lw_so, long long lw_si, const float* bias, float* y, float* z, const TwPtrs& tw,
+                     float scale, int herm, int act, cudaStream_t st) {
+  SynthParams p;
+  p.g = make_geom(s, cin);
+  p.CO = cout;
+  SynthCfg c;
+  int rc = synth_cfg(p.g, cout, c);
+  if (rc != DENO_OK) return rc;
+  p.sbo_out = (long long)cout * s.S;
+  p.spec = spec; p.u = u; p.lw = lw; p.lw_so = lw_so; p.lw_si = lw_si; p.bias = bias;
+  p.y = y; p.z = z;
+  p.twW = tw.last; p.twH = tw.mid; p.cl = tw.cl;
+  p.scale = scale; p.herm = herm; p.act = act;
+  p.R = c.R; p.PTS = c.PTS; p.tiles = c.tiles;
+  rc = allow_smem(plane_synthesis_kernel, c.smem, "plane_synthesis");
+  if (rc != DENO_OK) return rc;
+  const int grid = s.B * s.X * c.tiles;
+  DENO_LAUNCH(plane_synthesis_kernel, dim3(grid), dim3(c.threads), c.smem, st, p);
+  return check_launch("plane_synthesis");
+}
+
+int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, float* partial, float* glw, float* glb,
+                        cudaStream_t st) {
+  WgradCfg c;
+  int rc = wgrad_cfg(s, c);
+  if (rc != DENO_OK) return rc;
+  WgradParams p;
+  p.gx = make_geom(s, s.CI);
+  p.CO = s.CO;
+  p.sbo_g = (long long)s.CO * s.S;
+  p.gz = gz; p.x = x; p.partial = partial;
+  p.PTS = c.PTS; p.tiles = c.tiles;
+  rc = allow_smem(bypass_wgrad_partial_kernel, c.smem, "bypass_wgrad");
+  if (rc != DENO_OK) return rc;
+  DENO_LAUNCH(bypass_wgrad_partial_kernel, dim3(c.ncta), dim3(c.threads), c.smem, st, p);
+  rc = check_launch("bypass_wgrad_partial");
+  if (rc != DENO_OK) return rc;
+  WgradReduceParams r;
+  r.partial = partial; r.ncta = c.ncta;
+  r.nw = s.CO * s.CI; r.nj = r.nw + s.CO;
+  r.glw = glw; r.glb = glb;
+  DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+  return check_launch("bypass_wgrad_reduce");
+}
+
+}  // namespace
+
+// ==========================================================================================
+// extern "C" surface
+// ==========================================================================================
+extern "C" {
+
+int deno_spectral_abi_version(void) { return DENO_SPECTRAL_ABI_VERSION; }
+
+const char* deno_last_error(void) { return g_error.c_str(); }
+
+int deno_spectral_last_launch_count(void) { return g_launches; }
+
+size_t deno_spectral_num_modes(const deno_spectral_desc* desc) {
+  Shape s;
+  if (parse_desc(desc, s) != DENO_OK) return 0;
+  return (size_t)s.M;
+}
+
+size_t deno_spectral_twiddle_bytes(const deno_spectral_desc* desc) {
+  Shape s;
+  if (parse_desc(desc, s) != DENO_OK) return 0;
+  return tw_layout(s).total * sizeof(float);
+}
+
+int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, size_t bytes) {
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  const TwLayout t = tw_layout(s);
+  if (host_buf == nullptr || bytes < t.total * sizeof(float)) return fail(DENO_E_INVALID, "twiddle buffer too small");
+  float* base = static_cast<float*>(host_buf);
+  fill_axis(base + t.last, s.W, s.MW, s.MWp, s.mW, /*half=*/true);
+  if (s.ndim >= 2) {
+    fill_axis(base + t.mid, s.H, s.KH, s.KH4, s.mH, false);
+  } else {
+    fill_axis(base + t.mid, 1, 1, s.KH4, 0, true);
+  }
+  if (s.ndim == 3) fill_axis(base + t.outer, s.X, s.KX, s.KX4, s.mX, false);
+  for (int l = 0; l < s.MWp; ++l) {
+    float c = 0.f;
+    if (l < s.MW) {
+      c = 2.f;
+      if (l == 0) c = 1.f;
+      if ((s.W % 2) == 0 && l == s.W / 2) c = 1.f;
+    }
+    base[t.cl + l] = c;
+  }
+  return DENO_OK;
+}
+
+size_t deno_spectral_workspace_bytes(const deno_spectral_desc* desc, int backward) {
+  Shape s;
+  if (parse_desc(desc, s) != DENO_OK) return 0;
+  if (!backward) return fwd_ws(s).total;
+  BwdWs w;
+  if (bwd_ws(s, w) != DENO_OK) return 0;
+  return w.total;
+}
+
+size_t deno_spectral_xhat_bytes(const deno_spectral_desc* desc) {
+  Shape s;
+  if (parse_desc(desc, s) != DENO_OK) return 0;
+  return (size_t)s.B * s.CI * s.M * 8;
+}
+
+int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void* const* w_blocks,
+                      const float* lin_w, const float* lin_b, const void* twiddles, float* y,
+                      float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  if (!x || !w_blocks || !lin_w || !twiddles || !y || !workspace) return fail(DENO_E_INVALID, "null pointer argument");
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < nblk; ++j)
+    if (w_blocks[j] == nullptr) return fail(DENO_E_INVALID, "null weight block");
+  const FwdWs ws = fwd_ws(s);
+  if (workspace_bytes < ws.total) return fail(DENO_E_WORKSPACE, "workspace too small for deno_spectral_fwd");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* wsb = static_cast<char*>(workspace);
+  const TwPtrs tw = tw_ptrs(s, twiddles);
+  float2* xhat = xhat_saved ? static_cast<float2*>(xhat_saved) : reinterpret_cast<float2*>(wsb + ws.xhat);
+  float2* yhat = reinterpret_cast<float2*>(wsb + ws.yhat);
+
+  if (s.ndim == 3) {
+    float2* t2 = reinterpret_cast<float2*>(wsb + ws.t2);
+    float2* v = reinterpret_cast<float2*>(wsb + ws.v);
+    if ((rc = launch_analysis(s, s.CI, x, nullptr, nullptr, t2, tw, 1.0f, 0, st))) return rc;
+    if ((rc = launch_outer(s, s.CI, true, t2, xhat, tw, st))) return rc;
+    if ((rc = launch_mix(s, false, xhat, yhat, w_blocks, st))) return rc;
+    if ((rc = launch_outer(s, s.CO, false, yhat, v, tw, st))) return rc;
+    return launch_synthesis(s, s.CI, s.CO, v, x, lin_w, s.CI, 1, lin_b, y, z_saved, tw, (float)(1.0 / (double)s.S), 1,
+                            s.act, st);
+  }
+  if ((rc = launch_analysis(s, s.CI, x, nullptr, nullptr, xhat, tw, 1.0f, 0, st))) return rc;
+  if ((rc = launch_mix(s, false, xhat, yhat, w_blocks, st))) return rc;
+  return launch_synthesis(s, s.CI, s.CO, yhat, x, lin_w, s.CI, 1, lin_b, y, z_saved, tw, (float)(1.0 / (double)s.S), 1,
+                          s.act, st);
+}
+
+int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const float* x,
+                      const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                      const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                      float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  if (!gy || !x || !z_saved || !xhat_saved || !w_blocks || !lin_w || !twiddles || !workspace)
+    return fail(DENO_E_INVALID, "null pointer argument");
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < nblk; ++j) {
+    if (w_blocks[j] == nullptr) return fail(DENO_E_INVALID, "null weight block");
+    if (gw_blocks != nullptr && gw_blocks[j] == nullptr) return fail(DENO_E_INVALID, "null weight-gradient block");
+  }
+  BwdWs ws;
+  if ((rc = bwd_ws(s, ws))) return rc;
+  if (workspace_bytes < ws.total) return fail(DENO_E_WORKSPACE, "workspace too small for deno_spectral_bwd");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* wsb = static_cast<char*>(workspace);
+  const TwPtrs tw = tw_ptrs(s, twiddles);
+  float* gz = reinterpret_cast<float*>(wsb + ws.gz);
+  float2* ghat = reinterpret_cast<float2*>(wsb + ws.ghat);
+  float2* gxhat = reinterpret_cast<float2*>(wsb + ws.gxhat);
+  const float2* xhat = static_cast<const float2*>(xhat_saved);
+  const float inv_s = (float)(1.0 / (double)s.S);
+
+  // gz = gy * act'(z);  G^ = (c_l / S) * truncated DFT(gz)
+  if (s.ndim == 3) {
+    float2* t2 = reinterpret_cast<float2*>(wsb + ws.t2);
+    if ((rc = launch_analysis(s, s.CO, gy, z_saved, gz, t2, tw, inv_s, 1, st))) return rc;
+    if ((rc = launch_outer(s, s.CO, true, t2, ghat, tw, st))) return rc;
+  } else {
+    if ((rc = launch_analysis(s, s.CO, gy, z_saved, gz, ghat, tw, inv_s, 1, st))) return rc;
+  }
+  if (gw_blocks != nullptr) {
+    if ((rc = launch_mix_wgrad(s, xhat, ghat, gw_blocks, st))) return rc;
+  }
+  if (gx != nullptr) {
+    if ((rc = launch_mix(s, true, ghat, gxhat, w_blocks, st))) return rc;
+    const float2* spec = gxhat;
+    if (s.ndim == 3) {
+      float2* v = reinterpret_cast<float2*>(wsb + ws.v);
+      if ((rc = launch_outer(s, s.CI, false, gxhat, v, tw, st))) return rc;
+      spec = v;
+    }
+    // gx = Re sum G^x e^{+i theta} + W_l^T gz   (channels swap roles: "input" = gz with CO channels)
+    if ((rc = launch_synthesis(s, s.CO, s.CI, spec, gz, lin_w, 1, s.CI, nullptr, gx, nullptr, tw, 1.0f, 0,
+                               DENO_ACT_IDENTITY, st)))
+      return rc;
+  }
+  if (glin_w != nullptr || glin_b != nullptr) {
+    float* partial = reinterpret_cast<float*>(wsb + ws.partial);
+    if ((rc = launch_bypass_wgrad(s, gz, x, partial, glin_w, glin_b, st))) return rc;
+  }
+  return DENO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// spectral_common.cuh - shared definitions for the spectral-convolution kernels.
+//
+// Compiles two ways: with nvcc for sm_100a (the product) and, under -DDENO_EMULATE, with g++
+// against tests/emu/cuda_emu.h so that the CPU test-suite can exercise the SIMT kernels'
+// index arithmetic and launch geometry without a GPU (test infrastructure only).
+#pragma once
+
+#ifdef DENO_EMULATE
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define DENO_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define DENO_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#include <stdint.h>
+
+namespace deno {
+
+// Activation ids mirror enum deno_activation in include/deno_spectral.h
+// (table of /root/reference/Models/configs.py:17-19).
+enum : int { ACT_IDENTITY = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_RELU = 3, ACT_TANH = 4, ACT_LEAKYRELU = 5 };
+
+__device__ __forceinline__ float act_apply(int act, float z) {
+  switch (act) {
+    case ACT_GELU: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
+    case ACT_SILU: return z / (1.0f + expf(-z));
+    case ACT_RELU: return z > 0.0f ? z : 0.0f;
+    case ACT_TANH: return tanhf(z);
+    case ACT_LEAKYRELU: return z > 0.0f ? z : 0.01f * z;
+    default: return z;
+  }
+}
+
+__device__ __forceinline__ float act_grad(int act, float z) {
+  switch (act) {
+    case ACT_GELU: {
+      float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+      float pdf = expf(-0.5f * z * z) * 0.39894228040143267794f;
+      return cdf + z * pdf;
+    }
+    case ACT_SILU: {
+      float s = 1.0f / (1.0f + expf(-z));
+      return s * (1.0f + z * (1.0f - s));
+    }
+    case ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
+    case ACT_TANH: {
+      float t = tanhf(z);
+      return 1.0f - t * t;
+    }
+    case ACT_LEAKYRELU: return z > 0.0f ? 1.0f : 0.01f;
+    default: return 1.0f;
+  }
+}
+
+// A "plane problem": the real tensor is seen as NB' = NBO*NBI batches of C channels of contiguous
+// H x W planes (W fastest).  1-D layers use H = 1; 3-D layers (X,Y,Z) use planes (Y,Z) with
+// NBI = X, so the same plane kernels serve every dimensionality.
+struct PlaneGeom {
+  int H, W;             // plane rows / cols
+  int KH;               // packed modes along H (2*m, or 1 when H == 1)
+  int MW;               // retained modes along W (half spectrum)
+  int C;                // channels of the tensor this geometry addresses
+  int NBO, NBI;         // batch = bo * NBI + bi
+  long long sbo, sbi, sc;  // element strides of bo, bi, channel
+};
+
+__host__ __device__ __forceinline__ long long plane_base(const PlaneGeom& g, int bprime, int c) {
+  int bo = bprime / g.NBI;
+  int bi = bprime - bo * g.NBI;
+  return (long long)bo * g.sbo + (long long)bi * g.sbi + (long long)c * g.sc;
+}
+
+__host__ __device__ __forceinline__ int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Maps a packed mode index to (weight block, offset inside the block); see oracle/dft_truth.py
+// for the packed layout and spectral_layers.py:196-199,318-325 for the block order.
+struct ModeDecode {
+  int ndim;
+  int m1, m2, m3;  // modes per axis (unused ones = 1)
+  int M;           // total packed modes
+  int Mblk;        // modes per weight block
+};
+
+__host__ __device__ __forceinline__ void decode_mode(const ModeDecode& md, int p, int& blk, int& off) {
+  if (md.ndim == 1) {
+    blk = 0;
+    off = p;
+  } else if (md.ndim == 2) {
+    int k = p / md.m2, l = p - k * md.m2;
+    blk = k >= md.m1 ? 1 : 0;
+    off = (k - blk * md.m1) * md.m2 + l;
+  } else {
+    int l = p % md.m3;
+    int t = p / md.m3;
+    int k2 = t % (2 * md.m2);
+    int k1 = t / (2 * md.m2);
+    int b1 = k1 >= md.m1 ? 1 : 0, b2 = k2 >= md.m2 ? 1 : 0;
+    blk = b1 + 2 * b2;
+    off = ((k1 - b1 * md.m1) * md.m2 + (k2 - b2 * md.m2)) * md.m3 + l;
+  }
+}
+
+}  // namespace deno

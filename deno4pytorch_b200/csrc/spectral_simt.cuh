@@ -1,0 +1,589 @@
+// spectral_simt.cuh - fp32 SIMT kernels of the spectral-convolution path (all shapes).
+//
+// These are the general kernels: any grid size, any mode count, any channel count.  They
+// implement the truncated-DFT statement of the layer (oracle/dft_truth.py) stage by stage:
+//
+//   plane_analysis   x (or gy*act'(z))  -> packed plane spectrum        (forward truncated rDFT,
+//                                          replaces the full rfftn of spectral_layers.py:95,191,310)
+//   outer_analysis   3-D only: contracts the leading axis X
+//   mode_mix         per-mode complex channel product                   (compl_mul*, :73-82,172-181,287-297)
+//   mode_mix_wgrad   weight gradient of the product
+//   outer_synthesis  3-D only: expands the leading axis X
+//   plane_synthesis  zero-padded inverse transform fused with the 1x1 bypass conv, bias and the
+//                    activation (replaces zeros + scatter + irfftn + add + act, :96-110,194-203,311-333)
+//   bypass_wgrad     gradient of the 1x1 conv weight / bias (two-stage deterministic reduction)
+//
+// Twiddle tables are produced on the host in fp64 (capi.cu) and laid out padded:
+//   twW[y][MWp]  (cos, sin)(2 pi l y / W),   MWp = round_up(MW, 4), zero in the padding
+//   twH[x][KH4]  (cos, sin)(2 pi f_k x / H), KH4 = round_up(KH, 4), zero in the padding
+//   cl[MWp]      Hermitian weights of the C2R transform
+#pragma once
+#include "spectral_common.cuh"
+
+namespace deno {
+
+constexpr int kSynthMaxRows = 8;  // rows per CTA tile in plane_synthesis (register accumulators)
+
+// ----------------------------------------------------------------------------------------------
+// plane_analysis
+// ----------------------------------------------------------------------------------------------
+struct AnalysisParams {
+  PlaneGeom g;
+  const float* u;      // x, or gy when FUSE_GZ
+  const float* z;      // FUSE_GZ: saved pre-activation
+  float* gz_out;       // FUSE_GZ: gz = gy * act'(z) is written here (same geometry as u)
+  float2* out;         // [nplanes][KH][MW]
+  const float2* twW;
+  const float2* twH;
+  const float* cl;
+  float scale;
+  int herm;            // multiply mode l by cl[l]
+  int act;
+  int nplanes;         // NBO*NBI*C
+  int G;               // planes per CTA
+  int RT;              // rows per tile (<= RTP)
+  int RTP;             // thread mapping: r = tid % RTP, lq = tid / RTP
+  int YC;              // columns per chunk
+  int RS;              // row split of stage 2
+};
+
+struct AnalysisSmem {
+  int xs, tws, ts, twh, acc, total;  // offsets / total in floats
+};
+
+__host__ __device__ inline AnalysisSmem analysis_smem(const AnalysisParams& p) {
+  const int MWp = round_up(p.g.MW, 4), KH4 = round_up(p.g.KH, 4);
+  AnalysisSmem s;
+  int off = 0;
+  s.xs = off;  off += round_up(p.RT * (p.YC + 1), 4);
+  s.tws = off; off += p.YC * MWp * 2;
+  s.ts = off;  off += p.RT * MWp * 2;
+  s.twh = off; off += p.g.H * KH4 * 2;
+  s.acc = off; off += p.RS * p.G * KH4 * p.g.MW * 2;
+  s.total = off;
+  return s;
+}
+
+template <bool FUSE_GZ>
+__global__ void plane_analysis_kernel(AnalysisParams p) {
+  DENO_DYN_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
+  const int MWp = round_up(MW, 4), KH4 = round_up(KH, 4), NLG = MWp / 4, KQ = KH4 / 4;
+  const int YCp = p.YC + 1;
+  const AnalysisSmem so = analysis_smem(p);
+  float* xs = smem + so.xs;
+  float2* tws = reinterpret_cast<float2*>(smem + so.tws);
+  float2* Ts = reinterpret_cast<float2*>(smem + so.ts);
+  float2* twHs = reinterpret_cast<float2*>(smem + so.twh);
+  float2* acc2 = reinterpret_cast<float2*>(smem + so.acc);
+
+  const int q0 = blockIdx.x * p.G;
+  const int Gc = min(p.G, p.nplanes - q0);
+  const int rows = Gc * H;
+  const int acc_stride = p.G * KH4 * MW;  // per row-split slice
+
+  for (int i = tid; i < H * KH4; i += nt) twHs[i] = p.twH[i];
+  for (int i = tid; i < p.RS * acc_stride; i += nt) acc2[i] = make_float2(0.f, 0.f);
+
+  const int r = tid % p.RTP, lq = tid / p.RTP;
+  const int ntask2 = p.G * KQ * MW;
+
+  for (int tile0 = 0; tile0 < rows; tile0 += p.RT) {
+    const int trows = min(p.RT, rows - tile0);
+    const bool active = (r < trows) && (lq < NLG);
+    float re0 = 0.f, re1 = 0.f, re2 = 0.f, re3 = 0.f, im0 = 0.f, im1 = 0.f, im2 = 0.f, im3 = 0.f;
+
+    for (int y0 = 0; y0 < W; y0 += p.YC) {
+      const int yc = min(p.YC, W - y0);
+      __syncthreads();  // previous chunk / previous tile fully consumed (also orders the init above)
+      for (int idx = tid; idx < trows * yc; idx += nt) {
+        const int rr = idx / yc, j = idx - rr * yc;
+        const int row = tile0 + rr;
+        const int gi = row / H, xr = row - gi * H;
+        const int q = q0 + gi;
+        const long long addr = plane_base(p.g, q / p.g.C, q % p.g.C) + (long long)xr * W + y0 + j;
+        float v = p.u[addr];
+        if (FUSE_GZ) {
+          v *= act_grad(p.act, p.z[addr]);
+          p.gz_out[addr] = v;
+        }
+        xs[rr * YCp + j] = v;
+      }
+      for (int idx = tid; idx < yc * MWp; idx += nt) tws[idx] = p.twW[(long long)y0 * MWp + idx];
+      __syncthreads();
+      if (active) {
+        const float* xrow = xs + r * YCp;
+        const float4* t4 = reinterpret_cast<const float4*>(tws) + lq * 2;
+        const int step = MWp / 2;
+#pragma unroll 4
+        for (int j = 0; j < yc; ++j) {
+          const float xv = xrow[j];
+          const float4 a = t4[j * step], b = t4[j * step + 1];
+          re0 = fmaf(xv, a.x, re0); im0 = fmaf(-xv, a.y, im0);
+          re1 = fmaf(xv, a.z, re1); im1 = fmaf(-xv, a.w, im1);
+          re2 = fmaf(xv, b.x, re2); im2 = fmaf(-xv, b.y, im2);
+          re3 = fmaf(xv, b.z, re3); im3 = fmaf(-xv, b.w, im3);
+        }
+      }
+    }
+    if (active) {
+      float2* t = Ts + r * MWp + lq * 4;
+      t[0] = make_float2(re0, im0);
+      t[1] = make_float2(re1, im1);
+      t[2] = make_float2(re2, im2);
+      t[3] = make_float2(re3, im3);
+    }
+    __syncthreads();
+    // stage 2: contract the rows of each plane against e^{-i phi(k, x)}; thread = (row split, plane, k quad, l)
+    for (int tt = tid; tt < ntask2 * p.RS; tt += nt) {
+      const int rs = tt / ntask2, task = tt - rs * ntask2;
+      const int l = task % MW;
+      const int kq = (task / MW) % KQ;
+      const int gi = task / (MW * KQ);
+      if (gi >= Gc) continue;
+      const int lo = max(gi * H, tile0), hi = min((gi + 1) * H, tile0 + trows);
+      float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int row = lo + rs; row < hi; row += p.RS) {
+        const float2 t = Ts[(row - tile0) * MWp + l];
+        const float4* e4 = reinterpret_cast<const float4*>(twHs + (row - gi * H) * KH4 + kq * 4);
+        const float4 ea = e4[0], eb = e4[1];
+        // (c - i s) * (tr + i ti) = (c tr + s ti) + i (c ti - s tr)
+        ar[0] = fmaf(ea.x, t.x, fmaf(ea.y, t.y, ar[0])); ai[0] = fmaf(ea.x, t.y, fmaf(-ea.y, t.x, ai[0]));
+        ar[1] = fmaf(ea.z, t.x, fmaf(ea.w, t.y, ar[1])); ai[1] = fmaf(ea.z, t.y, fmaf(-ea.w, t.x, ai[1]));
+        ar[2] = fmaf(eb.x, t.x, fmaf(eb.y, t.y, ar[2])); ai[2] = fmaf(eb.x, t.y, fmaf(-eb.y, t.x, ai[2]));
+        ar[3] = fmaf(eb.z, t.x, fmaf(eb.w, t.y, ar[3])); ai[3] = fmaf(eb.z, t.y, fmaf(-eb.w, t.x, ai[3]));
+      }
+      float2* a = acc2 + rs * acc_stride + (gi * KH4 + kq * 4) * MW + l;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 v = a[j * MW];
+        v.x += ar[j];
+        v.y += ai[j];
+        a[j * MW] = v;
+      }
+    }
+  }
+  __syncthreads();
+  for (int o = tid; o < Gc * KH * MW; o += nt) {
+    const int gi = o / (KH * MW);
+    const int rem = o - gi * KH * MW;
+    const int k = rem / MW, l = rem - k * MW;
+    float sr = 0.f, si = 0.f;
+    for (int rs = 0; rs < p.RS; ++rs) {
+      const float2 v = acc2[rs * acc_stride + (gi * KH4 + k) * MW + l];
+      sr += v.x;
+      si += v.y;
+    }
+    const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+    p.out[(long long)(q0 + gi) * KH * MW + rem] = make_float2(sr * f, si * f);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// outer axis (3-D): in/out are complex arrays indexed [b][x or k][c][Q] / [b][c][k][Q]
+// ----------------------------------------------------------------------------------------------
+struct OuterParams {
+  const float2* in;
+  float2* out;
+  const float2* twX;  // [X][KX4]
+  int B, C, X, KX, Q;
+};
+
+// out[b][c][k][q] = sum_x (cos - i sin)(k,x) * in[b][x][c][q];  thread = (q, k quad, c, b)
+__global__ void outer_analysis_kernel(OuterParams p) {
+  const int KX4 = round_up(p.KX, 4), KQ = KX4 / 4;
+  const long long total = (long long)p.B * p.C * KQ * p.Q;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int q = int(t % p.Q);
+    long long rest = t / p.Q;
+    const int kq = int(rest % KQ);
+    rest /= KQ;
+    const int c = int(rest % p.C);
+    const int b = int(rest / p.C);
+    float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+    const float2* src = p.in + ((long long)b * p.X * p.C + c) * p.Q + q;
+    for (int x = 0; x < p.X; ++x) {
+      const float2 v = src[(long long)x * p.C * p.Q];
+      const float4* e4 = reinterpret_cast<const float4*>(p.twX + x * KX4 + kq * 4);
+      const float4 ea = e4[0], eb = e4[1];
+      ar[0] = fmaf(ea.x, v.x, fmaf(ea.y, v.y, ar[0])); ai[0] = fmaf(ea.x, v.y, fmaf(-ea.y, v.x, ai[0]));
+      ar[1] = fmaf(ea.z, v.x, fmaf(ea.w, v.y, ar[1])); ai[1] = fmaf(ea.z, v.y, fmaf(-ea.w, v.x, ai[1]));
+      ar[2] = fmaf(eb.x, v.x, fmaf(eb.y, v.y, ar[2])); ai[2] = fmaf(eb.x, v.y, fmaf(-eb.y, v.x, ai[2]));
+      ar[3] = fmaf(eb.z, v.x, fmaf(eb.w, v.y, ar[3])); ai[3] = fmaf(eb.z, v.y, fmaf(-eb.w, v.x, ai[3]));
+    }
+    float2* dst = p.out + (((long long)b * p.C + c) * p.KX + kq * 4) * p.Q + q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (kq * 4 + j < p.KX) dst[(long long)j * p.Q] = make_float2(ar[j], ai[j]);
+  }
+}
+
+// out[b][x][c][q] = sum_k (cos + i sin)(k,x) * in[b][c][k][q];  thread = (q, x quad, c, b)
+__global__ void outer_synthesis_kernel(OuterParams p) {
+  const int KX4 = round_up(p.KX, 4);
+  const int XQ = (p.X + 3) / 4;
+  const long long total = (long long)p.B * p.C * XQ * p.Q;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int q = int(t % p.Q);
+    long long rest = t / p.Q;
+    const int xq = int(rest % XQ);
+    rest /= XQ;
+    const int c = int(rest % p.C);
+    const int b = int(rest / p.C);
+    float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+    const float2* src = p.in + (((long long)b * p.C + c) * p.KX) * p.Q + q;
+    for (int k = 0; k < p.KX; ++k) {
+      const float2 v = src[(long long)k * p.Q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = min(xq * 4 + j, p.X - 1);
+        const float2 e = p.twX[x * KX4 + k];
+        // (c + i s) * (vr + i vi)
+        ar[j] = fmaf(e.x, v.x, fmaf(-e.y, v.y, ar[j]));
+        ai[j] = fmaf(e.x, v.y, fmaf(e.y, v.x, ai[j]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = xq * 4 + j;
+      if (x < p.X) p.out[(((long long)b * p.X + x) * p.C + c) * p.Q + q] = make_float2(ar[j], ai[j]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// mode_mix:  out[b,co,p] = sum_ci in[b,ci,p] * (conj?) W[ci,co,p]
+// ----------------------------------------------------------------------------------------------
+struct MixParams {
+  const float2* in;
+  float2* out;
+  const float2* w[4];
+  ModeDecode md;
+  int B, CI, CO;
+  long long w_sci, w_sco;  // complex-element strides of the contracted / produced channel inside a block
+  int conj_w;
+};
+
+constexpr int kMixBatchTile = 4;
+
+// blockDim = (32 modes, 8 output channels); grid = (ceil(M/32), ceil(CO/8), ceil(B/4))
+__global__ void mode_mix_kernel(MixParams p) {
+  const int M = p.md.M;
+  const int pm = blockIdx.x * blockDim.x + threadIdx.x;
+  const int co = blockIdx.y * blockDim.y + threadIdx.y;
+  const int b0 = blockIdx.z * kMixBatchTile;
+  if (pm >= M || co >= p.CO) return;
+  int blk, off;
+  decode_mode(p.md, pm, blk, off);
+  const float2* wb = blk == 0 ? p.w[0] : (blk == 1 ? p.w[1] : (blk == 2 ? p.w[2] : p.w[3]));
+  const float2* w = wb + (long long)co * p.w_sco + off;
+  float ar[kMixBatchTile], ai[kMixBatchTile];
+#pragma unroll
+  for (int j = 0; j < kMixBatchTile; ++j) ar[j] = ai[j] = 0.f;
+  const float sgn = p.conj_w ? -1.0f : 1.0f;
+  for (int ci = 0; ci < p.CI; ++ci) {
+    float2 wv = w[(long long)ci * p.w_sci];
+    wv.y *= sgn;
+#pragma unroll
+    for (int j = 0; j < kMixBatchTile; ++j) {
+      const int b = min(b0 + j, p.B - 1);
+      const float2 v = p.in[((long long)b * p.CI + ci) * M + pm];
+      ar[j] = fmaf(v.x, wv.x, fmaf(-v.y, wv.y, ar[j]));
+      ai[j] = fmaf(v.x, wv.y, fmaf(v.y, wv.x, ai[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kMixBatchTile; ++j)
+    if (b0 + j < p.B) p.out[((long long)(b0 + j) * p.CO + co) * M + pm] = make_float2(ar[j], ai[j]);
+}
+
+// gW[i,o,p] = sum_b conj(xhat[b,i,p]) * ghat[b,o,p]
+struct MixWgradParams {
+  const float2* xhat;
+  const float2* ghat;
+  float2* gw[4];
+  ModeDecode md;
+  int B, CI, CO;
+};
+
+// blockDim = (32 modes, 8 output-channel quads); grid = (ceil(M/32), ceil(ceil(CO/4)/8), CI)
+__global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
+  const int M = p.md.M;
+  const int pm = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oq = blockIdx.y * blockDim.y + threadIdx.y;
+  const int ci = blockIdx.z;
+  if (pm >= M || oq * 4 >= p.CO) return;
+  int blk, off;
+  decode_mode(p.md, pm, blk, off);
+  float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = 0; b < p.B; ++b) {
+    const float2 xv = p.xhat[((long long)b * p.CI + ci) * M + pm];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = min(oq * 4 + j, p.CO - 1);
+      const float2 gv = p.ghat[((long long)b * p.CO + o) * M + pm];
+      // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
+      ar[j] = fmaf(xv.x, gv.x, fmaf(xv.y, gv.y, ar[j]));
+      ai[j] = fmaf(xv.x, gv.y, fmaf(-xv.y, gv.x, ai[j]));
+    }
+  }
+  float2* gb = blk == 0 ? p.gw[0] : (blk == 1 ? p.gw[1] : (blk == 2 ? p.gw[2] : p.gw[3]));
+  float2* dst = gb + ((long long)ci * p.CO) * p.md.Mblk + off;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (oq * 4 + j < p.CO) dst[(long long)(oq * 4 + j) * p.md.Mblk] = make_float2(ar[j], ai[j]);
+}
+
+// ----------------------------------------------------------------------------------------------
+// plane_synthesis: y = act( scale * sum_{k,l} c_l Re(spec e^{+i theta}) + sum_i W[o,i] u[i] + bias[o] )
+// ----------------------------------------------------------------------------------------------
+struct SynthParams {
+  PlaneGeom g;           // geometry of the bypass input u (C = CI channels)
+  int CO;                // produced channels
+  long long sbo_out;     // bo stride of the produced tensors (sbi / sc equal the input's)
+  const float2* spec;    // [NB'][CO][KH][MW]
+  const float* u;
+  const float* lw;       // bypass weight, W[o,i] = lw[o*lw_so + i*lw_si]
+  long long lw_so, lw_si;
+  const float* bias;     // may be null
+  float* y;
+  float* z;              // may be null
+  const float2* twW;
+  const float2* twH;
+  const float* cl;
+  float scale;
+  int herm;
+  int act;
+  int R;                 // rows per tile (1 when H == 1)
+  int PTS;               // points per tile (R*W when H > 1)
+  int tiles;             // tiles per plane
+};
+
+struct SynthSmem {
+  int xs, wls, bias, us, total;  // floats
+  int PTSp, COp, MWp;
+};
+
+__host__ __device__ inline SynthSmem synth_smem(const SynthParams& p) {
+  SynthSmem s;
+  s.PTSp = round_up(p.PTS, 4);
+  s.COp = round_up(p.CO, 8);
+  s.MWp = round_up(p.g.MW, 4);
+  int off = 0;
+  s.xs = off;   off += p.g.C * s.PTSp;
+  s.wls = off;  off += p.g.C * s.COp;
+  s.bias = off; off += s.COp;
+  s.us = off;   off += s.COp * p.R * s.MWp * 2;
+  s.total = off;
+  return s;
+}
+
+__global__ void plane_synthesis_kernel(SynthParams p) {
+  DENO_DYN_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = p.CO;
+  const int KH4 = round_up(KH, 4);
+  const SynthSmem so = synth_smem(p);
+  const int PTSp = so.PTSp, COp = so.COp, MWp = so.MWp, R = p.R;
+  float* xs = smem + so.xs;
+  float* wls = smem + so.wls;
+  float* bs = smem + so.bias;
+  float2* Us = reinterpret_cast<float2*>(smem + so.us);
+
+  const int bp = blockIdx.x / p.tiles;
+  const int tile = blockIdx.x - bp * p.tiles;
+  const int p0 = tile * p.PTS;
+  const int npts = min(p.PTS, H * W - p0);
+  const int x0 = p0 / W;
+  const int trows = (H > 1) ? min(R, H - x0) : 1;
+
+  // bypass operands
+  for (int idx = tid; idx < CI * COp; idx += nt) {
+    const int i = idx / COp, o = idx - i * COp;
+    wls[idx] = (o < CO) ? p.lw[(long long)o * p.lw_so + (long long)i * p.lw_si] : 0.f;
+  }
+  for (int o = tid; o < COp; o += nt) bs[o] = (p.bias != nullptr && o < CO) ? p.bias[o] : 0.f;
+  for (int idx = tid; idx < CI * npts; idx += nt) {
+    const int i = idx / npts, pt = idx - i * npts;
+    xs[i * PTSp + pt] = p.u[plane_base(p.g, bp, i) + p0 + pt];
+  }
+  // stage A: U[o][rr][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0+rr)}
+  for (int task = tid; task < COp * MWp; task += nt) {
+    const int o = task / MWp, l = task - o * MWp;
+    float ar[kSynthMaxRows], ai[kSynthMaxRows];
+#pragma unroll
+    for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
+    float f = 0.f;
+    if (o < CO && l < MW) {
+      f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+      const float2* sp = p.spec + ((long long)bp * CO + o) * KH * MW + l;
+      for (int k = 0; k < KH; ++k) {
+        const float2 s = sp[k * MW];
+#pragma unroll
+        for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+          if (rr < trows) {
+            const float2 e = p.twH[(x0 + rr) * KH4 + k];
+            ar[rr] = fmaf(s.x, e.x, fmaf(-s.y, e.y, ar[rr]));
+            ai[rr] = fmaf(s.x, e.y, fmaf(s.y, e.x, ai[rr]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kSynthMaxRows; ++rr)
+      if (rr < R) Us[(o * R + rr) * MWp + l] = make_float2(ar[rr] * f, ai[rr] * f);
+  }
+  __syncthreads();
+
+  // stage B: one point per thread, eight produced channels at a time
+  const int half = MWp / 2;
+  for (int pt = tid; pt < npts; pt += nt) {
+    const int P = p0 + pt;
+    const int xr = P / W;
+    const int yv = P - xr * W;
+    const int rr = xr - x0;
+    const float4* twp = reinterpret_cast<const float4*>(p.twW + (long long)yv * MWp);
+    const long long obase = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi + P;
+    for (int og = 0; og < COp; og += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = bs[og + j];
+      for (int i = 0; i < CI; ++i) {
+        const float xv = xs[i * PTSp + pt];
+        const float4* w4 = reinterpret_cast<const float4*>(wls + i * COp + og);
+        const float4 wa = w4[0], wb = w4[1];
+        acc[0] = fmaf(xv, wa.x, acc[0]); acc[1] = fmaf(xv, wa.y, acc[1]);
+        acc[2] = fmaf(xv, wa.z, acc[2]); acc[3] = fmaf(xv, wa.w, acc[3]);
+        acc[4] = fmaf(xv, wb.x, acc[4]); acc[5] = fmaf(xv, wb.y, acc[5]);
+        acc[6] = fmaf(xv, wb.z, acc[6]); acc[7] = fmaf(xv, wb.w, acc[7]);
+      }
+      for (int lc = 0; lc < half; ++lc) {
+        const float4 t = twp[lc];  // (c0, s0, c1, s1)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 uu = reinterpret_cast<const float4*>(Us + ((og + j) * R + rr) * MWp)[lc];
+          acc[j] = fmaf(uu.x, t.x, fmaf(-uu.y, t.y, fmaf(uu.z, t.z, fmaf(-uu.w, t.w, acc[j]))));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int o = og + j;
+        if (o < CO) {
+          const long long a = obase + (long long)o * p.g.sc;
+          if (p.z != nullptr) p.z[a] = acc[j];
+          p.y[a] = act_apply(p.act, acc[j]);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// bypass_wgrad: partial[cta][o*CI+i] = sum_pt gz[o,pt] x[i,pt];  partial[cta][CO*CI+o] = sum_pt gz[o,pt]
+// ----------------------------------------------------------------------------------------------
+struct WgradParams {
+  PlaneGeom gx;        // geometry of x (C = CI)
+  int CO;
+  long long sbo_g;     // bo stride of gz
+  const float* gz;
+  const float* x;
+  float* partial;      // [ncta][CO*CI + CO]
+  int PTS;             // points per tile (multiple of 4)
+  int tiles;           // tiles per plane
+};
+
+__host__ __device__ inline int wgrad_smem_floats(const WgradParams& p) {
+  return (round_up(p.CO, 1) + round_up(p.gx.C, 4)) * (p.PTS + 4);
+}
+
+__global__ void bypass_wgrad_partial_kernel(WgradParams p) {
+  DENO_DYN_SMEM(smem_raw);
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int CI = p.gx.C, CO = p.CO, CIp = round_up(CI, 4), CIQ = CIp / 4;
+  const int PTS = p.PTS, pitch = PTS + 4;
+  float* gs = smem;                 // [CO][pitch]
+  float* xs = smem + CO * pitch;    // [CIp][pitch]
+  const int bp = blockIdx.x / p.tiles;
+  const int tile = blockIdx.x - bp * p.tiles;
+  const int p0 = tile * PTS;
+  const int npts = min(PTS, p.gx.H * p.gx.W - p0);
+  const long long gbase = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
+
+  for (int idx = tid; idx < CO * PTS; idx += nt) {
+    const int o = idx / PTS, pt = idx - o * PTS;
+    gs[o * pitch + pt] = (pt < npts) ? p.gz[gbase + (long long)o * p.gx.sc + pt] : 0.f;
+  }
+  for (int idx = tid; idx < CIp * PTS; idx += nt) {
+    const int i = idx / PTS, pt = idx - i * PTS;
+    xs[i * pitch + pt] = (pt < npts && i < CI) ? p.x[plane_base(p.gx, bp, i) + p0 + pt] : 0.f;
+  }
+  __syncthreads();
+  float* out = p.partial + (long long)blockIdx.x * (CO * CI + CO);
+  for (int task = tid; task < CO * CIQ; task += nt) {
+    const int o = task / CIQ, iq = task - o * CIQ;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float4* g4 = reinterpret_cast<const float4*>(gs + o * pitch);
+    const float4* x0 = reinterpret_cast<const float4*>(xs + (iq * 4 + 0) * pitch);
+    const float4* x1 = reinterpret_cast<const float4*>(xs + (iq * 4 + 1) * pitch);
+    const float4* x2 = reinterpret_cast<const float4*>(xs + (iq * 4 + 2) * pitch);
+    const float4* x3 = reinterpret_cast<const float4*>(xs + (iq * 4 + 3) * pitch);
+    for (int v = 0; v < PTS / 4; ++v) {
+      const float4 g = g4[v];
+      float4 t = x0[v];
+      a0 = fmaf(g.x, t.x, fmaf(g.y, t.y, fmaf(g.z, t.z, fmaf(g.w, t.w, a0))));
+      t = x1[v];
+      a1 = fmaf(g.x, t.x, fmaf(g.y, t.y, fmaf(g.z, t.z, fmaf(g.w, t.w, a1))));
+      t = x2[v];
+      a2 = fmaf(g.x, t.x, fmaf(g.y, t.y, fmaf(g.z, t.z, fmaf(g.w, t.w, a2))));
+      t = x3[v];
+      a3 = fmaf(g.x, t.x, fmaf(g.y, t.y, fmaf(g.z, t.z, fmaf(g.w, t.w, a3))));
+    }
+    const int i = iq * 4;
+    if (i + 0 < CI) out[o * CI + i + 0] = a0;
+    if (i + 1 < CI) out[o * CI + i + 1] = a1;
+    if (i + 2 < CI) out[o * CI + i + 2] = a2;
+    if (i + 3 < CI) out[o * CI + i + 3] = a3;
+  }
+  for (int o = tid; o < CO; o += nt) {
+    float s = 0.f;
+    for (int pt = 0; pt < PTS; ++pt) s += gs[o * pitch + pt];
+    out[CO * CI + o] = s;
+  }
+}
+
+struct WgradReduceParams {
+  const float* partial;
+  int ncta, nj, nw;   // nj = CO*CI + CO outputs, the first nw go to glw, the rest to glb
+  float* glw;         // may be null
+  float* glb;         // may be null
+};
+
+// blockDim = (32 outputs, 8 slices); grid = ceil(nj / 32).  Fixed summation order -> deterministic.
+__global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
+  DENO_DYN_SMEM(smem_raw);
+  float* red = reinterpret_cast<float*>(smem_raw);  // [8][32]
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int slice = threadIdx.y;
+  float s = 0.f;
+  if (j < p.nj)
+    for (int c = slice; c < p.ncta; c += 8) s += p.partial[(long long)c * p.nj + j];
+  red[slice * 32 + threadIdx.x] = s;
+  __syncthreads();
+  if (slice == 0 && j < p.nj) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k * 32 + threadIdx.x];
+    if (j < p.nw) {
+      if (p.glw != nullptr) p.glw[j] = t;
+    } else if (p.glb != nullptr) {
+      p.glb[j - p.nw] = t;
+    }
+  }
+}
+
+}  // namespace deno

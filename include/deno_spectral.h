@@ -1,0 +1,120 @@
+/*
+ * deno_spectral.h - C ABI of the B200-native FNO spectral-convolution path.
+ *
+ * One shared library (libdeno_spectral.so, built by plain nvcc for sm_100a, no torch
+ * headers) exports the functions below.  They replace, for the hot path only, the
+ * library calls the reference makes from Python:
+ *
+ *   deno_spectral_fwd  <->  SpectralConv1d/2d/3d.forward
+ *                           /root/reference/Models/fno/spectral_layers.py:84-115, 183-208, 299-338
+ *                           (conv1x1 + rfftn + corner einsum + zero-pad + irfftn + add + activation)
+ *   deno_spectral_bwd  <->  the autograd graph PyTorch records for those lines
+ *                           (FftR2CBackward / BmmBackward / FftC2RBackward / ConvolutionBackward /
+ *                            GeluBackward), SURVEY.md section 2a
+ *
+ * Conventions
+ *   - every pointer except `desc`, the block-pointer arrays and `deno_spectral_twiddle_fill`'s
+ *     buffer is a DEVICE pointer; the caller (PyTorch) owns every buffer, the library never
+ *     allocates, frees or synchronises, and keeps no mutable global state;
+ *   - activations are contiguous channels-first fp32 `(B, C, *spatial)`;
+ *   - spectral weights are the reference's parameters as they sit in memory:
+ *     `(Cin, Cout, *modes)` complex64 == `(Cin, Cout, *modes, 2)` fp32, 1 / 2 / 4 blocks in the
+ *     reference's order weights1..4 (spectral_layers.py:65-68, 159-169, 272-284);
+ *   - `lin_w` is `linear.weight` `(Cout, Cin, 1[,1[,1]])`, `lin_b` is `linear.bias` `(Cout)`;
+ *   - a call only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = success; otherwise a DENO_E_* code and deno_last_error() (thread-local text).
+ *
+ * The reference-side binding (ctypes) is shown in INTEGRATION.md.
+ */
+#ifndef DENO_SPECTRAL_H_
+#define DENO_SPECTRAL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DENO_SPECTRAL_ABI_VERSION 1
+
+enum deno_status {
+  DENO_OK = 0,
+  DENO_E_INVALID = 1,     /* bad descriptor / null pointer / size mismatch            */
+  DENO_E_UNSUPPORTED = 2, /* legal for the reference but outside what the kernels do */
+  DENO_E_WORKSPACE = 3,   /* workspace_bytes smaller than deno_spectral_workspace_bytes */
+  DENO_E_CUDA = 4         /* a CUDA runtime call failed (text has cudaGetErrorString)  */
+};
+
+/* Activation table of /root/reference/Models/configs.py:17-19 (None -> SiLU on the Python side). */
+enum deno_activation {
+  DENO_ACT_IDENTITY = 0, /* used when a caller swaps `.activation` for Identity (Transformers.py:403) */
+  DENO_ACT_GELU = 1,     /* erf form, nn.GELU() default */
+  DENO_ACT_SILU = 2,
+  DENO_ACT_RELU = 3,
+  DENO_ACT_TANH = 4,
+  DENO_ACT_LEAKYRELU = 5 /* negative_slope 0.01 */
+};
+
+/* Shape of one layer call.  `spatial`/`modes` use the first `ndim` entries. */
+typedef struct deno_spectral_desc {
+  int32_t ndim;       /* 1, 2 or 3                                            */
+  int32_t batch;      /* B                                                    */
+  int32_t cin, cout;  /* in_dim, out_dim of the layer                         */
+  int32_t spatial[3]; /* padded grid sizes as seen by the layer               */
+  int32_t modes[3];   /* modes1..3 (retained modes per axis)                  */
+  int32_t act;        /* enum deno_activation                                 */
+  int32_t flags;      /* reserved, must be 0                                  */
+} deno_spectral_desc;
+
+int deno_spectral_abi_version(void);
+const char* deno_last_error(void);
+
+/* Number of retained complex modes M (1-D m; 2-D 2*m1*m2; 3-D 4*m1*m2*m3); 0 on a bad descriptor. */
+size_t deno_spectral_num_modes(const deno_spectral_desc* desc);
+
+/* Constant DFT tables.  The caller allocates `deno_spectral_twiddle_bytes` on the HOST, lets
+ * `deno_spectral_twiddle_fill` write them (computed in fp64, rounded once to fp32), copies the
+ * buffer to the device once per (shape, modes) and passes that device pointer as `twiddles`. */
+size_t deno_spectral_twiddle_bytes(const deno_spectral_desc* desc);
+int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, size_t bytes);
+
+/* Scratch the caller must provide to fwd / bwd (bytes, device memory, 256-byte aligned). */
+size_t deno_spectral_workspace_bytes(const deno_spectral_desc* desc, int backward);
+
+/* Bytes of the packed input spectrum X^ (B, Cin, M) complex64 that fwd can save for bwd. */
+size_t deno_spectral_xhat_bytes(const deno_spectral_desc* desc);
+
+/*
+ * y = act( irfftn(corner_mix(rfftn(x))) + conv1x1(x) + bias )
+ *   x          (B, Cin, *spatial) fp32
+ *   w_blocks   HOST array of 1/2/4 DEVICE pointers to the weight blocks
+ *   lin_b      may be NULL
+ *   y          (B, Cout, *spatial) fp32
+ *   z_saved    pre-activation, same shape as y; NULL for inference
+ *   xhat_saved packed spectrum of x for the weight gradient; NULL for inference
+ */
+int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void* const* w_blocks,
+                      const float* lin_w, const float* lin_b, const void* twiddles, float* y,
+                      float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/*
+ * Gradients of the same call.  Any of gx / gw_blocks / glin_w / glin_b may be NULL to skip it.
+ *   gy         (B, Cout, *spatial) fp32 cotangent
+ *   gw_blocks  HOST array of DEVICE pointers, same layout as the weights; PyTorch's convention for
+ *              complex leaves (grad = dL/dRe + i dL/dIm), overwritten (not accumulated)
+ */
+int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const float* x,
+                      const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                      const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                      float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Number of kernels the last fwd / bwd call on this thread enqueued (bench.py's gpu_launches). */
+int deno_spectral_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENO_SPECTRAL_H_ */

@@ -1,0 +1,112 @@
+"""Builds and drives the host-emulated kernel library (TEST INFRASTRUCTURE, see tests/emu/cuda_emu.h).
+
+The same capi.cu / spectral_simt.cuh that nvcc compiles for sm_100a are compiled here with g++
+and -DDENO_EMULATE; "device pointers" are numpy buffers.  Used only by the CPU test-suite to
+check index arithmetic, workspace carving and launch geometry before GPU time is spent.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from deno4pytorch_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC_DIR = os.path.join(ROOT, "deno4pytorch_b200", "csrc")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+OUT = os.path.join(EMU_DIR, "_build", "libdeno_spectral_emu.so")
+
+_lib = None
+
+
+def _stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".cu", ".cuh"))]
+    deps += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "deno_spectral.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if _stale():
+            os.makedirs(os.path.dirname(OUT), exist_ok=True)
+            cmd = ["g++", "-O2", "-g", "-std=c++17", "-DDENO_EMULATE", "-I", EMU_DIR, "-x", "c++",
+                   os.path.join(SRC_DIR, "capi.cu"), "-shared", "-fPIC", "-o", OUT]
+            subprocess.run(cmd, check=True)
+        _lib = _capi.bind(C.CDLL(OUT))
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as_blocks(weights):
+    out = []
+    for w in weights:
+        w = np.asarray(w)
+        if np.iscomplexobj(w):
+            w = np.ascontiguousarray(w.astype(np.complex64))
+        else:
+            w = np.ascontiguousarray(w.astype(np.float32))
+        out.append(w)
+    return out
+
+
+class EmuLayer:
+    """One layer call through the emulated C ABI."""
+
+    def __init__(self, x, weights, lin_w, lin_b, modes, act):
+        self.lib = load()
+        self.x = np.ascontiguousarray(x, dtype=np.float32)
+        self.w = _as_blocks(weights)
+        self.lin_w = np.ascontiguousarray(lin_w, dtype=np.float32)
+        self.lin_b = None if lin_b is None else np.ascontiguousarray(lin_b, dtype=np.float32)
+        B, cin = self.x.shape[:2]
+        spatial = self.x.shape[2:]
+        cout = self.lin_w.shape[0]
+        modes = (modes,) * len(spatial) if isinstance(modes, int) else tuple(modes)
+        self.desc = _capi.make_desc(B, cin, cout, spatial, modes, act)
+        self.out_shape = (B, cout) + tuple(spatial)
+        nb = self.lib.deno_spectral_twiddle_bytes(C.byref(self.desc))
+        if nb == 0:
+            raise _capi.DenoError(self.lib.deno_last_error().decode())
+        self.tw = np.zeros(nb // 4, dtype=np.float32)
+        _capi.check(self.lib, self.lib.deno_spectral_twiddle_fill(C.byref(self.desc), _ptr(self.tw), nb), "twiddle_fill")
+        self.M = self.lib.deno_spectral_num_modes(C.byref(self.desc))
+
+    def forward(self, save=True):
+        lib, d = self.lib, self.desc
+        y = np.full(self.out_shape, np.nan, dtype=np.float32)
+        self.z = np.full(self.out_shape, np.nan, dtype=np.float32) if save else None
+        self.xhat = np.full((self.x.shape[0], self.x.shape[1], self.M), np.nan, dtype=np.complex64) if save else None
+        nws = lib.deno_spectral_workspace_bytes(C.byref(d), 0)
+        ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
+        wptrs = _capi.pointer_array([w.ctypes.data for w in self.w])
+        rc = lib.deno_spectral_fwd(C.byref(d), _ptr(self.x), wptrs, _ptr(self.lin_w), _ptr(self.lin_b), _ptr(self.tw),
+                                   _ptr(y), _ptr(self.z), _ptr(self.xhat), _ptr(ws), nws, None)
+        _capi.check(lib, rc, "deno_spectral_fwd")
+        self.fwd_launches = lib.deno_spectral_last_launch_count()
+        return y
+
+    def backward(self, gy):
+        lib, d = self.lib, self.desc
+        gy = np.ascontiguousarray(gy, dtype=np.float32)
+        gx = np.full(self.x.shape, np.nan, dtype=np.float32)
+        gws = [np.full(w.shape, np.nan, dtype=w.dtype) for w in self.w]
+        glw = np.full(self.lin_w.shape, np.nan, dtype=np.float32)
+        glb = np.full((self.lin_w.shape[0],), np.nan, dtype=np.float32)
+        nws = lib.deno_spectral_workspace_bytes(C.byref(d), 1)
+        ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
+        wptrs = _capi.pointer_array([w.ctypes.data for w in self.w])
+        gwptrs = _capi.pointer_array([g.ctypes.data for g in gws])
+        rc = lib.deno_spectral_bwd(C.byref(d), _ptr(gy), _ptr(self.x), _ptr(self.z), _ptr(self.xhat), wptrs,
+                                   _ptr(self.lin_w), _ptr(self.tw), _ptr(gx), gwptrs, _ptr(glw), _ptr(glb), _ptr(ws),
+                                   nws, None)
+        _capi.check(lib, rc, "deno_spectral_bwd")
+        self.bwd_launches = lib.deno_spectral_last_launch_count()
+        return gx, gws, glw, glb
