@@ -1,0 +1,166 @@
+"""``spectral_conv`` - the autograd boundary between PyTorch and libdeno_spectral.so.
+
+One call = one ``SpectralConv{1,2,3}d.forward`` of the reference
+(/root/reference/Models/fno/spectral_layers.py:84-115, 183-208, 299-338); its backward is the
+hand-written adjoint, not autograd through library ops.  PyTorch is used
+here for device memory, streams and the autograd graph only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._lib import lib
+
+_TWIDDLES: Dict[tuple, torch.Tensor] = {}
+_LAUNCHES = {"count": 0}
+
+
+def launch_count() -> int:
+    """Kernels enqueued through this module since import (bench.py's ``gpu_launches``)."""
+    return _LAUNCHES["count"]
+
+
+def _normalize_modes(modes, ndim: int) -> Tuple[int, ...]:
+    if isinstance(modes, int):
+        return (modes,) * ndim
+    modes = tuple(int(m) for m in modes)
+    if len(modes) != ndim:
+        raise ValueError(f"expected {ndim} mode counts, got {modes}")
+    return modes
+
+
+def _desc_key(d: _capi.SpectralDesc):
+    return (d.ndim, d.batch, d.cin, d.cout, tuple(d.spatial), tuple(d.modes))
+
+
+def _twiddles(d: _capi.SpectralDesc, device: torch.device) -> torch.Tensor:
+    """Constant DFT tables: filled on the host in fp64 by the library, uploaded once per shape."""
+    key = (device.index, d.ndim, tuple(d.spatial), tuple(d.modes))
+    t = _TWIDDLES.get(key)
+    if t is None:
+        L = lib()
+        nbytes = L.deno_spectral_twiddle_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _capi.DenoError(L.deno_last_error().decode())
+        host = np.empty(nbytes // 4, dtype=np.float32)
+        _capi.check(L, L.deno_spectral_twiddle_fill(C.byref(d), host.ctypes.data_as(C.c_void_p), nbytes),
+                    "deno_spectral_twiddle_fill")
+        t = torch.from_numpy(host).to(device)
+        _TWIDDLES[key] = t
+    return t
+
+
+def _check_input(x: torch.Tensor, what: str):
+    if not x.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: deno4pytorch_b200 has no CPU path "
+                           "(the reference's own torch.fft path covers CPU tensors)")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{what} must be float32 (got {x.dtype}); the spectral path is fp32 in / fp32 out")
+
+
+def _check_weight(w: torch.Tensor, cin: int, cout: int, modes: Tuple[int, ...], j: int):
+    shape_c = (cin, cout) + modes
+    if w.dtype == torch.complex64 and tuple(w.shape) == shape_c:
+        return
+    if w.dtype == torch.float32 and tuple(w.shape) == shape_c + (2,):
+        return
+    raise RuntimeError(f"weights{j + 1} must be complex64 {shape_c} or float32 {shape_c + (2,)}, "
+                       f"got {w.dtype} {tuple(w.shape)}")
+
+
+class _SpectralConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lin_w, lin_b, modes, act, *weights):
+        L = lib()
+        _check_input(x, "input")
+        ndim = x.dim() - 2
+        if ndim not in (1, 2, 3):
+            raise RuntimeError("input must be (B, C, *spatial) with 1-3 spatial dims")
+        B, cin = x.shape[:2]
+        spatial = tuple(x.shape[2:])
+        cout = lin_w.shape[0]
+        if lin_w.shape[1] != cin or lin_w.numel() != cout * cin:
+            raise RuntimeError(f"linear.weight {tuple(lin_w.shape)} does not match {cin} input channels")
+        if len(weights) != 2 ** (ndim - 1):
+            raise RuntimeError(f"{ndim}-D layer needs {2 ** (ndim - 1)} weight blocks, got {len(weights)}")
+        for j, w in enumerate(weights):
+            _check_weight(w, cin, cout, modes, j)
+        d = _capi.make_desc(B, cin, cout, spatial, modes, act)
+
+        needs_grad = any(ctx.needs_input_grad)
+        xc = x.contiguous()
+        wc = [w.contiguous() for w in weights]
+        lw = lin_w.contiguous()
+        lb = None if lin_b is None else lin_b.contiguous()
+        dev = x.device
+        with torch.cuda.device(dev):
+            tw = _twiddles(d, dev)
+            y = torch.empty((B, cout) + spatial, dtype=torch.float32, device=dev)
+            z = torch.empty_like(y) if needs_grad else None
+            nmodes = L.deno_spectral_num_modes(C.byref(d))
+            xhat = torch.empty((B, cin, nmodes), dtype=torch.complex64, device=dev) if needs_grad else None
+            nws = L.deno_spectral_workspace_bytes(C.byref(d), 0)
+            ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = L.deno_spectral_fwd(C.byref(d), xc.data_ptr(), _capi.pointer_array([w.data_ptr() for w in wc]),
+                                     lw.data_ptr(), None if lb is None else lb.data_ptr(), tw.data_ptr(),
+                                     y.data_ptr(), None if z is None else z.data_ptr(),
+                                     None if xhat is None else xhat.data_ptr(), ws.data_ptr(), nws, stream)
+            _capi.check(L, rc, "deno_spectral_fwd")
+            _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
+        if needs_grad:
+            ctx.save_for_backward(xc, z, xhat, lw, *wc)
+            ctx.desc = d
+            ctx.has_bias = lin_b is not None
+            ctx.weight_meta = [(w.dtype, tuple(w.shape)) for w in weights]
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        L = lib()
+        xc, z, xhat, lw = ctx.saved_tensors[:4]
+        wc = ctx.saved_tensors[4:]
+        d = ctx.desc
+        need_x, need_lw, need_lb = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_w = any(ctx.needs_input_grad[5:])
+        dev = xc.device
+        gy = gy.contiguous()
+        with torch.cuda.device(dev):
+            tw = _twiddles(d, dev)
+            gx = torch.empty_like(xc) if need_x else None
+            gws = [torch.empty(shape, dtype=dtype, device=dev) for dtype, shape in ctx.weight_meta] if need_w else None
+            glw = torch.empty_like(lw) if need_lw else None
+            glb = torch.empty(lw.shape[0], dtype=torch.float32, device=dev) if (need_lb and ctx.has_bias) else None
+            nws = L.deno_spectral_workspace_bytes(C.byref(d), 1)
+            ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = L.deno_spectral_bwd(C.byref(d), gy.data_ptr(), xc.data_ptr(), z.data_ptr(), xhat.data_ptr(),
+                                     _capi.pointer_array([w.data_ptr() for w in wc]), lw.data_ptr(), tw.data_ptr(),
+                                     None if gx is None else gx.data_ptr(),
+                                     None if gws is None else _capi.pointer_array([g.data_ptr() for g in gws]),
+                                     None if glw is None else glw.data_ptr(), None if glb is None else glb.data_ptr(),
+                                     ws.data_ptr(), nws, stream)
+            _capi.check(L, rc, "deno_spectral_bwd")
+            _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
+        grads_w = tuple(gws) if gws is not None else (None,) * len(wc)
+        return (gx, glw, glb, None, None) + grads_w
+
+
+def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor], lin_w: torch.Tensor,
+                  lin_b: Optional[torch.Tensor], modes, activation: str = "gelu") -> torch.Tensor:
+    """``act(irfftn(corner_mix(rfftn(x))) + conv1x1(x) + bias)`` on the CUDA kernels.
+
+    ``x`` (B, Cin, *spatial) fp32 CUDA; ``weights`` the reference's 1/2/4 blocks (complex64 or the
+    fp32 ``(..., 2)`` real view); ``lin_w``/``lin_b`` the 1x1 conv parameters; ``activation`` one of
+    identity/gelu/silu/relu/tanh/leakyrelu.  Differentiable w.r.t. x, weights, lin_w, lin_b.
+    """
+    modes = _normalize_modes(modes, x.dim() - 2)
+    if activation not in _capi.ACTIVATION_IDS:
+        raise ValueError(f"unknown activation {activation!r}")
+    return _SpectralConvFn.apply(x, lin_w, lin_b, modes, activation, *weights)

@@ -1,0 +1,100 @@
+"""Batch-sharded data parallelism for the FNO stacks: one process per GPU, NCCL all-reduce of one
+flat fp32 gradient buffer.
+
+Replaces, for this path, the reference's ``setup_DDP`` + ``DistributedDataParallel`` wrapper
+(/root/reference/Utilizes/parallel_run.py:18-45, /root/reference/Demo/Turbulence_3d+t/run_train_DDP.py:272).
+Differences, all deliberate:
+  * parameters' ``.grad`` are views into ONE flat fp32 buffer (complex64 spectral weights as their
+    real view, which is also what c10d reduces), so the whole model needs a single collective and
+    no bucket copies;
+  * no per-step ``barrier()`` and no per-step scalar all-reduce + ``.item()`` (run_train_DDP.py:87-93):
+    the loss stays on the device.
+The data path has no other collective: samples are independent through the whole model.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def setup_ddp(backend: Optional[str] = None, verbose: bool = False):
+    """Env-var bootstrap with the reference's return convention ``(rank, local_rank, world_size, device)``
+    (parallel_run.py:18-45).  Works under ``torchrun`` / ``torch.distributed.run``; without the
+    launcher's variables it returns the single-process values and does not initialise a group."""
+    if "RANK" not in os.environ or "WORLD_SIZE" not in os.environ:
+        device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        return 0, 0, 1, device
+    rank = int(os.environ["RANK"])
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world_size = int(os.environ["WORLD_SIZE"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    use_cuda = torch.cuda.is_available()
+    if backend is None:
+        backend = "nccl" if use_cuda else "gloo"
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
+    else:
+        device = torch.device("cpu")
+    if not dist.is_initialized():
+        kwargs = {}
+        if use_cuda and backend == "nccl":
+            kwargs["device_id"] = device
+        dist.init_process_group(backend=backend, rank=rank, world_size=world_size, **kwargs)
+    if verbose:
+        print(f"rank {rank}/{world_size} local_rank {local_rank} device {device} backend {backend}", flush=True)
+    return rank, local_rank, world_size, device
+
+
+class FlatGradients:
+    """Owns one flat fp32 buffer and makes every parameter's ``.grad`` a view into it."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        device = self.params[0].device
+        sizes = []
+        for p in self.params:
+            if p.dtype not in (torch.float32, torch.complex64):
+                raise TypeError(f"unsupported parameter dtype {p.dtype}")
+            n = p.numel() * (2 if p.is_complex() else 1)
+            sizes.append((n + 3) // 4 * 4)  # keep every view 16-byte aligned
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        off = 0
+        for p, n in zip(self.params, sizes):
+            real_n = p.numel() * (2 if p.is_complex() else 1)
+            seg = self.flat[off:off + real_n]
+            if p.is_complex():
+                p.grad = torch.view_as_complex(seg.view(-1, 2)).view(p.shape)
+            else:
+                p.grad = seg.view(p.shape)
+            off += n
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None, async_op: bool = False):
+        """Sum over ranks then divide by world size (DDP's gradient averaging)."""
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return None
+        world = dist.get_world_size(group)
+        self.flat.div_(world)
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def shard_batch(t: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
+    """This rank's contiguous slice of a global batch (batch-sharded DP; no data-path collective)."""
+    n = t.shape[0]
+    if n % world_size != 0:
+        raise ValueError(f"global batch {n} not divisible by world size {world_size}")
+    per = n // world_size
+    return t[rank * per:(rank + 1) * per]

@@ -24,13 +24,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def _import_reference():
     if not os.path.isdir(REF):
         raise SystemExit(f"reference tree not found at {REF}")
-    # the reference must win over this repo's drop-in modules of the same name
-    for name in [m for m in sys.modules if m == "Models" or m.startswith("Models.") or m.startswith("fno")]:
-        del sys.modules[name]
-    sys.path.insert(0, REF)
-    from Models.fno import spectral_layers, FNOs  # noqa
-    assert spectral_layers.__file__.startswith(REF), spectral_layers.__file__
-    return spectral_layers, FNOs
+    sys.path.insert(0, os.path.dirname(HERE))
+    from golden_util import reference_modules
+    ctx = reference_modules()
+    mods = ctx.__enter__()  # kept for the life of the script: the reference must win over the drop-in
+    return mods
 
 
 def _np(t):

@@ -49,3 +49,36 @@ def rel_l2(a, b):
     denom = torch.linalg.vector_norm(b).item()
     num = torch.linalg.vector_norm(a - b).item()
     return num / max(denom, 1e-300)
+
+
+import contextlib
+import sys
+
+REFERENCE_ROOT = os.environ.get("DENO_REFERENCE", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@contextlib.contextmanager
+def reference_modules():
+    """Imports the REAL reference ``Models.fno`` (build container only).  This repo ships regular
+    packages called ``Models`` / ``fno`` (the drop-in), which would shadow the reference's
+    namespace packages, so they are hidden from sys.path / sys.modules for the duration."""
+    def ours(name):
+        return name in ("Models", "fno") or name.startswith(("Models.", "fno."))
+
+    saved_modules = {k: sys.modules.pop(k) for k in list(sys.modules) if ours(k)}
+    saved_path = list(sys.path)
+    saved_cwd = os.getcwd()
+    hidden = {_REPO_ROOT, os.path.join(_REPO_ROOT, "Models"), ""}
+    sys.path[:] = [REFERENCE_ROOT] + [p for p in saved_path if os.path.abspath(p or saved_cwd) not in hidden and p != ""]
+    os.chdir("/tmp")
+    try:
+        from Models.fno import FNOs, spectral_layers
+        assert spectral_layers.__file__.startswith(REFERENCE_ROOT), spectral_layers.__file__
+        yield spectral_layers, FNOs
+    finally:
+        os.chdir(saved_cwd)
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if ours(k)]:
+            del sys.modules[k]
+        sys.modules.update(saved_modules)

@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the reference fixtures, the CPU
+oracles and size-independent properties.  Tolerance: 1e-5 relative L2 in fp32 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import golden_names, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _layer_weights(params):
+    return [params[k] for k in sorted(k for k in params if k.startswith("weights"))]
+
+
+def _run_layer(x, ws, lw, lb, modes, act, cot):
+    from deno4pytorch_b200.functional import spectral_conv
+    dev = _dev()
+    xg = x.to(dev).requires_grad_(True)
+    wg = [w.to(dev).requires_grad_(True) for w in ws]
+    lwg = lw.to(dev).requires_grad_(True)
+    lbg = None if lb is None else lb.to(dev).requires_grad_(True)
+    y = spectral_conv(xg, wg, lwg, lbg, modes, act)
+    (y * cot.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    return y, xg.grad, [w.grad for w in wg], lwg.grad, None if lbg is None else lbg.grad
+
+
+@pytest.mark.parametrize("name", golden_names("layer"))
+def test_layer_matches_reference_fixture(name):
+    g = load_golden(name)
+    m = g["meta"]
+    p = g["params"]
+    y, gx, gws, glw, glb = _run_layer(g["inputs"]["x"], _layer_weights(p), p["linear.weight"], p["linear.bias"],
+                                      m["modes"], m["activation"] or "silu", g["cot"])
+    assert rel_l2(y.cpu(), g["out"]) < TOL
+    assert rel_l2(gx.cpu(), g["grad_inputs"]["x"]) < TOL
+    for gw, k in zip(gws, sorted(k for k in g["grads"] if k.startswith("weights"))):
+        assert rel_l2(gw.cpu(), g["grads"][k]) < TOL, k
+    assert rel_l2(glw.cpu(), g["grads"]["linear.weight"]) < TOL
+    assert rel_l2(glb.cpu(), g["grads"]["linear.bias"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("model"))
+def test_model_matches_reference_fixture_and_state_dict_roundtrip(name):
+    import deno4pytorch_b200 as d4
+    g = load_golden(name)
+    m = dict(g["meta"])
+    nd = m.pop("ndim")
+    m.pop("kind")
+    model = {1: d4.FNO1d, 2: d4.FNO2d, 3: d4.FNO3d}[nd](**m)
+    missing = model.load_state_dict(g["params"], strict=True)  # reference checkpoint loads unchanged
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(_dev())
+    x = g["inputs"]["x"].to(_dev()).requires_grad_(True)
+    y = model(x, g["inputs"]["grid"].to(_dev()))
+    assert rel_l2(y.cpu(), g["out"]) < TOL
+    (y * g["cot"].to(_dev())).sum().backward()
+    assert rel_l2(x.grad.cpu(), g["grad_inputs"]["x"]) < 2e-5
+    for k, p in model.named_parameters():
+        assert rel_l2(p.grad.cpu(), g["grads"][k]) < 2e-5, k
+    back = {k: v.cpu() for k, v in model.state_dict().items()}
+    assert set(back) == set(g["params"])
+    for k in back:
+        assert back[k].dtype == g["params"][k].dtype and torch.equal(back[k], g["params"][k])
+
+
+SHAPES = [
+    # (B, cin, cout, spatial, modes, act): reduced-batch versions of BASELINE.json's configs
+    (3, 64, 64, (1026,), (16,), "gelu"),          # C1 layer
+    (2, 32, 32, (94, 94), (12, 12), "gelu"),      # C2 layer
+    (2, 64, 64, (72, 72), (12, 12), "gelu"),      # C3 layer
+    (1, 128, 128, (229, 59), (12, 12), "gelu"),   # C4a layer
+    (1, 128, 128, (137, 137), (12, 12), "gelu"),  # C4b layer
+    (1, 32, 32, (70, 70, 46), (8, 8, 8), "gelu"),  # C5 layer
+    (2, 5, 7, (33, 20), (16, 11), "silu"),        # ragged channels, max modes
+    (2, 6, 6, (128, 40), (64, 16), "tanh"),       # the (64, 16) modes of the Airfoil/Pipe demos
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s[3]) for s in SHAPES])
+def test_layer_matches_cpu_oracle_at_config_shapes(shape):
+    """Isolated-branch-safe check: weights rescaled so the spectral branch is O(1) of the bypass."""
+    from oracle import fno_port
+    B, cin, cout, spatial, modes, act = shape
+    nd = len(spatial)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn((B, cin) + spatial, generator=gen)
+    ws = [torch.view_as_complex(torch.randn((cin, cout) + modes + (2,), generator=gen) / cin)
+          for _ in range(2 ** (nd - 1))]
+    lw = torch.randn((cout, cin) + (1,) * nd, generator=gen) / cin ** 0.5
+    lb = torch.randn(cout, generator=gen)
+    cot = torch.randn((B, cout) + spatial, generator=gen)
+
+    xr = x.clone().requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    lwr, lbr = lw.clone().requires_grad_(True), lb.clone().requires_grad_(True)
+    ref = fno_port.spectral_conv(xr, wr, lwr, lbr, modes, activation=act)
+    (ref * cot).sum().backward()
+
+    y, gx, gws, glw, glb = _run_layer(x, ws, lw, lb, modes, act, cot)
+    assert rel_l2(y.cpu(), ref) < TOL
+    assert rel_l2(gx.cpu(), xr.grad) < TOL
+    for a, b in zip(gws, wr):
+        assert rel_l2(a.cpu(), b.grad) < TOL
+    assert rel_l2(glw.cpu(), lwr.grad) < TOL
+    assert rel_l2(glb.cpu(), lbr.grad) < TOL
+
+
+def test_isolated_spectral_branch_bandlimited_input():
+    """linear zeroed, identity activation, smooth input: y must equal the input's low-pass content
+    mixed by W - compared against the fp64 truth (hazard (i)-(iii))."""
+    from oracle import dft_truth
+    rng = np.random.default_rng(5)
+    B, cin, cout, spatial, modes = 2, 4, 3, (40, 36), (5, 6)
+    yy, xx = np.meshgrid(np.arange(spatial[1]), np.arange(spatial[0]))
+    x = np.stack([np.stack([np.cos(2 * np.pi * (a + 1) * xx / spatial[0] + b) * np.sin(2 * np.pi * (c + 1) * yy / spatial[1])
+                            for c in range(cin)]) for a, b in [(0, 0.3), (2, 1.1)]]).astype(np.float32)
+    ws = [(rng.standard_normal((cin, cout) + modes) + 1j * rng.standard_normal((cin, cout) + modes)).astype(np.complex64)
+          for _ in range(2)]
+    lw = np.zeros((cout, cin, 1, 1), dtype=np.float32)
+    cot = rng.standard_normal((B, cout) + spatial).astype(np.float32)
+    truth = dft_truth.forward(x, ws, lw, None, modes, activation="identity")
+    tb = dft_truth.backward(x, truth, cot)
+    y, gx, gws, glw, _ = _run_layer(torch.from_numpy(x), [torch.from_numpy(w) for w in ws], torch.from_numpy(lw), None,
+                                    modes, "identity", torch.from_numpy(cot))
+    assert rel_l2(y.cpu(), truth["y"]) < TOL
+    assert rel_l2(gx.cpu(), tb["gx"]) < TOL
+    for a, b in zip(gws, tb["gweights"]):
+        assert rel_l2(a.cpu(), torch.from_numpy(b)) < TOL
+
+
+def test_full_size_properties_darcy_batch20():
+    """BASELINE.json configs[1] at full size (20, 32, 94, 94): properties that need no oracle run.
+    (a) linearity of the pre-activation in x, (b) batch independence, (c) determinism."""
+    from deno4pytorch_b200.functional import spectral_conv
+    dev = _dev()
+    gen = torch.Generator().manual_seed(3)
+    B, C, S, modes = 20, 32, (94, 94), (12, 12)
+    x1 = torch.randn((B, C) + S, generator=gen).to(dev)
+    x2 = torch.randn((B, C) + S, generator=gen).to(dev)
+    ws = [torch.view_as_complex(torch.randn((C, C) + modes + (2,), generator=gen) / C).to(dev) for _ in range(2)]
+    lw = (torch.randn(C, C, 1, 1, generator=gen) / C ** 0.5).to(dev)
+    f = lambda t: spectral_conv(t, ws, lw, None, modes, "identity")
+    a, b, ab = f(x1), f(x2), f(x1 + 2.0 * x2)
+    assert rel_l2(ab.cpu(), (a + 2.0 * b).cpu()) < 5e-6
+    sub = f(x1[3:5].contiguous())
+    assert rel_l2(sub.cpu(), a[3:5].cpu()) < 1e-6
+    assert torch.equal(f(x1), a)
+
+
+def test_noncontiguous_input_and_modes_int():
+    """padding=0 hands the first layer a permuted view (SURVEY section 8a layout facts)."""
+    from deno4pytorch_b200.functional import spectral_conv
+    from oracle import fno_port
+    gen = torch.Generator().manual_seed(9)
+    xl = torch.randn(2, 16, 18, 6, generator=gen)       # channels-last storage
+    x = xl.permute(0, 3, 1, 2)                          # (B, C, H, W) view, channel stride 1
+    assert not x.is_contiguous()
+    ws = [torch.view_as_complex(torch.randn(6, 6, 4, 4, 2, generator=gen) / 6) for _ in range(2)]
+    lw = torch.randn(6, 6, 1, 1, generator=gen)
+    ref = fno_port.spectral_conv(x, ws, lw, None, 4, activation="gelu")
+    y = spectral_conv(x.to(_dev()), [w.to(_dev()) for w in ws], lw.to(_dev()), None, 4, "gelu")
+    assert rel_l2(y.cpu(), ref) < TOL
+
+
+def test_rollout_ten_steps_error_growth():
+    """Autoregressive use (Demo/Turbulence_2d+t/run_FNO&UNet.py:61-70): 10 chained model calls."""
+    import deno4pytorch_b200 as d4
+    from oracle import fno_port
+    torch.manual_seed(2)
+    cfg = dict(in_dim=4, out_dim=1, modes=(5, 5), width=12, depth=2, hidden=24, steps=1, padding=3)
+    model = d4.FNO2d(**cfg)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    xx = torch.randn(2, 20, 20, 4)
+    grid = fno_port.make_grid(2, (20, 20))
+    model = model.to(_dev())
+    a, b = xx.to(_dev()), xx.clone()
+    gd = grid.to(_dev())
+    with torch.no_grad():
+        for _ in range(10):
+            im = model(a, gd)
+            a = torch.cat((a[..., 1:], im), dim=-1)
+            imr = fno_port.fno_forward(params, b, grid, ndim=2, modes=(5, 5), depth=2, padding=3)
+            b = torch.cat((b[..., 1:], imr), dim=-1)
+    assert rel_l2(a.cpu(), b) < 1e-5
+
+
+def test_identity_swap_and_dropout_path():
+    """Callers re-assign .activation (Transformers.py:403) and may train with dropout > 0."""
+    import deno4pytorch_b200 as d4
+    from oracle import fno_port
+    torch.manual_seed(4)
+    layer = d4.SpectralConv2d(3, 5, (3, 4), dropout=0.0, norm="ortho", activation="silu")
+    x = torch.randn(2, 3, 12, 14)
+    ws = [layer.weights1.detach(), layer.weights2.detach()]
+    layer.activation = torch.nn.Identity()
+    ref = fno_port.spectral_conv(x, ws, layer.linear.weight.detach(), layer.linear.bias.detach(), (3, 4),
+                                 activation="identity")
+    layer = layer.to(_dev())
+    assert rel_l2(layer(x.to(_dev())).cpu(), ref) < TOL
+    layer.dropout.p = 0.5
+    layer.train()
+    y = layer(x.to(_dev()))
+    assert y.shape == ref.shape and torch.isfinite(y).all()
+    layer.eval()
+    assert rel_l2(layer(x.to(_dev())).cpu(), ref) < TOL
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    from deno4pytorch_b200.functional import spectral_conv
+    x = torch.randn(1, 2, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        spectral_conv(x, [torch.zeros(2, 2, 3, dtype=torch.cfloat)], torch.zeros(2, 2, 1), None, 3, "gelu")
+
+
+def test_training_step_matches_oracle_adam():
+    """Three optimiser steps (Adam as in the demos) track the CPU port."""
+    import deno4pytorch_b200 as d4
+    from oracle import fno_port
+    torch.manual_seed(6)
+    cfg = dict(in_dim=1, out_dim=1, modes=(4, 4), width=8, depth=2, hidden=16, steps=1, padding=3)
+    model = d4.FNO2d(**cfg)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x, t = torch.randn(4, 13, 13, 1), torch.randn(4, 13, 13, 1)
+    grid = fno_port.make_grid(4, (13, 13))
+    port = fno_port.PortTrainer(params, ndim=2, modes=(4, 4), depth=2, padding=3)
+    model = model.to(_dev())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.7, 0.9), weight_decay=1e-4)
+    for _ in range(3):
+        ref_loss = port.step(x, grid, t)
+        loss = torch.nn.functional.mse_loss(model(x.to(_dev()), grid.to(_dev())), t.to(_dev()))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(loss.item() - ref_loss) / ref_loss < 1e-5
+    for k, p in model.named_parameters():
+        assert rel_l2(p.detach().cpu(), port.params[k].detach()) < 1e-5, k

@@ -105,21 +105,14 @@ def test_truth_vs_port_fp64_isolated_spectral_branch():
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_port_matches_live_reference_darcy_shape():
     """Direct check against the imported reference at the C2 (Darcy) layer shape, reduced batch."""
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
-             if k == "Models" or k.startswith("Models.") or k == "fno" or k.startswith("fno.")}
-    sys.path.insert(0, "/root/reference")
-    try:
-        from Models.fno.FNOs import FNO2d as RefFNO2d
+    from golden_util import reference_modules
+    with reference_modules() as (_, ref_fnos):
         torch.manual_seed(0)
-        ref = RefFNO2d(in_dim=1, out_dim=1, modes=(12, 12), width=32, depth=4, steps=1, padding=9, activation="gelu")
+        ref = ref_fnos.FNO2d(in_dim=1, out_dim=1, modes=(12, 12), width=32, depth=4, steps=1, padding=9,
+                             activation="gelu")
         x = torch.randn(2, 85, 85, 1)
         grid = fno_port.make_grid(2, (85, 85))
         want = ref(x, grid)
         params = {k: v.detach() for k, v in ref.state_dict().items()}
-        got = fno_port.fno_forward(params, x, grid, ndim=2, modes=(12, 12), depth=4, padding=9)
-        assert rel_l2(got, want) < TOL
-    finally:
-        sys.path.remove("/root/reference")
-        for k in [k for k in sys.modules if k == "Models" or k.startswith("Models.") or k == "fno" or k.startswith("fno.")]:
-            del sys.modules[k]
-        sys.modules.update(saved)
+    got = fno_port.fno_forward(params, x, grid, ndim=2, modes=(12, 12), depth=4, padding=9)
+    assert rel_l2(got, want) < TOL
