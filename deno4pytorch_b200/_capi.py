@@ -41,6 +41,11 @@ def make_desc(batch, cin, cout, spatial, modes, act) -> SpectralDesc:
     return d
 
 
+class ProfileRecord(C.Structure):
+    """struct deno_profile_record"""
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_float)]
+
+
 _DESC_P = C.POINTER(SpectralDesc)
 _PP = C.POINTER(C.c_void_p)
 
@@ -48,6 +53,8 @@ _PROTOTYPES = {
     "deno_spectral_abi_version": (C.c_int, []),
     "deno_last_error": (C.c_char_p, []),
     "deno_spectral_last_launch_count": (C.c_int, []),
+    "deno_profile_begin": (C.c_int, []),
+    "deno_profile_end": (C.c_int, [C.POINTER(ProfileRecord), C.c_int]),
     "deno_spectral_num_modes": (C.c_size_t, [_DESC_P]),
     "deno_spectral_twiddle_bytes": (C.c_size_t, [_DESC_P]),
     "deno_spectral_twiddle_fill": (C.c_int, [_DESC_P, C.c_void_p, C.c_size_t]),

@@ -3,13 +3,14 @@
 // Host-side orchestration only: validates the descriptor, carves the caller's workspace,
 // picks launch geometry and enqueues the kernels of spectral_simt.cuh (and, for the shapes it
 // covers, the tcgen05 path of spectral_tc.cuh) on the caller's stream.  No allocation, no
-// synchronisation, no global mutable state.
+// synchronisation, no global mutable state (except the opt-in profiling list).
 #include "../../include/deno_spectral.h"
 
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -273,8 +274,47 @@ int bwd_ws(const Shape& s, BwdWs& w) {
 // ------------------------------------------------------------------------------------------
 // Launch helpers
 // ------------------------------------------------------------------------------------------
-int check_launch(const char* what) {
+// Optional per-launch event bracketing (deno_profile_begin / deno_profile_end).
+struct ProfEntry {
+  const char* name;
+#ifndef DENO_EMULATE
+  cudaEvent_t start, stop;
+#endif
+};
+// Process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default.
+bool g_profiling = false;
+std::vector<ProfEntry> g_prof;
+std::mutex g_prof_mutex;
+
+void prof_before(const char* what, cudaStream_t st) {
+  if (!g_profiling) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  ProfEntry e;
+  e.name = what;
+#ifndef DENO_EMULATE
+  cudaEventCreate(&e.start);
+  cudaEventCreate(&e.stop);
+  cudaEventRecord(e.start, st);
+#else
+  (void)st;
+#endif
+  g_prof.push_back(e);
+}
+
+void prof_after(cudaStream_t st) {
+  if (!g_profiling) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (g_prof.empty()) return;
+#ifndef DENO_EMULATE
+  cudaEventRecord(g_prof.back().stop, st);
+#else
+  (void)st;
+#endif
+}
+
+int check_launch(const char* what, cudaStream_t st) {
   ++g_launches;
+  prof_after(st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(DENO_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
   return DENO_OK;
@@ -323,13 +363,15 @@ int launch_analysis(const Shape& s, int channels, const float* u, const float* z
   if (z != nullptr) {
     rc = allow_smem(plane_analysis_kernel<true>, c.smem, "plane_analysis");
     if (rc != DENO_OK) return rc;
+    prof_before("plane_analysis_gz", st);
     DENO_LAUNCH(plane_analysis_kernel<true>, dim3(grid), dim3(c.threads), c.smem, st, p);
   } else {
     rc = allow_smem(plane_analysis_kernel<false>, c.smem, "plane_analysis");
     if (rc != DENO_OK) return rc;
+    prof_before("plane_analysis", st);
     DENO_LAUNCH(plane_analysis_kernel<false>, dim3(grid), dim3(c.threads), c.smem, st, p);
   }
-  return check_launch("plane_analysis");
+  return check_launch("plane_analysis", st);
 }
 
 int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, float2* out, const TwPtrs& tw,
@@ -341,12 +383,13 @@ int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, 
                                    : (long long)s.B * channels * ((s.X + 3) / 4) * s.Q;
   long long blocks = (units + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
+  prof_before(analysis ? "outer_analysis" : "outer_synthesis", st);
   if (analysis) {
     DENO_LAUNCH(outer_analysis_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p);
   } else {
     DENO_LAUNCH(outer_synthesis_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p);
   }
-  return check_launch(analysis ? "outer_analysis" : "outer_synthesis");
+  return check_launch(analysis ? "outer_analysis" : "outer_synthesis", st);
 }
 
 int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks,
@@ -368,8 +411,9 @@ int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, con
   }
   dim3 block(32, 8);
   dim3 grid((s.M + 31) / 32, (p.CO + 7) / 8, (s.B + kMixBatchTile - 1) / kMixBatchTile);
+  prof_before(backward ? "mode_mix_bwd" : "mode_mix", st);
   DENO_LAUNCH(mode_mix_kernel, grid, block, 0, st, p);
-  return check_launch("mode_mix");
+  return check_launch("mode_mix", st);
 }
 
 int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, void* const* gw_blocks, cudaStream_t st) {
@@ -381,8 +425,9 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
   p.B = s.B; p.CI = s.CI; p.CO = s.CO;
   dim3 block(32, 8);
   dim3 grid((s.M + 31) / 32, ((s.CO + 3) / 4 + 7) / 8, s.CI);
+  prof_before("mode_mix_wgrad", st);
   DENO_LAUNCH(mode_mix_wgrad_kernel, grid, block, 0, st, p);
-  return check_launch("mode_mix_wgrad");
+  return check_launch("mode_mix_wgrad", st);
 }
 
 // spec [B*X][CO][KH][MW] + bypass(u) -> y (, z)
@@ -404,8 +449,9 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
   rc = allow_smem(plane_synthesis_kernel, c.smem, "plane_synthesis");
   if (rc != DENO_OK) return rc;
   const int grid = s.B * s.X * c.tiles;
+  prof_before(bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr ? "plane_synthesis" : "plane_synthesis_bwd", st);
   DENO_LAUNCH(plane_synthesis_kernel, dim3(grid), dim3(c.threads), c.smem, st, p);
-  return check_launch("plane_synthesis");
+  return check_launch("plane_synthesis", st);
 }
 
 int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, float* partial, float* glw, float* glb,
@@ -421,15 +467,17 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, float* 
   p.PTS = c.PTS; p.tiles = c.tiles;
   rc = allow_smem(bypass_wgrad_partial_kernel, c.smem, "bypass_wgrad");
   if (rc != DENO_OK) return rc;
+  prof_before("bypass_wgrad_partial", st);
   DENO_LAUNCH(bypass_wgrad_partial_kernel, dim3(c.ncta), dim3(c.threads), c.smem, st, p);
-  rc = check_launch("bypass_wgrad_partial");
+  rc = check_launch("bypass_wgrad_partial", st);
   if (rc != DENO_OK) return rc;
   WgradReduceParams r;
   r.partial = partial; r.ncta = c.ncta;
   r.nw = s.CO * s.CI; r.nj = r.nw + s.CO;
   r.glw = glw; r.glb = glb;
+  prof_before("bypass_wgrad_reduce", st);
   DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
-  return check_launch("bypass_wgrad_reduce");
+  return check_launch("bypass_wgrad_reduce", st);
 }
 
 }  // namespace
@@ -444,6 +492,35 @@ int deno_spectral_abi_version(void) { return DENO_SPECTRAL_ABI_VERSION; }
 const char* deno_last_error(void) { return g_error.c_str(); }
 
 int deno_spectral_last_launch_count(void) { return g_launches; }
+
+int deno_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  g_prof.clear();
+  g_profiling = true;
+  return DENO_OK;
+}
+
+int deno_profile_end(deno_profile_record* records, int capacity) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  g_profiling = false;
+  const int n = (int)g_prof.size();
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+#ifndef DENO_EMULATE
+    cudaEventSynchronize(g_prof[i].stop);
+    cudaEventElapsedTime(&ms, g_prof[i].start, g_prof[i].stop);
+    cudaEventDestroy(g_prof[i].start);
+    cudaEventDestroy(g_prof[i].stop);
+#endif
+    if (records != nullptr && i < capacity) {
+      strncpy(records[i].name, g_prof[i].name, sizeof(records[i].name) - 1);
+      records[i].name[sizeof(records[i].name) - 1] = 0;
+      records[i].ms = ms;
+    }
+  }
+  g_prof.clear();
+  return n;
+}
 
 size_t deno_spectral_num_modes(const deno_spectral_desc* desc) {
   Shape s;

@@ -114,6 +114,21 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
 /* Number of kernels the last fwd / bwd call on this thread enqueued (bench.py's gpu_launches). */
 int deno_spectral_last_launch_count(void);
 
+/*
+ * Per-kernel attribution (measurement aid, not used on the product path).  Between
+ * deno_profile_begin() and deno_profile_end() every kernel this thread enqueues is bracketed by
+ * cudaEventRecord on its stream.  deno_profile_end() synchronises those events and writes up to
+ * `capacity` records in launch order; it returns the number of launches seen (may exceed capacity).
+ * Not usable during CUDA-graph capture.
+ */
+typedef struct deno_profile_record {
+  char name[32];   /* kernel family, e.g. "plane_synthesis" */
+  float ms;        /* device time between the two events */
+} deno_profile_record;
+
+int deno_profile_begin(void);
+int deno_profile_end(deno_profile_record* records, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

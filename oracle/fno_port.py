@@ -212,4 +212,4 @@ class PortTrainer:
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()
-        return float(loss)
+        return loss.item()
