@@ -202,12 +202,23 @@ int synth_cfg(const PlaneGeom& g, int CO, SynthCfg& c) {
     p.R = c.R; p.PTS = c.PTS;
     c.smem = (size_t)synth_smem(p).total * sizeof(float);
   } else {
+    // pick the rows-per-tile that wastes the fewest CTA slots in the last wave (148 SMs x resident CTAs)
     int best = 0;
+    double best_eff = -1.0;
     for (int R = kSynthMaxRows; R >= 1; --R) {
       if (R > g.H) continue;
       p.R = R; p.PTS = R * g.W;
       const size_t bytes = (size_t)synth_smem(p).total * sizeof(float);
-      if (bytes <= 72 * 1024) { best = R; break; }
+      if (bytes > (size_t)kMaxSmemBytes) continue;
+      int per_sm = (int)((228 * 1024) / (bytes + 1024));
+      if (per_sm > 8) per_sm = 8;          // 256 threads per CTA, 2048 per SM
+      if (per_sm < 1) per_sm = 1;
+      const long long ctas = (long long)g.NBO * g.NBI * ((g.H + R - 1) / R);
+      const long long slots = 148LL * per_sm;
+      const long long waves = (ctas + slots - 1) / slots;
+      double eff = (double)ctas / (double)(waves * slots);
+      if (per_sm < 2) eff *= 0.7;          // a lone CTA per SM cannot overlap its phases
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = R; }
     }
     if (best == 0) best = 1;
     c.R = best;
@@ -224,18 +235,17 @@ int synth_cfg(const PlaneGeom& g, int CO, SynthCfg& c) {
 struct WgradCfg { int PTS, tiles, ncta, threads; size_t smem; };
 
 int wgrad_cfg(const Shape& s, WgradCfg& c) {
-  const int rowsum = s.CO + round_up(s.CI, 4);
-  int pts = (96 * 1024 / 4) / rowsum - 4;
-  pts &= ~3;
+  const int rows = s.CO + round_up(s.CI, 8) + 1;
+  int pts = ((96 * 1024 / 4) / rows - 4) / 32 * 32;
   if (pts > 512) pts = 512;
-  if (pts < 4) return fail(DENO_E_UNSUPPORTED, "too many channels for bypass_wgrad");
+  if (pts < 32) return fail(DENO_E_UNSUPPORTED, "too many channels for bypass_wgrad");
   const int plane = s.H * s.W;
-  if (pts > round_up(plane, 4)) pts = round_up(plane, 4);
+  if (pts > round_up(plane, 32)) pts = round_up(plane, 32);
   c.PTS = pts;
   c.tiles = (plane + pts - 1) / pts;
   c.ncta = s.B * s.X * c.tiles;
   c.threads = 256;
-  c.smem = (size_t)rowsum * (pts + 4) * sizeof(float);
+  c.smem = (size_t)rows * (pts + 4) * sizeof(float);
   return DENO_OK;
 }
 
@@ -446,11 +456,25 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
   p.twW = tw.last; p.twH = tw.mid; p.cl = tw.cl;
   p.scale = scale; p.herm = herm; p.act = act;
   p.R = c.R; p.PTS = c.PTS; p.tiles = c.tiles;
-  rc = allow_smem(plane_synthesis_kernel, c.smem, "plane_synthesis");
-  if (rc != DENO_OK) return rc;
   const int grid = s.B * s.X * c.tiles;
-  prof_before(bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr ? "plane_synthesis" : "plane_synthesis_bwd", st);
-  DENO_LAUNCH(plane_synthesis_kernel, dim3(grid), dim3(c.threads), c.smem, st, p);
+  const char* label = (bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr) ? "plane_synthesis" : "plane_synthesis_bwd";
+#define DENO_SYNTH_CASE(ACT)                                                                       \
+  case ACT:                                                                                        \
+    rc = allow_smem(plane_synthesis_kernel<ACT>, c.smem, "plane_synthesis");                       \
+    if (rc != DENO_OK) return rc;                                                                  \
+    prof_before(label, st);                                                                        \
+    DENO_LAUNCH(plane_synthesis_kernel<ACT>, dim3(grid), dim3(c.threads), c.smem, st, p);          \
+    break;
+  switch (act) {
+    DENO_SYNTH_CASE(ACT_IDENTITY)
+    DENO_SYNTH_CASE(ACT_GELU)
+    DENO_SYNTH_CASE(ACT_SILU)
+    DENO_SYNTH_CASE(ACT_RELU)
+    DENO_SYNTH_CASE(ACT_TANH)
+    DENO_SYNTH_CASE(ACT_LEAKYRELU)
+    default: return fail(DENO_E_INVALID, "unknown activation id");
+  }
+#undef DENO_SYNTH_CASE
   return check_launch("plane_synthesis", st);
 }
 

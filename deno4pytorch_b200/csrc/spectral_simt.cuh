@@ -88,6 +88,7 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
   for (int i = tid; i < p.RS * acc_stride; i += nt) acc2[i] = make_float2(0.f, 0.f);
 
   const int r = tid % p.RTP, lq = tid / p.RTP;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
   const int ntask2 = p.G * KQ * MW;
 
   for (int tile0 = 0; tile0 < rows; tile0 += p.RT) {
@@ -98,18 +99,19 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
     for (int y0 = 0; y0 < W; y0 += p.YC) {
       const int yc = min(p.YC, W - y0);
       __syncthreads();  // previous chunk / previous tile fully consumed (also orders the init above)
-      for (int idx = tid; idx < trows * yc; idx += nt) {
-        const int rr = idx / yc, j = idx - rr * yc;
+      for (int rr = warp; rr < trows; rr += nwarps) {
         const int row = tile0 + rr;
         const int gi = row / H, xr = row - gi * H;
         const int q = q0 + gi;
-        const long long addr = plane_base(p.g, q / p.g.C, q % p.g.C) + (long long)xr * W + y0 + j;
-        float v = p.u[addr];
-        if (FUSE_GZ) {
-          v *= act_grad(p.act, p.z[addr]);
-          p.gz_out[addr] = v;
+        const long long rbase = plane_base(p.g, q / p.g.C, q % p.g.C) + (long long)xr * W + y0;
+        for (int j = lane; j < yc; j += 32) {
+          float v = p.u[rbase + j];
+          if (FUSE_GZ) {
+            v *= act_grad(p.act, p.z[rbase + j]);
+            p.gz_out[rbase + j] = v;
+          }
+          xs[rr * YCp + j] = v;
         }
-        xs[rr * YCp + j] = v;
       }
       for (int idx = tid; idx < yc * MWp; idx += nt) tws[idx] = p.twW[(long long)y0 * MWp + idx];
       __syncthreads();
@@ -285,6 +287,7 @@ __global__ void mode_mix_kernel(MixParams p) {
 #pragma unroll
   for (int j = 0; j < kMixBatchTile; ++j) ar[j] = ai[j] = 0.f;
   const float sgn = p.conj_w ? -1.0f : 1.0f;
+#pragma unroll 8
   for (int ci = 0; ci < p.CI; ++ci) {
     float2 wv = w[(long long)ci * p.w_sci];
     wv.y *= sgn;
@@ -320,6 +323,7 @@ __global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
   int blk, off;
   decode_mode(p.md, pm, blk, off);
   float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
   for (int b = 0; b < p.B; ++b) {
     const float2 xv = p.xhat[((long long)b * p.CI + ci) * M + pm];
 #pragma unroll
@@ -382,6 +386,7 @@ __host__ __device__ inline SynthSmem synth_smem(const SynthParams& p) {
   return s;
 }
 
+template <int ACT>
 __global__ void plane_synthesis_kernel(SynthParams p) {
   DENO_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
@@ -403,14 +408,14 @@ __global__ void plane_synthesis_kernel(SynthParams p) {
   const int trows = (H > 1) ? min(R, H - x0) : 1;
 
   // bypass operands
-  for (int idx = tid; idx < CI * COp; idx += nt) {
-    const int i = idx / COp, o = idx - i * COp;
-    wls[idx] = (o < CO) ? p.lw[(long long)o * p.lw_so + (long long)i * p.lw_si] : 0.f;
-  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  for (int i = warp; i < CI; i += nwarps)
+    for (int o = lane; o < COp; o += 32)
+      wls[i * COp + o] = (o < CO) ? p.lw[(long long)o * p.lw_so + (long long)i * p.lw_si] : 0.f;
   for (int o = tid; o < COp; o += nt) bs[o] = (p.bias != nullptr && o < CO) ? p.bias[o] : 0.f;
-  for (int idx = tid; idx < CI * npts; idx += nt) {
-    const int i = idx / npts, pt = idx - i * npts;
-    xs[i * PTSp + pt] = p.u[plane_base(p.g, bp, i) + p0 + pt];
+  for (int i = warp; i < CI; i += nwarps) {
+    const float* src = p.u + plane_base(p.g, bp, i) + p0;
+    for (int pt = lane; pt < npts; pt += 32) xs[i * PTSp + pt] = src[pt];
   }
   // stage A: U[o][rr][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0+rr)}
   for (int task = tid; task < COp * MWp; task += nt) {
@@ -476,7 +481,7 @@ __global__ void plane_synthesis_kernel(SynthParams p) {
         if (o < CO) {
           const long long a = obase + (long long)o * p.g.sc;
           if (p.z != nullptr) p.z[a] = acc[j];
-          p.y[a] = act_apply(p.act, acc[j]);
+          p.y[a] = act_apply(ACT, acc[j]);
         }
       }
     }
@@ -497,42 +502,55 @@ struct WgradParams {
   int tiles;           // tiles per plane
 };
 
+// shared memory: gz tile [CO][pitch], x tile [CIp + 1][pitch] (last row = zeros), pitch = PTS + 4 with
+// PTS a multiple of 32 so that eight consecutive rows start in eight different bank quads.
 __host__ __device__ inline int wgrad_smem_floats(const WgradParams& p) {
-  return (round_up(p.CO, 1) + round_up(p.gx.C, 4)) * (p.PTS + 4);
+  return (p.CO + round_up(p.gx.C, 8) + 1) * (p.PTS + 4);
 }
 
 __global__ void bypass_wgrad_partial_kernel(WgradParams p) {
   DENO_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int CI = p.gx.C, CO = p.CO, CIp = round_up(CI, 4), CIQ = CIp / 4;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  const int CI = p.gx.C, CO = p.CO, CIp = round_up(CI, 8), JB = (CIp + 31) / 32;
   const int PTS = p.PTS, pitch = PTS + 4;
   float* gs = smem;                 // [CO][pitch]
-  float* xs = smem + CO * pitch;    // [CIp][pitch]
+  float* xs = smem + CO * pitch;    // [CIp + 1][pitch]
   const int bp = blockIdx.x / p.tiles;
   const int tile = blockIdx.x - bp * p.tiles;
   const int p0 = tile * PTS;
   const int npts = min(PTS, p.gx.H * p.gx.W - p0);
   const long long gbase = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
 
-  for (int idx = tid; idx < CO * PTS; idx += nt) {
-    const int o = idx / PTS, pt = idx - o * PTS;
-    gs[o * pitch + pt] = (pt < npts) ? p.gz[gbase + (long long)o * p.gx.sc + pt] : 0.f;
+  for (int o = warp; o < CO; o += nwarps) {
+    const float* src = p.gz + gbase + (long long)o * p.gx.sc;
+    for (int pt = lane; pt < PTS; pt += 32) gs[o * pitch + pt] = (pt < npts) ? src[pt] : 0.f;
   }
-  for (int idx = tid; idx < CIp * PTS; idx += nt) {
-    const int i = idx / PTS, pt = idx - i * PTS;
-    xs[i * pitch + pt] = (pt < npts && i < CI) ? p.x[plane_base(p.gx, bp, i) + p0 + pt] : 0.f;
+  for (int i = warp; i <= CIp; i += nwarps) {
+    const float* src = p.x + plane_base(p.gx, bp, i < CI ? i : 0) + p0;
+    for (int pt = lane; pt < PTS; pt += 32) xs[i * pitch + pt] = (pt < npts && i < CI) ? src[pt] : 0.f;
   }
   __syncthreads();
   float* out = p.partial + (long long)blockIdx.x * (CO * CI + CO);
-  for (int task = tid; task < CO * CIQ; task += nt) {
-    const int o = task / CIQ, iq = task - o * CIQ;
+  // task = (o, block of 32 input channels, iq); the thread owns input channels iq, iq+8, iq+16, iq+24 of the block
+  for (int task = tid; task < CO * JB * 8; task += nt) {
+    const int iq = task & 7;
+    const int jb = (task >> 3) % JB;
+    const int o = (task >> 3) / JB;
+    int irow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = jb * 32 + iq + 8 * j;
+      irow[j] = i < CIp ? i : CIp;
+    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float4* g4 = reinterpret_cast<const float4*>(gs + o * pitch);
-    const float4* x0 = reinterpret_cast<const float4*>(xs + (iq * 4 + 0) * pitch);
-    const float4* x1 = reinterpret_cast<const float4*>(xs + (iq * 4 + 1) * pitch);
-    const float4* x2 = reinterpret_cast<const float4*>(xs + (iq * 4 + 2) * pitch);
-    const float4* x3 = reinterpret_cast<const float4*>(xs + (iq * 4 + 3) * pitch);
+    const float4* x0 = reinterpret_cast<const float4*>(xs + irow[0] * pitch);
+    const float4* x1 = reinterpret_cast<const float4*>(xs + irow[1] * pitch);
+    const float4* x2 = reinterpret_cast<const float4*>(xs + irow[2] * pitch);
+    const float4* x3 = reinterpret_cast<const float4*>(xs + irow[3] * pitch);
+#pragma unroll 2
     for (int v = 0; v < PTS / 4; ++v) {
       const float4 g = g4[v];
       float4 t = x0[v];
@@ -544,16 +562,20 @@ __global__ void bypass_wgrad_partial_kernel(WgradParams p) {
       t = x3[v];
       a3 = fmaf(g.x, t.x, fmaf(g.y, t.y, fmaf(g.z, t.z, fmaf(g.w, t.w, a3))));
     }
-    const int i = iq * 4;
-    if (i + 0 < CI) out[o * CI + i + 0] = a0;
-    if (i + 1 < CI) out[o * CI + i + 1] = a1;
-    if (i + 2 < CI) out[o * CI + i + 2] = a2;
-    if (i + 3 < CI) out[o * CI + i + 3] = a3;
+    const int i = jb * 32 + iq;
+    if (i < CI) out[o * CI + i] = a0;
+    if (i + 8 < CI) out[o * CI + i + 8] = a1;
+    if (i + 16 < CI) out[o * CI + i + 16] = a2;
+    if (i + 24 < CI) out[o * CI + i + 24] = a3;
   }
-  for (int o = tid; o < CO; o += nt) {
-    float s = 0.f;
-    for (int pt = 0; pt < PTS; ++pt) s += gs[o * pitch + pt];
-    out[CO * CI + o] = s;
+  for (int o = tid; o < CO; o += nt) {   // bias gradient (fixed summation order)
+    const float4* g4 = reinterpret_cast<const float4*>(gs + o * pitch);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int v = 0; v < PTS / 4; ++v) {
+      const float4 g = g4[v];
+      s0 += g.x; s1 += g.y; s2 += g.z; s3 += g.w;
+    }
+    out[CO * CI + o] = (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -572,6 +594,7 @@ __global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
   const int slice = threadIdx.y;
   float s = 0.f;
   if (j < p.nj)
+#pragma unroll 8
     for (int c = slice; c < p.ncta; c += 8) s += p.partial[(long long)c * p.nj + j];
   red[slice * 32 + threadIdx.x] = s;
   __syncthreads();
