@@ -8,6 +8,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -125,7 +126,8 @@ ModeDecode make_decode(const Shape& s) {
 // Twiddle tables (host, fp64 -> fp32)
 // ------------------------------------------------------------------------------------------
 struct TwLayout {
-  size_t last, mid, outer, cl, total;  // float offsets
+  size_t last, mid, outer, cl, synth_ae, total;  // float offsets
+  int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
 };
 
 TwLayout tw_layout(const Shape& s) {
@@ -135,8 +137,44 @@ TwLayout tw_layout(const Shape& s) {
   t.mid = off;   off += (size_t)s.H * s.KH4 * 2;
   t.outer = off; off += (s.ndim == 3) ? (size_t)s.X * s.KX4 * 2 : 0;
   t.cl = off;    off += (size_t)s.MWp;
+  t.nchunks = (s.W + 127) / 128;
+  t.KE = 2 * s.MWp;
+  t.synth_ae = off; off += (size_t)t.nchunks * 2 * t.KE * 128;
   t.total = off;
   return t;
+}
+
+float tf32_mask(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u &= 0xFFFFE000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+
+// Last-axis twiddles as tcgen05 A-operand images (K-major, SBO = 128, LBO = 2048), split hi/lo from fp64:
+// column k = 2l holds cos(2 pi l y / W), k = 2l+1 holds sin(2 pi l y / W); zero outside the grid / modes.
+void fill_synth_ae(float* dst, const Shape& s, const TwLayout& t) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int c = 0; c < t.nchunks; ++c) {
+    float* hi = dst + (size_t)c * 2 * t.KE * 128;
+    float* lo = hi + (size_t)t.KE * 128;
+    for (int yl = 0; yl < 128; ++yl) {
+      for (int k = 0; k < t.KE; ++k) {
+        const int y = c * 128 + yl, l = k / 2;
+        double v = 0.0;
+        if (y < s.W && l < s.MW) {
+          const long long r = ((long long)l * y) % s.W;
+          const double ang = two_pi * (double)r / (double)s.W;
+          v = (k & 1) ? sin(ang) : cos(ang);
+        }
+        const float h = tf32_mask((float)v);
+        const int off = kmajor_off(yl, k, 128) / 4;
+        hi[off] = h;
+        lo[off] = (float)(v - (double)h);
+      }
+    }
+  }
 }
 
 void fill_axis(float* dst, int n, int nfreq, int pitch, int m, bool half) {
@@ -343,7 +381,7 @@ int allow_smem(K kernel, size_t bytes, const char* what) {
   return DENO_OK;
 }
 
-struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; };
+struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; const float* synth_ae; };
 
 TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   const float* base = static_cast<const float*>(twiddles);
@@ -353,6 +391,7 @@ TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   p.mid = reinterpret_cast<const float2*>(base + t.mid);
   p.outer = reinterpret_cast<const float2*>(base + t.outer);
   p.cl = base + t.cl;
+  p.synth_ae = base + t.synth_ae;
   return p;
 }
 
@@ -440,6 +479,84 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
   return check_launch("mode_mix_wgrad", st);
 }
 
+// DENO_SPECTRAL_PATH = auto (default) | simt | tc : which kernels serve the stages both paths implement.
+enum class PathPref { Auto, Simt, Tc };
+PathPref path_pref() {
+  const char* e = getenv("DENO_SPECTRAL_PATH");
+  if (e == nullptr) return PathPref::Auto;
+  if (strcmp(e, "simt") == 0) return PathPref::Simt;
+  if (strcmp(e, "tc") == 0) return PathPref::Tc;
+  return PathPref::Auto;
+}
+
+#ifndef DENO_EMULATE
+// Tensor-core synthesis: returns DENO_OK after launching, or -1 when the shape is outside what the
+// tcgen05 kernel covers (caller falls back to the SIMT kernel).
+int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
+  const int CI = p.g.C, CO = p.CO;
+  if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;
+  const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
+  const TwLayout tl = tw_layout(s);
+  int bestR = 0;
+  double best_eff = -1.0;
+  const int maxR = p.g.H > 1 ? (p.g.H < kSynthMaxRows ? p.g.H : kSynthMaxRows) : 1;
+  for (int R = maxR; R >= 1; --R) {
+    const size_t bytes = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, R).total;
+    if (bytes > (size_t)kMaxSmemBytes) continue;
+    int per_sm = (int)((228 * 1024) / (bytes + 2048));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const long long ctas = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks;
+    const long long slots = 148LL * per_sm;
+    const long long waves = (ctas + slots - 1) / slots;
+    double eff = (double)ctas / (double)(waves * slots);
+    eff *= (1.0 - 0.25 / R);               // per-CTA setup (weights, twiddles, stage A) amortises over R rows
+    if (eff > best_eff + 1e-9) { best_eff = eff; bestR = R; }
+  }
+  if (bestR == 0) return -1;
+  tc::SynthTcParams q;
+  p.R = bestR;
+  p.PTS = bestR * p.g.W;
+  p.tiles = (p.g.H + bestR - 1) / bestR;
+  q.s = p;
+  q.ae = tw.synth_ae;
+  q.KE = tl.KE;
+  q.nchunks = tl.nchunks;
+  int cols = 32;
+  while (cols < 2 * CO) cols *= 2;
+  q.tmem_cols = cols;
+  const size_t smem = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, bestR).total;
+  const int grid = s.B * s.X * p.tiles * tl.nchunks;
+  int rc = DENO_OK;
+#define DENO_TC_CASE2(ACT, CIPV)                                                                    \
+  {                                                                                                 \
+    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV>, smem, "plane_synthesis_tc");          \
+    if (rc != DENO_OK) return rc;                                                                   \
+    prof_before(label, st);                                                                         \
+    tc::plane_synthesis_tc_kernel<ACT, CIPV><<<dim3(grid), dim3(256), smem, st>>>(q);               \
+  }
+#define DENO_TC_CASE(ACT)                                                                           \
+  case ACT:                                                                                         \
+    if (CIP == 8) DENO_TC_CASE2(ACT, 8)                                                             \
+    else if (CIP == 16) DENO_TC_CASE2(ACT, 16)                                                      \
+    else if (CIP == 32) DENO_TC_CASE2(ACT, 32)                                                      \
+    else DENO_TC_CASE2(ACT, 64)                                                                     \
+    break;
+  switch (act) {
+    DENO_TC_CASE(ACT_IDENTITY)
+    DENO_TC_CASE(ACT_GELU)
+    DENO_TC_CASE(ACT_SILU)
+    DENO_TC_CASE(ACT_RELU)
+    DENO_TC_CASE(ACT_TANH)
+    DENO_TC_CASE(ACT_LEAKYRELU)
+    default: return fail(DENO_E_INVALID, "unknown activation id");
+  }
+#undef DENO_TC_CASE
+#undef DENO_TC_CASE2
+  return check_launch("plane_synthesis_tc", st);
+}
+#endif
+
 // spec [B*X][CO][KH][MW] + bypass(u) -> y (, z)
 int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, const float* u, const float* lw,
                      long long lw_so, long long lw_si, const float* bias, float* y, float* z, const TwPtrs& tw,
@@ -458,6 +575,15 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
   p.R = c.R; p.PTS = c.PTS; p.tiles = c.tiles;
   const int grid = s.B * s.X * c.tiles;
   const char* label = (bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr) ? "plane_synthesis" : "plane_synthesis_bwd";
+#ifndef DENO_EMULATE
+  const PathPref pref = path_pref();
+  if (pref != PathPref::Simt) {
+    const bool is_fwd = (bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr);
+    rc = try_launch_synthesis_tc(s, p, tw, act, is_fwd ? "plane_synthesis_tc" : "plane_synthesis_bwd_tc", st);
+    if (rc >= 0) return rc;
+    if (pref == PathPref::Tc) return fail(DENO_E_UNSUPPORTED, "DENO_SPECTRAL_PATH=tc but the shape is outside the tcgen05 synthesis kernel");
+  }
+#endif
 #define DENO_SYNTH_CASE(ACT)                                                                       \
   case ACT:                                                                                        \
     rc = allow_smem(plane_synthesis_kernel<ACT>, c.smem, "plane_synthesis");                       \
@@ -572,6 +698,7 @@ int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, s
     fill_axis(base + t.mid, 1, 1, s.KH4, 0, true);
   }
   if (s.ndim == 3) fill_axis(base + t.outer, s.X, s.KX, s.KX4, s.mX, false);
+  fill_synth_ae(base + t.synth_ae, s, t);
   for (int l = 0; l < s.MWp; ++l) {
     float c = 0.f;
     if (l < s.MW) {

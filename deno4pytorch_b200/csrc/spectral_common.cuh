@@ -102,4 +102,10 @@ __host__ __device__ __forceinline__ void decode_mode(const ModeDecode& md, int p
   }
 }
 
+// Byte offset of element (r, k) inside a tcgen05 K-major, no-swizzle operand image with `rows` rows:
+// 128-byte core matrices (8 rows x 4 fp32), row groups contiguous (SBO = 128), LBO = 16 * rows.
+__host__ __device__ __forceinline__ int kmajor_off(int r, int k, int rows) {
+  return (r & 7) * 16 + (r >> 3) * 128 + (k & 3) * 4 + (k >> 2) * (16 * rows);
+}
+
 }  // namespace deno

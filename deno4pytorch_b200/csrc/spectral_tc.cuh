@@ -1,4 +1,319 @@
-// spectral_tc.cuh - tcgen05 / TMEM tensor-core kernels (sm_100a only).  Filled in once the SIMT
-// path is parity-green; see DESIGN.md.
+// spectral_tc.cuh - tcgen05 / TMEM tensor-core kernels of the spectral path (sm_100a only).
+//
+// All GEMM-shaped work of a stage runs on the 5th-generation tensor cores with fp32-level accuracy
+// through the 3xTF32 split (a = a_hi + a_lo, b = b_hi + b_lo; a*b ~ a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,
+// relative error ~2^-21; hardware truncates fp32 operands to tf32, so a_hi is the explicitly masked
+// value and the products are exact - measured 6e-7 end to end by tools/tc_probe.cu).
+//
+// Operand convention (pinned on hardware by tools/tc_probe.cu and tools/tc_layout_scan.cu):
+// kind::tf32, cta_group::1, M = 128, both operands K-major, SWIZZLE_NONE.  An operand with R rows
+// (M rows of A / N rows of B) and K columns is stored as 128-byte core matrices of 8 rows x 4 columns:
+//     byte(r, k) = (r % 8) * 16 + (r / 8) * SBO + (k % 4) * 4 + (k / 4) * LBO
+// Every image here uses SBO = 128 (row groups contiguous) and LBO = 128 * (R / 8); one MMA consumes
+// K = 8, i.e. two core-matrix columns, so consecutive K steps advance the start address by 2 * LBO.
+// The accumulator D[m][n] lands in TMEM lane m, column n.
 #pragma once
-#include "spectral_common.cuh"
+#include "spectral_simt.cuh"
+
+namespace deno {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// warp-collective
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+
+using deno::kmajor_off;
+
+// ----------------------------------------------------------------------------------------------
+// plane_synthesis_tc: same contract as plane_synthesis_kernel (spectral_simt.cuh).
+//   D[y, o] = sum_i x[i, y] * Wl[o, i]                       (bypass 1x1 conv,   K = CIP)
+//           + sum_l cos(psi_l y) * U_r[o, l] - sin(psi_l y) * U_i[o, l]   (last-axis synthesis, K = KE)
+// One CTA = (batch entry b', R consecutive rows, one 128-wide column chunk); per row one M = 128 tile.
+// ----------------------------------------------------------------------------------------------
+struct SynthTcParams {
+  SynthParams s;          // geometry, pointers, scale, herm (act is a template argument)
+  const float* ae;        // pre-split twiddle images [chunk][hi|lo][KE * 128] floats
+  int KE;                 // 2 * MWp rounded up to a multiple of 8
+  int nchunks;            // column chunks of 128 per row
+  int tmem_cols;          // power of two >= 2 * CO, >= 32
+};
+
+struct SynthTcSmem {
+  int bw_hi, bw_lo, ae_hi, ae_lo, bu, ax_hi, ax_lo, bias, total;  // byte offsets
+  int bu_one;                                                     // bytes of one (hi or lo) U image
+};
+
+__host__ __device__ inline SynthTcSmem synth_tc_smem(int CIP, int CO, int KE, int R) {
+  SynthTcSmem m;
+  int off = 0;
+  m.bw_hi = off; off += CIP * CO * 4;
+  m.bw_lo = off; off += CIP * CO * 4;
+  m.ae_hi = off; off += KE * 128 * 4;
+  m.ae_lo = off; off += KE * 128 * 4;
+  m.bu_one = KE * CO * 4;
+  m.bu = off;    off += 2 * R * m.bu_one;   // [row][hi|lo]
+  m.ax_hi = off; off += CIP * 128 * 4;
+  m.ax_lo = off; off += CIP * 128 * 4;
+  m.bias = off;  off += CO * 4;
+  m.total = off;
+  return m;
+}
+
+template <int ACT, int CIP>
+__global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t mbar[2];
+  const SynthParams& p = q.s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = p.CO;
+  const int KH4 = round_up(KH, 4);
+  const int KE = q.KE, R = p.R;
+  const SynthTcSmem so = synth_tc_smem(CIP, CO, KE, R);
+  constexpr int NIT = CIP / 8;            // (point, channel-quad) items per thread: 128 * CIP/4 / 256
+
+  // CTA coordinates
+  int bid = blockIdx.x;
+  const int chunk = bid % q.nchunks; bid /= q.nchunks;
+  const int tile = bid % p.tiles;
+  const int bp = bid / p.tiles;
+  const int x0 = tile * R;
+  const int trows = (H > 1) ? min(R, H - x0) : 1;
+  const int y0 = chunk * 128;
+  const int ny = min(128, W - y0);
+
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)q.tmem_cols);
+  if (tid == 32) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+
+  // ---- constant operands -------------------------------------------------------------------
+  // bypass weight image B_W[n = o][k = i], split on the fly
+  for (int idx = tid; idx < CO * CIP; idx += 256) {
+    const int o = idx / CIP, i = idx - o * CIP;
+    const float w = (i < CI) ? p.lw[(long long)o * p.lw_so + (long long)i * p.lw_si] : 0.f;
+    float hi, lo;
+    split_tf32(w, hi, lo);
+    const int off = kmajor_off(o, i, CO);
+    *reinterpret_cast<float*>(smem + so.bw_hi + off) = hi;
+    *reinterpret_cast<float*>(smem + so.bw_lo + off) = lo;
+  }
+  {  // twiddle images are stored in their final layout: straight 16-byte copies (hi and lo are adjacent)
+    const float4* src = reinterpret_cast<const float4*>(q.ae + (long long)chunk * 2 * KE * 128);
+    float4* dst = reinterpret_cast<float4*>(smem + so.ae_hi);
+    for (int idx = tid; idx < 2 * KE * 128 / 4; idx += 256) dst[idx] = src[idx];
+  }
+  float* bias_s = reinterpret_cast<float*>(smem + so.bias);
+  for (int o = tid; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
+
+  // ---- stage A: U[r][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0 + r)}, written as B operand images ----
+  {
+    unsigned char* bu = smem + so.bu;
+    for (int idx = tid; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int task = tid; task < CO * MW; task += 256) {
+      const int o = task / MW, l = task - o * MW;
+      float ar[kSynthMaxRows], ai[kSynthMaxRows];
+#pragma unroll
+      for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
+      const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+      const float2* sp = p.spec + ((long long)bp * CO + o) * KH * MW + l;
+      for (int k = 0; k < KH; ++k) {
+        const float2 sv = sp[k * MW];
+#pragma unroll
+        for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+          if (rr < trows) {
+            const float2 e = p.twH[(x0 + rr) * KH4 + k];
+            ar[rr] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[rr]));
+            ai[rr] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[rr]));
+          }
+        }
+      }
+      const int off = kmajor_off(o, 2 * l, CO);   // k = 2l (cos partner) and 2l+1 (sin partner) share a 16-byte row
+#pragma unroll
+      for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+        if (rr < trows) {
+          float h0, l0, h1, l1;
+          split_tf32(ar[rr] * f, h0, l0);
+          split_tf32(-ai[rr] * f, h1, l1);
+          unsigned char* base = bu + (2 * rr) * so.bu_one + off;
+          *reinterpret_cast<float2*>(base) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(base + so.bu_one) = make_float2(l0, l1);
+        }
+      }
+    }
+  }
+
+  // ---- x row prefetch (registers) ------------------------------------------------------------
+  float xr[NIT][4];
+  const long long ubase = plane_base(p.g, bp, 0);
+  auto prefetch = [&](int rr) {
+    const long long rowoff = ubase + (long long)(x0 + rr) * W + y0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int item = it * 256 + tid;
+      const int pt = item & 127, cq = item >> 7;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = cq * 4 + j;
+        xr[it][j] = (pt < ny && ch < CI) ? p.u[rowoff + (long long)ch * p.g.sc + pt] : 0.f;
+      }
+    }
+  };
+  prefetch(0);
+
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, CO);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t lbo_m = 16 * 128;   // images with 128 rows (A operands)
+  const uint32_t lbo_n = 16 * CO;    // images with CO rows (B operands)
+
+  const int wq = warp & 3, wg = warp >> 2;          // TMEM lane quadrant / column half
+  const int ncol_half = CO / 2;
+  const int yl = wq * 32 + lane;                    // this thread's point inside the chunk
+  const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
+
+  auto epilogue = [&](int rr) {
+    const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)((rr & 1) * CO + wg * ncol_half);
+    const long long pbase = obase_b + (long long)(x0 + rr) * W + y0 + yl;
+    for (int c0 = 0; c0 < ncol_half; c0 += 16) {
+      float v[16];
+      tmem_ld16(tb + c0, v);
+      if (yl < ny) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int o = wg * ncol_half + c0 + j;
+          const float zz = v[j] + bias_s[o];
+          const long long a = pbase + (long long)o * p.g.sc;
+          if (p.z != nullptr) p.z[a] = zz;
+          p.y[a] = act_apply(ACT, zz);
+        }
+      }
+    }
+  };
+
+  for (int rr = 0; rr < trows; ++rr) {
+    if (rr > 0) mbar_wait(&mbar[(rr - 1) & 1], ((rr - 1) >> 1) & 1);   // MMA(rr-1) done: A_X free, D(rr-1) ready
+    // registers -> A_X images (hi / lo)
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int item = it * 256 + tid;
+      const int pt = item & 127, cq = item >> 7;
+      float4 hi, lo;
+      split_tf32(xr[it][0], hi.x, lo.x);
+      split_tf32(xr[it][1], hi.y, lo.y);
+      split_tf32(xr[it][2], hi.z, lo.z);
+      split_tf32(xr[it][3], hi.w, lo.w);
+      const int off = kmajor_off(pt, cq * 4, 128);
+      *reinterpret_cast<float4*>(smem + so.ax_hi + off) = hi;
+      *reinterpret_cast<float4*>(smem + so.ax_lo + off) = lo;
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t d = tmem + (uint32_t)((rr & 1) * CO);
+      uint32_t accum = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {      // hi*hi, lo*hi, hi*lo
+        const uint32_t ax = sbase + (pass == 1 ? so.ax_lo : so.ax_hi);
+        const uint32_t bw = sbase + (pass == 2 ? so.bw_lo : so.bw_hi);
+        for (int s = 0; s < CIP / 8; ++s) {
+          mma_tf32(d, make_desc(ax + s * 2 * lbo_m, lbo_m, 128), make_desc(bw + s * 2 * lbo_n, lbo_n, 128), idesc, accum);
+          accum = 1;
+        }
+        const uint32_t ae = sbase + (pass == 1 ? so.ae_lo : so.ae_hi);
+        const uint32_t bu = sbase + so.bu + (2 * rr + (pass == 2 ? 1 : 0)) * so.bu_one;
+        for (int s = 0; s < KE / 8; ++s)
+          mma_tf32(d, make_desc(ae + s * 2 * lbo_m, lbo_m, 128), make_desc(bu + s * 2 * lbo_n, lbo_n, 128), idesc, 1);
+      }
+      mma_commit(&mbar[rr & 1]);
+    }
+    if (rr + 1 < trows) prefetch(rr + 1);
+    if (rr > 0) {
+      fence_after_sync();
+      epilogue(rr - 1);
+    }
+  }
+  mbar_wait(&mbar[(trows - 1) & 1], ((trows - 1) >> 1) & 1);
+  fence_after_sync();
+  epilogue(trows - 1);
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)q.tmem_cols);
+}
+
+}  // namespace tc
+}  // namespace deno

@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+@pytest.fixture(params=["simt", "auto"], autouse=True)
+def spectral_path(request, monkeypatch):
+    """Every parity test runs twice: SIMT kernels only, and the default dispatch (tcgen05 kernels
+    wherever they cover the shape).  The library reads DENO_SPECTRAL_PATH on every call."""
+    monkeypatch.setenv("DENO_SPECTRAL_PATH", request.param)
+    return request.param
+
+
 def _dev():
     return torch.device("cuda", 0)
 

@@ -75,8 +75,18 @@ def test_twiddle_tables_are_fp64_accurate(built_lib):
     f = np.concatenate([np.arange(12), np.arange(229 - 12, 229)])
     ang = 2 * np.pi * np.outer(np.arange(229), f) / 229
     assert np.abs(mid[..., 0] - np.cos(ang)).max() < 1e-7 and np.abs(mid[..., 1] - np.sin(ang)).max() < 1e-7
-    cl = buf[-12:]
+    off = 59 * 12 * 2 + 229 * 24 * 2
+    cl = buf[off:off + 12]
     assert cl.tolist() == [1.0] + [2.0] * 11
+    # tensor-core twiddle images: hi + lo reproduces the fp64 value to ~1e-11, hi has a tf32 mantissa
+    ae = buf[off + 12:]
+    assert ae.size == 1 * 2 * 24 * 128
+    hi, lo = ae[:24 * 128], ae[24 * 128:]
+    assert (hi.view(np.uint32) & 0x1FFF).max() == 0
+    y, l = 37, 5
+    o = ((y & 7) * 16 + (y >> 3) * 128 + ((2 * l) & 3) * 4 + ((2 * l) >> 2) * 2048) // 4
+    want = np.cos(2 * np.pi * l * y / 59)
+    assert abs(float(hi[o]) + float(lo[o]) - want) < 1e-10
 
 
 @pytest.mark.parametrize("name", golden_names("model"))
