@@ -497,6 +497,8 @@ int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int
   if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;
   const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
   const TwLayout tl = tw_layout(s);
+  // stage A stages the packed spectrum through the A_X area: at least one output channel must fit
+  if (2 * CIP * 128 * 4 - round_up(kSynthMaxRows * p.g.KH, 2) * 8 < p.g.KH * p.g.MW * 8) return -1;
   int bestR = 0;
   double best_eff = -1.0;
   const int maxR = p.g.H > 1 ? (p.g.H < kSynthMaxRows ? p.g.H : kSynthMaxRows) : 1;

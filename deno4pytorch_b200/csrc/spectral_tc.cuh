@@ -173,44 +173,6 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   float* bias_s = reinterpret_cast<float*>(smem + so.bias);
   for (int o = tid; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
 
-  // ---- stage A: U[r][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0 + r)}, written as B operand images ----
-  {
-    unsigned char* bu = smem + so.bu;
-    for (int idx = tid; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    for (int task = tid; task < CO * MW; task += 256) {
-      const int o = task / MW, l = task - o * MW;
-      float ar[kSynthMaxRows], ai[kSynthMaxRows];
-#pragma unroll
-      for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
-      const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
-      const float2* sp = p.spec + ((long long)bp * CO + o) * KH * MW + l;
-      for (int k = 0; k < KH; ++k) {
-        const float2 sv = sp[k * MW];
-#pragma unroll
-        for (int rr = 0; rr < kSynthMaxRows; ++rr) {
-          if (rr < trows) {
-            const float2 e = p.twH[(x0 + rr) * KH4 + k];
-            ar[rr] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[rr]));
-            ai[rr] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[rr]));
-          }
-        }
-      }
-      const int off = kmajor_off(o, 2 * l, CO);   // k = 2l (cos partner) and 2l+1 (sin partner) share a 16-byte row
-#pragma unroll
-      for (int rr = 0; rr < kSynthMaxRows; ++rr) {
-        if (rr < trows) {
-          float h0, l0, h1, l1;
-          split_tf32(ar[rr] * f, h0, l0);
-          split_tf32(-ai[rr] * f, h1, l1);
-          unsigned char* base = bu + (2 * rr) * so.bu_one + off;
-          *reinterpret_cast<float2*>(base) = make_float2(h0, h1);
-          *reinterpret_cast<float2*>(base + so.bu_one) = make_float2(l0, l1);
-        }
-      }
-    }
-  }
-
   // ---- x row prefetch (registers) ------------------------------------------------------------
   float xr[NIT][4];
   const long long ubase = plane_base(p.g, bp, 0);
@@ -228,6 +190,65 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     }
   };
   prefetch(0);
+
+  // ---- stage A: U[r][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0 + r)}, written as B operand images ----
+  // The packed spectrum of this batch entry is staged through the (still unused) A_X area in chunks of
+  // OC output channels with fully coalesced loads, so the k-loop below runs out of shared memory.
+  {
+    unsigned char* bu = smem + so.bu;
+    for (int idx = tid; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2* twr = reinterpret_cast<float2*>(smem + so.ax_hi);            // [trows][KH] row twiddles
+    float2* sps = twr + round_up(kSynthMaxRows * KH, 2);                 // [OC][KH*MW] spectrum chunk
+    const int Q = KH * MW;
+    const int avail = 2 * CIP * 128 * 4 - round_up(kSynthMaxRows * KH, 2) * 8;
+    int OC = avail / (Q * 8);
+    if (OC > CO) OC = CO;
+    for (int idx = tid; idx < trows * KH; idx += 256) {
+      const int rr = idx / KH, k = idx - rr * KH;
+      twr[idx] = p.twH[(x0 + rr) * KH4 + k];
+    }
+    for (int o0 = 0; o0 < CO; o0 += OC) {
+      const int oc = min(OC, CO - o0);
+      __syncthreads();   // previous chunk consumed (first pass: zero fill / twiddles ordered before use)
+      const float2* src = p.spec + ((long long)bp * CO + o0) * Q;
+      for (int idx = tid; idx < oc * Q; idx += 256) sps[idx] = src[idx];
+      __syncthreads();
+      for (int task = tid; task < oc * MW; task += 256) {
+        const int ol = task / MW, l = task - ol * MW;
+        const int o = o0 + ol;
+        float ar[kSynthMaxRows], ai[kSynthMaxRows];
+#pragma unroll
+        for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
+        const float2* sp = sps + ol * Q + l;
+#pragma unroll 4
+        for (int k = 0; k < KH; ++k) {
+          const float2 sv = sp[k * MW];
+#pragma unroll
+          for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+            if (rr < trows) {
+              const float2 e = twr[rr * KH + k];
+              ar[rr] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[rr]));
+              ai[rr] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[rr]));
+            }
+          }
+        }
+        const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+        const int off = kmajor_off(o, 2 * l, CO);   // k = 2l (cos partner) and 2l+1 (sin partner) share a 16-byte row
+#pragma unroll
+        for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+          if (rr < trows) {
+            float h0, l0, h1, l1;
+            split_tf32(ar[rr] * f, h0, l0);
+            split_tf32(-ai[rr] * f, h1, l1);
+            unsigned char* base = bu + (2 * rr) * so.bu_one + off;
+            *reinterpret_cast<float2*>(base) = make_float2(h0, h1);
+            *reinterpret_cast<float2*>(base + so.bu_one) = make_float2(l0, l1);
+          }
+        }
+      }
+    }
+    __syncthreads();     // the A_X area is about to be overwritten by the first row tile
+  }
 
   fence_before_sync();
   __syncthreads();
