@@ -224,6 +224,7 @@ def layer_roofline(workload: str, device, hbm_peak: float, reps: int = 20):
         "plane_synthesis": 3 * A + spec_small,              # read x, write y and z
         "plane_analysis_gz": 3 * A + spec_small,            # read gy, z; write gz
         "plane_synthesis_bwd": 2 * A + spec_small,          # read gz, write gx
+        "plane_analysis_tc": A + spec_small, "plane_analysis_gz_tc": 3 * A + spec_small,
         "plane_synthesis_tc": 3 * A + spec_small, "plane_synthesis_bwd_tc": 2 * A + spec_small,
         "bypass_wgrad_partial": 2 * A,                      # read gz, x
         "mode_mix": 2 * spec_small + Wb, "mode_mix_bwd": 2 * spec_small + Wb, "mode_mix_wgrad": 2 * spec_small + Wb,

@@ -126,8 +126,9 @@ ModeDecode make_decode(const Shape& s) {
 // Twiddle tables (host, fp64 -> fp32)
 // ------------------------------------------------------------------------------------------
 struct TwLayout {
-  size_t last, mid, outer, cl, synth_ae, total;  // float offsets
+  size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, total;  // float offsets
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
+  int N1, Wp, Hp, KHp;                           // tensor-core analysis images: E1 [hi|lo][N1*Wp], A2 [hi|lo][KHp*2*Hp]
 };
 
 TwLayout tw_layout(const Shape& s) {
@@ -140,6 +141,13 @@ TwLayout tw_layout(const Shape& s) {
   t.nchunks = (s.W + 127) / 128;
   t.KE = 2 * s.MWp;
   t.synth_ae = off; off += (size_t)t.nchunks * 2 * t.KE * 128;
+  t.N1 = round_up(2 * s.MWp, 32);
+  t.Wp = round_up(s.W, 8);
+  t.Hp = round_up(s.H, 8);
+  t.KHp = round_up(s.KH, 8);
+  const bool an = (s.ndim >= 2 && s.H <= 128);   // shapes the tensor-core analysis kernel can take
+  t.an_e1 = off; off += an ? (size_t)2 * t.N1 * t.Wp : 0;
+  t.an_a2 = off; off += an ? (size_t)2 * t.KHp * 2 * t.Hp : 0;
   t.total = off;
   return t;
 }
@@ -381,7 +389,46 @@ int allow_smem(K kernel, size_t bytes, const char* what) {
   return DENO_OK;
 }
 
-struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; const float* synth_ae; };
+// Analysis operand images (see plane_analysis_tc_kernel): E1[n][y] (n = 2l: cos, 2l+1: -sin of 2 pi l y / W)
+// as a B operand with N1 rows, and A2[k][k'] (k' < Hp: cos, else sin of 2 pi f_k x / H) as an A operand.
+void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
+  const double two_pi = 6.283185307179586476925286766559;
+  if (!(s.ndim >= 2 && s.H <= 128)) return;
+  float* e1hi = base + t.an_e1;
+  float* e1lo = e1hi + (size_t)t.N1 * t.Wp;
+  for (int n = 0; n < t.N1; ++n)
+    for (int y = 0; y < t.Wp; ++y) {
+      const int l = n / 2;
+      double v = 0.0;
+      if (l < s.MW && y < s.W) {
+        const double ang = two_pi * (double)(((long long)l * y) % s.W) / (double)s.W;
+        v = (n & 1) ? -sin(ang) : cos(ang);
+      }
+      const float h = tf32_mask((float)v);
+      const int off = kmajor_off(n, y, t.N1) / 4;
+      e1hi[off] = h;
+      e1lo[off] = (float)(v - (double)h);
+    }
+  float* a2hi = base + t.an_a2;
+  float* a2lo = a2hi + (size_t)t.KHp * 2 * t.Hp;
+  for (int k = 0; k < t.KHp; ++k)
+    for (int kk = 0; kk < 2 * t.Hp; ++kk) {
+      const int x = kk < t.Hp ? kk : kk - t.Hp;
+      double v = 0.0;
+      if (k < s.KH && x < s.H) {
+        const long long f = (k < s.mH) ? k : (long long)s.H - 2 * s.mH + k;
+        const double ang = two_pi * (double)((f * x) % s.H) / (double)s.H;
+        v = kk < t.Hp ? cos(ang) : sin(ang);
+      }
+      const float h = tf32_mask((float)v);
+      const int off = kmajor_off(k, kk, t.KHp) / 4;
+      a2hi[off] = h;
+      a2lo[off] = (float)(v - (double)h);
+    }
+}
+
+struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; const float* synth_ae;
+                const float* an_e1; const float* an_a2; };
 
 TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   const float* base = static_cast<const float*>(twiddles);
@@ -392,12 +439,67 @@ TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   p.outer = reinterpret_cast<const float2*>(base + t.outer);
   p.cl = base + t.cl;
   p.synth_ae = base + t.synth_ae;
+  p.an_e1 = base + t.an_e1;
+  p.an_a2 = base + t.an_a2;
   return p;
 }
+
+// DENO_SPECTRAL_PATH = auto (default) | simt | tc : which kernels serve the stages both paths implement.
+enum class PathPref { Auto, Simt, Tc };
+PathPref path_pref() {
+  const char* e = getenv("DENO_SPECTRAL_PATH");
+  if (e == nullptr) return PathPref::Auto;
+  if (strcmp(e, "simt") == 0) return PathPref::Simt;
+  if (strcmp(e, "tc") == 0) return PathPref::Tc;
+  return PathPref::Auto;
+}
+
+#ifndef DENO_EMULATE
+// Tensor-core analysis; -1 when the shape is outside the kernel's coverage.
+int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const float* z, float* gz_out, float2* out,
+                           const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
+  if (s.ndim < 2 || s.H > 128) return -1;
+  const TwLayout tl = tw_layout(s);
+  if (tl.N1 > 256) return -1;
+  const bool gz = (z != nullptr);
+  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(s.H, s.W, tl.N1, tl.Wp, tl.Hp, tl.KHp, gz);
+  if (sm.total > kMaxSmemBytes - 1024) return -1;
+  tc::AnalysisTcParams p;
+  p.g = make_geom(s, channels);
+  p.u = u; p.z = z; p.gz_out = gz_out; p.out = out;
+  p.e1 = tw.an_e1; p.a2 = tw.an_a2; p.cl = tw.cl;
+  p.scale = scale; p.herm = herm; p.act = s.act;
+  p.nplanes = s.B * s.X * channels;
+  p.N1 = tl.N1; p.Wp = tl.Wp; p.Hp = tl.Hp; p.KHp = tl.KHp;
+  const int grid = p.nplanes < 148 ? p.nplanes : 148;
+  int rc;
+  if (gz) {
+    rc = allow_smem(tc::plane_analysis_tc_kernel<true>, (size_t)sm.total, "plane_analysis_tc");
+    if (rc != DENO_OK) return rc;
+    prof_before("plane_analysis_gz_tc", st);
+    tc::plane_analysis_tc_kernel<true><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);
+  } else {
+    rc = allow_smem(tc::plane_analysis_tc_kernel<false>, (size_t)sm.total, "plane_analysis_tc");
+    if (rc != DENO_OK) return rc;
+    prof_before("plane_analysis_tc", st);
+    tc::plane_analysis_tc_kernel<false><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);
+  }
+  return check_launch("plane_analysis_tc", st);
+}
+#endif
 
 // x / (gy, z) -> packed plane spectra [B*X][C][KH][MW]
 int launch_analysis(const Shape& s, int channels, const float* u, const float* z, float* gz_out, float2* out,
                     const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
+#ifndef DENO_EMULATE
+  {
+    const PathPref pref = path_pref();
+    if (pref != PathPref::Simt) {
+      const int trc = try_launch_analysis_tc(s, channels, u, z, gz_out, out, tw, scale, herm, st);
+      if (trc >= 0) return trc;
+    }
+  }
+#endif
   AnalysisParams p;
   p.g = make_geom(s, channels);
   AnalysisCfg c;
@@ -477,16 +579,6 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
   prof_before("mode_mix_wgrad", st);
   DENO_LAUNCH(mode_mix_wgrad_kernel, grid, block, 0, st, p);
   return check_launch("mode_mix_wgrad", st);
-}
-
-// DENO_SPECTRAL_PATH = auto (default) | simt | tc : which kernels serve the stages both paths implement.
-enum class PathPref { Auto, Simt, Tc };
-PathPref path_pref() {
-  const char* e = getenv("DENO_SPECTRAL_PATH");
-  if (e == nullptr) return PathPref::Auto;
-  if (strcmp(e, "simt") == 0) return PathPref::Simt;
-  if (strcmp(e, "tc") == 0) return PathPref::Tc;
-  return PathPref::Auto;
 }
 
 #ifndef DENO_EMULATE
@@ -701,6 +793,7 @@ int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, s
   }
   if (s.ndim == 3) fill_axis(base + t.outer, s.X, s.KX, s.KX4, s.mX, false);
   fill_synth_ae(base + t.synth_ae, s, t);
+  fill_analysis_images(base, s, t);
   for (int l = 0; l < s.MWp; ++l) {
     float c = 0.f;
     if (l < s.MW) {

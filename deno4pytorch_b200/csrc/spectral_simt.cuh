@@ -271,6 +271,7 @@ struct MixParams {
 };
 
 constexpr int kMixBatchTile = 4;
+constexpr int kMixUnroll = 8;
 
 // blockDim = (32 modes, 8 output channels); grid = (ceil(M/32), ceil(CO/8), ceil(B/4))
 __global__ void mode_mix_kernel(MixParams p) {
@@ -287,16 +288,29 @@ __global__ void mode_mix_kernel(MixParams p) {
 #pragma unroll
   for (int j = 0; j < kMixBatchTile; ++j) ar[j] = ai[j] = 0.f;
   const float sgn = p.conj_w ? -1.0f : 1.0f;
-#pragma unroll 8
-  for (int ci = 0; ci < p.CI; ++ci) {
-    float2 wv = w[(long long)ci * p.w_sci];
-    wv.y *= sgn;
+  const float2* inb[kMixBatchTile];
 #pragma unroll
-    for (int j = 0; j < kMixBatchTile; ++j) {
-      const int b = min(b0 + j, p.B - 1);
-      const float2 v = p.in[((long long)b * p.CI + ci) * M + pm];
-      ar[j] = fmaf(v.x, wv.x, fmaf(-v.y, wv.y, ar[j]));
-      ai[j] = fmaf(v.x, wv.y, fmaf(v.y, wv.x, ai[j]));
+  for (int j = 0; j < kMixBatchTile; ++j) inb[j] = p.in + ((long long)min(b0 + j, p.B - 1) * p.CI) * M + pm;
+  // The loop is latency-bound (every operand comes from L2), so all loads of a batch of kMixUnroll
+  // contracted channels are issued before any of them is consumed.
+  for (int ci0 = 0; ci0 < p.CI; ci0 += kMixUnroll) {
+    float2 wv[kMixUnroll], v[kMixUnroll][kMixBatchTile];
+#pragma unroll
+    for (int u = 0; u < kMixUnroll; ++u) {
+      const int ci = min(ci0 + u, p.CI - 1);
+      wv[u] = w[(long long)ci * p.w_sci];
+#pragma unroll
+      for (int j = 0; j < kMixBatchTile; ++j) v[u][j] = inb[j][(long long)ci * M];
+    }
+#pragma unroll
+    for (int u = 0; u < kMixUnroll; ++u) {
+      const float wr = (ci0 + u < p.CI) ? wv[u].x : 0.f;
+      const float wi = (ci0 + u < p.CI) ? wv[u].y * sgn : 0.f;
+#pragma unroll
+      for (int j = 0; j < kMixBatchTile; ++j) {
+        ar[j] = fmaf(v[u][j].x, wr, fmaf(-v[u][j].y, wi, ar[j]));
+        ai[j] = fmaf(v[u][j].x, wi, fmaf(v[u][j].y, wr, ai[j]));
+      }
     }
   }
 #pragma unroll
@@ -323,16 +337,28 @@ __global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
   int blk, off;
   decode_mode(p.md, pm, blk, off);
   float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int b = 0; b < p.B; ++b) {
-    const float2 xv = p.xhat[((long long)b * p.CI + ci) * M + pm];
+  const float2* xp = p.xhat + (long long)ci * M + pm;
+  const float2* gp[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int o = min(oq * 4 + j, p.CO - 1);
-      const float2 gv = p.ghat[((long long)b * p.CO + o) * M + pm];
-      // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
-      ar[j] = fmaf(xv.x, gv.x, fmaf(xv.y, gv.y, ar[j]));
-      ai[j] = fmaf(xv.x, gv.y, fmaf(-xv.y, gv.x, ai[j]));
+  for (int j = 0; j < 4; ++j) gp[j] = p.ghat + (long long)min(oq * 4 + j, p.CO - 1) * M + pm;
+  for (int b0 = 0; b0 < p.B; b0 += 4) {   // batched loads: the loop is L2-latency-bound
+    float2 xv[4], gv[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = min(b0 + u, p.B - 1);
+      xv[u] = xp[(long long)b * p.CI * M];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gv[u][j] = gp[j][(long long)b * p.CO * M];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float xr = (b0 + u < p.B) ? xv[u].x : 0.f, xi = (b0 + u < p.B) ? xv[u].y : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
+        ar[j] = fmaf(xr, gv[u][j].x, fmaf(xi, gv[u][j].y, ar[j]));
+        ai[j] = fmaf(xr, gv[u][j].y, fmaf(-xi, gv[u][j].x, ai[j]));
+      }
     }
   }
   float2* gb = blk == 0 ? p.gw[0] : (blk == 1 ? p.gw[1] : (blk == 2 ? p.gw[2] : p.gw[3]));

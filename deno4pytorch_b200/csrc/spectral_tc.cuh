@@ -336,5 +336,233 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)q.tmem_cols);
 }
 
+// ----------------------------------------------------------------------------------------------
+// plane_analysis_tc: same contract as plane_analysis_kernel (spectral_simt.cuh) for planes with
+// H <= 128 rows.  Two chained GEMMs per plane, both on the tensor cores:
+//   stage 1  D1[x, n]  = sum_y u[x, y] * E1[n, y]          n = 2l: cos, 2l+1: -sin      (K = Wp)
+//            -> D1[x, 2l] + i D1[x, 2l+1] = T[x, l] = sum_y u[x,y] e^{-i psi_l y}
+//   stage 2  D2[k, n]  = sum_x cos(phi_k x) * Ba[x, n] + sin(phi_k x) * Bb[x, n]       (K = 2 Hp)
+//            with Ba = (Tr, Ti), Bb = (Ti, -Tr)  ->  D2[k, 2l] + i D2[k, 2l+1] = sum_x e^{-i phi_k x} T[x, l]
+// D1 goes TMEM -> registers -> (split) -> shared memory as the B operand of stage 2.
+// One persistent CTA per SM loops over planes; the next plane streams into a staging buffer with
+// cp.async while the current one is on the tensor cores.
+// ----------------------------------------------------------------------------------------------
+struct AnalysisTcParams {
+  PlaneGeom g;
+  const float* u;        // x, or gy when FUSE_GZ
+  const float* z;
+  float* gz_out;
+  float2* out;           // [nplanes][KH][MW]
+  const float* e1;       // [hi|lo] images, N1 rows x Wp
+  const float* a2;       // [hi|lo] images, KHp rows x 2*Hp
+  const float* cl;
+  float scale;
+  int herm;
+  int act;
+  int nplanes;
+  int N1, Wp, Hp, KHp;
+};
+
+struct AnalysisTcSmem {
+  int e1, a2, ab, stage, total;   // byte offsets
+  int e1_one, a2_one, a_one, b2_one, b2_lbo;
+};
+
+__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int N1, int Wp, int Hp, int KHp, bool gz) {
+  AnalysisTcSmem m;
+  m.e1_one = N1 * Wp * 4;
+  m.a2_one = KHp * 2 * Hp * 4;
+  m.a_one = Hp * Wp * 4;
+  m.b2_lbo = 16 * N1 + 16;                  // padded K-direction stride: conflict-free scalar stores
+  m.b2_one = (2 * Hp / 4) * m.b2_lbo;
+  int off = 0;
+  m.e1 = off; off += 2 * m.e1_one;
+  m.a2 = off; off += 2 * m.a2_one;
+  m.ab = off; off += 2 * (m.a_one > m.b2_one ? m.a_one : m.b2_one);   // A images, later aliased by the B2 images
+  m.stage = off; off += round_up(H * W, 4) * 4 * (gz ? 2 : 1);
+  m.total = off;
+  return m;
+}
+
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <bool FUSE_GZ>
+__global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t mbar[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
+  const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KHp = p.KHp;
+  const AnalysisTcSmem so = analysis_tc_smem(H, W, N1, Wp, Hp, KHp, FUSE_GZ);
+  const int HW = H * W;
+  float* stage = reinterpret_cast<float*>(smem + so.stage);
+  float* stage_z = stage + round_up(HW, 4);
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 2 * N1 <= 32 ? 32u : (2 * N1 <= 64 ? 64u : (2 * N1 <= 128 ? 128u : (2 * N1 <= 256 ? 256u : 512u))));
+  if (tid == 32) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  {  // constant operand images (final layout in global memory): straight copies
+    const float4* s1 = reinterpret_cast<const float4*>(p.e1);
+    float4* d1 = reinterpret_cast<float4*>(smem + so.e1);
+    for (int i = tid; i < 2 * so.e1_one / 16; i += 256) d1[i] = s1[i];
+    const float4* s2 = reinterpret_cast<const float4*>(p.a2);
+    float4* d2 = reinterpret_cast<float4*>(smem + so.a2);
+    for (int i = tid; i < 2 * so.a2_one / 16; i += 256) d2[i] = s2[i];
+  }
+  auto prefetch_plane = [&](int q) {
+    const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+    for (int i = tid; i < HW; i += 256) {
+      cp_async4(stage + i, p.u + base + i);
+      if (FUSE_GZ) cp_async4(stage_z + i, p.z + base + i);
+    }
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < p.nplanes) prefetch_plane(blockIdx.x);
+
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)N1;
+  const uint32_t idesc = make_idesc_tf32(128, N1);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t lbo_a = 16 * Hp, lbo_e1 = 16 * N1, lbo_a2 = 16 * KHp, lbo_b2 = (uint32_t)so.b2_lbo;
+  const int wq = warp & 3, wg = warp >> 2;
+  const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / mode k of D2)
+  uint32_t phase = 0;
+
+  for (int q = blockIdx.x; q < p.nplanes; q += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();                                   // staging(q) complete and visible
+    if (FUSE_GZ) {                                     // gz = gy * act'(z): coalesced store, kept in staging
+      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+      for (int i = tid; i < HW; i += 256) {
+        const float v = stage[i] * act_grad(p.act, stage_z[i]);
+        stage[i] = v;
+        p.gz_out[base + i] = v;
+      }
+      __syncthreads();
+    }
+    // staging -> A images (hi / lo), rows fastest across lanes: 8 lanes fill one 128-byte core matrix
+    for (int item = tid; item < (Wp / 4) * Hp; item += 256) {
+      const int yq = item / Hp, row = item - yq * Hp;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = yq * 4 + j;
+        v[j] = (row < H && y < W) ? stage[row * W + y] : 0.f;
+      }
+      float4 hi, lo;
+      split_tf32(v[0], hi.x, lo.x);
+      split_tf32(v[1], hi.y, lo.y);
+      split_tf32(v[2], hi.z, lo.z);
+      split_tf32(v[3], hi.w, lo.w);
+      const int off = kmajor_off(row, yq * 4, Hp);
+      *reinterpret_cast<float4*>(smem + so.ab + off) = hi;
+      *reinterpret_cast<float4*>(smem + so.ab + so.a_one + off) = lo;
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();                                   // A images complete; staging is free again
+    if (q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);
+    if (tid == 0) {
+      fence_after_sync();
+      uint32_t accum = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {           // hi*hi, lo*hi, hi*lo
+        const uint32_t a = sbase + so.ab + (pass == 1 ? so.a_one : 0);
+        const uint32_t b = sbase + so.e1 + (pass == 2 ? so.e1_one : 0);
+        for (int s2 = 0; s2 < Wp / 8; ++s2) {
+          mma_tf32(tmem_d1, make_desc(a + s2 * 2 * lbo_a, lbo_a, 128), make_desc(b + s2 * 2 * lbo_e1, lbo_e1, 128), idesc, accum);
+          accum = 1;
+        }
+      }
+      mma_commit(&mbar[0]);
+    }
+    mbar_wait(&mbar[0], phase);
+    fence_after_sync();
+    // D1 -> B2 images (alias the A images, which the finished stage-1 MMAs no longer read)
+    {
+      const int ncol_half = N1 / 2;
+      unsigned char* b2hi = smem + so.ab;
+      unsigned char* b2lo = b2hi + so.b2_one;
+      for (int c0 = 0; c0 < ncol_half; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_half + c0), v);
+        if (xrow < Hp) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const int n = wg * ncol_half + c0 + j;                 // even column: Tr, n + 1: Ti
+            const float tr = xrow < H ? v[j] : 0.f, ti = xrow < H ? v[j + 1] : 0.f;
+            float trh, trl, tih, til;
+            split_tf32(tr, trh, trl);
+            split_tf32(ti, tih, til);
+            // element (row n, k') at (n&7)*16 + (n>>3)*128 + (k'&3)*4 + (k'>>2)*b2_lbo
+            const int r0 = (n & 7) * 16 + (n >> 3) * 128, r1 = ((n + 1) & 7) * 16 + ((n + 1) >> 3) * 128;
+            const int kc = (xrow & 3) * 4 + (xrow >> 2) * so.b2_lbo;                       // k' = x        (cos partner)
+            const int ks = ((Hp + xrow) & 3) * 4 + ((Hp + xrow) >> 2) * so.b2_lbo;         // k' = Hp + x   (sin partner)
+            *reinterpret_cast<float*>(b2hi + r0 + kc) = trh;  *reinterpret_cast<float*>(b2lo + r0 + kc) = trl;   // Ba[x, 2l]   = Tr
+            *reinterpret_cast<float*>(b2hi + r1 + kc) = tih;  *reinterpret_cast<float*>(b2lo + r1 + kc) = til;   // Ba[x, 2l+1] = Ti
+            *reinterpret_cast<float*>(b2hi + r0 + ks) = tih;  *reinterpret_cast<float*>(b2lo + r0 + ks) = til;   // Bb[x, 2l]   = Ti
+            *reinterpret_cast<float*>(b2hi + r1 + ks) = -trh; *reinterpret_cast<float*>(b2lo + r1 + ks) = -trl;  // Bb[x, 2l+1] = -Tr
+          }
+        }
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      uint32_t accum = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = sbase + so.a2 + (pass == 1 ? so.a2_one : 0);
+        const uint32_t b = sbase + so.ab + (pass == 2 ? so.b2_one : 0);
+        for (int s2 = 0; s2 < 2 * Hp / 8; ++s2) {
+          mma_tf32(tmem_d2, make_desc(a + s2 * 2 * lbo_a2, lbo_a2, 128), make_desc(b + s2 * 2 * lbo_b2, lbo_b2, 128), idesc, accum);
+          accum = 1;
+        }
+      }
+      mma_commit(&mbar[1]);
+    }
+    mbar_wait(&mbar[1], phase);
+    fence_after_sync();
+    // epilogue: lane k of D2 holds mode k; columns (2l, 2l+1) = (re, im)
+    if (warp < 4) {
+      float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
+      for (int c0 = 0; c0 < N1; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
+        if (xrow < KH) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const int l = (c0 + j) >> 1;
+            if (l < MW) {
+              const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+              dst[l] = make_float2(v[j] * f, v[j + 1] * f);
+            }
+          }
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();                                   // TMEM and the A/B2 area are reused by the next plane
+    phase ^= 1;
+  }
+  cp_async_wait_all();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 2 * N1 <= 32 ? 32u : (2 * N1 <= 64 ? 64u : (2 * N1 <= 128 ? 128u : (2 * N1 <= 256 ? 256u : 512u))));
+}
+
 }  // namespace tc
 }  // namespace deno

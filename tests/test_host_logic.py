@@ -79,7 +79,7 @@ def test_twiddle_tables_are_fp64_accurate(built_lib):
     cl = buf[off:off + 12]
     assert cl.tolist() == [1.0] + [2.0] * 11
     # tensor-core twiddle images: hi + lo reproduces the fp64 value to ~1e-11, hi has a tf32 mantissa
-    ae = buf[off + 12:]
+    ae = buf[off + 12:off + 12 + 2 * 24 * 128]
     assert ae.size == 1 * 2 * 24 * 128
     hi, lo = ae[:24 * 128], ae[24 * 128:]
     assert (hi.view(np.uint32) & 0x1FFF).max() == 0
