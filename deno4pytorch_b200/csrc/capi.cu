@@ -33,6 +33,7 @@ int fail(int code, const std::string& msg) {
 }
 
 constexpr size_t kAlign = 256;
+constexpr int kWgradTcMaxCtas = 2 * 148;   // persistent CTAs of bypass_wgrad_tc
 constexpr int kMaxSmemBytes = 227 * 1024;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
@@ -322,7 +323,8 @@ int bwd_ws(const Shape& s, BwdWs& w) {
   w.gxhat = off;   off += align_up((size_t)s.B * s.CI * s.M * 8);
   w.t2 = off;      off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
   w.v = off;       off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
-  w.partial = off; off += align_up((size_t)wc.ncta * ((size_t)s.CO * s.CI + s.CO) * 4);
+  const size_t nparts = (size_t)(wc.ncta > kWgradTcMaxCtas ? wc.ncta : kWgradTcMaxCtas);   // either kernel's partial count
+  w.partial = off; off += align_up(nparts * ((size_t)s.CO * s.CI + s.CO) * 4);
   w.total = off;
   return DENO_OK;
 }
@@ -599,6 +601,7 @@ int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int
     if (bytes > (size_t)kMaxSmemBytes) continue;
     int per_sm = (int)((228 * 1024) / (bytes + 2048));
     if (per_sm > 4) per_sm = 4;
+    if (per_sm * 6 * CO > 512) per_sm = 512 / (6 * CO) > 0 ? 512 / (6 * CO) : 1;   // TMEM columns per SM
     if (per_sm < 1) per_sm = 1;
     const long long ctas = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks;
     const long long slots = 148LL * per_sm;
@@ -617,7 +620,8 @@ int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int
   q.KE = tl.KE;
   q.nchunks = tl.nchunks;
   int cols = 32;
-  while (cols < 2 * CO) cols *= 2;
+  while (cols < 6 * CO) cols *= 2;
+  if (cols > 512) return -1;
   q.tmem_cols = cols;
   const size_t smem = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, bestR).total;
   const int grid = s.B * s.X * p.tiles * tl.nchunks;
@@ -698,11 +702,66 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
   return check_launch("plane_synthesis", st);
 }
 
+#ifndef DENO_EMULATE
+// Tensor-core bypass weight gradient; returns the number of partials written, or -1 if not applicable.
+int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, float* partial, cudaStream_t st) {
+  if (s.CO > 128 || s.CI + 1 > 256) return -1;
+  tc::WgradTcParams p;
+  p.gx = make_geom(s, s.CI);
+  p.CO = s.CO;
+  p.sbo_g = (long long)s.CO * s.S;
+  p.gz = gz; p.x = x; p.partial = partial;
+  const int HW = s.H * s.W;
+  p.tiles_per_plane = (HW + 127) / 128;
+  p.ntiles = s.B * s.X * p.tiles_per_plane;
+  p.COp = round_up(s.CO, 8);
+  p.NB = round_up(s.CI + 1, 16);
+  p.vec4 = (HW % 4 == 0) ? 1 : 0;
+  const tc::WgradTcSmem sm = tc::wgrad_tc_smem(p.COp, p.NB);
+  if (sm.total > kMaxSmemBytes - 1024) return -1;
+  const int need = (s.CO + s.CI + 7) / 8;
+  if (need > 16) return -1;
+  const int per_sm = 1;   // the accumulator tiles take up to all 512 TMEM columns
+  int grid = 148 * per_sm;
+  if (grid > p.ntiles) grid = p.ntiles;
+  int rc;
+#define DENO_WG_CASE(NITV)                                                                         \
+  {                                                                                                \
+    rc = allow_smem(tc::bypass_wgrad_tc_kernel<NITV>, (size_t)sm.total, "bypass_wgrad_tc");        \
+    if (rc != DENO_OK) return -2;                                                                  \
+    prof_before("bypass_wgrad_tc", st);                                                            \
+    tc::bypass_wgrad_tc_kernel<NITV><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);          \
+  }
+  if (need <= 2) DENO_WG_CASE(2)
+  else if (need <= 4) DENO_WG_CASE(4)
+  else if (need <= 8) DENO_WG_CASE(8)
+  else DENO_WG_CASE(16)
+#undef DENO_WG_CASE
+  if (check_launch("bypass_wgrad_tc", st) != DENO_OK) return -2;
+  return grid;
+}
+#endif
+
 int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, float* partial, float* glw, float* glb,
                         cudaStream_t st) {
   WgradCfg c;
   int rc = wgrad_cfg(s, c);
   if (rc != DENO_OK) return rc;
+#ifndef DENO_EMULATE
+  if (path_pref() != PathPref::Simt) {
+    const int nparts = try_launch_bypass_wgrad_tc(s, gz, x, partial, st);
+    if (nparts == -2) return DENO_E_CUDA;
+    if (nparts > 0) {
+      WgradReduceParams r;
+      r.partial = partial; r.ncta = nparts;
+      r.nw = s.CO * s.CI; r.nj = r.nw + s.CO;
+      r.glw = glw; r.glb = glb;
+      prof_before("bypass_wgrad_reduce", st);
+      DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+      return check_launch("bypass_wgrad_reduce", st);
+    }
+  }
+#endif
   WgradParams p;
   p.gx = make_geom(s, s.CI);
   p.CO = s.CO;

@@ -54,6 +54,35 @@ __device__ __forceinline__ float act_grad(int act, float z) {
   }
 }
 
+// y = act(z) and d = act'(z) in one go (the forward epilogue saves d for the backward pass).
+__device__ __forceinline__ void act_apply_grad(int act, float z, float& y, float& d) {
+  switch (act) {
+    case ACT_GELU: {
+      const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
+      const float pdf = expf(-0.5f * z * z) * 0.39894228040143267794f;
+      y = z * cdf;
+      d = cdf + z * pdf;
+      return;
+    }
+    case ACT_SILU: {
+      const float s = 1.0f / (1.0f + expf(-z));
+      y = z * s;
+      d = s * (1.0f + z * (1.0f - s));
+      return;
+    }
+    case ACT_TANH: {
+      const float t = tanhf(z);
+      y = t;
+      d = 1.0f - t * t;
+      return;
+    }
+    default:
+      y = act_apply(act, z);
+      d = act_grad(act, z);
+      return;
+  }
+}
+
 // A "plane problem": the real tensor is seen as NB' = NBO*NBI batches of C channels of contiguous
 // H x W planes (W fastest).  1-D layers use H = 1; 3-D layers (X,Y,Z) use planes (Y,Z) with
 // NBI = X, so the same plane kernels serve every dimensionality.

@@ -30,7 +30,7 @@ constexpr int kSynthMaxRows = 8;  // rows per CTA tile in plane_synthesis (regis
 struct AnalysisParams {
   PlaneGeom g;
   const float* u;      // x, or gy when FUSE_GZ
-  const float* z;      // FUSE_GZ: saved pre-activation
+  const float* z;      // FUSE_GZ: saved activation derivative act'(z)
   float* gz_out;       // FUSE_GZ: gz = gy * act'(z) is written here (same geometry as u)
   float2* out;         // [nplanes][KH][MW]
   const float2* twW;
@@ -107,7 +107,7 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
         for (int j = lane; j < yc; j += 32) {
           float v = p.u[rbase + j];
           if (FUSE_GZ) {
-            v *= act_grad(p.act, p.z[rbase + j]);
+            v *= p.z[rbase + j];
             p.gz_out[rbase + j] = v;
           }
           xs[rr * YCp + j] = v;
@@ -381,7 +381,7 @@ struct SynthParams {
   long long lw_so, lw_si;
   const float* bias;     // may be null
   float* y;
-  float* z;              // may be null
+  float* z;              // may be null; receives act'(pre-activation) for the backward pass
   const float2* twW;
   const float2* twH;
   const float* cl;
@@ -506,8 +506,14 @@ __global__ void plane_synthesis_kernel(SynthParams p) {
         const int o = og + j;
         if (o < CO) {
           const long long a = obase + (long long)o * p.g.sc;
-          if (p.z != nullptr) p.z[a] = acc[j];
-          p.y[a] = act_apply(ACT, acc[j]);
+          if (p.z != nullptr) {
+            float yv, dv;
+            act_apply_grad(ACT, acc[j], yv, dv);
+            p.z[a] = dv;
+            p.y[a] = yv;
+          } else {
+            p.y[a] = act_apply(ACT, acc[j]);
+          }
         }
       }
     }

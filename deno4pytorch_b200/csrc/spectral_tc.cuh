@@ -100,7 +100,7 @@ struct SynthTcParams {
   const float* ae;        // pre-split twiddle images [chunk][hi|lo][KE * 128] floats
   int KE;                 // 2 * MWp rounded up to a multiple of 8
   int nchunks;            // column chunks of 128 per row
-  int tmem_cols;          // power of two >= 2 * CO, >= 32
+  int tmem_cols;          // power of two >= 6 * CO (two row buffers x three split-pass tiles)
 };
 
 struct SynthTcSmem {
@@ -265,19 +265,27 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
 
   auto epilogue = [&](int rr) {
-    const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)((rr & 1) * CO + wg * ncol_half);
+    const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)((rr & 1) * 3 * CO + wg * ncol_half);
     const long long pbase = obase_b + (long long)(x0 + rr) * W + y0 + yl;
     for (int c0 = 0; c0 < ncol_half; c0 += 16) {
-      float v[16];
+      float v[16], v1[16], v2[16];
       tmem_ld16(tb + c0, v);
+      tmem_ld16(tb + CO + c0, v1);
+      tmem_ld16(tb + 2 * CO + c0, v2);
       if (yl < ny) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int o = wg * ncol_half + c0 + j;
-          const float zz = v[j] + bias_s[o];
+          const float zz = (v[j] + bias_s[o]) + (v1[j] + v2[j]);
           const long long a = pbase + (long long)o * p.g.sc;
-          if (p.z != nullptr) p.z[a] = zz;
-          p.y[a] = act_apply(ACT, zz);
+          if (p.z != nullptr) {
+            float yv, dv;
+            act_apply_grad(ACT, zz, yv, dv);
+            p.z[a] = dv;
+            p.y[a] = yv;
+          } else {
+            p.y[a] = act_apply(ACT, zz);
+          }
         }
       }
     }
@@ -304,20 +312,25 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-      const uint32_t d = tmem + (uint32_t)((rr & 1) * CO);
-      uint32_t accum = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {      // hi*hi, lo*hi, hi*lo
-        const uint32_t ax = sbase + (pass == 1 ? so.ax_lo : so.ax_hi);
-        const uint32_t bw = sbase + (pass == 2 ? so.bw_lo : so.bw_hi);
-        for (int s = 0; s < CIP / 8; ++s) {
-          mma_tf32(d, make_desc(ax + s * 2 * lbo_m, lbo_m, 128), make_desc(bw + s * 2 * lbo_n, lbo_n, 128), idesc, accum);
-          accum = 1;
+      // Back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency (measured ~120
+      // cycles each at N = 32), so the three split passes (hi*hi, lo*hi, hi*lo) accumulate into three
+      // separate TMEM tiles and are issued round-robin; the epilogue adds the tiles.
+      const uint32_t d = tmem + (uint32_t)((rr & 1) * 3 * CO);
+      for (int s = 0; s < CIP / 8; ++s) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ax = sbase + (pass == 1 ? so.ax_lo : so.ax_hi);
+          const uint32_t bw = sbase + (pass == 2 ? so.bw_lo : so.bw_hi);
+          mma_tf32(d + pass * CO, make_desc(ax + s * 2 * lbo_m, lbo_m, 128), make_desc(bw + s * 2 * lbo_n, lbo_n, 128), idesc, s > 0 ? 1u : 0u);
         }
-        const uint32_t ae = sbase + (pass == 1 ? so.ae_lo : so.ae_hi);
-        const uint32_t bu = sbase + so.bu + (2 * rr + (pass == 2 ? 1 : 0)) * so.bu_one;
-        for (int s = 0; s < KE / 8; ++s)
-          mma_tf32(d, make_desc(ae + s * 2 * lbo_m, lbo_m, 128), make_desc(bu + s * 2 * lbo_n, lbo_n, 128), idesc, 1);
+      }
+      for (int s = 0; s < KE / 8; ++s) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ae = sbase + (pass == 1 ? so.ae_lo : so.ae_hi);
+          const uint32_t bu = sbase + so.bu + (2 * rr + (pass == 2 ? 1 : 0)) * so.bu_one;
+          mma_tf32(d + pass * CO, make_desc(ae + s * 2 * lbo_m, lbo_m, 128), make_desc(bu + s * 2 * lbo_n, lbo_n, 128), idesc, 1u);
+        }
       }
       mma_commit(&mbar[rr & 1]);
     }
@@ -403,7 +416,8 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   float* stage = reinterpret_cast<float*>(smem + so.stage);
   float* stage_z = stage + round_up(HW, 4);
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 2 * N1 <= 32 ? 32u : (2 * N1 <= 64 ? 64u : (2 * N1 <= 128 ? 128u : (2 * N1 <= 256 ? 256u : 512u))));
+  const uint32_t tmem_cols = 6 * N1 <= 64 ? 64u : (6 * N1 <= 128 ? 128u : (6 * N1 <= 256 ? 256u : 512u));
+  if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
   if (tid == 32) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)N1;
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // three split-pass tiles per stage
   const uint32_t idesc = make_idesc_tf32(128, N1);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t lbo_a = 16 * Hp, lbo_e1 = 16 * N1, lbo_a2 = 16 * KHp, lbo_b2 = (uint32_t)so.b2_lbo;
@@ -445,7 +459,7 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     if (FUSE_GZ) {                                     // gz = gy * act'(z): coalesced store, kept in staging
       const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
       for (int i = tid; i < HW; i += 256) {
-        const float v = stage[i] * act_grad(p.act, stage_z[i]);
+        const float v = stage[i] * stage_z[i];
         stage[i] = v;
         p.gz_out[base + i] = v;
       }
@@ -475,14 +489,13 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     if (q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);
     if (tid == 0) {
       fence_after_sync();
-      uint32_t accum = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {           // hi*hi, lo*hi, hi*lo
-        const uint32_t a = sbase + so.ab + (pass == 1 ? so.a_one : 0);
-        const uint32_t b = sbase + so.e1 + (pass == 2 ? so.e1_one : 0);
-        for (int s2 = 0; s2 < Wp / 8; ++s2) {
-          mma_tf32(tmem_d1, make_desc(a + s2 * 2 * lbo_a, lbo_a, 128), make_desc(b + s2 * 2 * lbo_e1, lbo_e1, 128), idesc, accum);
-          accum = 1;
+      // three independent accumulator tiles (one per split pass), issued round-robin: see plane_synthesis_tc
+      for (int s2 = 0; s2 < Wp / 8; ++s2) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {         // hi*hi, lo*hi, hi*lo
+          const uint32_t a = sbase + so.ab + (pass == 1 ? so.a_one : 0);
+          const uint32_t b = sbase + so.e1 + (pass == 2 ? so.e1_one : 0);
+          mma_tf32(tmem_d1 + pass * N1, make_desc(a + s2 * 2 * lbo_a, lbo_a, 128), make_desc(b + s2 * 2 * lbo_e1, lbo_e1, 128), idesc, s2 > 0 ? 1u : 0u);
         }
       }
       mma_commit(&mbar[0]);
@@ -495,8 +508,13 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
       unsigned char* b2hi = smem + so.ab;
       unsigned char* b2lo = b2hi + so.b2_one;
       for (int c0 = 0; c0 < ncol_half; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_half + c0), v);
+        float v[16], v1[16], v2[16];
+        const uint32_t ta = tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_half + c0);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + N1, v1);
+        tmem_ld16(ta + 2 * N1, v2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += v1[j] + v2[j];
         if (xrow < Hp) {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
@@ -522,14 +540,12 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     __syncthreads();
     if (tid == 0) {
       fence_after_sync();
-      uint32_t accum = 0;
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = sbase + so.a2 + (pass == 1 ? so.a2_one : 0);
-        const uint32_t b = sbase + so.ab + (pass == 2 ? so.b2_one : 0);
-        for (int s2 = 0; s2 < 2 * Hp / 8; ++s2) {
-          mma_tf32(tmem_d2, make_desc(a + s2 * 2 * lbo_a2, lbo_a2, 128), make_desc(b + s2 * 2 * lbo_b2, lbo_b2, 128), idesc, accum);
-          accum = 1;
+      for (int s2 = 0; s2 < 2 * Hp / 8; ++s2) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = sbase + so.a2 + (pass == 1 ? so.a2_one : 0);
+          const uint32_t b = sbase + so.ab + (pass == 2 ? so.b2_one : 0);
+          mma_tf32(tmem_d2 + pass * N1, make_desc(a + s2 * 2 * lbo_a2, lbo_a2, 128), make_desc(b + s2 * 2 * lbo_b2, lbo_b2, 128), idesc, s2 > 0 ? 1u : 0u);
         }
       }
       mma_commit(&mbar[1]);
@@ -540,8 +556,13 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     if (warp < 4) {
       float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
       for (int c0 = 0; c0 < N1; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
+        float v[16], v1[16], v2[16];
+        const uint32_t ta = tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + N1, v1);
+        tmem_ld16(ta + 2 * N1, v2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += v1[j] + v2[j];
         if (xrow < KH) {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
@@ -561,7 +582,188 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   cp_async_wait_all();
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 2 * N1 <= 32 ? 32u : (2 * N1 <= 64 ? 64u : (2 * N1 <= 128 ? 128u : (2 * N1 <= 256 ? 256u : 512u))));
+  if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ----------------------------------------------------------------------------------------------
+// bypass_wgrad_tc: gradient of the 1x1 bypass conv as one long-K GEMM on the tensor cores.
+//   D[o, i] = sum_pt gz[o, pt] * x[i, pt]   (i < CI),     D[o, CI] = sum_pt gz[o, pt]   (bias gradient:
+//   the B operand carries one extra row of ones).  Both operands are K-major as they sit in memory
+//   (points contiguous), K = points.  Persistent CTAs accumulate over their tiles of 128 points in TMEM
+//   and write one partial (CO x (CI+1)) each; bypass_wgrad_reduce_kernel sums the partials in fixed order.
+// ----------------------------------------------------------------------------------------------
+struct WgradTcParams {
+  PlaneGeom gx;          // geometry of x (C = CI)
+  int CO;
+  long long sbo_g;       // bo stride of gz
+  const float* gz;
+  const float* x;
+  float* partial;        // [gridDim.x][CO*CI + CO]
+  int tiles_per_plane;   // ceil(H*W / 128)
+  int ntiles;            // NB' * tiles_per_plane
+  int COp, NB;           // image rows: CO rounded to 8; CI + 1 rounded to 16
+  int vec4;              // H*W % 4 == 0: 16-byte global loads are aligned
+};
+
+struct WgradTcSmem {
+  int g_hi, g_lo, x_hi, x_lo, total;
+  int g_lbo, x_lbo;
+};
+
+__host__ __device__ inline WgradTcSmem wgrad_tc_smem(int COp, int NB) {
+  WgradTcSmem m;
+  m.g_lbo = 16 * COp + 16;     // padded K-direction strides: conflict-free 16-byte stores
+  m.x_lbo = 16 * NB + 16;
+  int off = 0;
+  m.g_hi = off; off += 32 * m.g_lbo;
+  m.g_lo = off; off += 32 * m.g_lbo + 2048;   // slack: the M = 128 descriptor reads 16 row groups
+  m.x_hi = off; off += 32 * m.x_lbo;
+  m.x_lo = off; off += 32 * m.x_lbo;
+  m.total = off + 2048;
+  return m;
+}
+
+template <int NIT>   // (row, point-quad) items per thread: (COp + CIp8) * 32 / 256 rounded up
+__global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int CI = p.gx.C, CO = p.CO, COp = p.COp, NB = p.NB;
+  const WgradTcSmem so = wgrad_tc_smem(COp, NB);
+  const int HW = p.gx.H * p.gx.W;
+  const int nrows = CO + CI;                 // rows streamed per tile: gz channels then x channels
+  const int nacc = (6 * NB <= 512) ? 6 : 3;   // independent accumulator tiles: split pass x (K-step parity)
+  uint32_t ncols = 32;
+  while ((int)ncols < nacc * NB) ncols *= 2;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  if (tid == 32) {
+    mbar_init(&mbar, 1);
+    mbar_fence_init();
+  }
+  // constant rows of the x images: zero everything once, then the ones row (hi = 1, lo = 0)
+  for (int i = tid; i < (so.total - so.g_hi) / 16; i += 256) reinterpret_cast<float4*>(smem + so.g_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  for (int k = tid; k < 128; k += 256)
+    *reinterpret_cast<float*>(smem + so.x_hi + (CI & 7) * 16 + (CI >> 3) * 128 + (k & 3) * 4 + (k >> 2) * so.x_lbo) = 1.0f;
+
+  float4 regs[NIT];
+  auto prefetch = [&](int t) {
+    const int bp = t / p.tiles_per_plane;
+    const int p0 = (t - bp * p.tiles_per_plane) * 128;
+    const long long gbase = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
+    const long long xbase = plane_base(p.gx, bp, 0) + p0;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int item = it * 256 + tid;
+      const int row = item >> 5, pq = item & 31;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nrows) {
+        const float* src = (row < CO) ? p.gz + gbase + (long long)row * p.gx.sc : p.x + xbase + (long long)(row - CO) * p.gx.sc;
+        const int pt = pq * 4;
+        if (p.vec4 && p0 + pt + 3 < HW) {
+          v = *reinterpret_cast<const float4*>(src + pt);
+        } else {
+          if (p0 + pt + 0 < HW) v.x = src[pt + 0];
+          if (p0 + pt + 1 < HW) v.y = src[pt + 1];
+          if (p0 + pt + 2 < HW) v.z = src[pt + 2];
+          if (p0 + pt + 3 < HW) v.w = src[pt + 3];
+        }
+      }
+      regs[it] = v;
+    }
+  };
+  int t = blockIdx.x;
+  if (t < p.ntiles) prefetch(t);
+
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, NB);
+  const uint32_t sbase = smem_u32(smem);
+  uint32_t phase = 0, accum = 0;
+  bool pending = false;
+
+  for (; t < p.ntiles; t += gridDim.x) {
+    if (pending) {                                   // previous tile's MMAs still read the images
+      mbar_wait(&mbar, phase);
+      phase ^= 1;
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int item = it * 256 + tid;
+      const int row = item >> 5, pq = item & 31;
+      if (row < nrows) {
+        float4 hi, lo;
+        split_tf32(regs[it].x, hi.x, lo.x);
+        split_tf32(regs[it].y, hi.y, lo.y);
+        split_tf32(regs[it].z, hi.z, lo.z);
+        split_tf32(regs[it].w, hi.w, lo.w);
+        if (row < CO) {
+          const int off = (row & 7) * 16 + (row >> 3) * 128 + pq * so.g_lbo;
+          *reinterpret_cast<float4*>(smem + so.g_hi + off) = hi;
+          *reinterpret_cast<float4*>(smem + so.g_lo + off) = lo;
+        } else {
+          const int r = row - CO;
+          const int off = (r & 7) * 16 + (r >> 3) * 128 + pq * so.x_lbo;
+          *reinterpret_cast<float4*>(smem + so.x_hi + off) = hi;
+          *reinterpret_cast<float4*>(smem + so.x_lo + off) = lo;
+        }
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      for (int s2 = 0; s2 < 16; ++s2) {
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {         // hi*hi, lo*hi, hi*lo
+          const uint32_t a = sbase + (pass == 1 ? so.g_lo : so.g_hi);
+          const uint32_t b = sbase + (pass == 2 ? so.x_lo : so.x_hi);
+          const int tile = (nacc == 6) ? pass * 2 + (s2 & 1) : pass;
+          const uint32_t first = (nacc == 6) ? (s2 < 2 ? 1u : 0u) : (s2 < 1 ? 1u : 0u);
+          mma_tf32(tmem + tile * NB, make_desc(a + s2 * 2 * so.g_lbo, so.g_lbo, 128), make_desc(b + s2 * 2 * so.x_lbo, so.x_lbo, 128), idesc,
+                   (accum == 0 && first) ? 0u : 1u);
+        }
+      }
+      accum = 1;
+      mma_commit(&mbar);
+    }
+    pending = true;
+    if (t + (int)gridDim.x < p.ntiles) prefetch(t + gridDim.x);
+  }
+  if (pending) mbar_wait(&mbar, phase);
+  fence_after_sync();
+  // D[o][i] -> partial; lane o of TMEM = output channel o
+  float* out = p.partial + (long long)blockIdx.x * (CO * CI + CO);
+  if (warp < 4) {
+    const int o = (warp & 3) * 32 + lane;
+    for (int c0 = 0; c0 < NB; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+      for (int a = 1; a < nacc; ++a) {
+        float w[16];
+        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * NB + c0), w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += w[j];
+      }
+      if (o < CO) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = c0 + j;
+          const float val = pending ? v[j] : 0.f;
+          if (i < CI) out[o * CI + i] = val;
+          else if (i == CI) out[CO * CI + o] = val;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
 }  // namespace tc

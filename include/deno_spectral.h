@@ -91,7 +91,8 @@ size_t deno_spectral_xhat_bytes(const deno_spectral_desc* desc);
  *   w_blocks   HOST array of 1/2/4 DEVICE pointers to the weight blocks
  *   lin_b      may be NULL
  *   y          (B, Cout, *spatial) fp32
- *   z_saved    pre-activation, same shape as y; NULL for inference
+ *   z_saved    opaque state for bwd, same shape as y (holds act'(z) at the pre-activation z);
+ *              NULL for inference
  *   xhat_saved packed spectrum of x for the weight gradient; NULL for inference
  */
 int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void* const* w_blocks,

@@ -22,7 +22,7 @@ def _run_case(x, ws, lin_w, lin_b, modes, act, cot):
     truth = dft_truth.forward(x, ws, lin_w, lin_b, modes, activation=act)
     assert np.isfinite(y).all()
     assert rel_l2(y, truth["y"]) < TOL
-    assert rel_l2(layer.z, truth["z"]) < TOL
+    assert rel_l2(layer.z, truth["dact"]) < TOL   # fwd saves act'(z) for the backward pass
     xh = truth["xhat"].reshape(layer.xhat.shape)
     assert rel_l2(layer.xhat, xh) < TOL
     gx, gws, glw, glb = layer.backward(cot)
