@@ -12,6 +12,59 @@ from .spectral_layers import SpectralConv1d, SpectralConv2d, SpectralConv3d, nn,
 _LAYER = {1: SpectralConv1d, 2: SpectralConv2d, 3: SpectralConv3d}
 
 
+class _TallLinearFn(torch.autograd.Function):
+    """``F.linear`` for inputs with very many rows (every grid point of every sample) and few features.
+
+    Forward and grad_input are plain cuBLAS GEMMs.  grad_weight is a GEMM whose reduction dimension is
+    the row count (144 500 for the Darcy config); cuBLAS' fp32 heuristics run it as two CTAs looping
+    over all rows (239 us per call on B200, profiles/r1i_launch_list.txt), so it is expressed here as a
+    batched GEMM over row chunks followed by a short sum (split-K), and grad_bias as a two-stage sum.
+    Same arithmetic, different summation order (fp32 both ways)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gx = gw = gb = None
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if ctx.needs_input_grad[0]:
+            gx = (g2 @ weight).view(x.shape)
+        rows = g2.shape[0]
+        chunks = _split_rows(rows)
+        if ctx.needs_input_grad[1]:
+            x2 = x.reshape(-1, x.shape[-1])
+            if chunks > 1:
+                gw = torch.bmm(g2.view(chunks, rows // chunks, -1).transpose(1, 2),
+                               x2.view(chunks, rows // chunks, -1)).sum(0)
+            else:
+                gw = g2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.view(chunks, rows // chunks, -1).sum(1).sum(0) if chunks > 1 else g2.sum(0)
+        return gx, gw, gb
+
+
+def _split_rows(rows: int) -> int:
+    """Largest divisor of ``rows`` that leaves chunks of at least 512 rows, capped at 512 chunks."""
+    if rows < 8192:
+        return 1
+    best = 1
+    for c in range(2, 513):
+        if rows % c == 0 and rows // c >= 512:
+            best = c
+    return best
+
+
+def _tall_linear(x, layer: nn.Linear):
+    if x.is_cuda and x.dtype == torch.float32:
+        return _TallLinearFn.apply(x, layer.weight, layer.bias)
+    return layer(x)
+
+
 class _FNONd(nn.Module):
     ndim = 0
 
@@ -38,7 +91,7 @@ class _FNONd(nn.Module):
     def forward(self, x, grid):
         """x: (B, *spatial, steps*in_dim), grid: (B, *spatial, ndim) -> (B, *spatial, out_dim)."""
         nd = self.ndim
-        h = self.fc0(torch.cat((x, grid), dim=-1))
+        h = _tall_linear(torch.cat((x, grid), dim=-1), self.fc0)
         h = h.movedim(-1, 1)
         if self.padding != 0:
             h = F.pad(h, [0, self.padding] * nd)
@@ -47,7 +100,7 @@ class _FNONd(nn.Module):
         if self.padding != 0:
             h = h[(Ellipsis,) + (slice(None, -self.padding),) * nd]
         h = h.movedim(1, -1)
-        return self.fc2(F.gelu(self.fc1(h)))
+        return _tall_linear(F.gelu(_tall_linear(h, self.fc1)), self.fc2)
 
 
 class FNO1d(_FNONd):

@@ -33,7 +33,7 @@ int fail(int code, const std::string& msg) {
 }
 
 constexpr size_t kAlign = 256;
-constexpr int kWgradTcMaxCtas = 2 * 148;   // persistent CTAs of bypass_wgrad_tc
+constexpr int kWgradTcMaxCtas = 4 * 148;   // partials of bypass_wgrad_tc: 148 persistent CTAs x up to 4 stacked batch entries
 constexpr int kMaxSmemBytes = 227 * 1024;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
@@ -703,26 +703,30 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
 }
 
 #ifndef DENO_EMULATE
-// Tensor-core bypass weight gradient; returns the number of partials written, or -1 if not applicable.
+// Tensor-core bypass weight gradient; returns the number of partials written, -1 if not applicable, -2 on error.
 int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, float* partial, cudaStream_t st) {
-  if (s.CO > 128 || s.CI + 1 > 256) return -1;
+  const int COs = round_up(s.CO, 8), CIs = round_up(s.CI, 8);
+  if (COs > 128 || CIs > 128) return -1;
+  int NS = 4;
+  while (NS > 1 && (NS * COs > 128 || NS * CIs > 128)) NS /= 2;
+  if ((NS * CIs) % 16 != 0) return -1;
   tc::WgradTcParams p;
   p.gx = make_geom(s, s.CI);
   p.CO = s.CO;
   p.sbo_g = (long long)s.CO * s.S;
   p.gz = gz; p.x = x; p.partial = partial;
+  p.NS = NS; p.COs = COs; p.CIs = CIs;
   const int HW = s.H * s.W;
-  p.tiles_per_plane = (HW + 127) / 128;
-  p.ntiles = s.B * s.X * p.tiles_per_plane;
-  p.COp = round_up(s.CO, 8);
-  p.NB = round_up(s.CI + 1, 16);
+  p.tiles_per_plane = (HW + tc::kWgradKT - 1) / tc::kWgradKT;
+  p.nbatch = s.B * s.X;
+  p.ngroups = (p.nbatch + NS - 1) / NS;
+  p.ntiles = p.ngroups * p.tiles_per_plane;
   p.vec4 = (HW % 4 == 0) ? 1 : 0;
-  const tc::WgradTcSmem sm = tc::wgrad_tc_smem(p.COp, p.NB);
+  const tc::WgradTcSmem sm = tc::wgrad_tc_smem(NS, COs, CIs);
   if (sm.total > kMaxSmemBytes - 1024) return -1;
-  const int need = (s.CO + s.CI + 7) / 8;
+  const int need = (NS * (s.CO + s.CI) * 16 + 255) / 256;
   if (need > 16) return -1;
-  const int per_sm = 1;   // the accumulator tiles take up to all 512 TMEM columns
-  int grid = 148 * per_sm;
+  int grid = 148;                         // one persistent CTA per SM (the accumulators take up to 512 TMEM columns)
   if (grid > p.ntiles) grid = p.ntiles;
   int rc;
 #define DENO_WG_CASE(NITV)                                                                         \
@@ -732,18 +736,17 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
     prof_before("bypass_wgrad_tc", st);                                                            \
     tc::bypass_wgrad_tc_kernel<NITV><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);          \
   }
-  if (need <= 2) DENO_WG_CASE(2)
-  else if (need <= 4) DENO_WG_CASE(4)
+  if (need <= 4) DENO_WG_CASE(4)
   else if (need <= 8) DENO_WG_CASE(8)
   else DENO_WG_CASE(16)
 #undef DENO_WG_CASE
   if (check_launch("bypass_wgrad_tc", st) != DENO_OK) return -2;
-  return grid;
+  return grid * NS;
 }
 #endif
 
-int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, float* partial, float* glw, float* glb,
-                        cudaStream_t st) {
+int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const float2* ghat, float* partial, float* glw,
+                        float* glb, cudaStream_t st) {
   WgradCfg c;
   int rc = wgrad_cfg(s, c);
   if (rc != DENO_OK) return rc;
@@ -754,11 +757,22 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, float* 
     if (nparts > 0) {
       WgradReduceParams r;
       r.partial = partial; r.ncta = nparts;
-      r.nw = s.CO * s.CI; r.nj = r.nw + s.CO;
-      r.glw = glw; r.glb = glb;
-      prof_before("bypass_wgrad_reduce", st);
-      DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
-      return check_launch("bypass_wgrad_reduce", st);
+      r.nw = s.CO * s.CI; r.nj = r.nw;         // the tensor-core partials carry no bias column
+      r.glw = glw; r.glb = nullptr;
+      if (glw != nullptr) {
+        prof_before("bypass_wgrad_reduce", st);
+        DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+        rc = check_launch("bypass_wgrad_reduce", st);
+        if (rc != DENO_OK) return rc;
+      }
+      if (glb != nullptr) {
+        tc::BiasDcParams bp;
+        bp.ghat = ghat; bp.glb = glb; bp.B = s.B; bp.CO = s.CO; bp.M = s.M; bp.s_total = (float)s.S;
+        prof_before("bias_from_dc", st);
+        tc::bias_from_dc_kernel<<<dim3((s.CO + 127) / 128), dim3(128), 0, st>>>(bp);
+        rc = check_launch("bias_from_dc", st);
+      }
+      return rc;
     }
   }
 #endif
@@ -970,7 +984,7 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
   }
   if (glin_w != nullptr || glin_b != nullptr) {
     float* partial = reinterpret_cast<float*>(wsb + ws.partial);
-    if ((rc = launch_bypass_wgrad(s, gz, x, partial, glin_w, glin_b, st))) return rc;
+    if ((rc = launch_bypass_wgrad(s, gz, x, ghat, partial, glin_w, glin_b, st))) return rc;
   }
   return DENO_OK;
 }

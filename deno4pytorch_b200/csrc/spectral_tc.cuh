@@ -82,6 +82,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   lo = v - hi;
@@ -315,24 +321,35 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       // Back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency (measured ~120
       // cycles each at N = 32), so the three split passes (hi*hi, lo*hi, hi*lo) accumulate into three
       // separate TMEM tiles and are issued round-robin; the epilogue adds the tiles.
+      // The issuing thread is the critical path (a single lane, nothing to hide ALU latency behind):
+      // descriptors are built once and advanced by a constant per K step.
       const uint32_t d = tmem + (uint32_t)((rr & 1) * 3 * CO);
+      const uint64_t inc_m = (uint64_t)((2 * lbo_m) >> 4), inc_n = (uint64_t)((2 * lbo_n) >> 4);
+      uint64_t axh = make_desc(sbase + so.ax_hi, lbo_m, 128), axl = make_desc(sbase + so.ax_lo, lbo_m, 128);
+      uint64_t bwh = make_desc(sbase + so.bw_hi, lbo_n, 128), bwl = make_desc(sbase + so.bw_lo, lbo_n, 128);
+#pragma unroll
       for (int s = 0; s < CIP / 8; ++s) {
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t ax = sbase + (pass == 1 ? so.ax_lo : so.ax_hi);
-          const uint32_t bw = sbase + (pass == 2 ? so.bw_lo : so.bw_hi);
-          mma_tf32(d + pass * CO, make_desc(ax + s * 2 * lbo_m, lbo_m, 128), make_desc(bw + s * 2 * lbo_n, lbo_n, 128), idesc, s > 0 ? 1u : 0u);
+        const uint32_t acc = s > 0 ? 1u : 0u;
+        if (leader) {
+          mma_tf32(d, axh, bwh, idesc, acc);            // hi * hi
+          mma_tf32(d + CO, axl, bwh, idesc, acc);       // lo * hi
+          mma_tf32(d + 2 * CO, axh, bwl, idesc, acc);   // hi * lo
         }
+        axh += inc_m; axl += inc_m; bwh += inc_n; bwl += inc_n;
       }
+      uint64_t aeh = make_desc(sbase + so.ae_hi, lbo_m, 128), ael = make_desc(sbase + so.ae_lo, lbo_m, 128);
+      uint64_t buh = make_desc(sbase + so.bu + (2 * rr) * so.bu_one, lbo_n, 128);
+      uint64_t bul = make_desc(sbase + so.bu + (2 * rr + 1) * so.bu_one, lbo_n, 128);
       for (int s = 0; s < KE / 8; ++s) {
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t ae = sbase + (pass == 1 ? so.ae_lo : so.ae_hi);
-          const uint32_t bu = sbase + so.bu + (2 * rr + (pass == 2 ? 1 : 0)) * so.bu_one;
-          mma_tf32(d + pass * CO, make_desc(ae + s * 2 * lbo_m, lbo_m, 128), make_desc(bu + s * 2 * lbo_n, lbo_n, 128), idesc, 1u);
+        if (leader) {
+          mma_tf32(d, aeh, buh, idesc, 1u);
+          mma_tf32(d + CO, ael, buh, idesc, 1u);
+          mma_tf32(d + 2 * CO, aeh, bul, idesc, 1u);
         }
+        aeh += inc_m; ael += inc_m; buh += inc_n; bul += inc_n;
       }
-      mma_commit(&mbar[rr & 1]);
+      if (leader) mma_commit(&mbar[rr & 1]);
+      __syncwarp();
     }
     if (rr + 1 < trows) prefetch(rr + 1);
     if (rr > 0) {
@@ -490,15 +507,20 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     if (tid == 0) {
       fence_after_sync();
       // three independent accumulator tiles (one per split pass), issued round-robin: see plane_synthesis_tc
+      uint64_t ah = make_desc(sbase + so.ab, lbo_a, 128), al = make_desc(sbase + so.ab + so.a_one, lbo_a, 128);
+      uint64_t bh = make_desc(sbase + so.e1, lbo_e1, 128), bl = make_desc(sbase + so.e1 + so.e1_one, lbo_e1, 128);
+      const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
       for (int s2 = 0; s2 < Wp / 8; ++s2) {
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {         // hi*hi, lo*hi, hi*lo
-          const uint32_t a = sbase + so.ab + (pass == 1 ? so.a_one : 0);
-          const uint32_t b = sbase + so.e1 + (pass == 2 ? so.e1_one : 0);
-          mma_tf32(tmem_d1 + pass * N1, make_desc(a + s2 * 2 * lbo_a, lbo_a, 128), make_desc(b + s2 * 2 * lbo_e1, lbo_e1, 128), idesc, s2 > 0 ? 1u : 0u);
+        const uint32_t acc = s2 > 0 ? 1u : 0u;
+        if (leader) {
+          mma_tf32(tmem_d1, ah, bh, idesc, acc);            // hi * hi
+          mma_tf32(tmem_d1 + N1, al, bh, idesc, acc);       // lo * hi
+          mma_tf32(tmem_d1 + 2 * N1, ah, bl, idesc, acc);   // hi * lo
         }
+        ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
       }
-      mma_commit(&mbar[0]);
+      if (leader) mma_commit(&mbar[0]);
+      __syncwarp();
     }
     mbar_wait(&mbar[0], phase);
     fence_after_sync();
@@ -538,17 +560,23 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       fence_after_sync();
+      const bool leader = elect_one();
+      uint64_t ah = make_desc(sbase + so.a2, lbo_a2, 128), al = make_desc(sbase + so.a2 + so.a2_one, lbo_a2, 128);
+      uint64_t bh = make_desc(sbase + so.ab, lbo_b2, 128), bl = make_desc(sbase + so.ab + so.b2_one, lbo_b2, 128);
+      const uint64_t inc_a = (uint64_t)((2 * lbo_a2) >> 4), inc_b = (uint64_t)((2 * lbo_b2) >> 4);
       for (int s2 = 0; s2 < 2 * Hp / 8; ++s2) {
-#pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a = sbase + so.a2 + (pass == 1 ? so.a2_one : 0);
-          const uint32_t b = sbase + so.ab + (pass == 2 ? so.b2_one : 0);
-          mma_tf32(tmem_d2 + pass * N1, make_desc(a + s2 * 2 * lbo_a2, lbo_a2, 128), make_desc(b + s2 * 2 * lbo_b2, lbo_b2, 128), idesc, s2 > 0 ? 1u : 0u);
+        const uint32_t acc = s2 > 0 ? 1u : 0u;
+        if (leader) {
+          mma_tf32(tmem_d2, ah, bh, idesc, acc);
+          mma_tf32(tmem_d2 + N1, al, bh, idesc, acc);
+          mma_tf32(tmem_d2 + 2 * N1, ah, bl, idesc, acc);
         }
+        ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
       }
-      mma_commit(&mbar[1]);
+      if (leader) mma_commit(&mbar[1]);
+      __syncwarp();
     }
     mbar_wait(&mbar[1], phase);
     fence_after_sync();
@@ -586,11 +614,15 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
 }
 
 // ----------------------------------------------------------------------------------------------
-// bypass_wgrad_tc: gradient of the 1x1 bypass conv as one long-K GEMM on the tensor cores.
-//   D[o, i] = sum_pt gz[o, pt] * x[i, pt]   (i < CI),     D[o, CI] = sum_pt gz[o, pt]   (bias gradient:
-//   the B operand carries one extra row of ones).  Both operands are K-major as they sit in memory
-//   (points contiguous), K = points.  Persistent CTAs accumulate over their tiles of 128 points in TMEM
-//   and write one partial (CO x (CI+1)) each; bypass_wgrad_reduce_kernel sums the partials in fixed order.
+// bypass_wgrad_tc: gradient of the 1x1 bypass conv weight as one long-K GEMM on the tensor cores.
+//   gW[o, i] = sum_{b, pt} gz[b, o, pt] * x[b, i, pt]        (K = points; both operands K-major as stored)
+// A tcgen05.mma costs the same ~74 cycles for every N <= 128 (tools/tc_mma_bench.cu), and a single
+// 32 x 32 product would use 6 % of a 128 x 128 instruction, so NS batch entries are stacked along BOTH
+// M and N:  D[(j,o), (j',i)] = sum_pt gz[b_j, o, pt] * x[b_j', i, pt];  only the diagonal blocks j = j'
+// are wanted, but the instruction count drops NS-fold.  Persistent CTAs accumulate over their tiles of
+// KT = 64 points in TMEM (three split-pass tiles) and write NS partials (CO x CI) each;
+// bypass_wgrad_reduce_kernel sums the partials in a fixed order.  The bias gradient comes from the DC
+// mode of the packed spectrum G^ (bias_from_dc_kernel), which is exactly sum_pt gz.
 // ----------------------------------------------------------------------------------------------
 struct WgradTcParams {
   PlaneGeom gx;          // geometry of x (C = CI)
@@ -598,77 +630,86 @@ struct WgradTcParams {
   long long sbo_g;       // bo stride of gz
   const float* gz;
   const float* x;
-  float* partial;        // [gridDim.x][CO*CI + CO]
-  int tiles_per_plane;   // ceil(H*W / 128)
-  int ntiles;            // NB' * tiles_per_plane
-  int COp, NB;           // image rows: CO rounded to 8; CI + 1 rounded to 16
+  float* partial;        // [gridDim.x * NS][CO*CI]
+  int NS;                // stacked batch entries per tile
+  int COs, CIs;          // per-slot row counts (CO, CI rounded up to 8)
+  int tiles_per_plane;   // ceil(H*W / 64)
+  int ngroups;           // ceil(NB' / NS)
+  int ntiles;            // ngroups * tiles_per_plane
+  int nbatch;            // NB'
   int vec4;              // H*W % 4 == 0: 16-byte global loads are aligned
 };
+
+constexpr int kWgradKT = 64;   // points per tile
 
 struct WgradTcSmem {
   int g_hi, g_lo, x_hi, x_lo, total;
   int g_lbo, x_lbo;
 };
 
-__host__ __device__ inline WgradTcSmem wgrad_tc_smem(int COp, int NB) {
+__host__ __device__ inline WgradTcSmem wgrad_tc_smem(int NS, int COs, int CIs) {
   WgradTcSmem m;
-  m.g_lbo = 16 * COp + 16;     // padded K-direction strides: conflict-free 16-byte stores
-  m.x_lbo = 16 * NB + 16;
+  const int mrows = 128;                 // the M = 128 descriptor always reads 16 row groups
+  const int nrows = NS * CIs;
+  m.g_lbo = 16 * mrows + 16;             // padded K-direction strides: conflict-free 16-byte stores
+  m.x_lbo = 16 * nrows + 16;
   int off = 0;
-  m.g_hi = off; off += 32 * m.g_lbo;
-  m.g_lo = off; off += 32 * m.g_lbo + 2048;   // slack: the M = 128 descriptor reads 16 row groups
-  m.x_hi = off; off += 32 * m.x_lbo;
-  m.x_lo = off; off += 32 * m.x_lbo;
-  m.total = off + 2048;
+  m.g_hi = off; off += (kWgradKT / 4) * m.g_lbo;
+  m.g_lo = off; off += (kWgradKT / 4) * m.g_lbo;
+  m.x_hi = off; off += (kWgradKT / 4) * m.x_lbo;
+  m.x_lo = off; off += (kWgradKT / 4) * m.x_lbo;
+  m.total = off + 256;
   return m;
 }
 
-template <int NIT>   // (row, point-quad) items per thread: (COp + CIp8) * 32 / 256 rounded up
+template <int NIT>   // (row, point-quad) items per thread: NS * (CO + CI) * 16 / 256 rounded up
 __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t mbar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int CI = p.gx.C, CO = p.CO, COp = p.COp, NB = p.NB;
-  const WgradTcSmem so = wgrad_tc_smem(COp, NB);
+  const int CI = p.gx.C, CO = p.CO, NS = p.NS, COs = p.COs, CIs = p.CIs;
+  const WgradTcSmem so = wgrad_tc_smem(NS, COs, CIs);
   const int HW = p.gx.H * p.gx.W;
-  const int nrows = CO + CI;                 // rows streamed per tile: gz channels then x channels
-  const int nacc = (6 * NB <= 512) ? 6 : 3;   // independent accumulator tiles: split pass x (K-step parity)
+  const int rows_per_slot = CO + CI;
+  const int nrows = NS * rows_per_slot;      // rows streamed per tile
+  const int N = NS * CIs;
   uint32_t ncols = 32;
-  while ((int)ncols < nacc * NB) ncols *= 2;
+  while ((int)ncols < 3 * N) ncols *= 2;
 
   if (warp == 0) tmem_alloc(&tmem_slot, ncols);
   if (tid == 32) {
     mbar_init(&mbar, 1);
     mbar_fence_init();
   }
-  // constant rows of the x images: zero everything once, then the ones row (hi = 1, lo = 0)
-  for (int i = tid; i < (so.total - so.g_hi) / 16; i += 256) reinterpret_cast<float4*>(smem + so.g_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  for (int k = tid; k < 128; k += 256)
-    *reinterpret_cast<float*>(smem + so.x_hi + (CI & 7) * 16 + (CI >> 3) * 128 + (k & 3) * 4 + (k >> 2) * so.x_lbo) = 1.0f;
+  for (int i = tid; i < so.total / 16; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   float4 regs[NIT];
   auto prefetch = [&](int t) {
-    const int bp = t / p.tiles_per_plane;
-    const int p0 = (t - bp * p.tiles_per_plane) * 128;
-    const long long gbase = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
-    const long long xbase = plane_base(p.gx, bp, 0) + p0;
+    const int grp = t / p.tiles_per_plane;
+    const int p0 = (t - grp * p.tiles_per_plane) * kWgradKT;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int item = it * 256 + tid;
-      const int row = item >> 5, pq = item & 31;
+      const int row = item >> 4, pq = item & 15;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < nrows) {
-        const float* src = (row < CO) ? p.gz + gbase + (long long)row * p.gx.sc : p.x + xbase + (long long)(row - CO) * p.gx.sc;
-        const int pt = pq * 4;
-        if (p.vec4 && p0 + pt + 3 < HW) {
-          v = *reinterpret_cast<const float4*>(src + pt);
-        } else {
-          if (p0 + pt + 0 < HW) v.x = src[pt + 0];
-          if (p0 + pt + 1 < HW) v.y = src[pt + 1];
-          if (p0 + pt + 2 < HW) v.z = src[pt + 2];
-          if (p0 + pt + 3 < HW) v.w = src[pt + 3];
+        const int j = row / rows_per_slot, r = row - j * rows_per_slot;
+        const int bp = grp * NS + j;
+        if (bp < p.nbatch) {
+          const long long base = (r < CO)
+              ? (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + (long long)r * p.gx.sc
+              : plane_base(p.gx, bp, r - CO);
+          const float* src = ((r < CO) ? p.gz : p.x) + base + p0;
+          const int pt = pq * 4;
+          if (p.vec4 && p0 + pt + 3 < HW) {
+            v = *reinterpret_cast<const float4*>(src + pt);
+          } else {
+            if (p0 + pt + 0 < HW) v.x = src[pt + 0];
+            if (p0 + pt + 1 < HW) v.y = src[pt + 1];
+            if (p0 + pt + 2 < HW) v.z = src[pt + 2];
+            if (p0 + pt + 3 < HW) v.w = src[pt + 3];
+          }
         }
       }
       regs[it] = v;
@@ -681,7 +722,7 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = make_idesc_tf32(128, NB);
+  const uint32_t idesc = make_idesc_tf32(128, N);
   const uint32_t sbase = smem_u32(smem);
   uint32_t phase = 0, accum = 0;
   bool pending = false;
@@ -694,20 +735,22 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int item = it * 256 + tid;
-      const int row = item >> 5, pq = item & 31;
+      const int row = item >> 4, pq = item & 15;
       if (row < nrows) {
+        const int j = row / rows_per_slot, r = row - j * rows_per_slot;
         float4 hi, lo;
         split_tf32(regs[it].x, hi.x, lo.x);
         split_tf32(regs[it].y, hi.y, lo.y);
         split_tf32(regs[it].z, hi.z, lo.z);
         split_tf32(regs[it].w, hi.w, lo.w);
-        if (row < CO) {
-          const int off = (row & 7) * 16 + (row >> 3) * 128 + pq * so.g_lbo;
+        if (r < CO) {
+          const int ir = j * COs + r;
+          const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * so.g_lbo;
           *reinterpret_cast<float4*>(smem + so.g_hi + off) = hi;
           *reinterpret_cast<float4*>(smem + so.g_lo + off) = lo;
         } else {
-          const int r = row - CO;
-          const int off = (r & 7) * 16 + (r >> 3) * 128 + pq * so.x_lbo;
+          const int ir = j * CIs + (r - CO);
+          const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * so.x_lbo;
           *reinterpret_cast<float4*>(smem + so.x_hi + off) = hi;
           *reinterpret_cast<float4*>(smem + so.x_lo + off) = lo;
         }
@@ -716,47 +759,48 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {                                 // warp-uniform issue loop, MMA predicated on the elected lane
       fence_after_sync();
-      for (int s2 = 0; s2 < 16; ++s2) {
+      const bool leader = elect_one();
+      uint64_t gh = make_desc(sbase + so.g_hi, so.g_lbo, 128), gl = make_desc(sbase + so.g_lo, so.g_lbo, 128);
+      uint64_t xh = make_desc(sbase + so.x_hi, so.x_lbo, 128), xl = make_desc(sbase + so.x_lo, so.x_lbo, 128);
+      const uint64_t inc_g = (uint64_t)((2 * so.g_lbo) >> 4), inc_x = (uint64_t)((2 * so.x_lbo) >> 4);
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {         // hi*hi, lo*hi, hi*lo
-          const uint32_t a = sbase + (pass == 1 ? so.g_lo : so.g_hi);
-          const uint32_t b = sbase + (pass == 2 ? so.x_lo : so.x_hi);
-          const int tile = (nacc == 6) ? pass * 2 + (s2 & 1) : pass;
-          const uint32_t first = (nacc == 6) ? (s2 < 2 ? 1u : 0u) : (s2 < 1 ? 1u : 0u);
-          mma_tf32(tmem + tile * NB, make_desc(a + s2 * 2 * so.g_lbo, so.g_lbo, 128), make_desc(b + s2 * 2 * so.x_lbo, so.x_lbo, 128), idesc,
-                   (accum == 0 && first) ? 0u : 1u);
+      for (int s2 = 0; s2 < kWgradKT / 8; ++s2) {
+        const uint32_t acc = (accum == 0 && s2 == 0) ? 0u : 1u;
+        if (leader) {
+          mma_tf32(tmem, gh, xh, idesc, acc);              // hi * hi
+          mma_tf32(tmem + N, gl, xh, idesc, acc);          // lo * hi
+          mma_tf32(tmem + 2 * N, gh, xl, idesc, acc);      // hi * lo
         }
+        gh += inc_g; gl += inc_g; xh += inc_x; xl += inc_x;
       }
-      accum = 1;
-      mma_commit(&mbar);
+      if (leader) mma_commit(&mbar);
+      __syncwarp();
     }
+    accum = 1;
     pending = true;
     if (t + (int)gridDim.x < p.ntiles) prefetch(t + gridDim.x);
   }
   if (pending) mbar_wait(&mbar, phase);
   fence_after_sync();
-  // D[o][i] -> partial; lane o of TMEM = output channel o
-  float* out = p.partial + (long long)blockIdx.x * (CO * CI + CO);
+  // lane (j, o) of TMEM holds row o of slot j; its diagonal block sits at columns j*CIs .. j*CIs + CI
   if (warp < 4) {
-    const int o = (warp & 3) * 32 + lane;
-    for (int c0 = 0; c0 < NB; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-      for (int a = 1; a < nacc; ++a) {
-        float w[16];
-        tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * NB + c0), w);
+    const int row = (warp & 3) * 32 + lane;
+    const int j = row / COs, o = row - j * COs;
+    const bool valid = pending && j < NS && o < CO;
+    float* out = p.partial + ((long long)blockIdx.x * NS + (j < NS ? j : 0)) * (CO * CI) + (long long)o * CI;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16], v1[16], v2[16];
+      const uint32_t ta = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+      tmem_ld16(ta, v);
+      tmem_ld16(ta + N, v1);
+      tmem_ld16(ta + 2 * N, v2);
+      if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += w[j];
-      }
-      if (o < CO) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int i = c0 + j;
-          const float val = pending ? v[j] : 0.f;
-          if (i < CI) out[o * CI + i] = val;
-          else if (i == CI) out[CO * CI + o] = val;
+        for (int jj = 0; jj < 16; ++jj) {
+          const int i = c0 + jj - j * CIs;
+          if (i >= 0 && i < CI) out[i] = v[jj] + (v1[jj] + v2[jj]);
         }
       }
     }
@@ -764,6 +808,16 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+// glb[o] = S * sum_b Re G^[b, o, mode 0]  (the DC mode of the scaled spectrum is sum_pt gz / S)
+struct BiasDcParams { const float2* ghat; float* glb; int B, CO, M; float s_total; };
+__global__ void bias_from_dc_kernel(BiasDcParams p) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= p.CO) return;
+  float acc = 0.f;
+  for (int b = 0; b < p.B; ++b) acc += p.ghat[((long long)b * p.CO + o) * p.M].x;
+  p.glb[o] = acc * p.s_total;
 }
 
 }  // namespace tc
