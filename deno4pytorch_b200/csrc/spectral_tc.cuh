@@ -316,8 +316,9 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       fence_after_sync();
+      const bool leader = elect_one();   // warp-uniform loop (descriptors in uniform registers); one lane issues
       // Back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency (measured ~120
       // cycles each at N = 32), so the three split passes (hi*hi, lo*hi, hi*lo) accumulate into three
       // separate TMEM tiles and are issued round-robin; the epilogue adds the tiles.
@@ -504,8 +505,9 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     fence_before_sync();
     __syncthreads();                                   // A images complete; staging is free again
     if (q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);
-    if (tid == 0) {
+    if (warp == 0) {
       fence_after_sync();
+      const bool leader = elect_one();
       // three independent accumulator tiles (one per split pass), issued round-robin: see plane_synthesis_tc
       uint64_t ah = make_desc(sbase + so.ab, lbo_a, 128), al = make_desc(sbase + so.ab + so.a_one, lbo_a, 128);
       uint64_t bh = make_desc(sbase + so.e1, lbo_e1, 128), bl = make_desc(sbase + so.e1 + so.e1_one, lbo_e1, 128);
@@ -684,32 +686,54 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
   }
   for (int i = tid; i < so.total / 16; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // The (row, point-quad) -> (slot, channel, image offset) map does not depend on the tile: decode it once.
+  // meta: bit 31 valid, bit 30 "gz row", bits 28..29 slot j, bits 0..27 byte offset inside the hi image.
   float4 regs[NIT];
+  uint32_t meta[NIT];
+  int roff[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int item = it * 256 + tid;
+    const int row = item >> 4, pq = item & 15;
+    meta[it] = 0u;
+    roff[it] = 0;
+    if (row < nrows) {
+      const int j = row / rows_per_slot, r = row - j * rows_per_slot;
+      const bool isg = r < CO;
+      const int ir = isg ? j * COs + r : j * CIs + (r - CO);
+      const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * (isg ? so.g_lbo : so.x_lbo);
+      meta[it] = 0x80000000u | (isg ? 0x40000000u : 0u) | ((uint32_t)j << 28) | (uint32_t)off;
+      roff[it] = (int)((isg ? r : r - CO) * p.gx.sc) + pq * 4;
+    }
+  }
   auto prefetch = [&](int t) {
     const int grp = t / p.tiles_per_plane;
     const int p0 = (t - grp * p.tiles_per_plane) * kWgradKT;
+    long long gb[4], xb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int bp = min(grp * NS + j, p.nbatch - 1);
+      gb[j] = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
+      xb[j] = plane_base(p.gx, bp, 0) + p0;
+    }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-      const int item = it * 256 + tid;
-      const int row = item >> 4, pq = item & 15;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < nrows) {
-        const int j = row / rows_per_slot, r = row - j * rows_per_slot;
-        const int bp = grp * NS + j;
-        if (bp < p.nbatch) {
-          const long long base = (r < CO)
-              ? (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + (long long)r * p.gx.sc
-              : plane_base(p.gx, bp, r - CO);
-          const float* src = ((r < CO) ? p.gz : p.x) + base + p0;
-          const int pt = pq * 4;
-          if (p.vec4 && p0 + pt + 3 < HW) {
-            v = *reinterpret_cast<const float4*>(src + pt);
-          } else {
-            if (p0 + pt + 0 < HW) v.x = src[pt + 0];
-            if (p0 + pt + 1 < HW) v.y = src[pt + 1];
-            if (p0 + pt + 2 < HW) v.z = src[pt + 2];
-            if (p0 + pt + 3 < HW) v.w = src[pt + 3];
-          }
+      const uint32_t m = meta[it];
+      const int j = (int)((m >> 28) & 3u);
+      if ((m & 0x80000000u) && grp * NS + j < p.nbatch) {
+        const bool isg = (m & 0x40000000u) != 0u;
+        const long long base = isg ? (j == 0 ? gb[0] : (j == 1 ? gb[1] : (j == 2 ? gb[2] : gb[3])))
+                                   : (j == 0 ? xb[0] : (j == 1 ? xb[1] : (j == 2 ? xb[2] : xb[3])));
+        const float* src = (isg ? p.gz : p.x) + base + roff[it];
+        const int pt = p0 + ((it * 256 + tid) & 15) * 4;
+        if (p.vec4 && pt + 3 < HW) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (pt + 0 < HW) v.x = src[0];
+          if (pt + 1 < HW) v.y = src[1];
+          if (pt + 2 < HW) v.z = src[2];
+          if (pt + 3 < HW) v.w = src[3];
         }
       }
       regs[it] = v;
@@ -734,26 +758,17 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-      const int item = it * 256 + tid;
-      const int row = item >> 4, pq = item & 15;
-      if (row < nrows) {
-        const int j = row / rows_per_slot, r = row - j * rows_per_slot;
+      const uint32_t m = meta[it];
+      if (m & 0x80000000u) {
         float4 hi, lo;
         split_tf32(regs[it].x, hi.x, lo.x);
         split_tf32(regs[it].y, hi.y, lo.y);
         split_tf32(regs[it].z, hi.z, lo.z);
         split_tf32(regs[it].w, hi.w, lo.w);
-        if (r < CO) {
-          const int ir = j * COs + r;
-          const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * so.g_lbo;
-          *reinterpret_cast<float4*>(smem + so.g_hi + off) = hi;
-          *reinterpret_cast<float4*>(smem + so.g_lo + off) = lo;
-        } else {
-          const int ir = j * CIs + (r - CO);
-          const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * so.x_lbo;
-          *reinterpret_cast<float4*>(smem + so.x_hi + off) = hi;
-          *reinterpret_cast<float4*>(smem + so.x_lo + off) = lo;
-        }
+        const bool isg = (m & 0x40000000u) != 0u;
+        unsigned char* dst = smem + (isg ? so.g_hi : so.x_hi) + (m & 0x0FFFFFFFu);
+        *reinterpret_cast<float4*>(dst) = hi;
+        *reinterpret_cast<float4*>(dst + (isg ? so.g_lo - so.g_hi : so.x_lo - so.x_hi)) = lo;
       }
     }
     fence_proxy_async();
