@@ -577,7 +577,7 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
   for (int j = 0; j < 4; ++j) p.gw[j] = static_cast<float2*>(gw_blocks[j < nblk ? j : 0]);
   p.B = s.B; p.CI = s.CI; p.CO = s.CO;
   dim3 block(32, 8);
-  dim3 grid((s.M + 31) / 32, ((s.CO + 3) / 4 + 7) / 8, s.CI);
+  dim3 grid((s.M + 31) / 32, ((s.CO + kMixWgradOut - 1) / kMixWgradOut + 7) / 8, s.CI);
   prof_before("mode_mix_wgrad", st);
   DENO_LAUNCH(mode_mix_wgrad_kernel, grid, block, 0, st, p);
   return check_launch("mode_mix_wgrad", st);

@@ -16,7 +16,37 @@
 
 #include <stdint.h>
 
+// Compiler-level scheduling fence: memory operations may not be moved across it.  Used after a batch of
+// independent global loads so that all of them are in flight before the first one is consumed.
+#ifdef DENO_EMULATE
+#define DENO_SCHED_FENCE() do { } while (0)
+#else
+#define DENO_SCHED_FENCE() asm volatile("" ::: "memory")
+#endif
+
 namespace deno {
+
+// Ordered (asm volatile) global loads: ptxas keeps them in program order, so a batch written before the
+// arithmetic really is issued as a batch - the way to get memory-level parallelism in the small
+// latency-bound kernels (mode_mix*, reductions), where plain loads get re-interleaved with their uses.
+__device__ __forceinline__ float2 ldg_ordered(const float2* p) {
+#ifdef DENO_EMULATE
+  return *p;
+#else
+  float2 v;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+#endif
+}
+__device__ __forceinline__ float ldg_ordered(const float* p) {
+#ifdef DENO_EMULATE
+  return *p;
+#else
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+#endif
+}
 
 // Activation ids mirror enum deno_activation in include/deno_spectral.h
 // (table of /root/reference/Models/configs.py:17-19).

@@ -270,7 +270,7 @@ struct MixParams {
   int conj_w;
 };
 
-constexpr int kMixBatchTile = 4;
+constexpr int kMixBatchTile = 1;   // one batch entry per thread: the kernel is latency-bound, so favour more warps
 constexpr int kMixUnroll = 8;
 
 // blockDim = (32 modes, 8 output channels); grid = (ceil(M/32), ceil(CO/8), ceil(B/4))
@@ -298,10 +298,11 @@ __global__ void mode_mix_kernel(MixParams p) {
 #pragma unroll
     for (int u = 0; u < kMixUnroll; ++u) {
       const int ci = min(ci0 + u, p.CI - 1);
-      wv[u] = w[(long long)ci * p.w_sci];
+      wv[u] = ldg_ordered(w + (long long)ci * p.w_sci);
 #pragma unroll
-      for (int j = 0; j < kMixBatchTile; ++j) v[u][j] = inb[j][(long long)ci * M];
+      for (int j = 0; j < kMixBatchTile; ++j) v[u][j] = ldg_ordered(inb[j] + (long long)ci * M);
     }
+    DENO_SCHED_FENCE();   // keep the whole batch of loads ahead of the arithmetic (the compiler otherwise re-serialises them)
 #pragma unroll
     for (int u = 0; u < kMixUnroll; ++u) {
       const float wr = (ci0 + u < p.CI) ? wv[u].x : 0.f;
@@ -327,34 +328,38 @@ struct MixWgradParams {
   int B, CI, CO;
 };
 
-// blockDim = (32 modes, 8 output-channel quads); grid = (ceil(M/32), ceil(ceil(CO/4)/8), CI)
+constexpr int kMixWgradOut = 1;   // output channels per thread (latency-bound: favour more warps)
+
+// blockDim = (32 modes, 8 output channels); grid = (ceil(M/32), ceil(CO/8), CI)
 __global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
   const int M = p.md.M;
   const int pm = blockIdx.x * blockDim.x + threadIdx.x;
   const int oq = blockIdx.y * blockDim.y + threadIdx.y;
   const int ci = blockIdx.z;
-  if (pm >= M || oq * 4 >= p.CO) return;
+  if (pm >= M || oq * kMixWgradOut >= p.CO) return;
   int blk, off;
   decode_mode(p.md, pm, blk, off);
-  float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
-  const float2* xp = p.xhat + (long long)ci * M + pm;
-  const float2* gp[4];
+  float ar[kMixWgradOut], ai[kMixWgradOut];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) gp[j] = p.ghat + (long long)min(oq * 4 + j, p.CO - 1) * M + pm;
-  for (int b0 = 0; b0 < p.B; b0 += 4) {   // batched loads: the loop is L2-latency-bound
-    float2 xv[4], gv[4][4];
+  for (int j = 0; j < kMixWgradOut; ++j) ar[j] = ai[j] = 0.f;
+  const float2* xp = p.xhat + (long long)ci * M + pm;
+  const float2* gp[kMixWgradOut];
+#pragma unroll
+  for (int j = 0; j < kMixWgradOut; ++j) gp[j] = p.ghat + (long long)min(oq * kMixWgradOut + j, p.CO - 1) * M + pm;
+  for (int b0 = 0; b0 < p.B; b0 += 4) {
+    float2 xv[4], gv[4][kMixWgradOut];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int b = min(b0 + u, p.B - 1);
-      xv[u] = xp[(long long)b * p.CI * M];
+      xv[u] = ldg_ordered(xp + (long long)b * p.CI * M);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) gv[u][j] = gp[j][(long long)b * p.CO * M];
+      for (int j = 0; j < kMixWgradOut; ++j) gv[u][j] = ldg_ordered(gp[j] + (long long)b * p.CO * M);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float xr = (b0 + u < p.B) ? xv[u].x : 0.f, xi = (b0 + u < p.B) ? xv[u].y : 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kMixWgradOut; ++j) {
         // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
         ar[j] = fmaf(xr, gv[u][j].x, fmaf(xi, gv[u][j].y, ar[j]));
         ai[j] = fmaf(xr, gv[u][j].y, fmaf(-xi, gv[u][j].x, ai[j]));
@@ -364,8 +369,8 @@ __global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
   float2* gb = blk == 0 ? p.gw[0] : (blk == 1 ? p.gw[1] : (blk == 2 ? p.gw[2] : p.gw[3]));
   float2* dst = gb + ((long long)ci * p.CO) * p.md.Mblk + off;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (oq * 4 + j < p.CO) dst[(long long)(oq * 4 + j) * p.md.Mblk] = make_float2(ar[j], ai[j]);
+  for (int j = 0; j < kMixWgradOut; ++j)
+    if (oq * kMixWgradOut + j < p.CO) dst[(long long)(oq * kMixWgradOut + j) * p.md.Mblk] = make_float2(ar[j], ai[j]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -625,9 +630,20 @@ __global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int slice = threadIdx.y;
   float s = 0.f;
-  if (j < p.nj)
-#pragma unroll 8
-    for (int c = slice; c < p.ncta; c += 8) s += p.partial[(long long)c * p.nj + j];
+  if (j < p.nj) {
+    for (int c0 = slice; c0 < p.ncta; c0 += 64) {   // eight loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + 8 * u;
+        v[u] = ldg_ordered(p.partial + (long long)min(c, p.ncta - 1) * p.nj + j);
+        if (c >= p.ncta) v[u] = 0.f;
+      }
+      DENO_SCHED_FENCE();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+  }
   red[slice * 32 + threadIdx.x] = s;
   __syncthreads();
   if (slice == 0 && j < p.nj) {

@@ -831,7 +831,17 @@ __global__ void bias_from_dc_kernel(BiasDcParams p) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= p.CO) return;
   float acc = 0.f;
-  for (int b = 0; b < p.B; ++b) acc += p.ghat[((long long)b * p.CO + o) * p.M].x;
+  for (int b0 = 0; b0 < p.B; b0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v[u] = ldg_ordered(reinterpret_cast<const float*>(p.ghat + ((long long)min(b0 + u, p.B - 1) * p.CO + o) * p.M));
+      if (b0 + u >= p.B) v[u] = 0.f;
+    }
+    DENO_SCHED_FENCE();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
   p.glb[o] = acc * p.s_total;
 }
 
