@@ -593,21 +593,20 @@ int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int
   const TwLayout tl = tw_layout(s);
   // stage A stages the packed spectrum through the A_X area: at least one output channel must fit
   if (2 * CIP * 128 * 4 - round_up(kSynthMaxRows * p.g.KH, 2) * 8 < p.g.KH * p.g.MW * 8) return -1;
+  int cols = 32;
+  while (cols < 6 * CO) cols *= 2;
+  if (cols > 512) return -1;
+  // One persistent, warp-specialised CTA per SM; pick the rows per unit that balance the units over 148 CTAs.
   int bestR = 0;
   double best_eff = -1.0;
   const int maxR = p.g.H > 1 ? (p.g.H < kSynthMaxRows ? p.g.H : kSynthMaxRows) : 1;
   for (int R = maxR; R >= 1; --R) {
-    const size_t bytes = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, R).total;
-    if (bytes > (size_t)kMaxSmemBytes) continue;
-    int per_sm = (int)((228 * 1024) / (bytes + 2048));
-    if (per_sm > 4) per_sm = 4;
-    if (per_sm * 6 * CO > 512) per_sm = 512 / (6 * CO) > 0 ? 512 / (6 * CO) : 1;   // TMEM columns per SM
-    if (per_sm < 1) per_sm = 1;
-    const long long ctas = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks;
-    const long long slots = 148LL * per_sm;
-    const long long waves = (ctas + slots - 1) / slots;
-    double eff = (double)ctas / (double)(waves * slots);
-    eff *= (1.0 - 0.25 / R);               // per-CTA setup (weights, twiddles, stage A) amortises over R rows
+    const size_t bytes = (size_t)tc::synth_ws_smem(CIP, CO, tl.KE, R).total;
+    if (bytes > (size_t)kMaxSmemBytes - 2048) continue;
+    const long long units = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks;
+    const long long waves = (units + 147) / 148;
+    double eff = (double)units / (double)(waves * 148);
+    eff *= (1.0 - 0.3 / R);               // per-unit drain + stage A amortise over R rows
     if (eff > best_eff + 1e-9) { best_eff = eff; bestR = R; }
   }
   if (bestR == 0) return -1;
@@ -619,19 +618,17 @@ int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int
   q.ae = tw.synth_ae;
   q.KE = tl.KE;
   q.nchunks = tl.nchunks;
-  int cols = 32;
-  while (cols < 6 * CO) cols *= 2;
-  if (cols > 512) return -1;
   q.tmem_cols = cols;
-  const size_t smem = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, bestR).total;
-  const int grid = s.B * s.X * p.tiles * tl.nchunks;
+  const size_t smem = (size_t)tc::synth_ws_smem(CIP, CO, tl.KE, bestR).total;
+  const long long nunits = (long long)s.B * s.X * p.tiles * tl.nchunks;
+  const int grid = (int)(nunits < 148 ? nunits : 148);
   int rc = DENO_OK;
 #define DENO_TC_CASE2(ACT, CIPV)                                                                    \
   {                                                                                                 \
-    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV>, smem, "plane_synthesis_tc");          \
+    rc = allow_smem(tc::plane_synthesis_ws_kernel<ACT, CIPV>, smem, "plane_synthesis_ws");          \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    tc::plane_synthesis_tc_kernel<ACT, CIPV><<<dim3(grid), dim3(256), smem, st>>>(q);               \
+    tc::plane_synthesis_ws_kernel<ACT, CIPV><<<dim3(grid), dim3(tc::kWsThreads), smem, st>>>(q);    \
   }
 #define DENO_TC_CASE(ACT)                                                                           \
   case ACT:                                                                                         \

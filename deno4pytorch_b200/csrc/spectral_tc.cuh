@@ -368,6 +368,287 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
 }
 
 // ----------------------------------------------------------------------------------------------
+// plane_synthesis_ws: warp-specialised version of plane_synthesis_tc (same math, same operand images).
+//   warps 0-7   epilogue : TMEM -> registers -> bias + activation (+ derivative) -> coalesced global stores
+//   warps 8-11  loaders  : global x row -> registers -> tf32 split -> A_X image (two stages)
+//   warp  12    MMA      : one elected lane issues the 3 x (CIP/8 + KE/8) tcgen05.mma of a row
+// The roles hand rows to each other through mbarriers (A_X full/empty, D full/empty), so loading row r+1,
+// the tensor-core work of row r and the epilogue of row r-1 overlap inside one persistent CTA per SM.
+// ----------------------------------------------------------------------------------------------
+constexpr int kWsEpiWarps = 8, kWsLoadWarps = 4;
+constexpr int kWsThreads = (kWsEpiWarps + kWsLoadWarps + 1) * 32;
+
+struct SynthWsSmem {
+  int bw_hi, bw_lo, ae_hi, ae_lo, bu, ax, bias, total;  // byte offsets
+  int bu_one, ax_one;
+};
+
+__host__ __device__ inline SynthWsSmem synth_ws_smem(int CIP, int CO, int KE, int R) {
+  SynthWsSmem m;
+  int off = 0;
+  m.bw_hi = off; off += CIP * CO * 4;
+  m.bw_lo = off; off += CIP * CO * 4;
+  m.ae_hi = off; off += KE * 128 * 4;
+  m.ae_lo = off; off += KE * 128 * 4;
+  m.bu_one = KE * CO * 4;
+  m.bu = off;    off += 2 * R * m.bu_one;        // [row][hi|lo]
+  m.ax_one = CIP * 128 * 4;
+  m.ax = off;    off += 4 * m.ax_one;            // [stage][hi|lo]
+  m.bias = off;  off += CO * 4;
+  m.total = off;
+  return m;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int ACT, int CIP>
+__global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(SynthTcParams q) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar_ax_full[2], bar_ax_empty[2], bar_d_full[2], bar_d_empty[2];
+  const SynthParams& p = q.s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = kWsThreads;
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = p.CO;
+  const int KH4 = round_up(KH, 4);
+  const int KE = q.KE, R = p.R;
+  const SynthWsSmem so = synth_ws_smem(CIP, CO, KE, R);
+  constexpr int NCQ = CIP / 4;            // channel quads per point (one loader thread = one point)
+
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)q.tmem_cols);
+  if (tid == 32) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_ax_full[s], kWsLoadWarps * 32);
+      mbar_init(&bar_ax_empty[s], 1);
+      mbar_init(&bar_d_full[s], 1);
+      mbar_init(&bar_d_empty[s], kWsEpiWarps * 32);
+    }
+    mbar_fence_init();
+  }
+  // bypass weight image B_W[n = o][k = i], split on the fly (constant for the CTA's lifetime)
+  for (int idx = tid; idx < CO * CIP; idx += nt) {
+    const int o = idx / CIP, i = idx - o * CIP;
+    const float w = (i < CI) ? p.lw[(long long)o * p.lw_so + (long long)i * p.lw_si] : 0.f;
+    float hi, lo;
+    split_tf32(w, hi, lo);
+    const int off = kmajor_off(o, i, CO);
+    *reinterpret_cast<float*>(smem + so.bw_hi + off) = hi;
+    *reinterpret_cast<float*>(smem + so.bw_lo + off) = lo;
+  }
+  float* bias_s = reinterpret_cast<float*>(smem + so.bias);
+  for (int o = tid; o < CO; o += nt) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, CO);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t lbo_m = 16 * 128, lbo_n = 16 * CO;
+  const int nunits = p.g.NBO * p.g.NBI * p.tiles * q.nchunks;
+  int cur_chunk = -1;
+  int it0 = 0;                            // rows handled so far by this CTA (drives stage / parity of the barriers)
+
+  for (int unit = blockIdx.x; unit < nunits; unit += gridDim.x) {
+    int bid = unit;
+    const int chunk = bid % q.nchunks; bid /= q.nchunks;
+    const int tile = bid % p.tiles;
+    const int bp = bid / p.tiles;
+    const int x0 = tile * R;
+    const int trows = (H > 1) ? min(R, H - x0) : 1;
+    const int y0 = chunk * 128;
+    const int ny = min(128, W - y0);
+
+    // ---- per-unit setup by all warps: twiddle images (if the column chunk changed) and stage A ----
+    if (chunk != cur_chunk) {
+      const float4* src = reinterpret_cast<const float4*>(q.ae + (long long)chunk * 2 * KE * 128);
+      float4* dst = reinterpret_cast<float4*>(smem + so.ae_hi);
+      for (int idx = tid; idx < 2 * KE * 128 / 4; idx += nt) dst[idx] = src[idx];
+      cur_chunk = chunk;
+    }
+    {
+      unsigned char* bu = smem + so.bu;
+      for (int idx = tid; idx < 2 * R * so.bu_one / 16; idx += nt) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2* twr = reinterpret_cast<float2*>(smem + so.ax);               // [trows][KH] row twiddles
+      float2* sps = twr + round_up(kSynthMaxRows * KH, 2);                 // [OC][KH*MW] spectrum chunk
+      const int Q = KH * MW;
+      const int avail = 4 * so.ax_one - round_up(kSynthMaxRows * KH, 2) * 8;
+      int OC = avail / (Q * 8);
+      if (OC > CO) OC = CO;
+      for (int idx = tid; idx < trows * KH; idx += nt) {
+        const int rr = idx / KH, k = idx - rr * KH;
+        twr[idx] = p.twH[(x0 + rr) * KH4 + k];
+      }
+      for (int o0 = 0; o0 < CO; o0 += OC) {
+        const int oc = min(OC, CO - o0);
+        __syncthreads();
+        const float2* src = p.spec + ((long long)bp * CO + o0) * Q;
+        for (int idx = tid; idx < oc * Q; idx += nt) sps[idx] = src[idx];
+        __syncthreads();
+        for (int task = tid; task < oc * MW; task += nt) {
+          const int ol = task / MW, l = task - ol * MW;
+          const int o = o0 + ol;
+          float ar[kSynthMaxRows], ai[kSynthMaxRows];
+#pragma unroll
+          for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
+          const float2* sp = sps + ol * Q + l;
+#pragma unroll 4
+          for (int k = 0; k < KH; ++k) {
+            const float2 sv = sp[k * MW];
+#pragma unroll
+            for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+              if (rr < trows) {
+                const float2 e = twr[rr * KH + k];
+                ar[rr] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[rr]));
+                ai[rr] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[rr]));
+              }
+            }
+          }
+          const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+          const int off = kmajor_off(o, 2 * l, CO);
+#pragma unroll
+          for (int rr = 0; rr < kSynthMaxRows; ++rr) {
+            if (rr < trows) {
+              float h0, l0, h1, l1;
+              split_tf32(ar[rr] * f, h0, l0);
+              split_tf32(-ai[rr] * f, h1, l1);
+              unsigned char* base = bu + (2 * rr) * so.bu_one + off;
+              *reinterpret_cast<float2*>(base) = make_float2(h0, h1);
+              *reinterpret_cast<float2*>(base + so.bu_one) = make_float2(l0, l1);
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncthreads();     // operand images complete; the A_X stages are free for the loaders
+    }
+
+    if (warp < kWsEpiWarps) {
+      // ===== epilogue warps =====
+      const int wq = warp & 3, wg = warp >> 2;
+      const int ncol_half = CO / 2;
+      const int yl = wq * 32 + lane;
+      const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
+      for (int rr = 0; rr < trows; ++rr) {
+        const int i = it0 + rr, st = i & 1;
+        mbar_wait(&bar_d_full[st], (uint32_t)((i >> 1) & 1));
+        fence_after_sync();
+        const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(st * 3 * CO + wg * ncol_half);
+        const long long pbase = obase_b + (long long)(x0 + rr) * W + y0 + yl;
+        for (int c0 = 0; c0 < ncol_half; c0 += 16) {
+          float v[16], v1[16], v2[16];
+          tmem_ld16(tb + c0, v);
+          tmem_ld16(tb + CO + c0, v1);
+          tmem_ld16(tb + 2 * CO + c0, v2);
+          if (c0 + 16 >= ncol_half) {          // last TMEM read of this row by this thread: release the buffer early
+            fence_before_sync();
+            mbar_arrive(&bar_d_empty[st]);
+          }
+          if (yl < ny) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int o = wg * ncol_half + c0 + j;
+              const float zz = (v[j] + bias_s[o]) + (v1[j] + v2[j]);
+              const long long a = pbase + (long long)o * p.g.sc;
+              if (p.z != nullptr) {
+                float yv, dv;
+                act_apply_grad(ACT, zz, yv, dv);
+                p.z[a] = dv;
+                p.y[a] = yv;
+              } else {
+                p.y[a] = act_apply(ACT, zz);
+              }
+            }
+          }
+        }
+      }
+    } else if (warp < kWsEpiWarps + kWsLoadWarps) {
+      // ===== loader warps: one thread = one point of the row, all channel quads =====
+      const int pt = tid - kWsEpiWarps * 32;
+      const long long ubase = plane_base(p.g, bp, 0) + y0 + pt;
+      float xr[NCQ][4];
+      auto prefetch = [&](int rr) {
+        const long long rowoff = ubase + (long long)(x0 + rr) * W;
+#pragma unroll
+        for (int cq = 0; cq < NCQ; ++cq) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = cq * 4 + j;
+            xr[cq][j] = (pt < ny && ch < CI) ? p.u[rowoff + (long long)ch * p.g.sc] : 0.f;
+          }
+        }
+      };
+      prefetch(0);
+      for (int rr = 0; rr < trows; ++rr) {
+        const int i = it0 + rr, st = i & 1;
+        mbar_wait(&bar_ax_empty[st], (uint32_t)(((i >> 1) & 1) ^ 1));
+        unsigned char* axh = smem + so.ax + st * 2 * so.ax_one;
+#pragma unroll
+        for (int cq = 0; cq < NCQ; ++cq) {
+          float4 hi, lo;
+          split_tf32(xr[cq][0], hi.x, lo.x);
+          split_tf32(xr[cq][1], hi.y, lo.y);
+          split_tf32(xr[cq][2], hi.z, lo.z);
+          split_tf32(xr[cq][3], hi.w, lo.w);
+          const int off = kmajor_off(pt, cq * 4, 128);
+          *reinterpret_cast<float4*>(axh + off) = hi;
+          *reinterpret_cast<float4*>(axh + so.ax_one + off) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&bar_ax_full[st]);
+        if (rr + 1 < trows) prefetch(rr + 1);
+      }
+    } else {
+      // ===== MMA warp =====
+      const bool leader = elect_one();
+      const uint64_t inc_m = (uint64_t)((2 * lbo_m) >> 4), inc_n = (uint64_t)((2 * lbo_n) >> 4);
+      for (int rr = 0; rr < trows; ++rr) {
+        const int i = it0 + rr, st = i & 1;
+        const uint32_t par = (uint32_t)((i >> 1) & 1);
+        mbar_wait(&bar_ax_full[st], par);
+        mbar_wait(&bar_d_empty[st], par ^ 1);
+        fence_after_sync();
+        const uint32_t d = tmem + (uint32_t)(st * 3 * CO);
+        const uint32_t axs = sbase + so.ax + st * 2 * so.ax_one;
+        uint64_t axh = make_desc(axs, lbo_m, 128), axl = make_desc(axs + so.ax_one, lbo_m, 128);
+        uint64_t bwh = make_desc(sbase + so.bw_hi, lbo_n, 128), bwl = make_desc(sbase + so.bw_lo, lbo_n, 128);
+#pragma unroll
+        for (int s = 0; s < CIP / 8; ++s) {
+          const uint32_t acc = s > 0 ? 1u : 0u;
+          if (leader) {
+            mma_tf32(d, axh, bwh, idesc, acc);            // hi * hi
+            mma_tf32(d + CO, axl, bwh, idesc, acc);       // lo * hi
+            mma_tf32(d + 2 * CO, axh, bwl, idesc, acc);   // hi * lo
+          }
+          axh += inc_m; axl += inc_m; bwh += inc_n; bwl += inc_n;
+        }
+        uint64_t aeh = make_desc(sbase + so.ae_hi, lbo_m, 128), ael = make_desc(sbase + so.ae_lo, lbo_m, 128);
+        uint64_t buh = make_desc(sbase + so.bu + (2 * rr) * so.bu_one, lbo_n, 128);
+        uint64_t bul = make_desc(sbase + so.bu + (2 * rr + 1) * so.bu_one, lbo_n, 128);
+        for (int s = 0; s < KE / 8; ++s) {
+          if (leader) {
+            mma_tf32(d, aeh, buh, idesc, 1u);
+            mma_tf32(d + CO, ael, buh, idesc, 1u);
+            mma_tf32(d + 2 * CO, aeh, bul, idesc, 1u);
+          }
+          aeh += inc_m; ael += inc_m; buh += inc_n; bul += inc_n;
+        }
+        if (leader) {
+          mma_commit(&bar_ax_empty[st]);     // the A_X stage may be overwritten once these MMAs retire
+          mma_commit(&bar_d_full[st]);       // ... and the accumulators are ready for the epilogue warps
+        }
+        __syncwarp();
+      }
+    }
+    it0 += trows;
+    fence_before_sync();
+    __syncthreads();      // unit drained: every role is done with the images, the A_X stages and TMEM
+    fence_after_sync();
+  }
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)q.tmem_cols);
+}
+
+// ----------------------------------------------------------------------------------------------
 // plane_analysis_tc: same contract as plane_analysis_kernel (spectral_simt.cuh) for planes with
 // H <= 128 rows.  Two chained GEMMs per plane, both on the tensor cores:
 //   stage 1  D1[x, n]  = sum_y u[x, y] * E1[n, y]          n = 2l: cos, 2l+1: -sin      (K = Wp)
