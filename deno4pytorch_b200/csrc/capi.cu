@@ -807,6 +807,23 @@ const char* deno_last_error(void) { return g_error.c_str(); }
 
 int deno_spectral_last_launch_count(void) { return g_launches; }
 
+int deno_debug_read(long long* host, int count, int clear) {
+#ifndef DENO_EMULATE
+  if (host == nullptr || count < 0 || count > 64) return fail(DENO_E_INVALID, "deno_debug_read: bad arguments");
+  cudaError_t e = cudaMemcpyFromSymbol(host, tc::g_dbg, sizeof(long long) * count);
+  if (e != cudaSuccess) return fail(DENO_E_CUDA, cudaGetErrorString(e));
+  if (clear) {
+    long long zeros[64] = {0};
+    e = cudaMemcpyToSymbol(tc::g_dbg, zeros, sizeof(zeros));
+    if (e != cudaSuccess) return fail(DENO_E_CUDA, cudaGetErrorString(e));
+  }
+#else
+  for (int i = 0; i < count; ++i) host[i] = 0;
+  (void)clear;
+#endif
+  return DENO_OK;
+}
+
 int deno_profile_begin(void) {
   std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_prof.clear();

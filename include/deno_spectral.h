@@ -130,6 +130,11 @@ typedef struct deno_profile_record {
 int deno_profile_begin(void);
 int deno_profile_end(deno_profile_record* records, int capacity);
 
+/* Phase-timing scratch of the warp-specialised kernels (64 x int64 clock64() sums written by CTA 0;
+ * slots documented in spectral_tc.cuh).  Copies it to `host`, optionally clears it.  Synchronises the
+ * device: measurement aid only. */
+int deno_debug_read(long long* host, int count, int clear);
+
 #ifdef __cplusplus
 }
 #endif
