@@ -588,7 +588,7 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
 // tcgen05 kernel covers (caller falls back to the SIMT kernel).
 int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
   const int CI = p.g.C, CO = p.CO;
-  if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;
+  if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;   // CO / 4 columns per epilogue warp, multiples of 8
   const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
   const TwLayout tl = tw_layout(s);
   // stage A stages the packed spectrum through the A_X area: at least one output channel must fit

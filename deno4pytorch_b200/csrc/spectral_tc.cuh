@@ -87,6 +87,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -374,13 +385,13 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
 
 // ----------------------------------------------------------------------------------------------
 // plane_synthesis_ws: warp-specialised version of plane_synthesis_tc (same math, same operand images).
-//   warps 0-7   epilogue : TMEM -> registers -> bias + activation (+ derivative) -> coalesced global stores
-//   warps 8-11  loaders  : global x row -> registers -> tf32 split -> A_X image (two stages)
-//   warp  12    MMA      : one elected lane issues the 3 x (CIP/8 + KE/8) tcgen05.mma of a row
+//   warps 0-15  epilogue : TMEM -> registers -> bias + activation (+ derivative) -> coalesced global stores
+//   warps 16-19 loaders  : global x row -> registers -> tf32 split -> A_X image (two stages)
+//   warp  20    MMA      : one elected lane issues the 3 x (CIP/8 + KE/8) tcgen05.mma of a row
 // The roles hand rows to each other through mbarriers (A_X full/empty, D full/empty), so loading row r+1,
 // the tensor-core work of row r and the epilogue of row r-1 overlap inside one persistent CTA per SM.
 // ----------------------------------------------------------------------------------------------
-constexpr int kWsEpiWarps = 8, kWsLoadWarps = 4;
+constexpr int kWsEpiWarps = 16, kWsLoadWarps = 4;   // the epilogue is latency-bound per warp: give it many warps
 constexpr int kWsThreads = (kWsEpiWarps + kWsLoadWarps + 1) * 32;
 
 struct SynthWsSmem {
@@ -503,20 +514,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
           }
         }
         __syncthreads();
-        for (int task = tid; task < oc * MW; task += nt) {
-          const int ol = task / MW, l = task - ol * MW;
+        // task = (row half, output channel, mode): two threads share an (o, l) pair, four rows each
+        for (int task = tid; task < 2 * oc * MW; task += nt) {
+          const int half = task / (oc * MW), t2 = task - half * (oc * MW);
+          const int ol = t2 / MW, l = t2 - ol * MW;
           const int o = o0 + ol;
-          float ar[kSynthMaxRows], ai[kSynthMaxRows];
+          const int r0 = half * (kSynthMaxRows / 2);
+          float ar[kSynthMaxRows / 2], ai[kSynthMaxRows / 2];
 #pragma unroll
-          for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
+          for (int rr = 0; rr < kSynthMaxRows / 2; ++rr) ar[rr] = ai[rr] = 0.f;
           const float2* sp = sps + ol * Q + l;
 #pragma unroll 4
           for (int k = 0; k < KH; ++k) {
             const float2 sv = sp[k * MW];
 #pragma unroll
-            for (int rr = 0; rr < kSynthMaxRows; ++rr) {
-              if (rr < trows) {
-                const float2 e = twr[rr * KH + k];
+            for (int rr = 0; rr < kSynthMaxRows / 2; ++rr) {
+              if (r0 + rr < trows) {
+                const float2 e = twr[(r0 + rr) * KH + k];
                 ar[rr] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[rr]));
                 ai[rr] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[rr]));
               }
@@ -525,12 +539,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
           const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
           const int off = kmajor_off(o, 2 * l, CO);
 #pragma unroll
-          for (int rr = 0; rr < kSynthMaxRows; ++rr) {
-            if (rr < trows) {
+          for (int rr = 0; rr < kSynthMaxRows / 2; ++rr) {
+            if (r0 + rr < trows) {
               float h0, l0, h1, l1;
               split_tf32(ar[rr] * f, h0, l0);
               split_tf32(-ai[rr] * f, h1, l1);
-              unsigned char* base = bu + (2 * rr) * so.bu_one + off;
+              unsigned char* base = bu + (2 * (r0 + rr)) * so.bu_one + off;
               *reinterpret_cast<float2*>(base) = make_float2(h0, h1);
               *reinterpret_cast<float2*>(base + so.bu_one) = make_float2(l0, l1);
             }
@@ -544,9 +558,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
     const long long t_roles0 = clock64();
 
     if (warp < kWsEpiWarps) {
-      // ===== epilogue warps =====
+      // ===== epilogue warps: lane quadrant wq of TMEM, column slice wg =====
       const int wq = warp & 3, wg = warp >> 2;
-      const int ncol_half = CO / 2;
+      const int ncol_per = CO / (kWsEpiWarps / 4);          // columns per warp (multiple of 8)
       const int yl = wq * 32 + lane;
       const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
       for (int rr = 0; rr < trows; ++rr) {
@@ -556,31 +570,33 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
         fence_after_sync();
         const long long te1 = clock64();
         if (warp == 0) DENO_DBG_ADD(1, te1 - te0);                       // slot 1: epilogue waits for D
-        const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(st * 3 * CO + wg * ncol_half);
+        const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(st * 3 * CO + wg * ncol_per);
         const long long pbase = obase_b + (long long)(x0 + rr) * W + y0 + yl;
-        for (int c0 = 0; c0 < ncol_half; c0 += 16) {
-          float v[16], v1[16], v2[16];
-          tmem_ld16(tb + c0, v);
-          tmem_ld16(tb + CO + c0, v1);
-          tmem_ld16(tb + 2 * CO + c0, v2);
-          if (c0 + 16 >= ncol_half) {          // last TMEM read of this row by this thread: release the buffer early
+        for (int c0 = 0; c0 < ncol_per; c0 += 8) {
+          float v[8], v1[8], v2[8];
+          tmem_ld8(tb + c0, v);
+          tmem_ld8(tb + CO + c0, v1);
+          tmem_ld8(tb + 2 * CO + c0, v2);
+          if (c0 + 8 >= ncol_per) {            // last TMEM read of this row by this thread: release the buffer early
             fence_before_sync();
             mbar_arrive(&bar_d_empty[st]);
           }
           if (yl < ny) {
+            float zz[8], yv[8], dv[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int o = wg * ncol_half + c0 + j;
-              const float zz = (v[j] + bias_s[o]) + (v1[j] + v2[j]);
-              const long long a = pbase + (long long)o * p.g.sc;
-              if (p.z != nullptr) {
-                float yv, dv;
-                act_apply_grad(ACT, zz, yv, dv);
-                p.z[a] = dv;
-                p.y[a] = yv;
-              } else {
-                p.y[a] = act_apply(ACT, zz);
+            for (int j = 0; j < 8; ++j) zz[j] = (v[j] + bias_s[wg * ncol_per + c0 + j]) + (v1[j] + v2[j]);
+            if (p.z != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) act_apply_grad(ACT, zz[j], yv[j], dv[j]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const long long a = pbase + (long long)(wg * ncol_per + c0 + j) * p.g.sc;
+                p.z[a] = dv[j];
+                p.y[a] = yv[j];
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) p.y[pbase + (long long)(wg * ncol_per + c0 + j) * p.g.sc] = act_apply(ACT, zz[j]);
             }
           }
         }
