@@ -386,12 +386,12 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
 // ----------------------------------------------------------------------------------------------
 // plane_synthesis_ws: warp-specialised version of plane_synthesis_tc (same math, same operand images).
 //   warps 0-15  epilogue : TMEM -> registers -> bias + activation (+ derivative) -> coalesced global stores
-//   warps 16-19 loaders  : global x row -> registers -> tf32 split -> A_X image (two stages)
-//   warp  20    MMA      : one elected lane issues the 3 x (CIP/8 + KE/8) tcgen05.mma of a row
+//   warps 16-23 loaders  : global x row -> registers (two rows in flight) -> tf32 split -> A_X image (two stages)
+//   warp  24    MMA      : one elected lane issues the 3 x (CIP/8 + KE/8) tcgen05.mma of a row
 // The roles hand rows to each other through mbarriers (A_X full/empty, D full/empty), so loading row r+1,
 // the tensor-core work of row r and the epilogue of row r-1 overlap inside one persistent CTA per SM.
 // ----------------------------------------------------------------------------------------------
-constexpr int kWsEpiWarps = 16, kWsLoadWarps = 4;   // the epilogue is latency-bound per warp: give it many warps
+constexpr int kWsEpiWarps = 16, kWsLoadWarps = 8;   // the epilogue is latency-bound per warp: give it many warps
 constexpr int kWsThreads = (kWsEpiWarps + kWsLoadWarps + 1) * 32;
 
 struct SynthWsSmem {
@@ -603,23 +603,26 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
         if (warp == 0) DENO_DBG_ADD(2, clock64() - te1);                 // slot 2: epilogue work per row
       }
     } else if (warp < kWsEpiWarps + kWsLoadWarps) {
-      // ===== loader warps: one thread = one point of the row, all channel quads =====
-      const int pt = tid - kWsEpiWarps * 32;
+      // ===== loader warps: one thread = one point of the row and half of the channel quads; two rows of
+      // loads are kept in flight (register double buffer) so the DRAM latency never gates the MMA warp =====
+      const int lt = tid - kWsEpiWarps * 32;
+      const int pt = lt & 127, chalf = lt >> 7;
+      constexpr int NQ = NCQ / 2 > 0 ? NCQ / 2 : 1;        // channel quads per loader thread
+      const int cq0 = chalf * NQ;
       const long long ubase = plane_base(p.g, bp, 0) + y0 + pt;
-      float xr[NCQ][4];
-      auto prefetch = [&](int rr) {
+      float xa[NQ][4], xb[NQ][4];
+      auto prefetch = [&](int rr, float (&xr)[NQ][4]) {
         const long long rowoff = ubase + (long long)(x0 + rr) * W;
 #pragma unroll
-        for (int cq = 0; cq < NCQ; ++cq) {
+        for (int c = 0; c < NQ; ++c) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int ch = cq * 4 + j;
-            xr[cq][j] = (pt < ny && ch < CI) ? p.u[rowoff + (long long)ch * p.g.sc] : 0.f;
+            const int ch = (cq0 + c) * 4 + j;
+            xr[c][j] = (pt < ny && ch < CI && cq0 + c < NCQ) ? p.u[rowoff + (long long)ch * p.g.sc] : 0.f;
           }
         }
       };
-      prefetch(0);
-      for (int rr = 0; rr < trows; ++rr) {
+      auto publish = [&](int rr, float (&xr)[NQ][4]) {
         const int i = it0 + rr, st = i & 1;
         const long long tl0 = clock64();
         mbar_wait(&bar_ax_empty[st], (uint32_t)(((i >> 1) & 1) ^ 1));
@@ -627,20 +630,31 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
         if (warp == kWsEpiWarps) DENO_DBG_ADD(3, tl1 - tl0);             // slot 3: loader waits for a free stage
         unsigned char* axh = smem + so.ax + st * 2 * so.ax_one;
 #pragma unroll
-        for (int cq = 0; cq < NCQ; ++cq) {
-          float4 hi, lo;
-          split_tf32(xr[cq][0], hi.x, lo.x);
-          split_tf32(xr[cq][1], hi.y, lo.y);
-          split_tf32(xr[cq][2], hi.z, lo.z);
-          split_tf32(xr[cq][3], hi.w, lo.w);
-          const int off = kmajor_off(pt, cq * 4, 128);
-          *reinterpret_cast<float4*>(axh + off) = hi;
-          *reinterpret_cast<float4*>(axh + so.ax_one + off) = lo;
+        for (int c = 0; c < NQ; ++c) {
+          if (cq0 + c < NCQ) {
+            float4 hi, lo;
+            split_tf32(xr[c][0], hi.x, lo.x);
+            split_tf32(xr[c][1], hi.y, lo.y);
+            split_tf32(xr[c][2], hi.z, lo.z);
+            split_tf32(xr[c][3], hi.w, lo.w);
+            const int off = kmajor_off(pt, (cq0 + c) * 4, 128);
+            *reinterpret_cast<float4*>(axh + off) = hi;
+            *reinterpret_cast<float4*>(axh + so.ax_one + off) = lo;
+          }
         }
         fence_proxy_async();
         mbar_arrive(&bar_ax_full[st]);
         if (warp == kWsEpiWarps) DENO_DBG_ADD(4, clock64() - tl1);       // slot 4: loader split + store (incl. wait for LDG data)
-        if (rr + 1 < trows) prefetch(rr + 1);
+      };
+      prefetch(0, xa);
+      if (trows > 1) prefetch(1, xb);
+      for (int rr = 0; rr < trows; rr += 2) {
+        publish(rr, xa);
+        if (rr + 2 < trows) prefetch(rr + 2, xa);
+        if (rr + 1 < trows) {
+          publish(rr + 1, xb);
+          if (rr + 3 < trows) prefetch(rr + 3, xb);
+        }
       }
     } else {
       // ===== MMA warp =====
