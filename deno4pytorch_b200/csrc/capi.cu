@@ -586,7 +586,7 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
 #ifndef DENO_EMULATE
 // Tensor-core synthesis: returns DENO_OK after launching, or -1 when the shape is outside what the
 // tcgen05 kernel covers (caller falls back to the SIMT kernel).
-int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
+int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
   const int CI = p.g.C, CO = p.CO;
   if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;   // CO / 4 columns per epilogue warp, multiples of 8
   const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
@@ -649,6 +649,83 @@ int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int
 #undef DENO_TC_CASE
 #undef DENO_TC_CASE2
   return check_launch("plane_synthesis_tc", st);
+}
+
+// Bulk-synchronous variant (two CTAs per SM, every warp does every phase).  Measured faster than the
+// warp-specialised kernel at the Darcy shape (profiles/r1t_phase_probe.txt), so it is the default;
+// DENO_SYNTH_WS=1 selects the warp-specialised kernel.
+int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
+  const int CI = p.g.C, CO = p.CO;
+  if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;
+  const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
+  const TwLayout tl = tw_layout(s);
+  // stage A stages the packed spectrum through the A_X area: at least one output channel must fit
+  if (2 * CIP * 128 * 4 - round_up(kSynthMaxRows * p.g.KH, 2) * 8 < p.g.KH * p.g.MW * 8) return -1;
+  int bestR = 0;
+  double best_eff = -1.0;
+  const int maxR = p.g.H > 1 ? (p.g.H < kSynthMaxRows ? p.g.H : kSynthMaxRows) : 1;
+  for (int R = maxR; R >= 1; --R) {
+    const size_t bytes = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, R).total;
+    if (bytes > (size_t)kMaxSmemBytes) continue;
+    int per_sm = (int)((228 * 1024) / (bytes + 2048));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm * 6 * CO > 512) per_sm = 512 / (6 * CO) > 0 ? 512 / (6 * CO) : 1;   // TMEM columns per SM
+    if (per_sm < 1) per_sm = 1;
+    const long long ctas = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks;
+    const long long slots = 148LL * per_sm;
+    const long long waves = (ctas + slots - 1) / slots;
+    double eff = (double)ctas / (double)(waves * slots);
+    eff *= (1.0 - 0.25 / R);               // per-CTA setup (weights, twiddles, stage A) amortises over R rows
+    if (eff > best_eff + 1e-9) { best_eff = eff; bestR = R; }
+  }
+  if (bestR == 0) return -1;
+  tc::SynthTcParams q;
+  p.R = bestR;
+  p.PTS = bestR * p.g.W;
+  p.tiles = (p.g.H + bestR - 1) / bestR;
+  q.s = p;
+  q.ae = tw.synth_ae;
+  q.KE = tl.KE;
+  q.nchunks = tl.nchunks;
+  int cols = 32;
+  while (cols < 6 * CO) cols *= 2;
+  if (cols > 512) return -1;
+  q.tmem_cols = cols;
+  const size_t smem = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, bestR).total;
+  const int grid = s.B * s.X * p.tiles * tl.nchunks;
+  int rc = DENO_OK;
+#define DENO_TC_CASE2(ACT, CIPV)                                                                    \
+  {                                                                                                 \
+    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV>, smem, "plane_synthesis_tc");          \
+    if (rc != DENO_OK) return rc;                                                                   \
+    prof_before(label, st);                                                                         \
+    tc::plane_synthesis_tc_kernel<ACT, CIPV><<<dim3(grid), dim3(256), smem, st>>>(q);               \
+  }
+#define DENO_TC_CASE(ACT)                                                                           \
+  case ACT:                                                                                         \
+    if (CIP == 8) DENO_TC_CASE2(ACT, 8)                                                             \
+    else if (CIP == 16) DENO_TC_CASE2(ACT, 16)                                                      \
+    else if (CIP == 32) DENO_TC_CASE2(ACT, 32)                                                      \
+    else DENO_TC_CASE2(ACT, 64)                                                                     \
+    break;
+  switch (act) {
+    DENO_TC_CASE(ACT_IDENTITY)
+    DENO_TC_CASE(ACT_GELU)
+    DENO_TC_CASE(ACT_SILU)
+    DENO_TC_CASE(ACT_RELU)
+    DENO_TC_CASE(ACT_TANH)
+    DENO_TC_CASE(ACT_LEAKYRELU)
+    default: return fail(DENO_E_INVALID, "unknown activation id");
+  }
+#undef DENO_TC_CASE
+#undef DENO_TC_CASE2
+  return check_launch("plane_synthesis_tc", st);
+}
+
+int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
+  const char* e = getenv("DENO_SYNTH_WS");
+  if (e != nullptr && e[0] == '1') return try_launch_synthesis_ws(s, p, tw, act, label, st);
+  return try_launch_synthesis_bulk(s, p, tw, act, label, st);
 }
 #endif
 
