@@ -884,6 +884,22 @@ const char* deno_last_error(void) { return g_error.c_str(); }
 
 int deno_spectral_last_launch_count(void) { return g_launches; }
 
+int deno_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, const float* step, void* stream) {
+  g_launches = 0;
+  if (!p || !g || !m || !v || !step) return fail(DENO_E_INVALID, "deno_adam_step: null pointer argument");
+  if (n == 0) return DENO_OK;
+  AdamParams a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.n = (long long)n;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = ((long long)n + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  prof_before("adam_flat", st);
+  DENO_LAUNCH(adam_flat_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a);
+  return check_launch("adam_flat", st);
+}
+
 int deno_debug_read(long long* host, int count, int clear) {
 #ifndef DENO_EMULATE
   if (host == nullptr || count < 0 || count > 64) return fail(DENO_E_INVALID, "deno_debug_read: bad arguments");

@@ -657,4 +657,37 @@ __global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// adam_flat: one fused Adam step over a flat fp32 parameter buffer (complex64 weights as their real
+// view, which is also how torch.optim.Adam treats them).  Same update as torch.optim.Adam(amsgrad=False):
+//   g += wd * p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// The step count t is read from device memory so the launch can be replayed from a CUDA graph.
+// ----------------------------------------------------------------------------------------------
+struct AdamParams {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  float lr, beta1, beta2, eps, weight_decay;
+  const float* step;   // device scalar: t (already incremented for this step)
+};
+
+__global__ void adam_flat_kernel(AdamParams a) {
+  const float t = a.step[0];
+  const float bc1 = 1.0f - powf(a.beta1, t);
+  const float bc2 = 1.0f - powf(a.beta2, t);
+  const float step_size = a.lr / bc1;
+  const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const float pv = a.p[i];
+    const float gv = fmaf(a.weight_decay, pv, a.g[i]);
+    const float mv = fmaf(a.beta1, a.m[i], (1.0f - a.beta1) * gv);
+    const float vv = fmaf(a.beta2, a.v[i], (1.0f - a.beta2) * gv * gv);
+    a.m[i] = mv;
+    a.v[i] = vv;
+    a.p[i] = pv - step_size * (mv / fmaf(sqrtf(vv), inv_sqrt_bc2, a.eps));
+  }
+}
+
 }  // namespace deno

@@ -91,6 +91,56 @@ class FlatGradients:
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class FlatParameters:
+    """Moves every trainable parameter into ONE flat fp32 buffer (``p.data`` becomes a view; names, shapes and
+    dtypes - hence the state dict - are unchanged) and pairs it with a ``FlatGradients`` buffer of the same
+    layout, so the optimiser can be a single fused kernel over flat arrays."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.grads = FlatGradients(params)
+        self.params = self.grads.params
+        self.flat = torch.zeros_like(self.grads.flat)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                real_n = p.numel() * (2 if p.is_complex() else 1)
+                seg = self.flat[off:off + real_n]
+                src = torch.view_as_real(p.data).reshape(-1) if p.is_complex() else p.data.reshape(-1)
+                seg.copy_(src)
+                p.data = torch.view_as_complex(seg.view(-1, 2)).view(p.shape) if p.is_complex() else seg.view(p.shape)
+                off += (real_n + 3) // 4 * 4
+
+
+class FlatAdam:
+    """torch.optim.Adam's update (no amsgrad) as ONE kernel launch over ``FlatParameters`` (libdeno_spectral's
+    ``deno_adam_step``).  The step counter lives on the device, so ``step()`` can be captured in a CUDA graph."""
+
+    def __init__(self, flat: FlatParameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.flat = flat
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=flat.flat.device)
+
+    def zero_grad(self):
+        self.flat.grads.zero()
+
+    def step(self):
+        from . import _capi
+        from ._lib import lib
+        L = lib()
+        f = self.flat
+        self.step_t.add_(1.0)
+        with torch.cuda.device(f.flat.device):
+            rc = L.deno_adam_step(f.flat.data_ptr(), f.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
+                                  self.exp_avg_sq.data_ptr(), f.flat.numel(), self.lr, self.betas[0], self.betas[1],
+                                  self.eps, self.weight_decay, self.step_t.data_ptr(),
+                                  torch.cuda.current_stream(f.flat.device).cuda_stream)
+        _capi.check(L, rc, "deno_adam_step")
+        from .functional import _LAUNCHES
+        _LAUNCHES["count"] += 1
+
+
 def shard_batch(t: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
     """This rank's contiguous slice of a global batch (batch-sharded DP; no data-path collective)."""
     n = t.shape[0]

@@ -15,14 +15,14 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from .parallel import FlatGradients
+from .parallel import FlatAdam, FlatGradients, FlatParameters
 
 
 class TrainStep:
     def __init__(self, model: torch.nn.Module, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor, *,
                  lr: float = 1e-3, betas=(0.7, 0.9), weight_decay: float = 1e-4,
                  loss_fn: Callable = F.mse_loss, forward_fn: Optional[Callable] = None,
-                 use_graph: bool = True, warmup: int = 3, group=None):
+                 use_graph: bool = True, warmup: int = 3, group=None, fused_adam: bool = True):
         """``x``/``grid``/``target`` are example device tensors fixing the shapes; later calls copy new
         data into static buffers.  ``forward_fn(model, x, grid, target) -> loss`` overrides the default
         single model call (e.g. the 10-step autoregressive rollout of Demo/Turbulence_2d+t)."""
@@ -32,9 +32,15 @@ class TrainStep:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.sx, self.sg, self.st = x.clone(), grid.clone(), target.clone()
-        self.grads = FlatGradients(model.parameters())
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
-                                    capturable=use_graph, foreach=True)
+        if fused_adam and x.is_cuda:
+            self.flat_params = FlatParameters(model.parameters())
+            self.grads = self.flat_params.grads
+            self.opt = FlatAdam(self.flat_params, lr=lr, betas=betas, weight_decay=weight_decay)
+        else:
+            self.flat_params = None
+            self.grads = FlatGradients(model.parameters())
+            self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
+                                        capturable=use_graph, foreach=True)
         self.loss = torch.zeros((), device=x.device)
         self.use_graph = use_graph
         self._g_bwd = self._g_opt = None

@@ -112,6 +112,16 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
                       float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/*
+ * One fused Adam step over flat fp32 buffers (all device pointers, `n` elements each), replacing the per-tensor
+ * foreach Adam of the reference demos (`torch.optim.Adam(..., betas=(0.7, 0.9), weight_decay=1e-4)`,
+ * /root/reference/Demo/Darcy_2d/run_FNO&UNet.py:209).  Same update rule as torch.optim.Adam (no amsgrad); complex
+ * parameters are passed as their real view.  `step` is a DEVICE scalar holding the 1-based step count as float,
+ * so the call can be captured in a CUDA graph.
+ */
+int deno_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, const float* step, void* stream);
+
 /* Number of kernels the last fwd / bwd call on this thread enqueued (bench.py's gpu_launches). */
 int deno_spectral_last_launch_count(void);
 

@@ -250,3 +250,34 @@ def test_training_step_matches_oracle_adam():
         assert abs(loss.item() - ref_loss) / ref_loss < 1e-5
     for k, p in model.named_parameters():
         assert rel_l2(p.detach().cpu(), port.params[k].detach()) < 1e-5, k
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainstep_fused_adam_and_graph_match_oracle(use_graph):
+    """TrainStep (flat parameters + one fused Adam kernel, optionally CUDA-graph replay) tracks the CPU port's
+    torch.optim.Adam for four steps on changing batches."""
+    import deno4pytorch_b200 as d4
+    from deno4pytorch_b200.training import TrainStep
+    from oracle import fno_port
+    torch.manual_seed(8)
+    cfg = dict(in_dim=1, out_dim=1, modes=(4, 4), width=8, depth=2, hidden=16, steps=1, padding=3)
+    model = d4.FNO2d(**cfg)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    xs = [torch.randn(4, 13, 13, 1, generator=gen) for _ in range(4)]
+    ts = [torch.randn(4, 13, 13, 1, generator=gen) for _ in range(4)]
+    grid = fno_port.make_grid(4, (13, 13))
+    port = fno_port.PortTrainer(params, ndim=2, modes=(4, 4), depth=2, padding=3)
+    model = model.to(_dev())
+    step = TrainStep(model, xs[0].to(_dev()), grid.to(_dev()), ts[0].to(_dev()), use_graph=use_graph, warmup=1)
+    # TrainStep's warm-up / capture ran optimiser steps on the example batch: restart both sides from the same state
+    model.load_state_dict({k: v.to(_dev()) for k, v in params.items()})
+    step.opt.exp_avg.zero_(); step.opt.exp_avg_sq.zero_(); step.opt.step_t.zero_()
+    for x, t in zip(xs, ts):
+        ref_loss = port.step(x, grid, t)
+        loss = float(step(x.to(_dev()), grid.to(_dev()), t.to(_dev())))
+        assert abs(loss - ref_loss) / ref_loss < 1e-5
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(params.keys())
+    for k, p in model.named_parameters():
+        assert rel_l2(p.detach().cpu(), port.params[k].detach()) < 1e-5, k
