@@ -798,7 +798,7 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
   p.vec4 = (HW % 4 == 0) ? 1 : 0;
   const tc::WgradTcSmem sm = tc::wgrad_tc_smem(NS, COs, CIs);
   if (sm.total > kMaxSmemBytes - 1024) return -1;
-  const int need = (NS * (s.CO + s.CI) * 16 + 255) / 256;
+  const int need = (NS * (s.CO + s.CI) * (tc::kWgradKT / 4) + 255) / 256;
   if (need > 16) return -1;
   int grid = 148;                         // one persistent CTA per SM (the accumulators take up to 512 TMEM columns)
   if (grid > p.ntiles) grid = p.ntiles;
@@ -808,7 +808,7 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
     rc = allow_smem(tc::bypass_wgrad_tc_kernel<NITV>, (size_t)sm.total, "bypass_wgrad_tc");        \
     if (rc != DENO_OK) return -2;                                                                  \
     prof_before("bypass_wgrad_tc", st);                                                            \
-    tc::bypass_wgrad_tc_kernel<NITV><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);          \
+    tc::bypass_wgrad_tc_kernel<NITV><<<dim3(grid), dim3(tc::kWgradThreads), (size_t)sm.total, st>>>(p);          \
   }
   if (need <= 4) DENO_WG_CASE(4)
   else if (need <= 8) DENO_WG_CASE(8)

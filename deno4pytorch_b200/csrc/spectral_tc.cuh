@@ -988,10 +988,13 @@ struct WgradTcParams {
   int vec4;              // H*W % 4 == 0: 16-byte global loads are aligned
 };
 
-constexpr int kWgradKT = 64;   // points per tile
+constexpr int kWgradKT = 32;        // points per tile (two shared-memory stages of operand images)
+constexpr int kWgradThreads = 288;  // 8 loader warps + 1 MMA warp
 
 struct WgradTcSmem {
-  int g_hi, g_lo, x_hi, x_lo, total;
+  int stage[2];          // byte offset of each stage: [g_hi | g_lo | x_hi | x_lo]
+  int g_lo, x_hi, x_lo;  // offsets inside a stage (g_hi = 0)
+  int total;
   int g_lbo, x_lbo;
 };
 
@@ -1001,20 +1004,26 @@ __host__ __device__ inline WgradTcSmem wgrad_tc_smem(int NS, int COs, int CIs) {
   const int nrows = NS * CIs;
   m.g_lbo = 16 * mrows + 16;             // padded K-direction strides: conflict-free 16-byte stores
   m.x_lbo = 16 * nrows + 16;
-  int off = 0;
-  m.g_hi = off; off += (kWgradKT / 4) * m.g_lbo;
-  m.g_lo = off; off += (kWgradKT / 4) * m.g_lbo;
-  m.x_hi = off; off += (kWgradKT / 4) * m.x_lbo;
-  m.x_lo = off; off += (kWgradKT / 4) * m.x_lbo;
-  m.total = off + 256;
+  const int g_one = (kWgradKT / 4) * m.g_lbo, x_one = (kWgradKT / 4) * m.x_lbo;
+  m.g_lo = g_one;
+  m.x_hi = 2 * g_one;
+  m.x_lo = 2 * g_one + x_one;
+  const int stage_bytes = 2 * g_one + 2 * x_one;
+  m.stage[0] = 0;
+  m.stage[1] = stage_bytes;
+  m.total = 2 * stage_bytes + 256;
+  (void)COs;
   return m;
 }
 
-template <int NIT>   // (row, point-quad) items per thread: NS * (CO + CI) * 16 / 256 rounded up
-__global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p) {
+// 8 loader warps stream (row, point-quad) items global -> registers (two tiles in flight) -> tf32 split ->
+// operand images (two stages); warp 8 issues the MMAs.  Stages are handed over with mbarriers
+// (full: 256 loader arrivals; empty: tcgen05.commit), so loads, splitting and tensor-core work overlap.
+template <int NIT>   // items per loader thread and tile: NS * (CO + CI) * (kWgradKT / 4) / 256 rounded up
+__global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(WgradTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_done;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int CI = p.gx.C, CO = p.CO, NS = p.NS, COs = p.COs, CIs = p.CIs;
   const WgradTcSmem so = wgrad_tc_smem(NS, COs, CIs);
@@ -1022,113 +1031,132 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
   const int rows_per_slot = CO + CI;
   const int nrows = NS * rows_per_slot;      // rows streamed per tile
   const int N = NS * CIs;
+  constexpr int QPR = kWgradKT / 4;          // point quads per row
   uint32_t ncols = 32;
   while ((int)ncols < 3 * N) ncols *= 2;
 
   if (warp == 0) tmem_alloc(&tmem_slot, ncols);
   if (tid == 32) {
-    mbar_init(&mbar, 1);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      mbar_init(&bar_full[s2], 256);
+      mbar_init(&bar_empty[s2], 1);
+    }
+    mbar_init(&bar_done, 1);
     mbar_fence_init();
   }
-  for (int i = tid; i < so.total / 16; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  // The (row, point-quad) -> (slot, channel, image offset) map does not depend on the tile: decode it once.
-  // meta: bit 31 valid, bit 30 "gz row", bits 28..29 slot j, bits 0..27 byte offset inside the hi image.
-  float4 regs[NIT];
-  uint32_t meta[NIT];
-  int roff[NIT];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int item = it * 256 + tid;
-    const int row = item >> 4, pq = item & 15;
-    meta[it] = 0u;
-    roff[it] = 0;
-    if (row < nrows) {
-      const int j = row / rows_per_slot, r = row - j * rows_per_slot;
-      const bool isg = r < CO;
-      const int ir = isg ? j * COs + r : j * CIs + (r - CO);
-      const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * (isg ? so.g_lbo : so.x_lbo);
-      meta[it] = 0x80000000u | (isg ? 0x40000000u : 0u) | ((uint32_t)j << 28) | (uint32_t)off;
-      roff[it] = (int)((isg ? r : r - CO) * p.gx.sc) + pq * 4;
-    }
-  }
-  auto prefetch = [&](int t) {
-    const int grp = t / p.tiles_per_plane;
-    const int p0 = (t - grp * p.tiles_per_plane) * kWgradKT;
-    long long gb[4], xb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int bp = min(grp * NS + j, p.nbatch - 1);
-      gb[j] = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
-      xb[j] = plane_base(p.gx, bp, 0) + p0;
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const uint32_t m = meta[it];
-      const int j = (int)((m >> 28) & 3u);
-      if ((m & 0x80000000u) && grp * NS + j < p.nbatch) {
-        const bool isg = (m & 0x40000000u) != 0u;
-        const long long base = isg ? (j == 0 ? gb[0] : (j == 1 ? gb[1] : (j == 2 ? gb[2] : gb[3])))
-                                   : (j == 0 ? xb[0] : (j == 1 ? xb[1] : (j == 2 ? xb[2] : xb[3])));
-        const float* src = (isg ? p.gz : p.x) + base + roff[it];
-        const int pt = p0 + ((it * 256 + tid) & 15) * 4;
-        if (p.vec4 && pt + 3 < HW) {
-          v = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (pt + 0 < HW) v.x = src[0];
-          if (pt + 1 < HW) v.y = src[1];
-          if (pt + 2 < HW) v.z = src[2];
-          if (pt + 3 < HW) v.w = src[3];
-        }
-      }
-      regs[it] = v;
-    }
-  };
-  int t = blockIdx.x;
-  if (t < p.ntiles) prefetch(t);
-
+  for (int i = tid; i < so.total / 16; i += kWgradThreads) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t idesc = make_idesc_tf32(128, N);
-  const uint32_t sbase = smem_u32(smem);
-  uint32_t phase = 0, accum = 0;
-  bool pending = false;
+  // tiles of this CTA: t = blockIdx.x + n * gridDim.x
+  const int ntile_cta = (p.ntiles > (int)blockIdx.x) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  for (; t < p.ntiles; t += gridDim.x) {
-    if (pending) {                                   // previous tile's MMAs still read the images
-      mbar_wait(&mbar, phase);
-      phase ^= 1;
-    }
+  if (warp < 8) {
+    // ===== loader warps =====
+    // The (row, point-quad) -> (slot, channel, image offset) map does not depend on the tile: decode it once.
+    // meta: bit 31 valid, bit 30 "gz row", bits 28..29 slot j, bits 0..27 byte offset inside the hi image.
+    uint32_t meta[NIT];
+    int roff[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-      const uint32_t m = meta[it];
-      if (m & 0x80000000u) {
-        float4 hi, lo;
-        split_tf32(regs[it].x, hi.x, lo.x);
-        split_tf32(regs[it].y, hi.y, lo.y);
-        split_tf32(regs[it].z, hi.z, lo.z);
-        split_tf32(regs[it].w, hi.w, lo.w);
-        const bool isg = (m & 0x40000000u) != 0u;
-        unsigned char* dst = smem + (isg ? so.g_hi : so.x_hi) + (m & 0x0FFFFFFFu);
-        *reinterpret_cast<float4*>(dst) = hi;
-        *reinterpret_cast<float4*>(dst + (isg ? so.g_lo - so.g_hi : so.x_lo - so.x_hi)) = lo;
+      const int item = it * 256 + tid;
+      const int row = item / QPR, pq = item - row * QPR;
+      meta[it] = 0u;
+      roff[it] = 0;
+      if (row < nrows) {
+        const int j = row / rows_per_slot, r = row - j * rows_per_slot;
+        const bool isg = r < CO;
+        const int ir = isg ? j * COs + r : j * CIs + (r - CO);
+        const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * (isg ? so.g_lbo : so.x_lbo);
+        meta[it] = 0x80000000u | (isg ? 0x40000000u : 0u) | ((uint32_t)j << 28) | (uint32_t)off;
+        roff[it] = (int)((isg ? r : r - CO) * p.gx.sc) + pq * 4;
       }
     }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {                                 // warp-uniform issue loop, MMA predicated on the elected lane
+    float4 ra[NIT], rb[NIT];
+    auto prefetch = [&](int n, float4 (&regs)[NIT]) {
+      const int t = (int)blockIdx.x + n * (int)gridDim.x;
+      const int grp = t / p.tiles_per_plane;
+      const int p0 = (t - grp * p.tiles_per_plane) * kWgradKT;
+      long long gb[4], xb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bp = min(grp * NS + j, p.nbatch - 1);
+        gb[j] = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
+        xb[j] = plane_base(p.gx, bp, 0) + p0;
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t m = meta[it];
+        const int j = (int)((m >> 28) & 3u);
+        if ((m & 0x80000000u) && grp * NS + j < p.nbatch) {
+          const bool isg = (m & 0x40000000u) != 0u;
+          const long long base = isg ? (j == 0 ? gb[0] : (j == 1 ? gb[1] : (j == 2 ? gb[2] : gb[3])))
+                                     : (j == 0 ? xb[0] : (j == 1 ? xb[1] : (j == 2 ? xb[2] : xb[3])));
+          const float* src = (isg ? p.gz : p.x) + base + roff[it];
+          const int pt = p0 + ((it * 256 + tid) % QPR) * 4;
+          if (p.vec4 && pt + 3 < HW) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (pt + 0 < HW) v.x = src[0];
+            if (pt + 1 < HW) v.y = src[1];
+            if (pt + 2 < HW) v.z = src[2];
+            if (pt + 3 < HW) v.w = src[3];
+          }
+        }
+        regs[it] = v;
+      }
+    };
+    auto publish = [&](int n, float4 (&regs)[NIT]) {
+      const int st = n & 1;
+      mbar_wait(&bar_empty[st], (uint32_t)(((n >> 1) & 1) ^ 1));      // MMAs of tile n-2 are done with this stage
+      unsigned char* base = smem + so.stage[st];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const uint32_t m = meta[it];
+        if (m & 0x80000000u) {
+          float4 hi, lo;
+          split_tf32(regs[it].x, hi.x, lo.x);
+          split_tf32(regs[it].y, hi.y, lo.y);
+          split_tf32(regs[it].z, hi.z, lo.z);
+          split_tf32(regs[it].w, hi.w, lo.w);
+          const bool isg = (m & 0x40000000u) != 0u;
+          unsigned char* dst = base + (isg ? 0 : so.x_hi) + (m & 0x0FFFFFFFu);
+          *reinterpret_cast<float4*>(dst) = hi;
+          *reinterpret_cast<float4*>(dst + (isg ? so.g_lo : so.x_lo - so.x_hi)) = lo;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&bar_full[st]);
+    };
+    if (ntile_cta > 0) prefetch(0, ra);
+    if (ntile_cta > 1) prefetch(1, rb);
+    for (int n = 0; n < ntile_cta; n += 2) {
+      publish(n, ra);
+      if (n + 2 < ntile_cta) prefetch(n + 2, ra);
+      if (n + 1 < ntile_cta) {
+        publish(n + 1, rb);
+        if (n + 3 < ntile_cta) prefetch(n + 3, rb);
+      }
+    }
+  } else {
+    // ===== MMA warp =====
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint32_t sbase = smem_u32(smem);
+    const uint64_t inc_g = (uint64_t)((2 * so.g_lbo) >> 4), inc_x = (uint64_t)((2 * so.x_lbo) >> 4);
+    for (int n = 0; n < ntile_cta; ++n) {
+      const int st = n & 1;
+      mbar_wait(&bar_full[st], (uint32_t)((n >> 1) & 1));
       fence_after_sync();
-      const bool leader = elect_one();
-      uint64_t gh = make_desc(sbase + so.g_hi, so.g_lbo, 128), gl = make_desc(sbase + so.g_lo, so.g_lbo, 128);
-      uint64_t xh = make_desc(sbase + so.x_hi, so.x_lbo, 128), xl = make_desc(sbase + so.x_lo, so.x_lbo, 128);
-      const uint64_t inc_g = (uint64_t)((2 * so.g_lbo) >> 4), inc_x = (uint64_t)((2 * so.x_lbo) >> 4);
+      const uint32_t b0 = sbase + so.stage[st];
+      uint64_t gh = make_desc(b0, so.g_lbo, 128), gl = make_desc(b0 + so.g_lo, so.g_lbo, 128);
+      uint64_t xh = make_desc(b0 + so.x_hi, so.x_lbo, 128), xl = make_desc(b0 + so.x_lo, so.x_lbo, 128);
 #pragma unroll
       for (int s2 = 0; s2 < kWgradKT / 8; ++s2) {
-        const uint32_t acc = (accum == 0 && s2 == 0) ? 0u : 1u;
+        const uint32_t acc = (n == 0 && s2 == 0) ? 0u : 1u;
         if (leader) {
           mma_tf32(tmem, gh, xh, idesc, acc);              // hi * hi
           mma_tf32(tmem + N, gl, xh, idesc, acc);          // lo * hi
@@ -1136,20 +1164,20 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
         }
         gh += inc_g; gl += inc_g; xh += inc_x; xl += inc_x;
       }
-      if (leader) mma_commit(&mbar);
+      if (leader) mma_commit(&bar_empty[st]);
       __syncwarp();
     }
-    accum = 1;
-    pending = true;
-    if (t + (int)gridDim.x < p.ntiles) prefetch(t + gridDim.x);
+    if (leader) mma_commit(&bar_done);
+    __syncwarp();
   }
-  if (pending) mbar_wait(&mbar, phase);
+  // every warp: wait for the last MMAs, then warps 0-3 turn the accumulators into partials
+  if (ntile_cta > 0) mbar_wait(&bar_done, 0);
   fence_after_sync();
   // lane (j, o) of TMEM holds row o of slot j; its diagonal block sits at columns j*CIs .. j*CIs + CI
   if (warp < 4) {
     const int row = (warp & 3) * 32 + lane;
     const int j = row / COs, o = row - j * COs;
-    const bool valid = pending && j < NS && o < CO;
+    const bool valid = j < NS && o < CO;
     float* out = p.partial + ((long long)blockIdx.x * NS + (j < NS ? j : 0)) * (CO * CI) + (long long)o * CI;
     for (int c0 = 0; c0 < N; c0 += 16) {
       float v[16], v1[16], v2[16];
@@ -1161,7 +1189,7 @@ __global__ void __launch_bounds__(256, 1) bypass_wgrad_tc_kernel(WgradTcParams p
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int i = c0 + jj - j * CIs;
-          if (i >= 0 && i < CI) out[i] = v[jj] + (v1[jj] + v2[jj]);
+          if (i >= 0 && i < CI) out[i] = ntile_cta > 0 ? v[jj] + (v1[jj] + v2[jj]) : 0.f;
         }
       }
     }

@@ -23,14 +23,18 @@ ws = [torch.view_as_complex(torch.rand((Cc, Cc) + modes + (2,), generator=gen) /
 lw = (torch.randn((Cc, Cc) + (1,) * nd, generator=gen) / Cc ** 0.5).to(dev).requires_grad_(True)
 lb = torch.zeros(Cc, device=dev, requires_grad=True)
 L = lib()
-buf = (C.c_longlong * 16)()
+buf = (C.c_longlong * 32)()
+gy = torch.randn((B, Cc) + spatial, generator=gen).to(dev)
 for it in range(3):
+    L.deno_debug_read(buf, 32, 1)
     y = spectral_conv(x, ws, lw, lb, modes, "gelu")
+    y.backward(gy)
     torch.cuda.synchronize()
-    L.deno_debug_read(buf, 16, 1)
+    L.deno_debug_read(buf, 32, 0)
 names = ["unit setup", "epi wait D", "epi work", "load wait stage", "load split+sts", "mma wait A_X", "mma wait D free",
          "mma issue", "roles total", "rows"]
 vals = list(buf)[:10]
 print(name, {n: v for n, v in zip(names, vals)})
 rows = max(vals[9], 1)
 print("per row cycles:", {n: round(v / rows) for n, v in zip(names[1:9], vals[1:9])}, "setup per unit-row", round(vals[0] / rows))
+
