@@ -798,8 +798,8 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
   p.vec4 = (HW % 4 == 0) ? 1 : 0;
   const tc::WgradTcSmem sm = tc::wgrad_tc_smem(NS, COs, CIs);
   if (sm.total > kMaxSmemBytes - 1024) return -1;
-  const int need = (NS * (s.CO + s.CI) * (tc::kWgradKT / 4) + 255) / 256;
-  if (need > 16) return -1;
+  const int need = (NS * (s.CO + s.CI) * (tc::kWgradKT / 4) + tc::kWgradLoaders - 1) / tc::kWgradLoaders;
+  if (need > 8) return -1;
   int grid = 148;                         // one persistent CTA per SM (the accumulators take up to 512 TMEM columns)
   if (grid > p.ntiles) grid = p.ntiles;
   int rc;
@@ -810,9 +810,9 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
     prof_before("bypass_wgrad_tc", st);                                                            \
     tc::bypass_wgrad_tc_kernel<NITV><<<dim3(grid), dim3(tc::kWgradThreads), (size_t)sm.total, st>>>(p);          \
   }
-  if (need <= 4) DENO_WG_CASE(4)
-  else if (need <= 8) DENO_WG_CASE(8)
-  else DENO_WG_CASE(16)
+  if (need <= 2) DENO_WG_CASE(2)
+  else if (need <= 4) DENO_WG_CASE(4)
+  else DENO_WG_CASE(8)
 #undef DENO_WG_CASE
   if (check_launch("bypass_wgrad_tc", st) != DENO_OK) return -2;
   return grid * NS;

@@ -989,7 +989,8 @@ struct WgradTcParams {
 };
 
 constexpr int kWgradKT = 32;        // points per tile (two shared-memory stages of operand images)
-constexpr int kWgradThreads = 288;  // 8 loader warps + 1 MMA warp
+constexpr int kWgradLoaders = 512;  // loader threads (16 warps): bytes in flight per SM are what bounds this kernel
+constexpr int kWgradThreads = kWgradLoaders + 32;  // + 1 MMA warp
 
 struct WgradTcSmem {
   int stage[2];          // byte offset of each stage: [g_hi | g_lo | x_hi | x_lo]
@@ -1019,7 +1020,7 @@ __host__ __device__ inline WgradTcSmem wgrad_tc_smem(int NS, int COs, int CIs) {
 // 8 loader warps stream (row, point-quad) items global -> registers (two tiles in flight) -> tf32 split ->
 // operand images (two stages); warp 8 issues the MMAs.  Stages are handed over with mbarriers
 // (full: 256 loader arrivals; empty: tcgen05.commit), so loads, splitting and tensor-core work overlap.
-template <int NIT>   // items per loader thread and tile: NS * (CO + CI) * (kWgradKT / 4) / 256 rounded up
+template <int NIT>   // items per loader thread and tile: NS * (CO + CI) * (kWgradKT / 4) / kWgradLoaders rounded up
 __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(WgradTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
@@ -1038,7 +1039,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
   if (warp == 0) tmem_alloc(&tmem_slot, ncols);
   if (tid == 32) {
     for (int s2 = 0; s2 < 2; ++s2) {
-      mbar_init(&bar_full[s2], 256);
+      mbar_init(&bar_full[s2], kWgradLoaders);
       mbar_init(&bar_empty[s2], 1);
     }
     mbar_init(&bar_done, 1);
@@ -1053,7 +1054,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
   // tiles of this CTA: t = blockIdx.x + n * gridDim.x
   const int ntile_cta = (p.ntiles > (int)blockIdx.x) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp < 8) {
+  if (warp < kWgradLoaders / 32) {
     // ===== loader warps =====
     // The (row, point-quad) -> (slot, channel, image offset) map does not depend on the tile: decode it once.
     // meta: bit 31 valid, bit 30 "gz row", bits 28..29 slot j, bits 0..27 byte offset inside the hi image.
@@ -1061,7 +1062,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
     int roff[NIT];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-      const int item = it * 256 + tid;
+      const int item = it * kWgradLoaders + tid;
       const int row = item / QPR, pq = item - row * QPR;
       meta[it] = 0u;
       roff[it] = 0;
@@ -1096,7 +1097,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
           const long long base = isg ? (j == 0 ? gb[0] : (j == 1 ? gb[1] : (j == 2 ? gb[2] : gb[3])))
                                      : (j == 0 ? xb[0] : (j == 1 ? xb[1] : (j == 2 ? xb[2] : xb[3])));
           const float* src = (isg ? p.gz : p.x) + base + roff[it];
-          const int pt = p0 + ((it * 256 + tid) % QPR) * 4;
+          const int pt = p0 + ((it * kWgradLoaders + tid) % QPR) * 4;
           if (p.vec4 && pt + 3 < HW) {
             v = *reinterpret_cast<const float4*>(src);
           } else {
