@@ -771,7 +771,7 @@ template <bool FUSE_GZ>
 __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t mbar[2], bar_stage;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
   const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KHp = p.KHp;
@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   if (tid == 32) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
+    mbar_init(&bar_stage, 1);
     mbar_fence_init();
   }
   {  // constant operand images (final layout in global memory): straight copies
@@ -795,19 +796,49 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     float4* d2 = reinterpret_cast<float4*>(smem + so.a2);
     for (int i = tid; i < 2 * so.a2_one / 16; i += 256) d2[i] = s2[i];
   }
+  // Planes whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy per tensor
+  // (cp.async.bulk, completion on an mbarrier); others fall back to per-thread 4-byte cp.async.
+  const bool bulk = (HW % 4) == 0;
   auto prefetch_plane = [&](int q) {
     const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-    for (int i = tid; i < HW; i += 256) {
-      cp_async4(stage + i, p.u + base + i);
-      if (FUSE_GZ) cp_async4(stage_z + i, p.z + base + i);
+    if (bulk) {
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)HW * 4u;
+        const uint32_t bar = smem_u32(&bar_stage);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FUSE_GZ ? 2u * bytes : bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(stage)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
+        if (FUSE_GZ)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(stage_z)), "l"(p.z + base), "r"(bytes), "r"(bar) : "memory");
+      }
+    } else {
+      for (int i = tid; i < HW; i += 256) {
+        cp_async4(stage + i, p.u + base + i);
+        if (FUSE_GZ) cp_async4(stage_z + i, p.z + base + i);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   };
-  if ((int)blockIdx.x < p.nplanes) prefetch_plane(blockIdx.x);
-
+  // The (row, column-quad) items a thread turns into A-image core rows do not depend on the plane: decode once.
+  constexpr int kMaxItems = 12;
+  const int nitems = (Wp / 4) * Hp;
+  int it_src[kMaxItems], it_dst[kMaxItems];    // staging float offset (or -1), byte offset inside the hi image (or -1)
+#pragma unroll
+  for (int it = 0; it < kMaxItems; ++it) {
+    const int item = it * 256 + tid;
+    it_src[it] = -1;
+    it_dst[it] = -1;
+    if (item < nitems) {
+      const int yq = item / Hp, row = item - yq * Hp;
+      it_dst[it] = kmajor_off(row, yq * 4, Hp);
+      if (row < H) it_src[it] = row * W + yq * 4;
+    }
+  }
   fence_before_sync();
-  __syncthreads();
+  __syncthreads();                                     // barriers initialised, TMEM allocated, constant images stored
   fence_after_sync();
+  if ((int)blockIdx.x < p.nplanes) prefetch_plane(blockIdx.x);
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // three split-pass tiles per stage
   const uint32_t idesc = make_idesc_tf32(128, N1);
@@ -815,11 +846,16 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   const uint32_t lbo_a = 16 * Hp, lbo_e1 = 16 * N1, lbo_a2 = 16 * KHp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int wq = warp & 3, wg = warp >> 2;
   const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / mode k of D2)
-  uint32_t phase = 0;
+  uint32_t phase = 0, stage_phase = 0;
 
   for (int q = blockIdx.x; q < p.nplanes; q += gridDim.x) {
-    cp_async_wait_all();
+    const long long tq0 = clock64();
+    if (bulk) mbar_wait(&bar_stage, stage_phase);
+    else cp_async_wait_all();
+    stage_phase ^= 1;
     __syncthreads();                                   // staging(q) complete and visible
+    const long long tq1 = clock64();
+    if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);        // slot 32: wait for the staged plane
     if (FUSE_GZ) {                                     // gz = gy * act'(z): coalesced store, kept in staging
       const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
       for (int i = tid; i < HW; i += 256) {
@@ -830,7 +866,26 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
       __syncthreads();
     }
     // staging -> A images (hi / lo), rows fastest across lanes: 8 lanes fill one 128-byte core matrix
-    for (int item = tid; item < (Wp / 4) * Hp; item += 256) {
+#pragma unroll
+    for (int it = 0; it < kMaxItems; ++it) {
+      if (it_dst[it] >= 0) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (it_src[it] >= 0) {
+          const int y0c = (it * 256 + tid) / Hp * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (y0c + j < W) v[j] = stage[it_src[it] + j];
+        }
+        float4 hi, lo;
+        split_tf32(v[0], hi.x, lo.x);
+        split_tf32(v[1], hi.y, lo.y);
+        split_tf32(v[2], hi.z, lo.z);
+        split_tf32(v[3], hi.w, lo.w);
+        *reinterpret_cast<float4*>(smem + so.ab + it_dst[it]) = hi;
+        *reinterpret_cast<float4*>(smem + so.ab + so.a_one + it_dst[it]) = lo;
+      }
+    }
+    for (int item = kMaxItems * 256 + tid; item < nitems; item += 256) {   // planes larger than the register table
       const int yq = item / Hp, row = item - yq * Hp;
       float v[4];
 #pragma unroll
@@ -850,7 +905,11 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();                                   // A images complete; staging is free again
+    const long long tq2 = clock64();
+    if (warp == 1) DENO_DBG_ADD(33, tq2 - tq1);        // slot 33: (gz +) transform into A images
     if (q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);
+    const long long tq3 = clock64();
+    if (warp == 1) DENO_DBG_ADD(34, tq3 - tq2);        // slot 34: cp.async issue for the next plane
     if (warp == 0) {
       fence_after_sync();
       const bool leader = elect_one();
@@ -872,6 +931,8 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     }
     mbar_wait(&mbar[0], phase);
     fence_after_sync();
+    const long long tq4 = clock64();
+    if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);        // slot 35: stage-1 MMAs (issue + completion)
     // D1 -> B2 images (alias the A images, which the finished stage-1 MMAs no longer read)
     {
       const int ncol_half = N1 / 2;
@@ -908,6 +969,8 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
+    const long long tq5 = clock64();
+    if (warp == 1) DENO_DBG_ADD(36, tq5 - tq4);        // slot 36: D1 -> B2 conversion
     if (warp == 0) {
       fence_after_sync();
       const bool leader = elect_one();
@@ -928,6 +991,8 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     }
     mbar_wait(&mbar[1], phase);
     fence_after_sync();
+    const long long tq6 = clock64();
+    if (warp == 1) DENO_DBG_ADD(37, tq6 - tq5);        // slot 37: stage-2 MMAs
     // epilogue: lane k of D2 holds mode k; columns (2l, 2l+1) = (re, im)
     if (warp < 4) {
       float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
@@ -953,9 +1018,10 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     }
     fence_before_sync();
     __syncthreads();                                   // TMEM and the A/B2 area are reused by the next plane
+    if (warp == 1) { DENO_DBG_ADD(38, clock64() - tq6); DENO_DBG_ADD(39, 1); }   // slots 38/39: epilogue, planes
     phase ^= 1;
   }
-  cp_async_wait_all();
+  if (!bulk) cp_async_wait_all();
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);

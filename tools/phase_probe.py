@@ -23,14 +23,14 @@ ws = [torch.view_as_complex(torch.rand((Cc, Cc) + modes + (2,), generator=gen) /
 lw = (torch.randn((Cc, Cc) + (1,) * nd, generator=gen) / Cc ** 0.5).to(dev).requires_grad_(True)
 lb = torch.zeros(Cc, device=dev, requires_grad=True)
 L = lib()
-buf = (C.c_longlong * 32)()
+buf = (C.c_longlong * 48)()
 gy = torch.randn((B, Cc) + spatial, generator=gen).to(dev)
 for it in range(3):
-    L.deno_debug_read(buf, 32, 1)
+    L.deno_debug_read(buf, 48, 1)
     y = spectral_conv(x, ws, lw, lb, modes, "gelu")
     y.backward(gy)
     torch.cuda.synchronize()
-    L.deno_debug_read(buf, 32, 0)
+    L.deno_debug_read(buf, 48, 0)
 names = ["unit setup", "epi wait D", "epi work", "load wait stage", "load split+sts", "mma wait A_X", "mma wait D free",
          "mma issue", "roles total", "rows"]
 vals = list(buf)[:10]
@@ -38,3 +38,9 @@ print(name, {n: v for n, v in zip(names, vals)})
 rows = max(vals[9], 1)
 print("per row cycles:", {n: round(v / rows) for n, v in zip(names[1:9], vals[1:9])}, "setup per unit-row", round(vals[0] / rows))
 
+
+an = ["wait staged plane", "transform", "cp.async issue", "stage-1 MMA", "D1->B2", "stage-2 MMA", "epilogue", "planes"]
+av = list(buf)[32:40]
+pl = max(av[7], 1)
+print("analysis_tc CTA0 (fwd + gz variants summed):", {n: v for n, v in zip(an, av)})
+print("analysis per plane:", {n: round(v / pl) for n, v in zip(an[:7], av[:7])}, "sum", round(sum(av[:7]) / pl))
