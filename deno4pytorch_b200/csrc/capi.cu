@@ -479,12 +479,12 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
     rc = allow_smem(tc::plane_analysis_tc_kernel<true>, (size_t)sm.total, "plane_analysis_tc");
     if (rc != DENO_OK) return rc;
     prof_before("plane_analysis_gz_tc", st);
-    tc::plane_analysis_tc_kernel<true><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);
+    tc::plane_analysis_tc_kernel<true><<<dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st>>>(p);
   } else {
     rc = allow_smem(tc::plane_analysis_tc_kernel<false>, (size_t)sm.total, "plane_analysis_tc");
     if (rc != DENO_OK) return rc;
     prof_before("plane_analysis_tc", st);
-    tc::plane_analysis_tc_kernel<false><<<dim3(grid), dim3(256), (size_t)sm.total, st>>>(p);
+    tc::plane_analysis_tc_kernel<false><<<dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st>>>(p);
   }
   return check_launch("plane_analysis_tc", st);
 }

@@ -742,15 +742,18 @@ struct AnalysisTcParams {
 
 struct AnalysisTcSmem {
   int e1, a2, ab, stage, total;   // byte offsets
-  int e1_one, a2_one, a_one, b2_one, b2_lbo;
+  int e1_one, a2_one, a_one, a_lbo, b2_one, b2_lbo;
 };
+
+constexpr int kAnThreads = 512;   // 16 warps: every SIMT phase of the per-plane pipeline is latency-bound per warp
 
 __host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int N1, int Wp, int Hp, int KHp, bool gz) {
   AnalysisTcSmem m;
   m.e1_one = N1 * Wp * 4;
   m.a2_one = KHp * 2 * Hp * 4;
-  m.a_one = Hp * Wp * 4;
-  m.b2_lbo = 16 * N1 + 16;                  // padded K-direction stride: conflict-free scalar stores
+  m.a_lbo = 16 * Hp + 16;                   // padded K-direction strides: conflict-free stores when lanes walk along K
+  m.a_one = (Wp / 4) * m.a_lbo;
+  m.b2_lbo = 16 * N1 + 16;
   m.b2_one = (2 * Hp / 4) * m.b2_lbo;
   int off = 0;
   m.e1 = off; off += 2 * m.e1_one;
@@ -768,7 +771,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <bool FUSE_GZ>
-__global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
+__global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t mbar[2], bar_stage;
@@ -791,10 +794,10 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   {  // constant operand images (final layout in global memory): straight copies
     const float4* s1 = reinterpret_cast<const float4*>(p.e1);
     float4* d1 = reinterpret_cast<float4*>(smem + so.e1);
-    for (int i = tid; i < 2 * so.e1_one / 16; i += 256) d1[i] = s1[i];
+    for (int i = tid; i < 2 * so.e1_one / 16; i += kAnThreads) d1[i] = s1[i];
     const float4* s2 = reinterpret_cast<const float4*>(p.a2);
     float4* d2 = reinterpret_cast<float4*>(smem + so.a2);
-    for (int i = tid; i < 2 * so.a2_one / 16; i += 256) d2[i] = s2[i];
+    for (int i = tid; i < 2 * so.a2_one / 16; i += kAnThreads) d2[i] = s2[i];
   }
   // Planes whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy per tensor
   // (cp.async.bulk, completion on an mbarrier); others fall back to per-thread 4-byte cp.async.
@@ -813,28 +816,13 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
                        ::"r"(smem_u32(stage_z)), "l"(p.z + base), "r"(bytes), "r"(bar) : "memory");
       }
     } else {
-      for (int i = tid; i < HW; i += 256) {
+      for (int i = tid; i < HW; i += kAnThreads) {
         cp_async4(stage + i, p.u + base + i);
         if (FUSE_GZ) cp_async4(stage_z + i, p.z + base + i);
       }
       cp_async_commit();
     }
   };
-  // The (row, column-quad) items a thread turns into A-image core rows do not depend on the plane: decode once.
-  constexpr int kMaxItems = 12;
-  const int nitems = (Wp / 4) * Hp;
-  int it_src[kMaxItems], it_dst[kMaxItems];    // staging float offset (or -1), byte offset inside the hi image (or -1)
-#pragma unroll
-  for (int it = 0; it < kMaxItems; ++it) {
-    const int item = it * 256 + tid;
-    it_src[it] = -1;
-    it_dst[it] = -1;
-    if (item < nitems) {
-      const int yq = item / Hp, row = item - yq * Hp;
-      it_dst[it] = kmajor_off(row, yq * 4, Hp);
-      if (row < H) it_src[it] = row * W + yq * 4;
-    }
-  }
   fence_before_sync();
   __syncthreads();                                     // barriers initialised, TMEM allocated, constant images stored
   fence_after_sync();
@@ -843,7 +831,7 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // three split-pass tiles per stage
   const uint32_t idesc = make_idesc_tf32(128, N1);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t lbo_a = 16 * Hp, lbo_e1 = 16 * N1, lbo_a2 = 16 * KHp, lbo_b2 = (uint32_t)so.b2_lbo;
+  const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 16 * N1, lbo_a2 = 16 * KHp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int wq = warp & 3, wg = warp >> 2;
   const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / mode k of D2)
   uint32_t phase = 0, stage_phase = 0;
@@ -858,49 +846,32 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);        // slot 32: wait for the staged plane
     if (FUSE_GZ) {                                     // gz = gy * act'(z): coalesced store, kept in staging
       const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-      for (int i = tid; i < HW; i += 256) {
+      for (int i = tid; i < HW; i += kAnThreads) {
         const float v = stage[i] * stage_z[i];
         stage[i] = v;
         p.gz_out[base + i] = v;
       }
       __syncthreads();
     }
-    // staging -> A images (hi / lo), rows fastest across lanes: 8 lanes fill one 128-byte core matrix
+    // staging -> A images (hi / lo): one warp per row, lanes walk along the row (conflict-free reads of the
+    // staged plane; the padded K-direction stride makes the 16-byte image stores conflict-free as well)
+    for (int row = warp; row < Hp; row += kAnThreads / 32) {
+      for (int yq = lane; yq < Wp / 4; yq += 32) {
+        float v[4];
 #pragma unroll
-    for (int it = 0; it < kMaxItems; ++it) {
-      if (it_dst[it] >= 0) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (it_src[it] >= 0) {
-          const int y0c = (it * 256 + tid) / Hp * 4;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (y0c + j < W) v[j] = stage[it_src[it] + j];
+        for (int j = 0; j < 4; ++j) {
+          const int y = yq * 4 + j;
+          v[j] = (row < H && y < W) ? stage[row * W + y] : 0.f;
         }
         float4 hi, lo;
         split_tf32(v[0], hi.x, lo.x);
         split_tf32(v[1], hi.y, lo.y);
         split_tf32(v[2], hi.z, lo.z);
         split_tf32(v[3], hi.w, lo.w);
-        *reinterpret_cast<float4*>(smem + so.ab + it_dst[it]) = hi;
-        *reinterpret_cast<float4*>(smem + so.ab + so.a_one + it_dst[it]) = lo;
+        const int off = (row & 7) * 16 + (row >> 3) * 128 + yq * so.a_lbo;
+        *reinterpret_cast<float4*>(smem + so.ab + off) = hi;
+        *reinterpret_cast<float4*>(smem + so.ab + so.a_one + off) = lo;
       }
-    }
-    for (int item = kMaxItems * 256 + tid; item < nitems; item += 256) {   // planes larger than the register table
-      const int yq = item / Hp, row = item - yq * Hp;
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int y = yq * 4 + j;
-        v[j] = (row < H && y < W) ? stage[row * W + y] : 0.f;
-      }
-      float4 hi, lo;
-      split_tf32(v[0], hi.x, lo.x);
-      split_tf32(v[1], hi.y, lo.y);
-      split_tf32(v[2], hi.z, lo.z);
-      split_tf32(v[3], hi.w, lo.w);
-      const int off = kmajor_off(row, yq * 4, Hp);
-      *reinterpret_cast<float4*>(smem + so.ab + off) = hi;
-      *reinterpret_cast<float4*>(smem + so.ab + so.a_one + off) = lo;
     }
     fence_proxy_async();
     fence_before_sync();
@@ -935,21 +906,21 @@ __global__ void __launch_bounds__(256, 1) plane_analysis_tc_kernel(AnalysisTcPar
     if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);        // slot 35: stage-1 MMAs (issue + completion)
     // D1 -> B2 images (alias the A images, which the finished stage-1 MMAs no longer read)
     {
-      const int ncol_half = N1 / 2;
+      const int ncol_q = N1 / 4;                   // columns per warp group (N1 is a multiple of 32)
       unsigned char* b2hi = smem + so.ab;
       unsigned char* b2lo = b2hi + so.b2_one;
-      for (int c0 = 0; c0 < ncol_half; c0 += 16) {
-        float v[16], v1[16], v2[16];
-        const uint32_t ta = tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_half + c0);
-        tmem_ld16(ta, v);
-        tmem_ld16(ta + N1, v1);
-        tmem_ld16(ta + 2 * N1, v2);
+      for (int c0 = 0; c0 < ncol_q; c0 += 8) {
+        float v[8], v1[8], v2[8];
+        const uint32_t ta = tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_q + c0);
+        tmem_ld8(ta, v);
+        tmem_ld8(ta + N1, v1);
+        tmem_ld8(ta + 2 * N1, v2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += v1[j] + v2[j];
+        for (int j = 0; j < 8; ++j) v[j] += v1[j] + v2[j];
         if (xrow < Hp) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const int n = wg * ncol_half + c0 + j;                 // even column: Tr, n + 1: Ti
+          for (int j = 0; j < 8; j += 2) {
+            const int n = wg * ncol_q + c0 + j;                    // even column: Tr, n + 1: Ti
             const float tr = xrow < H ? v[j] : 0.f, ti = xrow < H ? v[j + 1] : 0.f;
             float trh, trl, tih, til;
             split_tf32(tr, trh, trl);
