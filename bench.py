@@ -227,6 +227,7 @@ def layer_roofline(workload: str, device, hbm_peak: float, reps: int = 20):
         "plane_analysis_tc": A + spec_small, "plane_analysis_gz_tc": 3 * A + spec_small,
         "plane_synthesis_tc": 3 * A + spec_small, "plane_synthesis_bwd_tc": 2 * A + spec_small,
         "bypass_wgrad_partial": 2 * A, "bypass_wgrad_tc": 2 * A,   # read gz, x
+        "mode_mix_bwd_fused": 3 * spec_small + 3 * Wb,      # read G^, X^, W; write G^x, gW
         "mode_mix": 2 * spec_small + Wb, "mode_mix_bwd": 2 * spec_small + Wb, "mode_mix_wgrad": 2 * spec_small + Wb,
     }
     dom = max(per_kernel, key=per_kernel.get)

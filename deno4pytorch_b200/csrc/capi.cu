@@ -583,6 +583,36 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
   return check_launch("mode_mix_wgrad", st);
 }
 
+// Fused launch of the backward consumers of G^ (see mode_mix_bwd_fused_kernel).  Any role may be disabled.
+int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat, float2* gxhat, const void* const* w_blocks,
+                         void* const* gw_blocks, float* glb_from_dc, cudaStream_t st) {
+  MixBwdFusedParams f;
+  memset(&f, 0, sizeof(f));
+  const int nblk = 1 << (s.ndim - 1);
+  f.mix.md = make_decode(s);
+  f.wg.md = f.mix.md;
+  if (gxhat != nullptr) {
+    f.mix.in = ghat; f.mix.out = gxhat;
+    for (int j = 0; j < 4; ++j) f.mix.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
+    f.mix.B = s.B; f.mix.CI = s.CO; f.mix.CO = s.CI;
+    f.mix.w_sci = f.mix.md.Mblk; f.mix.w_sco = (long long)s.CO * f.mix.md.Mblk;
+    f.mix.conj_w = 1;
+    f.ax = (s.M + 31) / 32; f.ay = (s.CI + 7) / 8; f.az = (s.B + kMixBatchTile - 1) / kMixBatchTile;
+  }
+  if (gw_blocks != nullptr) {
+    f.wg.xhat = xhat; f.wg.ghat = ghat;
+    for (int j = 0; j < 4; ++j) f.wg.gw[j] = static_cast<float2*>(gw_blocks[j < nblk ? j : 0]);
+    f.wg.B = s.B; f.wg.CI = s.CI; f.wg.CO = s.CO;
+    f.bx = (s.M + 31) / 32; f.by = ((s.CO + kMixWgradOut - 1) / kMixWgradOut + 7) / 8; f.bz = s.CI;
+  }
+  f.ghat = ghat; f.glb = glb_from_dc; f.B = s.B; f.CO = s.CO; f.M = s.M; f.s_total = (float)s.S;
+  const int total = f.ax * f.ay * f.az + f.bx * f.by * f.bz + (glb_from_dc != nullptr ? 1 : 0);
+  if (total == 0) return DENO_OK;
+  prof_before("mode_mix_bwd_fused", st);
+  DENO_LAUNCH(mode_mix_bwd_fused_kernel, dim3(total), dim3(32, 8), 0, st, f);
+  return check_launch("mode_mix_bwd_fused", st);
+}
+
 #ifndef DENO_EMULATE
 // Tensor-core synthesis: returns DENO_OK after launching, or -1 when the shape is outside what the
 // tcgen05 kernel covers (caller falls back to the SIMT kernel).
@@ -819,8 +849,24 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
 }
 #endif
 
+#ifndef DENO_EMULATE
+bool wgrad_tc_eligible(const Shape& s) {
+  if (path_pref() == PathPref::Simt) return false;
+  const int COs = round_up(s.CO, 8), CIs = round_up(s.CI, 8);
+  if (COs > 128 || CIs > 128) return false;
+  int NS = 4;
+  while (NS > 1 && (NS * COs > 128 || NS * CIs > 128)) NS /= 2;
+  if ((NS * CIs) % 16 != 0) return false;
+  if (tc::wgrad_tc_smem(NS, COs, CIs).total > kMaxSmemBytes - 1024) return false;
+  return (NS * (s.CO + s.CI) * (tc::kWgradKT / 4) + tc::kWgradLoaders - 1) / tc::kWgradLoaders <= 8;
+}
+#else
+bool wgrad_tc_eligible(const Shape&) { return false; }
+#endif
+
+// `bias_done`: the bias gradient was already produced from the DC mode by the fused mix kernel.
 int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const float2* ghat, float* partial, float* glw,
-                        float* glb, cudaStream_t st) {
+                        float* glb, bool bias_done, cudaStream_t st) {
   WgradCfg c;
   int rc = wgrad_cfg(s, c);
   if (rc != DENO_OK) return rc;
@@ -839,7 +885,7 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
         rc = check_launch("bypass_wgrad_reduce", st);
         if (rc != DENO_OK) return rc;
       }
-      if (glb != nullptr) {
+      if (glb != nullptr && !bias_done) {
         tc::BiasDcParams bp;
         bp.ghat = ghat; bp.glb = glb; bp.B = s.B; bp.CO = s.CO; bp.M = s.M; bp.s_total = (float)s.S;
         prof_before("bias_from_dc", st);
@@ -1073,11 +1119,12 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
   } else {
     if ((rc = launch_analysis(s, s.CO, gy, z_saved, gz, ghat, tw, inv_s, 1, st))) return rc;
   }
-  if (gw_blocks != nullptr) {
-    if ((rc = launch_mix_wgrad(s, xhat, ghat, gw_blocks, st))) return rc;
-  }
+  // one launch: G^x = conj(W) G^ (if gx is wanted), gW (if wanted) and, on the tensor-core wgrad path, the bias gradient
+  const bool bias_from_dc = (glin_b != nullptr) && wgrad_tc_eligible(s);
+  if ((rc = launch_mix_bwd_fused(s, xhat, ghat, gx != nullptr ? gxhat : nullptr, w_blocks, gw_blocks,
+                                 bias_from_dc ? glin_b : nullptr, st)))
+    return rc;
   if (gx != nullptr) {
-    if ((rc = launch_mix(s, true, ghat, gxhat, w_blocks, st))) return rc;
     const float2* spec = gxhat;
     if (s.ndim == 3) {
       float2* v = reinterpret_cast<float2*>(wsb + ws.v);
@@ -1091,7 +1138,7 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
   }
   if (glin_w != nullptr || glin_b != nullptr) {
     float* partial = reinterpret_cast<float*>(wsb + ws.partial);
-    if ((rc = launch_bypass_wgrad(s, gz, x, ghat, partial, glin_w, glin_b, st))) return rc;
+    if ((rc = launch_bypass_wgrad(s, gz, x, ghat, partial, glin_w, glin_b, bias_from_dc, st))) return rc;
   }
   return DENO_OK;
 }

@@ -274,11 +274,11 @@ constexpr int kMixBatchTile = 1;   // one batch entry per thread: the kernel is 
 constexpr int kMixUnroll = 8;
 
 // blockDim = (32 modes, 8 output channels); grid = (ceil(M/32), ceil(CO/8), ceil(B/4))
-__global__ void mode_mix_kernel(MixParams p) {
+__device__ __forceinline__ void mode_mix_body(const MixParams& p, int bx, int by, int bz) {
   const int M = p.md.M;
-  const int pm = blockIdx.x * blockDim.x + threadIdx.x;
-  const int co = blockIdx.y * blockDim.y + threadIdx.y;
-  const int b0 = blockIdx.z * kMixBatchTile;
+  const int pm = bx * blockDim.x + threadIdx.x;
+  const int co = by * blockDim.y + threadIdx.y;
+  const int b0 = bz * kMixBatchTile;
   if (pm >= M || co >= p.CO) return;
   int blk, off;
   decode_mode(p.md, pm, blk, off);
@@ -319,6 +319,8 @@ __global__ void mode_mix_kernel(MixParams p) {
     if (b0 + j < p.B) p.out[((long long)(b0 + j) * p.CO + co) * M + pm] = make_float2(ar[j], ai[j]);
 }
 
+__global__ void mode_mix_kernel(MixParams p) { mode_mix_body(p, blockIdx.x, blockIdx.y, blockIdx.z); }
+
 // gW[i,o,p] = sum_b conj(xhat[b,i,p]) * ghat[b,o,p]
 struct MixWgradParams {
   const float2* xhat;
@@ -331,11 +333,11 @@ struct MixWgradParams {
 constexpr int kMixWgradOut = 1;   // output channels per thread (latency-bound: favour more warps)
 
 // blockDim = (32 modes, 8 output channels); grid = (ceil(M/32), ceil(CO/8), CI)
-__global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
+__device__ __forceinline__ void mode_mix_wgrad_body(const MixWgradParams& p, int bx, int by, int bz) {
   const int M = p.md.M;
-  const int pm = blockIdx.x * blockDim.x + threadIdx.x;
-  const int oq = blockIdx.y * blockDim.y + threadIdx.y;
-  const int ci = blockIdx.z;
+  const int pm = bx * blockDim.x + threadIdx.x;
+  const int oq = by * blockDim.y + threadIdx.y;
+  const int ci = bz;
   if (pm >= M || oq * kMixWgradOut >= p.CO) return;
   int blk, off;
   decode_mode(p.md, pm, blk, off);
@@ -371,6 +373,57 @@ __global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
 #pragma unroll
   for (int j = 0; j < kMixWgradOut; ++j)
     if (oq * kMixWgradOut + j < p.CO) dst[(long long)(oq * kMixWgradOut + j) * p.md.Mblk] = make_float2(ar[j], ai[j]);
+}
+
+__global__ void mode_mix_wgrad_kernel(MixWgradParams p) { mode_mix_wgrad_body(p, blockIdx.x, blockIdx.y, blockIdx.z); }
+
+// One launch for the three small consumers of the packed gradient spectrum G^ in the backward pass:
+//   blocks [0, nA)        G^x = conj(W) G^            (mode_mix_body)
+//   blocks [nA, nA + nB)  gW  = sum_b conj(X^) G^     (mode_mix_wgrad_body)
+//   block  nA + nB        bias gradient from the DC mode: glb[o] = S * sum_b Re G^[b, o, 0]
+// Each of them is latency-bound and far too small to fill the GPU on its own; as separate launches they
+// cost ~8 us each at the Darcy shape.
+struct MixBwdFusedParams {
+  MixParams mix;
+  MixWgradParams wg;
+  int ax, ay, az;      // grid of the mix role (0 blocks when gx is not needed)
+  int bx, by, bz;      // grid of the weight-gradient role
+  const float2* ghat;  // bias role (glb == nullptr: disabled)
+  float* glb;
+  int B, CO, M;
+  float s_total;
+};
+
+__global__ void mode_mix_bwd_fused_kernel(MixBwdFusedParams f) {
+  int id = blockIdx.x;
+  const int nA = f.ax * f.ay * f.az, nB = f.bx * f.by * f.bz;
+  if (id < nA) {
+    const int x = id % f.ax, y = (id / f.ax) % f.ay, z = id / (f.ax * f.ay);
+    mode_mix_body(f.mix, x, y, z);
+    return;
+  }
+  id -= nA;
+  if (id < nB) {
+    const int x = id % f.bx, y = (id / f.bx) % f.by, z = id / (f.bx * f.by);
+    mode_mix_wgrad_body(f.wg, x, y, z);
+    return;
+  }
+  if (f.glb != nullptr) {
+    for (int o = threadIdx.y * blockDim.x + threadIdx.x; o < f.CO; o += blockDim.x * blockDim.y) {
+      float acc = 0.f;
+      for (int b0 = 0; b0 < f.B; b0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          v[u] = ldg_ordered(reinterpret_cast<const float*>(f.ghat + ((long long)min(b0 + u, f.B - 1) * f.CO + o) * f.M));
+          if (b0 + u >= f.B) v[u] = 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
+      }
+      f.glb[o] = acc * f.s_total;
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
