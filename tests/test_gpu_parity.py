@@ -281,3 +281,40 @@ def test_trainstep_fused_adam_and_graph_match_oracle(use_graph):
     assert list(sd.keys()) == list(params.keys())
     for k, p in model.named_parameters():
         assert rel_l2(p.detach().cpu(), port.params[k].detach()) < 1e-5, k
+
+
+@pytest.mark.parametrize("shape", [
+    (4, 32, 32, (94, 94), (12, 12)),       # Darcy layer, tensor-core kernels on the default path
+    (2, 6, 6, (128, 40), (64, 16)),        # large mode count, SIMT synthesis
+    (3, 16, 16, (1026,), (16,)),           # 1-D
+    (1, 8, 8, (20, 22, 18), (4, 5, 6)),    # 3-D
+], ids=["darcy", "modes64x16", "1d", "3d"])
+def test_bitwise_repeatability(shape):
+    """Every kernel uses a fixed summation order (no atomics), so repeated calls on the same inputs must be
+    bit-identical - forward output and all gradients.  Doubles as a race detector: 12 back-to-back runs."""
+    from deno4pytorch_b200.functional import spectral_conv
+    B, cin, cout, spatial, modes = shape
+    nd = len(spatial)
+    dev = _dev()
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn((B, cin) + spatial, generator=gen).to(dev)
+    ws = [torch.view_as_complex(torch.randn((cin, cout) + modes + (2,), generator=gen) / cin).to(dev)
+          for _ in range(2 ** (nd - 1))]
+    lw = (torch.randn((cout, cin) + (1,) * nd, generator=gen) / cin ** 0.5).to(dev)
+    lb = torch.randn(cout, generator=gen).to(dev)
+    cot = torch.randn((B, cout) + spatial, generator=gen).to(dev)
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        wg = [w.clone().requires_grad_(True) for w in ws]
+        lwg, lbg = lw.clone().requires_grad_(True), lb.clone().requires_grad_(True)
+        y = spectral_conv(xg, wg, lwg, lbg, modes, "gelu")
+        y.backward(cot)
+        return [y.detach(), xg.grad, lwg.grad, lbg.grad] + [w.grad for w in wg]
+
+    first = run()
+    for _ in range(11):
+        again = run()
+        for a, b in zip(first, again):
+            assert torch.equal(torch.view_as_real(a) if a.is_complex() else a,
+                               torch.view_as_real(b) if b.is_complex() else b)
