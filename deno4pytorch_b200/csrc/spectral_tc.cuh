@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   const int y0 = chunk * 128;
   const int ny = min(128, W - y0);
 
+  const long long tb0 = clock64();
   if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)q.tmem_cols);
   if (tid == 32) {
     mbar_init(&mbar[0], 1);
@@ -213,6 +214,8 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   };
   prefetch(0);
 
+  const long long tb1 = clock64();
+  if (warp == 1) DENO_DBG_ADD(48, tb1 - tb0);          // slot 48: TMEM alloc, weight / twiddle images, first prefetch issue
   // ---- stage A: U[r][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0 + r)}, written as B operand images ----
   // The packed spectrum of this batch entry is staged through the (still unused) A_X area in chunks of
   // OC output channels with fully coalesced loads, so the k-loop below runs out of shared memory.
@@ -233,22 +236,34 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       const int oc = min(OC, CO - o0);
       __syncthreads();   // previous chunk consumed (first pass: zero fill / twiddles ordered before use)
       const float2* src = p.spec + ((long long)bp * CO + o0) * Q;
-      for (int idx = tid; idx < oc * Q; idx += 256) sps[idx] = src[idx];
-      __syncthreads();
-      for (int task = tid; task < oc * MW; task += 256) {
-        const int ol = task / MW, l = task - ol * MW;
-        const int o = o0 + ol;
-        float ar[kSynthMaxRows], ai[kSynthMaxRows];
+      for (int idx0 = 0; idx0 < oc * Q; idx0 += 8 * 256) {     // eight independent loads in flight per thread
+        float2 tmp[8];
 #pragma unroll
-        for (int rr = 0; rr < kSynthMaxRows; ++rr) ar[rr] = ai[rr] = 0.f;
+        for (int u = 0; u < 8; ++u) tmp[u] = ldg_ordered(src + min(idx0 + u * 256 + tid, oc * Q - 1));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = idx0 + u * 256 + tid;
+          if (idx < oc * Q) sps[idx] = tmp[u];
+        }
+      }
+      __syncthreads();
+      // task = (row half, output channel, mode): two threads share an (o, l) pair, four rows each
+      for (int task = tid; task < 2 * oc * MW; task += 256) {
+        const int half = task / (oc * MW), t2 = task - half * (oc * MW);
+        const int ol = t2 / MW, l = t2 - ol * MW;
+        const int o = o0 + ol;
+        const int r0 = half * (kSynthMaxRows / 2);
+        float ar[kSynthMaxRows / 2], ai[kSynthMaxRows / 2];
+#pragma unroll
+        for (int rr = 0; rr < kSynthMaxRows / 2; ++rr) ar[rr] = ai[rr] = 0.f;
         const float2* sp = sps + ol * Q + l;
 #pragma unroll 4
         for (int k = 0; k < KH; ++k) {
           const float2 sv = sp[k * MW];
 #pragma unroll
-          for (int rr = 0; rr < kSynthMaxRows; ++rr) {
-            if (rr < trows) {
-              const float2 e = twr[rr * KH + k];
+          for (int rr = 0; rr < kSynthMaxRows / 2; ++rr) {
+            if (r0 + rr < trows) {
+              const float2 e = twr[(r0 + rr) * KH + k];
               ar[rr] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[rr]));
               ai[rr] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[rr]));
             }
@@ -257,12 +272,12 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
         const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
         const int off = kmajor_off(o, 2 * l, CO);   // k = 2l (cos partner) and 2l+1 (sin partner) share a 16-byte row
 #pragma unroll
-        for (int rr = 0; rr < kSynthMaxRows; ++rr) {
-          if (rr < trows) {
+        for (int rr = 0; rr < kSynthMaxRows / 2; ++rr) {
+          if (r0 + rr < trows) {
             float h0, l0, h1, l1;
             split_tf32(ar[rr] * f, h0, l0);
             split_tf32(-ai[rr] * f, h1, l1);
-            unsigned char* base = bu + (2 * rr) * so.bu_one + off;
+            unsigned char* base = bu + (2 * (r0 + rr)) * so.bu_one + off;
             *reinterpret_cast<float2*>(base) = make_float2(h0, h1);
             *reinterpret_cast<float2*>(base + so.bu_one) = make_float2(l0, l1);
           }
@@ -275,6 +290,8 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  const long long tb2 = clock64();
+  if (warp == 1) DENO_DBG_ADD(49, tb2 - tb1);          // slot 49: stage A
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = make_idesc_tf32(128, CO);
   const uint32_t sbase = smem_u32(smem);
@@ -314,7 +331,10 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   };
 
   for (int rr = 0; rr < trows; ++rr) {
+    const long long tr0 = clock64();
     if (rr > 0) mbar_wait(&mbar[(rr - 1) & 1], ((rr - 1) >> 1) & 1);   // MMA(rr-1) done: A_X free, D(rr-1) ready
+    const long long tr1 = clock64();
+    if (warp == 1) DENO_DBG_ADD(50, tr1 - tr0);        // slot 50: wait for the previous row's MMAs
     // registers -> A_X images (hi / lo)
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -331,7 +351,10 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     }
     fence_proxy_async();
     fence_before_sync();
+    const long long tr2 = clock64();
     __syncthreads();
+    const long long tr3 = clock64();
+    if (warp == 1) { DENO_DBG_ADD(51, tr2 - tr1); DENO_DBG_ADD(52, tr3 - tr2); }   // slots 51/52: split + store, barrier
     if (warp == 0) {
       fence_after_sync();
       const bool leader = elect_one();   // warp-uniform loop (descriptors in uniform registers); one lane issues
@@ -367,12 +390,16 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       }
       if (leader) mma_commit(&mbar[rr & 1]);
       __syncwarp();
+      DENO_DBG_ADD(53, clock64() - tr3);               // slot 53: MMA issue (warp 0)
     }
+    const long long tr4 = clock64();
     if (rr + 1 < trows) prefetch(rr + 1);
+    const long long tr5 = clock64();
     if (rr > 0) {
       fence_after_sync();
       epilogue(rr - 1);
     }
+    if (warp == 1) { DENO_DBG_ADD(54, tr5 - tr4); DENO_DBG_ADD(55, clock64() - tr5); DENO_DBG_ADD(56, 1); }  // prefetch issue, epilogue, rows
   }
   mbar_wait(&mbar[(trows - 1) & 1], ((trows - 1) >> 1) & 1);
   fence_after_sync();

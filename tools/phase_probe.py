@@ -23,14 +23,14 @@ ws = [torch.view_as_complex(torch.rand((Cc, Cc) + modes + (2,), generator=gen) /
 lw = (torch.randn((Cc, Cc) + (1,) * nd, generator=gen) / Cc ** 0.5).to(dev).requires_grad_(True)
 lb = torch.zeros(Cc, device=dev, requires_grad=True)
 L = lib()
-buf = (C.c_longlong * 48)()
+buf = (C.c_longlong * 64)()
 gy = torch.randn((B, Cc) + spatial, generator=gen).to(dev)
 for it in range(3):
-    L.deno_debug_read(buf, 48, 1)
+    L.deno_debug_read(buf, 64, 1)
     y = spectral_conv(x, ws, lw, lb, modes, "gelu")
     y.backward(gy)
     torch.cuda.synchronize()
-    L.deno_debug_read(buf, 48, 0)
+    L.deno_debug_read(buf, 64, 0)
 names = ["unit setup", "epi wait D", "epi work", "load wait stage", "load split+sts", "mma wait A_X", "mma wait D free",
          "mma issue", "roles total", "rows"]
 vals = list(buf)[:10]
@@ -44,3 +44,9 @@ av = list(buf)[32:40]
 pl = max(av[7], 1)
 print("analysis_tc CTA0 (fwd + gz variants summed):", {n: v for n, v in zip(an, av)})
 print("analysis per plane:", {n: round(v / pl) for n, v in zip(an[:7], av[:7])}, "sum", round(sum(av[:7]) / pl))
+
+sn = ["setup", "stage A", "wait prev MMA", "split+sts", "barrier", "mma issue", "prefetch issue", "epilogue(prev row)", "rows"]
+sv = list(buf)[48:57]
+rw = max(sv[8], 1)
+print("synthesis_tc (bulk) CTA0, fwd + bwd-x kernels summed:", {n: v for n, v in zip(sn, sv)})
+print("synthesis per row:", {n: round(v / rw) for n, v in zip(sn[2:8], sv[2:8])}, "| per CTA: setup", sv[0] // 2, "stage A", sv[1] // 2)
