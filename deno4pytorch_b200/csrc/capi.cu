@@ -129,7 +129,7 @@ ModeDecode make_decode(const Shape& s) {
 struct TwLayout {
   size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, total;  // float offsets
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
-  int N1, Wp, Hp, KHp;                           // tensor-core analysis images: E1 [hi|lo][N1*Wp], A2 [hi|lo][KHp*2*Hp]
+  int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [hi|lo][N1*Wp], A2 [hi|lo][KRp*Hp]
 };
 
 TwLayout tw_layout(const Shape& s) {
@@ -145,10 +145,11 @@ TwLayout tw_layout(const Shape& s) {
   t.N1 = round_up(2 * s.MWp, 32);
   t.Wp = round_up(s.W, 8);
   t.Hp = round_up(s.H, 8);
-  t.KHp = round_up(s.KH, 8);
-  const bool an = (s.ndim >= 2 && s.H <= 128);   // shapes the tensor-core analysis kernel can take
+  t.KS0 = round_up(s.KH, 32);                    // sin rows of the stage-2 operand start in their own TMEM lane quadrant
+  t.KRp = round_up(t.KS0 + s.KH, 8);
+  const bool an = (s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128);   // shapes the tensor-core analysis kernel can take
   t.an_e1 = off; off += an ? (size_t)2 * t.N1 * t.Wp : 0;
-  t.an_a2 = off; off += an ? (size_t)2 * t.KHp * 2 * t.Hp : 0;
+  t.an_a2 = off; off += an ? (size_t)2 * t.KRp * t.Hp : 0;
   t.total = off;
   return t;
 }
@@ -395,7 +396,7 @@ int allow_smem(K kernel, size_t bytes, const char* what) {
 // as a B operand with N1 rows, and A2[k][k'] (k' < Hp: cos, else sin of 2 pi f_k x / H) as an A operand.
 void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
   const double two_pi = 6.283185307179586476925286766559;
-  if (!(s.ndim >= 2 && s.H <= 128)) return;
+  if (!(s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128)) return;
   float* e1hi = base + t.an_e1;
   float* e1lo = e1hi + (size_t)t.N1 * t.Wp;
   for (int n = 0; n < t.N1; ++n)
@@ -412,18 +413,19 @@ void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
       e1lo[off] = (float)(v - (double)h);
     }
   float* a2hi = base + t.an_a2;
-  float* a2lo = a2hi + (size_t)t.KHp * 2 * t.Hp;
-  for (int k = 0; k < t.KHp; ++k)
-    for (int kk = 0; kk < 2 * t.Hp; ++kk) {
-      const int x = kk < t.Hp ? kk : kk - t.Hp;
+  float* a2lo = a2hi + (size_t)t.KRp * t.Hp;
+  for (int r = 0; r < t.KRp; ++r)
+    for (int x = 0; x < t.Hp; ++x) {
+      const bool is_cos = r < s.KH, is_sin = r >= t.KS0 && r < t.KS0 + s.KH;
+      const int k = is_cos ? r : r - t.KS0;
       double v = 0.0;
-      if (k < s.KH && x < s.H) {
+      if ((is_cos || is_sin) && x < s.H) {
         const long long f = (k < s.mH) ? k : (long long)s.H - 2 * s.mH + k;
         const double ang = two_pi * (double)((f * x) % s.H) / (double)s.H;
-        v = kk < t.Hp ? cos(ang) : sin(ang);
+        v = is_cos ? cos(ang) : sin(ang);
       }
       const float h = tf32_mask((float)v);
-      const int off = kmajor_off(k, kk, t.KHp) / 4;
+      const int off = kmajor_off(r, x, t.KRp) / 4;
       a2hi[off] = h;
       a2lo[off] = (float)(v - (double)h);
     }
@@ -462,9 +464,9 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
                            const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
   if (s.ndim < 2 || s.H > 128) return -1;
   const TwLayout tl = tw_layout(s);
-  if (tl.N1 > 256) return -1;
+  if (tl.N1 > 256 || tl.KS0 + s.KH > 128) return -1;
   const bool gz = (z != nullptr);
-  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(s.H, s.W, tl.N1, tl.Wp, tl.Hp, tl.KHp, gz);
+  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(s.H, s.W, tl.N1, tl.Wp, tl.Hp, tl.KRp, gz);
   if (sm.total > kMaxSmemBytes - 1024) return -1;
   tc::AnalysisTcParams p;
   p.g = make_geom(s, channels);
@@ -472,7 +474,7 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   p.e1 = tw.an_e1; p.a2 = tw.an_a2; p.cl = tw.cl;
   p.scale = scale; p.herm = herm; p.act = s.act;
   p.nplanes = s.B * s.X * channels;
-  p.N1 = tl.N1; p.Wp = tl.Wp; p.Hp = tl.Hp; p.KHp = tl.KHp;
+  p.N1 = tl.N1; p.Wp = tl.Wp; p.Hp = tl.Hp; p.KS0 = tl.KS0; p.KRp = tl.KRp;
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
   if (gz) {

@@ -232,8 +232,10 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       const int rr = idx / KH, k = idx - rr * KH;
       twr[idx] = p.twH[(x0 + rr) * KH4 + k];
     }
+    if (warp == 1) DENO_DBG_ADD(57, clock64() - tb1);   // slot 57: zero fill + row twiddles
     for (int o0 = 0; o0 < CO; o0 += OC) {
       const int oc = min(OC, CO - o0);
+      const long long tc0 = clock64();
       __syncthreads();   // previous chunk consumed (first pass: zero fill / twiddles ordered before use)
       const float2* src = p.spec + ((long long)bp * CO + o0) * Q;
       for (int idx0 = 0; idx0 < oc * Q; idx0 += 8 * 256) {     // eight independent loads in flight per thread
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
         }
       }
       __syncthreads();
+      const long long tc1 = clock64();
+      if (warp == 1) DENO_DBG_ADD(58, tc1 - tc0);       // slot 58: spectrum chunk load (incl. barriers)
       // task = (row half, output channel, mode): two threads share an (o, l) pair, four rows each
       for (int task = tid; task < 2 * oc * MW; task += 256) {
         const int half = task / (oc * MW), t2 = task - half * (oc * MW);
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
           }
         }
       }
+      if (warp == 1) { DENO_DBG_ADD(59, clock64() - tc1); DENO_DBG_ADD(60, 1); }   // slots 59/60: chunk compute, chunks
     }
     __syncthreads();     // the A_X area is about to be overwritten by the first row tile
   }
@@ -745,26 +750,28 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
 // H <= 128 rows.  Two chained GEMMs per plane, both on the tensor cores:
 //   stage 1  D1[x, n]  = sum_y u[x, y] * E1[n, y]          n = 2l: cos, 2l+1: -sin      (K = Wp)
 //            -> D1[x, 2l] + i D1[x, 2l+1] = T[x, l] = sum_y u[x,y] e^{-i psi_l y}
-//   stage 2  D2[k, n]  = sum_x cos(phi_k x) * Ba[x, n] + sin(phi_k x) * Bb[x, n]       (K = 2 Hp)
-//            with Ba = (Tr, Ti), Bb = (Ti, -Tr)  ->  D2[k, 2l] + i D2[k, 2l+1] = sum_x e^{-i phi_k x} T[x, l]
-// D1 goes TMEM -> registers -> (split) -> shared memory as the B operand of stage 2.
-// One persistent CTA per SM loops over planes; the next plane streams into a staging buffer with
-// cp.async while the current one is on the tensor cores.
+//   stage 2  D2[r, n]  = sum_x A2[r, x] * D1[x, n]          (K = Hp), rows r = k: cos(phi_k x), r = KS0 + k: sin(phi_k x)
+//            -> X^[k, l] = (D2[k,2l] + D2[KS0+k,2l+1]) + i (D2[k,2l+1] - D2[KS0+k,2l])     (e^{-i phi} (Tr + i Ti))
+// D1 goes TMEM -> registers -> (split) -> shared memory as the B operand of stage 2; the cos / sin halves of
+// D2 sit in different TMEM lane quadrants and are combined through a small shared-memory exchange.
+// One persistent CTA per SM loops over planes; the next plane streams into a staging buffer with one bulk
+// async copy (cp.async.bulk) while the current one is being processed, and stage 1 is issued per 32-column
+// chunk so the tensor core starts while the rest of the plane is still being split into operand images.
 // ----------------------------------------------------------------------------------------------
 struct AnalysisTcParams {
   PlaneGeom g;
   const float* u;        // x, or gy when FUSE_GZ
-  const float* z;
+  const float* z;        // FUSE_GZ: saved act'(z)
   float* gz_out;
   float2* out;           // [nplanes][KH][MW]
   const float* e1;       // [hi|lo] images, N1 rows x Wp
-  const float* a2;       // [hi|lo] images, KHp rows x 2*Hp
+  const float* a2;       // [hi|lo] images, KRp rows x Hp
   const float* cl;
   float scale;
   int herm;
   int act;
   int nplanes;
-  int N1, Wp, Hp, KHp;
+  int N1, Wp, Hp, KS0, KRp;
 };
 
 struct AnalysisTcSmem {
@@ -774,18 +781,19 @@ struct AnalysisTcSmem {
 
 constexpr int kAnThreads = 512;   // 16 warps: every SIMT phase of the per-plane pipeline is latency-bound per warp
 
-__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int N1, int Wp, int Hp, int KHp, bool gz) {
+__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int N1, int Wp, int Hp, int KRp, bool gz) {
   AnalysisTcSmem m;
   m.e1_one = N1 * Wp * 4;
-  m.a2_one = KHp * 2 * Hp * 4;
+  m.a2_one = KRp * Hp * 4;
   m.a_lbo = 16 * Hp + 16;                   // padded K-direction strides: conflict-free stores when lanes walk along K
   m.a_one = (Wp / 4) * m.a_lbo;
   m.b2_lbo = 16 * N1 + 16;
-  m.b2_one = (2 * Hp / 4) * m.b2_lbo;
+  m.b2_one = (Hp / 4) * m.b2_lbo;
   int off = 0;
   m.e1 = off; off += 2 * m.e1_one;
   m.a2 = off; off += 2 * m.a2_one;
-  m.ab = off; off += 2 * (m.a_one > m.b2_one ? m.a_one : m.b2_one);   // A images, later aliased by the B2 images
+  const int ab_one = m.a_one > m.b2_one ? m.a_one : m.b2_one;
+  m.ab = off; off += 2 * ab_one;            // A images; later aliased by the B2 images, then by the sin-row exchange
   m.stage = off; off += round_up(H * W, 4) * 4 * (gz ? 2 : 1);
   m.total = off;
   return m;
@@ -804,8 +812,8 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   __shared__ __align__(8) uint64_t mbar[2], bar_stage;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
-  const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KHp = p.KHp;
-  const AnalysisTcSmem so = analysis_tc_smem(H, W, N1, Wp, Hp, KHp, FUSE_GZ);
+  const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
+  const AnalysisTcSmem so = analysis_tc_smem(H, W, N1, Wp, Hp, KRp, FUSE_GZ);
   const int HW = H * W;
   float* stage = reinterpret_cast<float*>(smem + so.stage);
   float* stage_z = stage + round_up(HW, 4);
@@ -858,9 +866,11 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // three split-pass tiles per stage
   const uint32_t idesc = make_idesc_tf32(128, N1);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 16 * N1, lbo_a2 = 16 * KHp, lbo_b2 = (uint32_t)so.b2_lbo;
+  const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 16 * N1, lbo_a2 = 16 * KRp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int wq = warp & 3, wg = warp >> 2;
-  const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / mode k of D2)
+  const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / row r of D2)
+  const int nyq = Wp / 4;                 // column quads of a row
+  const int nchunk = (nyq + 7) / 8;       // stage 1 is issued per chunk of 8 quads (32 columns = 4 K steps)
   uint32_t phase = 0, stage_phase = 0;
 
   for (int q = blockIdx.x; q < p.nplanes; q += gridDim.x) {
@@ -880,58 +890,58 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       }
       __syncthreads();
     }
-    // staging -> A images (hi / lo): one warp per row, lanes walk along the row (conflict-free reads of the
-    // staged plane; the padded K-direction stride makes the 16-byte image stores conflict-free as well)
-    for (int row = warp; row < Hp; row += kAnThreads / 32) {
-      for (int yq = lane; yq < Wp / 4; yq += 32) {
-        float v[4];
+    // staging -> A images (hi / lo) chunk by chunk; the stage-1 MMAs of a chunk are issued as soon as it is stored
+    uint64_t ah = make_desc(sbase + so.ab, lbo_a, 128), al = make_desc(sbase + so.ab + so.a_one, lbo_a, 128);
+    uint64_t bh = make_desc(sbase + so.e1, lbo_e1, 128), bl = make_desc(sbase + so.e1 + so.e1_one, lbo_e1, 128);
+    const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
+    for (int c = 0; c < nchunk; ++c) {
+      const int yq = c * 8 + (lane & 7);
+      if (yq < nyq) {
+        for (int row = warp * 4 + (lane >> 3); row < Hp; row += (kAnThreads / 32) * 4) {
+          float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int y = yq * 4 + j;
-          v[j] = (row < H && y < W) ? stage[row * W + y] : 0.f;
+          for (int j = 0; j < 4; ++j) {
+            const int y = yq * 4 + j;
+            v[j] = (row < H && y < W) ? stage[row * W + y] : 0.f;
+          }
+          float4 hi, lo;
+          split_tf32(v[0], hi.x, lo.x);
+          split_tf32(v[1], hi.y, lo.y);
+          split_tf32(v[2], hi.z, lo.z);
+          split_tf32(v[3], hi.w, lo.w);
+          const int off = (row & 7) * 16 + (row >> 3) * 128 + yq * so.a_lbo;
+          *reinterpret_cast<float4*>(smem + so.ab + off) = hi;
+          *reinterpret_cast<float4*>(smem + so.ab + so.a_one + off) = lo;
         }
-        float4 hi, lo;
-        split_tf32(v[0], hi.x, lo.x);
-        split_tf32(v[1], hi.y, lo.y);
-        split_tf32(v[2], hi.z, lo.z);
-        split_tf32(v[3], hi.w, lo.w);
-        const int off = (row & 7) * 16 + (row >> 3) * 128 + yq * so.a_lbo;
-        *reinterpret_cast<float4*>(smem + so.ab + off) = hi;
-        *reinterpret_cast<float4*>(smem + so.ab + so.a_one + off) = lo;
+      }
+      fence_proxy_async();
+      fence_before_sync();
+      __syncthreads();
+      if (c == nchunk - 1 && q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);   // staging is free again
+      if (warp == 0) {
+        fence_after_sync();
+        const bool leader = elect_one();
+        const int s_end = min(c * 4 + 4, Wp / 8);
+        for (int s2 = c * 4; s2 < s_end; ++s2) {
+          const uint32_t acc = s2 > 0 ? 1u : 0u;
+          if (leader) {
+            mma_tf32(tmem_d1, ah, bh, idesc, acc);            // hi * hi
+            mma_tf32(tmem_d1 + N1, al, bh, idesc, acc);       // lo * hi
+            mma_tf32(tmem_d1 + 2 * N1, ah, bl, idesc, acc);   // hi * lo
+          }
+          ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
+        }
+        if (c == nchunk - 1 && leader) mma_commit(&mbar[0]);
+        __syncwarp();
       }
     }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();                                   // A images complete; staging is free again
-    const long long tq2 = clock64();
-    if (warp == 1) DENO_DBG_ADD(33, tq2 - tq1);        // slot 33: (gz +) transform into A images
-    if (q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);
     const long long tq3 = clock64();
-    if (warp == 1) DENO_DBG_ADD(34, tq3 - tq2);        // slot 34: cp.async issue for the next plane
-    if (warp == 0) {
-      fence_after_sync();
-      const bool leader = elect_one();
-      // three independent accumulator tiles (one per split pass), issued round-robin: see plane_synthesis_tc
-      uint64_t ah = make_desc(sbase + so.ab, lbo_a, 128), al = make_desc(sbase + so.ab + so.a_one, lbo_a, 128);
-      uint64_t bh = make_desc(sbase + so.e1, lbo_e1, 128), bl = make_desc(sbase + so.e1 + so.e1_one, lbo_e1, 128);
-      const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
-      for (int s2 = 0; s2 < Wp / 8; ++s2) {
-        const uint32_t acc = s2 > 0 ? 1u : 0u;
-        if (leader) {
-          mma_tf32(tmem_d1, ah, bh, idesc, acc);            // hi * hi
-          mma_tf32(tmem_d1 + N1, al, bh, idesc, acc);       // lo * hi
-          mma_tf32(tmem_d1 + 2 * N1, ah, bl, idesc, acc);   // hi * lo
-        }
-        ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
-      }
-      if (leader) mma_commit(&mbar[0]);
-      __syncwarp();
-    }
+    if (warp == 1) DENO_DBG_ADD(33, tq3 - tq1);        // slot 33: (gz +) chunked transform with stage-1 issue
     mbar_wait(&mbar[0], phase);
     fence_after_sync();
     const long long tq4 = clock64();
-    if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);        // slot 35: stage-1 MMAs (issue + completion)
-    // D1 -> B2 images (alias the A images, which the finished stage-1 MMAs no longer read)
+    if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);        // slot 35: wait for the stage-1 MMAs
+    // D1 -> B2 images [n][x] (alias the A images, which the finished stage-1 MMAs no longer read)
     {
       const int ncol_q = N1 / 4;                   // columns per warp group (N1 is a multiple of 32)
       unsigned char* b2hi = smem + so.ab;
@@ -942,24 +952,17 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         tmem_ld8(ta, v);
         tmem_ld8(ta + N1, v1);
         tmem_ld8(ta + 2 * N1, v2);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += v1[j] + v2[j];
         if (xrow < Hp) {
+          const int kc = (xrow & 3) * 4 + (xrow >> 2) * so.b2_lbo;     // k' = x
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const int n = wg * ncol_q + c0 + j;                    // even column: Tr, n + 1: Ti
-            const float tr = xrow < H ? v[j] : 0.f, ti = xrow < H ? v[j + 1] : 0.f;
-            float trh, trl, tih, til;
-            split_tf32(tr, trh, trl);
-            split_tf32(ti, tih, til);
-            // element (row n, k') at (n&7)*16 + (n>>3)*128 + (k'&3)*4 + (k'>>2)*b2_lbo
-            const int r0 = (n & 7) * 16 + (n >> 3) * 128, r1 = ((n + 1) & 7) * 16 + ((n + 1) >> 3) * 128;
-            const int kc = (xrow & 3) * 4 + (xrow >> 2) * so.b2_lbo;                       // k' = x        (cos partner)
-            const int ks = ((Hp + xrow) & 3) * 4 + ((Hp + xrow) >> 2) * so.b2_lbo;         // k' = Hp + x   (sin partner)
-            *reinterpret_cast<float*>(b2hi + r0 + kc) = trh;  *reinterpret_cast<float*>(b2lo + r0 + kc) = trl;   // Ba[x, 2l]   = Tr
-            *reinterpret_cast<float*>(b2hi + r1 + kc) = tih;  *reinterpret_cast<float*>(b2lo + r1 + kc) = til;   // Ba[x, 2l+1] = Ti
-            *reinterpret_cast<float*>(b2hi + r0 + ks) = tih;  *reinterpret_cast<float*>(b2lo + r0 + ks) = til;   // Bb[x, 2l]   = Ti
-            *reinterpret_cast<float*>(b2hi + r1 + ks) = -trh; *reinterpret_cast<float*>(b2lo + r1 + ks) = -trl;  // Bb[x, 2l+1] = -Tr
+          for (int j = 0; j < 8; ++j) {
+            const int n = wg * ncol_q + c0 + j;
+            const float t = xrow < H ? v[j] + (v1[j] + v2[j]) : 0.f;
+            float th, tl;
+            split_tf32(t, th, tl);
+            const int r0 = (n & 7) * 16 + (n >> 3) * 128;
+            *reinterpret_cast<float*>(b2hi + r0 + kc) = th;
+            *reinterpret_cast<float*>(b2lo + r0 + kc) = tl;
           }
         }
       }
@@ -972,17 +975,17 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     if (warp == 0) {
       fence_after_sync();
       const bool leader = elect_one();
-      uint64_t ah = make_desc(sbase + so.a2, lbo_a2, 128), al = make_desc(sbase + so.a2 + so.a2_one, lbo_a2, 128);
-      uint64_t bh = make_desc(sbase + so.ab, lbo_b2, 128), bl = make_desc(sbase + so.ab + so.b2_one, lbo_b2, 128);
-      const uint64_t inc_a = (uint64_t)((2 * lbo_a2) >> 4), inc_b = (uint64_t)((2 * lbo_b2) >> 4);
-      for (int s2 = 0; s2 < 2 * Hp / 8; ++s2) {
+      uint64_t a2h = make_desc(sbase + so.a2, lbo_a2, 128), a2l = make_desc(sbase + so.a2 + so.a2_one, lbo_a2, 128);
+      uint64_t b2h = make_desc(sbase + so.ab, lbo_b2, 128), b2l = make_desc(sbase + so.ab + so.b2_one, lbo_b2, 128);
+      const uint64_t inc_a2 = (uint64_t)((2 * lbo_a2) >> 4), inc_b2 = (uint64_t)((2 * lbo_b2) >> 4);
+      for (int s2 = 0; s2 < Hp / 8; ++s2) {
         const uint32_t acc = s2 > 0 ? 1u : 0u;
         if (leader) {
-          mma_tf32(tmem_d2, ah, bh, idesc, acc);
-          mma_tf32(tmem_d2 + N1, al, bh, idesc, acc);
-          mma_tf32(tmem_d2 + 2 * N1, ah, bl, idesc, acc);
+          mma_tf32(tmem_d2, a2h, b2h, idesc, acc);
+          mma_tf32(tmem_d2 + N1, a2l, b2h, idesc, acc);
+          mma_tf32(tmem_d2 + 2 * N1, a2h, b2l, idesc, acc);
         }
-        ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
+        a2h += inc_a2; a2l += inc_a2; b2h += inc_b2; b2l += inc_b2;
       }
       if (leader) mma_commit(&mbar[1]);
       __syncwarp();
@@ -991,27 +994,41 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     fence_after_sync();
     const long long tq6 = clock64();
     if (warp == 1) DENO_DBG_ADD(37, tq6 - tq5);        // slot 37: stage-2 MMAs
-    // epilogue: lane k of D2 holds mode k; columns (2l, 2l+1) = (re, im)
+    // epilogue: rows k (cos) and KS0 + k (sin) of D2 are combined through shared memory (the B2 area is free now)
+    float* xch = reinterpret_cast<float*>(smem + so.ab);      // [KH][N1] sin-row values
+    float dsum[32];                                           // this thread's D2 row (first 32 columns per pass)
+    const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
     if (warp < 4) {
-      float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
-      for (int c0 = 0; c0 < N1; c0 += 16) {
-        float v[16], v1[16], v2[16];
-        const uint32_t ta = tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0;
-        tmem_ld16(ta, v);
-        tmem_ld16(ta + N1, v1);
-        tmem_ld16(ta + 2 * N1, v2);
+      for (int c0 = 0; c0 < N1; c0 += 32) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += v1[j] + v2[j];
-        if (xrow < KH) {
+        for (int cc = 0; cc < 32; cc += 8) {
+          float v[8], v1[8], v2[8];
+          const uint32_t ta = tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c0 + cc);
+          tmem_ld8(ta, v);
+          tmem_ld8(ta + N1, v1);
+          tmem_ld8(ta + 2 * N1, v2);
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
+          for (int j = 0; j < 8; ++j) dsum[cc + j] = v[j] + (v1[j] + v2[j]);
+        }
+        if (is_sin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xch[(xrow - KS0) * N1 + c0 + j] = dsum[j];
+        }
+        // named barrier among the four epilogue warps only
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (is_cos) {
+          float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
             const int l = (c0 + j) >> 1;
             if (l < MW) {
+              const float sr = xch[xrow * N1 + c0 + j], si = xch[xrow * N1 + c0 + j + 1];
               const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
-              dst[l] = make_float2(v[j] * f, v[j + 1] * f);
+              dst[l] = make_float2((dsum[j] + si) * f, (dsum[j + 1] - sr) * f);
             }
           }
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
     fence_before_sync();

@@ -50,3 +50,7 @@ sv = list(buf)[48:57]
 rw = max(sv[8], 1)
 print("synthesis_tc (bulk) CTA0, fwd + bwd-x kernels summed:", {n: v for n, v in zip(sn, sv)})
 print("synthesis per row:", {n: round(v / rw) for n, v in zip(sn[2:8], sv[2:8])}, "| per CTA: setup", sv[0] // 2, "stage A", sv[1] // 2)
+
+xv = list(buf)[57:61]
+ch = max(xv[3], 1)
+print("stage A detail: zero+twiddles per CTA", xv[0] // 2, "| per chunk: load", xv[1] // ch, "compute", xv[2] // ch, "chunks", xv[3])
