@@ -795,7 +795,9 @@ __host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int N1,
   const int ab_one = m.a_one > m.b2_one ? m.a_one : m.b2_one;
   m.ab = off; off += 2 * ab_one;            // A images; later aliased by the B2 images, then by the sin-row exchange
   m.stage = off; off += round_up(H * W, 4) * 4 * (gz ? 2 : 1);
-  m.total = off;
+  // The M = 128 descriptors always read 16 row groups (2 KB) per core-matrix column, also for operands with
+  // fewer rows: keep that over-read inside the allocation for tiny planes.
+  m.total = off + 4096;
   return m;
 }
 
