@@ -87,6 +87,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// three 16-column TMEM loads (the split-pass tiles of one accumulator, `stride` columns apart) behind ONE wait
+__device__ __forceinline__ void tmem_ld16x3_sum(uint32_t taddr, uint32_t stride, float (&v)[16]) {
+  uint32_t a[16], b[16], c[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+        "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+      : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+        "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+      : "r"(taddr + stride));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]),
+        "=r"(c[8]), "=r"(c[9]), "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15])
+      : "r"(taddr + 2 * stride));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(a[j]) + (__uint_as_float(b[j]) + __uint_as_float(c[j]));
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile(
@@ -997,31 +1023,22 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     const long long tq6 = clock64();
     if (warp == 1) DENO_DBG_ADD(37, tq6 - tq5);        // slot 37: stage-2 MMAs
     // epilogue: rows k (cos) and KS0 + k (sin) of D2 are combined through shared memory (the B2 area is free now)
-    float* xch = reinterpret_cast<float*>(smem + so.ab);      // [KH][N1] sin-row values
-    float dsum[32];                                           // this thread's D2 row (first 32 columns per pass)
-    const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
     if (warp < 4) {
-      for (int c0 = 0; c0 < N1; c0 += 32) {
-#pragma unroll
-        for (int cc = 0; cc < 32; cc += 8) {
-          float v[8], v1[8], v2[8];
-          const uint32_t ta = tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(c0 + cc);
-          tmem_ld8(ta, v);
-          tmem_ld8(ta + N1, v1);
-          tmem_ld8(ta + 2 * N1, v2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dsum[cc + j] = v[j] + (v1[j] + v2[j]);
-        }
+      float* xch = reinterpret_cast<float*>(smem + so.ab);      // [KH][N1] sin-row values
+      const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
+      const bool warp_used = (wq * 32 < KH) || (wq * 32 + 32 > KS0 && wq * 32 < KS0 + KH);   // any cos / sin row in this quadrant
+      for (int c0 = 0; c0 < N1; c0 += 16) {
+        float dsum[16];
+        if (warp_used) tmem_ld16x3_sum(tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, (uint32_t)N1, dsum);
         if (is_sin) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) xch[(xrow - KS0) * N1 + c0 + j] = dsum[j];
+          for (int j = 0; j < 16; ++j) xch[(xrow - KS0) * N1 + c0 + j] = dsum[j];
         }
-        // named barrier among the four epilogue warps only
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only; columns differ per pass
         if (is_cos) {
           float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
+          for (int j = 0; j < 16; j += 2) {
             const int l = (c0 + j) >> 1;
             if (l < MW) {
               const float sr = xch[xrow * N1 + c0 + j], si = xch[xrow * N1 + c0 + j + 1];
@@ -1030,7 +1047,6 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
     }
     fence_before_sync();
