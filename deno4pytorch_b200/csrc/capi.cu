@@ -129,7 +129,7 @@ ModeDecode make_decode(const Shape& s) {
 struct TwLayout {
   size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, total;  // float offsets
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
-  int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [hi|lo][N1*Wp], A2 [hi|lo][KRp*Hp]
+  int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [2*N1 rows: hi, lo][Wp], A2 [hi|lo][KRp*Hp]
 };
 
 TwLayout tw_layout(const Shape& s) {
@@ -145,7 +145,7 @@ TwLayout tw_layout(const Shape& s) {
   t.N1 = round_up(2 * s.MWp, 32);
   t.Wp = round_up(s.W, 8);
   t.Hp = round_up(s.H, 8);
-  t.KS0 = round_up(s.KH, 32);                    // sin rows of the stage-2 operand start in their own TMEM lane quadrant
+  t.KS0 = s.KH;                                  // sin rows of the stage-2 operand follow the cos rows
   t.KRp = round_up(t.KS0 + s.KH, 8);
   const bool an = (s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128);   // shapes the tensor-core analysis kernel can take
   t.an_e1 = off; off += an ? (size_t)2 * t.N1 * t.Wp : 0;
@@ -393,12 +393,12 @@ int allow_smem(K kernel, size_t bytes, const char* what) {
 }
 
 // Analysis operand images (see plane_analysis_tc_kernel): E1[n][y] (n = 2l: cos, 2l+1: -sin of 2 pi l y / W)
-// as a B operand with N1 rows, and A2[k][k'] (k' < Hp: cos, else sin of 2 pi f_k x / H) as an A operand.
+// as ONE B operand image with 2 N1 rows (tf32 hi parts, then lo parts), and A2[r][x] (rows r < KH: cos, rows
+// KS0 + k: sin of 2 pi f_k x / H) as hi / lo A operand images.
 void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
   const double two_pi = 6.283185307179586476925286766559;
   if (!(s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128)) return;
-  float* e1hi = base + t.an_e1;
-  float* e1lo = e1hi + (size_t)t.N1 * t.Wp;
+  float* e1 = base + t.an_e1;                    // one B image: rows n (hi) and N1 + n (lo)
   for (int n = 0; n < t.N1; ++n)
     for (int y = 0; y < t.Wp; ++y) {
       const int l = n / 2;
@@ -408,9 +408,8 @@ void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
         v = (n & 1) ? -sin(ang) : cos(ang);
       }
       const float h = tf32_mask((float)v);
-      const int off = kmajor_off(n, y, t.N1) / 4;
-      e1hi[off] = h;
-      e1lo[off] = (float)(v - (double)h);
+      e1[kmajor_off(n, y, 2 * t.N1) / 4] = h;
+      e1[kmajor_off(t.N1 + n, y, 2 * t.N1) / 4] = (float)(v - (double)h);
     }
   float* a2hi = base + t.an_a2;
   float* a2lo = a2hi + (size_t)t.KRp * t.Hp;
@@ -464,9 +463,9 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
                            const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
   if (s.ndim < 2 || s.H > 128) return -1;
   const TwLayout tl = tw_layout(s);
-  if (tl.N1 > 256 || tl.KS0 + s.KH > 128) return -1;
+  if (6 * tl.N1 > 512 || tl.KS0 + s.KH > 128) return -1;
   const bool gz = (z != nullptr);
-  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(s.H, s.W, tl.N1, tl.Wp, tl.Hp, tl.KRp, gz);
+  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(s.H, s.W, s.KH, tl.N1, tl.Wp, tl.Hp, tl.KRp);
   if (sm.total > kMaxSmemBytes - 1024) return -1;
   tc::AnalysisTcParams p;
   p.g = make_geom(s, channels);

@@ -778,11 +778,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
 //            -> D1[x, 2l] + i D1[x, 2l+1] = T[x, l] = sum_y u[x,y] e^{-i psi_l y}
 //   stage 2  D2[r, n]  = sum_x A2[r, x] * D1[x, n]          (K = Hp), rows r = k: cos(phi_k x), r = KS0 + k: sin(phi_k x)
 //            -> X^[k, l] = (D2[k,2l] + D2[KS0+k,2l+1]) + i (D2[k,2l+1] - D2[KS0+k,2l])     (e^{-i phi} (Tr + i Ti))
-// D1 goes TMEM -> registers -> (split) -> shared memory as the B operand of stage 2; the cos / sin halves of
-// D2 sit in different TMEM lane quadrants and are combined through a small shared-memory exchange.
-// One persistent CTA per SM loops over planes; the next plane streams into a staging buffer with one bulk
-// async copy (cp.async.bulk) while the current one is being processed, and stage 1 is issued per 32-column
-// chunk so the tensor core starts while the rest of the plane is still being split into operand images.
+// 3xTF32: the B operand of each stage is ONE image with the hi rows followed by the lo rows, so
+// A_hi x [B_hi | B_lo] is a single N = 2 N1 instruction and A_lo x B_hi a second one (an instruction costs
+// the same for every N <= 128, tools/tc_mma_bench.cu).
+// One persistent CTA per SM; 16 worker warps + 1 MMA-issuing warp, software-pipelined over planes:
+//   workers : wait stage 1(q) | D1(q) TMEM -> split -> B2 image | plane q+1: (gy * act') -> A images |
+//             wait stage 2(q) | combine cos / sin rows of D2(q) through shared memory -> global
+//   MMA warp: stage 2(q) as soon as B2 is stored | bulk copy of plane q+2, L2 prefetch of q+3 | stage 1(q+1)
+// so the tensor core works on plane q+1 while the workers finish plane q.  Hand-offs to the MMA warp are
+// bar.arrive / bar.sync named barriers; completions come back through mbarriers (tcgen05.commit).
 // ----------------------------------------------------------------------------------------------
 struct AnalysisTcParams {
   PlaneGeom g;
@@ -790,7 +794,7 @@ struct AnalysisTcParams {
   const float* z;        // FUSE_GZ: saved act'(z)
   float* gz_out;
   float2* out;           // [nplanes][KH][MW]
-  const float* e1;       // [hi|lo] images, N1 rows x Wp
+  const float* e1;       // stacked [hi rows | lo rows] image, 2 N1 rows x Wp
   const float* a2;       // [hi|lo] images, KRp rows x Hp
   const float* cl;
   float scale;
@@ -801,26 +805,29 @@ struct AnalysisTcParams {
 };
 
 struct AnalysisTcSmem {
-  int e1, a2, ab, stage, total;   // byte offsets
-  int e1_one, a2_one, a_one, a_lbo, b2_one, b2_lbo;
+  int e1, a2, a, b2, xch, stage, total;   // byte offsets
+  int e1_bytes, a2_one, a_one, a_lbo, b2_bytes, b2_lbo;
 };
 
-constexpr int kAnThreads = 512;   // 16 warps: every SIMT phase of the per-plane pipeline is latency-bound per warp
+constexpr int kAnWorkers = 512;               // 16 worker warps: every SIMT phase of the pipeline is latency-bound per warp
+constexpr int kAnThreads = kAnWorkers + 32;   // + the MMA-issuing warp
+constexpr int kAnZRegs = 5;                   // float4 of act'(z) per worker loaded ahead of the staged plane
 
-__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int N1, int Wp, int Hp, int KRp, bool gz) {
+__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int KH, int N1, int Wp, int Hp, int KRp) {
   AnalysisTcSmem m;
-  m.e1_one = N1 * Wp * 4;
+  m.e1_bytes = 2 * N1 * Wp * 4;
   m.a2_one = KRp * Hp * 4;
   m.a_lbo = 16 * Hp + 16;                   // padded K-direction strides: conflict-free stores when lanes walk along K
   m.a_one = (Wp / 4) * m.a_lbo;
-  m.b2_lbo = 16 * N1 + 16;
-  m.b2_one = (Hp / 4) * m.b2_lbo;
+  m.b2_lbo = 16 * 2 * N1 + 16;
+  m.b2_bytes = (Hp / 4) * m.b2_lbo;
   int off = 0;
-  m.e1 = off; off += 2 * m.e1_one;
+  m.e1 = off; off += m.e1_bytes;
   m.a2 = off; off += 2 * m.a2_one;
-  const int ab_one = m.a_one > m.b2_one ? m.a_one : m.b2_one;
-  m.ab = off; off += 2 * ab_one;            // A images; later aliased by the B2 images, then by the sin-row exchange
-  m.stage = off; off += round_up(H * W, 4) * 4 * (gz ? 2 : 1);
+  m.a = off; off += 2 * m.a_one;
+  m.b2 = off; off += m.b2_bytes;
+  m.xch = off; off += round_up(KH * (N1 + 1) * 4, 16);
+  m.stage = off; off += round_up(H * W, 4) * 4;
   // The M = 128 descriptors always read 16 row groups (2 KB) per core-matrix column, also for operands with
   // fewer rows: keep that over-read inside the allocation for tiny planes.
   m.total = off + 4096;
@@ -832,6 +839,13 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+constexpr int kAnBarA = 2;         // A images stored (workers arrive, MMA warp syncs)
+constexpr int kAnBarEpi0 = 8;      // 8..11: sin rows exchanged, one barrier per worker warp group
+constexpr int kAnBarWorkers = 12;  // workers only
+constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp syncs)
 
 template <bool FUSE_GZ>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
@@ -841,10 +855,9 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
   const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
-  const AnalysisTcSmem so = analysis_tc_smem(H, W, N1, Wp, Hp, KRp, FUSE_GZ);
+  const AnalysisTcSmem so = analysis_tc_smem(H, W, KH, N1, Wp, Hp, KRp);
   const int HW = H * W;
   float* stage = reinterpret_cast<float*>(smem + so.stage);
-  float* stage_z = stage + round_up(HW, 4);
 
   const uint32_t tmem_cols = 6 * N1 <= 64 ? 64u : (6 * N1 <= 128 ? 128u : (6 * N1 <= 256 ? 256u : 512u));
   if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
@@ -857,204 +870,283 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   {  // constant operand images (final layout in global memory): straight copies
     const float4* s1 = reinterpret_cast<const float4*>(p.e1);
     float4* d1 = reinterpret_cast<float4*>(smem + so.e1);
-    for (int i = tid; i < 2 * so.e1_one / 16; i += kAnThreads) d1[i] = s1[i];
+    for (int i = tid; i < so.e1_bytes / 16; i += kAnThreads) d1[i] = s1[i];
     const float4* s2 = reinterpret_cast<const float4*>(p.a2);
     float4* d2 = reinterpret_cast<float4*>(smem + so.a2);
     for (int i = tid; i < 2 * so.a2_one / 16; i += kAnThreads) d2[i] = s2[i];
   }
-  // Planes whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy per tensor
-  // (cp.async.bulk, completion on an mbarrier); others fall back to per-thread 4-byte cp.async.
-  const bool bulk = (HW % 4) == 0;
-  auto prefetch_plane = [&](int q) {
-    const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-    if (bulk) {
-      if (tid == 0) {
-        const uint32_t bytes = (uint32_t)HW * 4u;
-        const uint32_t bar = smem_u32(&bar_stage);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FUSE_GZ ? 2u * bytes : bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(stage)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
-        if (FUSE_GZ)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(stage_z)), "l"(p.z + base), "r"(bytes), "r"(bar) : "memory");
-      }
-    } else {
-      for (int i = tid; i < HW; i += kAnThreads) {
-        cp_async4(stage + i, p.u + base + i);
-        if (FUSE_GZ) cp_async4(stage_z + i, p.z + base + i);
-      }
-      cp_async_commit();
-    }
-  };
+  fence_proxy_async();
   fence_before_sync();
   __syncthreads();                                     // barriers initialised, TMEM allocated, constant images stored
   fence_after_sync();
-  if ((int)blockIdx.x < p.nplanes) prefetch_plane(blockIdx.x);
   const uint32_t tmem = tmem_slot;
-  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // three split-pass tiles per stage
-  const uint32_t idesc = make_idesc_tf32(128, N1);
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // [hi*hi | hi*lo | lo*hi] tiles per stage
+  const uint32_t idesc_n2 = make_idesc_tf32(128, 2 * N1), idesc_n1 = make_idesc_tf32(128, N1);
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 16 * N1, lbo_a2 = 16 * KRp, lbo_b2 = (uint32_t)so.b2_lbo;
-  const int wq = warp & 3, wg = warp >> 2;
-  const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / row r of D2)
+  const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 32 * N1, lbo_a2 = 16 * KRp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int nyq = Wp / 4;                 // column quads of a row
-  const int nchunk = (nyq + 7) / 8;       // stage 1 is issued per chunk of 8 quads (32 columns = 4 K steps)
-  uint32_t phase = 0, stage_phase = 0;
+  const int nchunk = (nyq + 7) / 8;       // a warp covers 8 quads (32 columns) x 4 rows per step
+  const int nmine = (p.nplanes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // planes of this CTA
+  // Planes whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
+  // completion on an mbarrier) issued by the MMA warp; others fall back to per-thread 4-byte cp.async by the workers.
+  const bool bulk = (HW % 4) == 0;
 
-  for (int q = blockIdx.x; q < p.nplanes; q += gridDim.x) {
-    const long long tq0 = clock64();
-    if (bulk) mbar_wait(&bar_stage, stage_phase);
-    else cp_async_wait_all();
-    stage_phase ^= 1;
-    __syncthreads();                                   // staging(q) complete and visible
-    const long long tq1 = clock64();
-    if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);        // slot 32: wait for the staged plane
-    if (FUSE_GZ) {                                     // gz = gy * act'(z): coalesced store, kept in staging
+  if (warp == kAnWorkers / 32) {
+    // ------------------------------------------------------------------ MMA warp
+    const bool leader = elect_one();
+    auto l2_prefetch = [&](int j) {                    // pull plane j (and its act'(z)) into L2 ahead of its bulk copy
+      if (!bulk || j >= nmine || !leader) return;
+      const int q = blockIdx.x + j * gridDim.x;
       const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-      for (int i = tid; i < HW; i += kAnThreads) {
-        const float v = stage[i] * stage_z[i];
-        stage[i] = v;
-        p.gz_out[base + i] = v;
-      }
-      __syncthreads();
-    }
-    // staging -> A images (hi / lo) chunk by chunk; the stage-1 MMAs of a chunk are issued as soon as it is stored
-    uint64_t ah = make_desc(sbase + so.ab, lbo_a, 128), al = make_desc(sbase + so.ab + so.a_one, lbo_a, 128);
-    uint64_t bh = make_desc(sbase + so.e1, lbo_e1, 128), bl = make_desc(sbase + so.e1 + so.e1_one, lbo_e1, 128);
-    const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
-    for (int c = 0; c < nchunk; ++c) {
-      const int yq = c * 8 + (lane & 7);
-      if (yq < nyq) {
-        for (int row = warp * 4 + (lane >> 3); row < Hp; row += (kAnThreads / 32) * 4) {
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int y = yq * 4 + j;
-            v[j] = (row < H && y < W) ? stage[row * W + y] : 0.f;
-          }
-          float4 hi, lo;
-          split_tf32(v[0], hi.x, lo.x);
-          split_tf32(v[1], hi.y, lo.y);
-          split_tf32(v[2], hi.z, lo.z);
-          split_tf32(v[3], hi.w, lo.w);
-          const int off = (row & 7) * 16 + (row >> 3) * 128 + yq * so.a_lbo;
-          *reinterpret_cast<float4*>(smem + so.ab + off) = hi;
-          *reinterpret_cast<float4*>(smem + so.ab + so.a_one + off) = lo;
-        }
-      }
-      fence_proxy_async();
-      fence_before_sync();
-      __syncthreads();
-      if (c == nchunk - 1 && q + (int)gridDim.x < p.nplanes) prefetch_plane(q + gridDim.x);   // staging is free again
-      if (warp == 0) {
-        fence_after_sync();
-        const bool leader = elect_one();
-        const int s_end = min(c * 4 + 4, Wp / 8);
-        for (int s2 = c * 4; s2 < s_end; ++s2) {
-          const uint32_t acc = s2 > 0 ? 1u : 0u;
-          if (leader) {
-            mma_tf32(tmem_d1, ah, bh, idesc, acc);            // hi * hi
-            mma_tf32(tmem_d1 + N1, al, bh, idesc, acc);       // lo * hi
-            mma_tf32(tmem_d1 + 2 * N1, ah, bl, idesc, acc);   // hi * lo
-          }
-          ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
-        }
-        if (c == nchunk - 1 && leader) mma_commit(&mbar[0]);
-        __syncwarp();
-      }
-    }
-    const long long tq3 = clock64();
-    if (warp == 1) DENO_DBG_ADD(33, tq3 - tq1);        // slot 33: (gz +) chunked transform with stage-1 issue
-    mbar_wait(&mbar[0], phase);
-    fence_after_sync();
-    const long long tq4 = clock64();
-    if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);        // slot 35: wait for the stage-1 MMAs
-    // D1 -> B2 images [n][x] (alias the A images, which the finished stage-1 MMAs no longer read)
-    {
-      const int ncol_q = N1 / 4;                   // columns per warp group (N1 is a multiple of 32)
-      unsigned char* b2hi = smem + so.ab;
-      unsigned char* b2lo = b2hi + so.b2_one;
-      for (int c0 = 0; c0 < ncol_q; c0 += 8) {
-        float v[8], v1[8], v2[8];
-        const uint32_t ta = tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_q + c0);
-        tmem_ld8(ta, v);
-        tmem_ld8(ta + N1, v1);
-        tmem_ld8(ta + 2 * N1, v2);
-        if (xrow < Hp) {
-          const int kc = (xrow & 3) * 4 + (xrow >> 2) * so.b2_lbo;     // k' = x
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = wg * ncol_q + c0 + j;
-            const float t = xrow < H ? v[j] + (v1[j] + v2[j]) : 0.f;
-            float th, tl;
-            split_tf32(t, th, tl);
-            const int r0 = (n & 7) * 16 + (n >> 3) * 128;
-            *reinterpret_cast<float*>(b2hi + r0 + kc) = th;
-            *reinterpret_cast<float*>(b2lo + r0 + kc) = tl;
-          }
-        }
-      }
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    const long long tq5 = clock64();
-    if (warp == 1) DENO_DBG_ADD(36, tq5 - tq4);        // slot 36: D1 -> B2 conversion
-    if (warp == 0) {
+      const uint32_t bytes = (uint32_t)HW * 4u;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.u + base), "r"(bytes) : "memory");
+      if (FUSE_GZ) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.z + base), "r"(bytes) : "memory");
+    };
+    auto prefetch_plane = [&](int j) {                 // bulk copy of this CTA's j-th plane into the staging buffer
+      if (!bulk || j >= nmine || !leader) return;
+      const int q = blockIdx.x + j * gridDim.x;
+      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+      const uint32_t bytes = (uint32_t)HW * 4u;
+      const uint32_t bar = smem_u32(&bar_stage);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(stage)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
+    };
+    long long idle = 0;
+    auto stage1 = [&](int j) {                         // stage-1 MMAs of plane j once its A images are stored
+      uint64_t ah = make_desc(sbase + so.a, lbo_a, 128), al = make_desc(sbase + so.a + so.a_one, lbo_a, 128);
+      uint64_t be = make_desc(sbase + so.e1, lbo_e1, 128);
+      const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
+      const long long t0 = clock64();
+      nbar_sync(kAnBarA, kAnThreads);
       fence_after_sync();
-      const bool leader = elect_one();
+      idle += clock64() - t0;
+      prefetch_plane(j + 1);                           // every worker is past the staging buffer
+      l2_prefetch(j + 2);
+      for (int s2 = 0; s2 < Wp / 8; ++s2) {
+        const uint32_t acc = s2 > 0 ? 1u : 0u;
+        if (leader) {
+          mma_tf32(tmem_d1, ah, be, idesc_n2, acc);              // hi * [hi | lo]
+          mma_tf32(tmem_d1 + 2 * N1, al, be, idesc_n1, acc);     // lo * hi
+        }
+        ah += inc_a; al += inc_a; be += inc_b;
+      }
+      if (leader) mma_commit(&mbar[0]);
+      __syncwarp();
+    };
+    l2_prefetch(1);
+    prefetch_plane(0);
+    stage1(0);
+    for (int j = 0; j < nmine; ++j) {
+      const long long t0 = clock64();
+      nbar_sync(kAnBarB2, kAnThreads);                 // B2(j) stored; D1 and D2 of the previous plane drained
+      fence_after_sync();
+      idle += clock64() - t0;
       uint64_t a2h = make_desc(sbase + so.a2, lbo_a2, 128), a2l = make_desc(sbase + so.a2 + so.a2_one, lbo_a2, 128);
-      uint64_t b2h = make_desc(sbase + so.ab, lbo_b2, 128), b2l = make_desc(sbase + so.ab + so.b2_one, lbo_b2, 128);
+      uint64_t b2 = make_desc(sbase + so.b2, lbo_b2, 128);
       const uint64_t inc_a2 = (uint64_t)((2 * lbo_a2) >> 4), inc_b2 = (uint64_t)((2 * lbo_b2) >> 4);
       for (int s2 = 0; s2 < Hp / 8; ++s2) {
         const uint32_t acc = s2 > 0 ? 1u : 0u;
         if (leader) {
-          mma_tf32(tmem_d2, a2h, b2h, idesc, acc);
-          mma_tf32(tmem_d2 + N1, a2l, b2h, idesc, acc);
-          mma_tf32(tmem_d2 + 2 * N1, a2h, b2l, idesc, acc);
+          mma_tf32(tmem_d2, a2h, b2, idesc_n2, acc);
+          mma_tf32(tmem_d2 + 2 * N1, a2l, b2, idesc_n1, acc);
         }
-        a2h += inc_a2; a2l += inc_a2; b2h += inc_b2; b2l += inc_b2;
+        a2h += inc_a2; a2l += inc_a2; b2 += inc_b2;
       }
       if (leader) mma_commit(&mbar[1]);
       __syncwarp();
+      if (j + 1 < nmine) stage1(j + 1);
     }
-    mbar_wait(&mbar[1], phase);
-    fence_after_sync();
-    const long long tq6 = clock64();
-    if (warp == 1) DENO_DBG_ADD(37, tq6 - tq5);        // slot 37: stage-2 MMAs
-    // epilogue: rows k (cos) and KS0 + k (sin) of D2 are combined through shared memory (the B2 area is free now)
-    if (warp < 4) {
-      float* xch = reinterpret_cast<float*>(smem + so.ab);      // [KH][N1] sin-row values
-      const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
-      const bool warp_used = (wq * 32 < KH) || (wq * 32 + 32 > KS0 && wq * 32 < KS0 + KH);   // any cos / sin row in this quadrant
-      for (int c0 = 0; c0 < N1; c0 += 16) {
-        float dsum[16];
-        if (warp_used) tmem_ld16x3_sum(tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, (uint32_t)N1, dsum);
-        if (is_sin) {
+    if (leader) DENO_DBG_ADD(34, idle);                // slot 34: MMA warp waiting for the workers
+  } else {
+    // ------------------------------------------------------------------ workers
+    const int wq = warp & 3, wg = warp >> 2;
+    const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / row r of D2)
+    uint32_t phase = 0, stage_phase = 0;
+    auto issue_plane_cp_async = [&](int j) {           // non-bulk fallback
+      const int q = blockIdx.x + j * gridDim.x;
+      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+      for (int i = tid; i < HW; i += kAnWorkers) cp_async4(stage + i, p.u + base + i);
+      cp_async_commit();
+    };
+    auto transform = [&](int j) {                      // staged plane j -> (gz) -> A images (hi / lo)
+      const int q = blockIdx.x + j * gridDim.x;
+      const long long tq0 = clock64();
+      float4 zr[kAnZRegs];                             // act'(z) of this thread's first elements: in flight during the wait
+      if (FUSE_GZ && bulk) {
+        const float4* z4 = reinterpret_cast<const float4*>(p.z + plane_base(p.g, q / p.g.C, q % p.g.C));
 #pragma unroll
-          for (int j = 0; j < 16; ++j) xch[(xrow - KS0) * N1 + c0 + j] = dsum[j];
+        for (int r = 0; r < kAnZRegs; ++r) {
+          const int i = tid + r * kAnWorkers;
+          zr[r] = i < HW / 4 ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only; columns differ per pass
-        if (is_cos) {
-          float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
+      }
+      if (bulk) {
+        mbar_wait(&bar_stage, stage_phase);
+        stage_phase ^= 1;
+      } else {
+        cp_async_wait_all();
+        nbar_sync(kAnBarWorkers, kAnWorkers);
+      }
+      const long long tq1 = clock64();
+      if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);      // slot 32: wait for the staged plane
+      if (FUSE_GZ) {                                   // gz = gy * act'(z): coalesced store, kept in staging
+        const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+        if (bulk) {
+          float4* s4 = reinterpret_cast<float4*>(stage);
+          float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const int l = (c0 + j) >> 1;
-            if (l < MW) {
-              const float sr = xch[xrow * N1 + c0 + j], si = xch[xrow * N1 + c0 + j + 1];
-              const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
-              dst[l] = make_float2((dsum[j] + si) * f, (dsum[j + 1] - sr) * f);
+          for (int r = 0; r < kAnZRegs; ++r) {
+            const int i = tid + r * kAnWorkers;
+            if (i < HW / 4) {
+              const float4 a = s4[i], b = zr[r];
+              const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+              s4[i] = v;
+              g4[i] = v;
+            }
+          }
+          const float4* z4 = reinterpret_cast<const float4*>(p.z + base);
+          for (int i = tid + kAnZRegs * kAnWorkers; i < HW / 4; i += kAnWorkers) {   // planes beyond the register window
+            const float4 a = s4[i], b = __ldg(z4 + i);
+            const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            s4[i] = v;
+            g4[i] = v;
+          }
+        } else {
+          for (int i = tid; i < HW; i += kAnWorkers) {
+            const float v = stage[i] * __ldg(p.z + base + i);
+            stage[i] = v;
+            p.gz_out[base + i] = v;
+          }
+        }
+        nbar_sync(kAnBarWorkers, kAnWorkers);
+      }
+      const long long tq2 = clock64();
+      if (warp == 1) DENO_DBG_ADD(40, tq2 - tq1);      // slot 40: gz pass
+      {
+        const int r0 = warp * 4 + (lane >> 3), r1 = r0 + (kAnWorkers / 32) * 4;     // Hp <= 128: at most two rows per thread
+        const float* s0 = stage + r0 * W;
+        const float* s1 = stage + r1 * W;
+        for (int c = 0; c < nchunk; ++c) {
+          const int yq = c * 8 + (lane & 7);
+          if (yq < nyq) {
+            float v0[4], v1[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int y = yq * 4 + jj;
+              v0[jj] = (r0 < H && y < W) ? s0[y] : 0.f;
+              v1[jj] = (r1 < H && y < W) ? s1[y] : 0.f;
+            }
+            float4 hi, lo;
+            if (r0 < Hp) {
+              split_tf32(v0[0], hi.x, lo.x);
+              split_tf32(v0[1], hi.y, lo.y);
+              split_tf32(v0[2], hi.z, lo.z);
+              split_tf32(v0[3], hi.w, lo.w);
+              const int off = (r0 & 7) * 16 + (r0 >> 3) * 128 + yq * so.a_lbo;
+              *reinterpret_cast<float4*>(smem + so.a + off) = hi;
+              *reinterpret_cast<float4*>(smem + so.a + so.a_one + off) = lo;
+            }
+            if (r1 < Hp) {
+              split_tf32(v1[0], hi.x, lo.x);
+              split_tf32(v1[1], hi.y, lo.y);
+              split_tf32(v1[2], hi.z, lo.z);
+              split_tf32(v1[3], hi.w, lo.w);
+              const int off = (r1 & 7) * 16 + (r1 >> 3) * 128 + yq * so.a_lbo;
+              *reinterpret_cast<float4*>(smem + so.a + off) = hi;
+              *reinterpret_cast<float4*>(smem + so.a + so.a_one + off) = lo;
             }
           }
         }
       }
+      fence_proxy_async();
+      nbar_arrive(kAnBarA, kAnThreads);
+      if (!bulk && j + 1 < nmine) {
+        nbar_sync(kAnBarWorkers, kAnWorkers);          // every worker is past the staging buffer
+        issue_plane_cp_async(j + 1);
+      }
+      if (warp == 1) { DENO_DBG_ADD(33, clock64() - tq1); DENO_DBG_ADD(41, clock64() - tq2); }   // slots 33/41: (gz +) transform, chunk loop
+    };
+
+    if (!bulk) issue_plane_cp_async(0);
+    transform(0);
+    for (int j = 0; j < nmine; ++j) {
+      const int q = blockIdx.x + j * gridDim.x;
+      const long long tq3 = clock64();
+      mbar_wait(&mbar[0], phase);
+      fence_after_sync();
+      const long long tq4 = clock64();
+      if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);      // slot 35: wait for the stage-1 MMAs
+      // D1 -> B2 image [n][x]: hi rows n, lo rows N1 + n
+      {
+        const int ncol_q = N1 / 4;                 // columns per warp group (N1 is a multiple of 32)
+        unsigned char* b2hi = smem + so.b2;
+        unsigned char* b2lo = b2hi + (N1 >> 3) * 128;
+        for (int c0 = 0; c0 < ncol_q; c0 += 8) {
+          float v[8], v1[8], v2[8];
+          const uint32_t ta = tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * ncol_q + c0);
+          tmem_ld8(ta, v);
+          tmem_ld8(ta + N1, v1);
+          tmem_ld8(ta + 2 * N1, v2);
+          if (xrow < Hp) {
+            const int kc = (xrow & 3) * 4 + (xrow >> 2) * so.b2_lbo;     // k' = x
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const int n = wg * ncol_q + c0 + jj;
+              const float t = xrow < H ? v[jj] + (v1[jj] + v2[jj]) : 0.f;
+              float th, tl;
+              split_tf32(t, th, tl);
+              const int r0 = (n & 7) * 16 + (n >> 3) * 128;
+              *reinterpret_cast<float*>(b2hi + r0 + kc) = th;
+              *reinterpret_cast<float*>(b2lo + r0 + kc) = tl;
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      fence_before_sync();
+      nbar_arrive(kAnBarB2, kAnThreads);
+      const long long tq5 = clock64();
+      if (warp == 1) DENO_DBG_ADD(36, tq5 - tq4);      // slot 36: D1 -> B2 conversion
+      if (j + 1 < nmine) transform(j + 1);
+      const long long tq6 = clock64();
+      mbar_wait(&mbar[1], phase);
+      fence_after_sync();
+      const long long tq7 = clock64();
+      if (warp == 1) DENO_DBG_ADD(37, tq7 - tq6);      // slot 37: wait for the stage-2 MMAs
+      // epilogue: rows k (cos) and KS0 + k (sin) of D2 are combined through shared memory; warp group wg takes
+      // the column passes c0 = 16 wg, 16 wg + 64, ...
+      {
+        float* xch = reinterpret_cast<float*>(smem + so.xch);     // [KH][N1 + 1] sin-row values (odd pitch: conflict-free)
+        const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
+        const bool warp_used = (wq * 32 < KH) || (wq * 32 + 32 > KS0 && wq * 32 < KS0 + KH);   // any cos / sin row in this quadrant
+        for (int c0 = wg * 16; c0 < N1; c0 += 64) {
+          float dsum[16];
+          if (warp_used) tmem_ld16x3_sum(tmem_d2 + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, (uint32_t)N1, dsum);
+          if (is_sin) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) xch[(xrow - KS0) * (N1 + 1) + c0 + jj] = dsum[jj];
+          }
+          nbar_sync(kAnBarEpi0 + wg, 128);
+          if (is_cos) {
+            float2* dst = p.out + (long long)q * KH * MW + (long long)xrow * MW;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) {
+              const int l = (c0 + jj) >> 1;
+              if (l < MW) {
+                const float sr = xch[xrow * (N1 + 1) + c0 + jj], si = xch[xrow * (N1 + 1) + c0 + jj + 1];
+                const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+                dst[l] = make_float2((dsum[jj] + si) * f, (dsum[jj + 1] - sr) * f);
+              }
+            }
+          }
+        }
+      }
+      fence_before_sync();                             // D2 reads ordered before this thread's next hand-off
+      if (warp == 1) { DENO_DBG_ADD(38, clock64() - tq7); DENO_DBG_ADD(39, 1); }   // slots 38/39: epilogue, planes
+      phase ^= 1;
     }
-    fence_before_sync();
-    __syncthreads();                                   // TMEM and the A/B2 area are reused by the next plane
-    if (warp == 1) { DENO_DBG_ADD(38, clock64() - tq6); DENO_DBG_ADD(39, 1); }   // slots 38/39: epilogue, planes
-    phase ^= 1;
   }
-  if (!bulk) cp_async_wait_all();
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, tmem_cols);

@@ -25,32 +25,41 @@ lb = torch.zeros(Cc, device=dev, requires_grad=True)
 L = lib()
 buf = (C.c_longlong * 64)()
 gy = torch.randn((B, Cc) + spatial, generator=gen).to(dev)
-for it in range(3):
+
+
+def run(which):
+    """Phase counters of one forward ("fwd") or one backward ("bwd") after two warm-up passes."""
+    for it in range(3):
+        y = spectral_conv(x, ws, lw, lb, modes, "gelu")
+        torch.cuda.synchronize()
+        if which == "fwd" and it == 2:
+            L.deno_debug_read(buf, 64, 0)
+            return list(buf)
+        L.deno_debug_read(buf, 64, 1)
+        y.backward(gy)
+        torch.cuda.synchronize()
+        L.deno_debug_read(buf, 64, 0 if it == 2 else 1)
+    return list(buf)
+
+
+L.deno_debug_read(buf, 64, 1)
+for which in ("fwd", "bwd"):
+    v = run(which)
     L.deno_debug_read(buf, 64, 1)
-    y = spectral_conv(x, ws, lw, lb, modes, "gelu")
-    y.backward(gy)
-    torch.cuda.synchronize()
-    L.deno_debug_read(buf, 64, 0)
-names = ["unit setup", "epi wait D", "epi work", "load wait stage", "load split+sts", "mma wait A_X", "mma wait D free",
-         "mma issue", "roles total", "rows"]
-vals = list(buf)[:10]
-print(name, {n: v for n, v in zip(names, vals)})
-rows = max(vals[9], 1)
-print("per row cycles:", {n: round(v / rows) for n, v in zip(names[1:9], vals[1:9])}, "setup per unit-row", round(vals[0] / rows))
-
-
-an = ["wait staged plane", "transform", "cp.async issue", "stage-1 MMA", "D1->B2", "stage-2 MMA", "epilogue", "planes"]
-av = list(buf)[32:40]
-pl = max(av[7], 1)
-print("analysis_tc CTA0 (fwd + gz variants summed):", {n: v for n, v in zip(an, av)})
-print("analysis per plane:", {n: round(v / pl) for n, v in zip(an[:7], av[:7])}, "sum", round(sum(av[:7]) / pl))
-
-sn = ["setup", "stage A", "wait prev MMA", "split+sts", "barrier", "mma issue", "prefetch issue", "epilogue(prev row)", "rows"]
-sv = list(buf)[48:57]
-rw = max(sv[8], 1)
-print("synthesis_tc (bulk) CTA0, fwd + bwd-x kernels summed:", {n: v for n, v in zip(sn, sv)})
-print("synthesis per row:", {n: round(v / rw) for n, v in zip(sn[2:8], sv[2:8])}, "| per CTA: setup", sv[0] // 2, "stage A", sv[1] // 2)
-
-xv = list(buf)[57:61]
-ch = max(xv[3], 1)
-print("stage A detail: zero+twiddles per CTA", xv[0] // 2, "| per chunk: load", xv[1] // ch, "compute", xv[2] // ch, "chunks", xv[3])
+    an = ["wait staged plane", "transform", "mma warp idle", "stage-1 wait", "D1->B2", "stage-2 wait", "epilogue", "planes",
+          "gz pass", "chunk loop"]
+    av = v[32:42]
+    pl = max(av[7], 1)
+    print(f"[{which}] analysis_tc per plane (CTA 0, {av[7]} planes):",
+          {n: round(x_ / pl) for n, x_ in zip(an, av) if n != "planes"})
+    sn = ["setup", "stage A", "wait prev MMA", "split+sts", "barrier", "mma issue", "prefetch issue", "epilogue(prev row)", "rows"]
+    sv = v[48:57]
+    rw = max(sv[8], 1)
+    print(f"[{which}] synthesis_tc (bulk) CTA 0: setup {sv[0]} stage A {sv[1]} rows {sv[8]} | per row:",
+          {n: round(x_ / rw) for n, x_ in zip(sn[2:8], sv[2:8])})
+    xv = v[57:61]
+    ch = max(xv[3], 1)
+    print(f"[{which}] stage A detail: zero+twiddles {xv[0]} | per chunk: load {xv[1] // ch} compute {xv[2] // ch} chunks {xv[3]}")
+    wv = v[0:10]
+    if wv[9]:
+        print(f"[{which}] synthesis_ws slots:", wv)
