@@ -6,6 +6,11 @@ and ``forward(x, grid)`` follow /root/reference/Models/fno/FNOs.py:26-27,61 (1-D
 """
 from __future__ import annotations
 
+import ctypes as _C
+import os as _os
+
+from . import _capi
+from ._lib import lib as _lib
 from .spectral_layers import *  # noqa: F401,F403  (the reference module star-exports these names)
 from .spectral_layers import SpectralConv1d, SpectralConv2d, SpectralConv3d, nn, torch, F
 
@@ -65,6 +70,102 @@ def _tall_linear(x, layer: nn.Linear):
     return layer(x)
 
 
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _count_launches(L):
+    from .functional import _LAUNCHES
+    _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
+
+
+class _LiftFn(torch.autograd.Function):
+    """``pad(permute(fc0(cat(x, grid))))`` as one kernel (libdeno_spectral's ``deno_fno_lift_fwd/_bwd``,
+    include/deno_fno.h; /root/reference/Models/fno/FNOs.py:136-142)."""
+
+    @staticmethod
+    def forward(ctx, x, grid, w0, b0, desc):
+        L = _lib()
+        x, grid, w0, b0 = x.contiguous(), grid.contiguous(), w0.contiguous(), b0.contiguous()
+        nd = desc.ndim
+        padded = tuple(desc.spatial[a] + desc.padding for a in range(nd))
+        h = torch.empty((desc.batch, desc.width) + padded, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            _capi.check(L, L.deno_fno_lift_fwd(_C.byref(desc), x.data_ptr(), grid.data_ptr(), w0.data_ptr(),
+                                               b0.data_ptr(), h.data_ptr(), st), "deno_fno_lift_fwd")
+        _count_launches(L)
+        ctx.save_for_backward(x, grid, w0)
+        ctx.desc = desc
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        L = _lib()
+        x, grid, w0 = ctx.saved_tensors
+        desc = ctx.desc
+        gh = gh.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw0 = torch.empty_like(w0)
+        gb0 = torch.empty(w0.shape[0], dtype=torch.float32, device=gh.device)
+        nws = L.deno_fno_workspace_bytes(_C.byref(desc), _capi.FNO_WS_LIFT_BWD)
+        ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=gh.device)
+        with torch.cuda.device(gh.device):
+            st = torch.cuda.current_stream(gh.device).cuda_stream
+            _capi.check(L, L.deno_fno_lift_bwd(_C.byref(desc), gh.data_ptr(), x.data_ptr(), grid.data_ptr(),
+                                               w0.data_ptr(), _ptr(gx), gw0.data_ptr(), gb0.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), st), "deno_fno_lift_bwd")
+        _count_launches(L)
+        return gx, None, gw0, gb0, None
+
+
+class _ProjFn(torch.autograd.Function):
+    """``fc2(gelu(fc1(permute(crop(h)))))`` as one kernel; the hidden layer is never stored and is recomputed
+    in the backward pass (``deno_fno_proj_fwd/_bwd``; FNOs.py:147-152 of the reference)."""
+
+    @staticmethod
+    def forward(ctx, h, w1, b1, w2, b2, desc):
+        L = _lib()
+        h, w1, b1, w2, b2 = (t.contiguous() for t in (h, w1, b1, w2, b2))
+        nd = desc.ndim
+        y = torch.empty((desc.batch,) + tuple(desc.spatial[a] for a in range(nd)) + (desc.out_dim,),
+                        dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            st = torch.cuda.current_stream(h.device).cuda_stream
+            _capi.check(L, L.deno_fno_proj_fwd(_C.byref(desc), h.data_ptr(), w1.data_ptr(), b1.data_ptr(),
+                                               w2.data_ptr(), b2.data_ptr(), y.data_ptr(), st), "deno_fno_proj_fwd")
+        _count_launches(L)
+        ctx.save_for_backward(h, w1, b1, w2)
+        ctx.desc = desc
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = _lib()
+        h, w1, b1, w2 = ctx.saved_tensors
+        desc = ctx.desc
+        gy = gy.contiguous()
+        dev = gy.device
+        gh = torch.empty_like(h)
+        gw1, gb1, gw2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+        gb2 = torch.empty(w2.shape[0], dtype=torch.float32, device=dev)
+        nws = L.deno_fno_workspace_bytes(_C.byref(desc), _capi.FNO_WS_PROJ_BWD)
+        ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _capi.check(L, L.deno_fno_proj_bwd(_C.byref(desc), gy.data_ptr(), h.data_ptr(), w1.data_ptr(),
+                                               b1.data_ptr(), w2.data_ptr(), gh.data_ptr(), gw1.data_ptr(),
+                                               gb1.data_ptr(), gw2.data_ptr(), gb2.data_ptr(), ws.data_ptr(),
+                                               ws.numel(), st), "deno_fno_proj_bwd")
+        _count_launches(L)
+        return gh, gw1, gb1, gw2, gb2, None
+
+
+def _fused_ends_enabled() -> bool:
+    """``DENO_FUSED_ENDS=0`` keeps lift / projection on the torch-op path (read per call; A/B measurements)."""
+    return _os.environ.get("DENO_FUSED_ENDS", "1") != "0"
+
+
 class _FNONd(nn.Module):
     ndim = 0
 
@@ -91,16 +192,37 @@ class _FNONd(nn.Module):
     def forward(self, x, grid):
         """x: (B, *spatial, steps*in_dim), grid: (B, *spatial, ndim) -> (B, *spatial, out_dim)."""
         nd = self.ndim
-        h = _tall_linear(torch.cat((x, grid), dim=-1), self.fc0)
-        h = h.movedim(-1, 1)
-        if self.padding != 0:
-            h = F.pad(h, [0, self.padding] * nd)
+        desc = self._ends_desc(x, grid)
+        if desc is not None:
+            h = _LiftFn.apply(x, grid, self.fc0.weight, self.fc0.bias, desc)
+        else:
+            h = _tall_linear(torch.cat((x, grid), dim=-1), self.fc0)
+            h = h.movedim(-1, 1)
+            if self.padding != 0:
+                h = F.pad(h, [0, self.padding] * nd)
         for layer in self.convs:
             h = layer(h)
+        if desc is not None:
+            return _ProjFn.apply(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, desc)
         if self.padding != 0:
             h = h[(Ellipsis,) + (slice(None, -self.padding),) * nd]
         h = h.movedim(1, -1)
         return _tall_linear(F.gelu(_tall_linear(h, self.fc1)), self.fc2)
+
+    def _ends_desc(self, x, grid):
+        """Descriptor of the fused lift / projection kernels, or None when this call stays on torch ops
+        (CPU tensors fail later in the spectral layer; unusual dtypes, a grid that needs a gradient or a shape
+        outside include/deno_fno.h's coverage take the op-by-op path)."""
+        nd = self.ndim
+        if not (_fused_ends_enabled() and x.is_cuda and grid.is_cuda and x.dtype == torch.float32
+                and grid.dtype == torch.float32 and x.dim() == nd + 2 and grid.dim() == nd + 2
+                and x.shape[:-1] == grid.shape[:-1] and not grid.requires_grad
+                and self.fc0.weight.dtype == torch.float32
+                and x.shape[-1] + grid.shape[-1] == self.fc0.in_features):
+            return None
+        desc = _capi.make_fno_desc(x.shape[0], self.width, self.hidden, x.shape[-1], grid.shape[-1], self.out_dim,
+                                   tuple(x.shape[1:-1]), self.padding)
+        return desc if _lib().deno_fno_supported(_C.byref(desc)) else None
 
 
 class FNO1d(_FNONd):

@@ -41,12 +41,43 @@ def make_desc(batch, cin, cout, spatial, modes, act) -> SpectralDesc:
     return d
 
 
+class FnoDesc(C.Structure):
+    """struct deno_fno_desc (include/deno_fno.h)"""
+    _fields_ = [
+        ("ndim", C.c_int32),
+        ("batch", C.c_int32),
+        ("width", C.c_int32),
+        ("hidden", C.c_int32),
+        ("in_feats", C.c_int32),
+        ("grid_feats", C.c_int32),
+        ("out_dim", C.c_int32),
+        ("spatial", C.c_int32 * 3),
+        ("padding", C.c_int32),
+    ]
+
+
+FNO_WS_LIFT_BWD, FNO_WS_PROJ_BWD = 0, 1
+
+
+def make_fno_desc(batch, width, hidden, in_feats, grid_feats, out_dim, spatial, padding) -> FnoDesc:
+    nd = len(spatial)
+    assert 1 <= nd <= 3
+    d = FnoDesc()
+    d.ndim, d.batch, d.width, d.hidden = nd, int(batch), int(width), int(hidden)
+    d.in_feats, d.grid_feats, d.out_dim, d.padding = int(in_feats), int(grid_feats), int(out_dim), int(padding)
+    for a in range(3):
+        d.spatial[a] = int(spatial[a]) if a < nd else 0
+    return d
+
+
 class ProfileRecord(C.Structure):
     """struct deno_profile_record"""
     _fields_ = [("name", C.c_char * 32), ("ms", C.c_float)]
 
 
 _DESC_P = C.POINTER(SpectralDesc)
+_FNO_P = C.POINTER(FnoDesc)
+_V = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
 
 _PROTOTYPES = {
@@ -68,6 +99,12 @@ _PROTOTYPES = {
     "deno_spectral_bwd": (C.c_int, [_DESC_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
                                     C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),
+    "deno_fno_supported": (C.c_int, [_FNO_P]),
+    "deno_fno_workspace_bytes": (C.c_size_t, [_FNO_P, C.c_int]),
+    "deno_fno_lift_fwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V]),
+    "deno_fno_lift_bwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V, _V, _V, C.c_size_t, _V]),
+    "deno_fno_proj_fwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V, _V]),
+    "deno_fno_proj_bwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, C.c_size_t, _V]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -25,7 +25,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "deno_spectral.h"))
+    deps += [os.path.join(os.path.dirname(HERE), "include", h) for h in ("deno_spectral.h", "deno_fno.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -33,6 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("DENO_EXTRA_NVCC_FLAGS", "").split()      # experiments only (e.g. -DDENO_EXP_...)
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -5,6 +5,7 @@
 // covers, the tcgen05 path of spectral_tc.cuh) on the caller's stream.  No allocation, no
 // synchronisation, no global mutable state (except the opt-in profiling list).
 #include "../../include/deno_spectral.h"
+#include "../../include/deno_fno.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -16,8 +17,10 @@
 #include <vector>
 
 #include "spectral_simt.cuh"
+#include "fno_pointwise.cuh"
 #ifndef DENO_EMULATE
 #include "spectral_tc.cuh"
+#include "fno_proj_tc.cuh"
 #endif
 
 namespace {
@@ -809,7 +812,7 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
 
 #ifndef DENO_EMULATE
 // Tensor-core bypass weight gradient; returns the number of partials written, -1 if not applicable, -2 on error.
-int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, float* partial, cudaStream_t st) {
+int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, float* partial, cudaStream_t st, int gz_tps = 0) {
   const int COs = round_up(s.CO, 8), CIs = round_up(s.CI, 8);
   if (COs > 128 || CIs > 128) return -1;
   int NS = 4;
@@ -827,6 +830,7 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
   p.ngroups = (p.nbatch + NS - 1) / NS;
   p.ntiles = p.ngroups * p.tiles_per_plane;
   p.vec4 = (HW % 4 == 0) ? 1 : 0;
+  p.gz_tps = gz_tps;
   const tc::WgradTcSmem sm = tc::wgrad_tc_smem(NS, COs, CIs);
   if (sm.total > kMaxSmemBytes - 1024) return -1;
   const int need = (NS * (s.CO + s.CI) * (tc::kWgradKT / 4) + tc::kWgradLoaders - 1) / tc::kWgradLoaders;
@@ -878,7 +882,7 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
     if (nparts > 0) {
       WgradReduceParams r;
       r.partial = partial; r.ncta = nparts;
-      r.nw = s.CO * s.CI; r.nj = r.nw;         // the tensor-core partials carry no bias column
+      r.nw = s.CO * s.CI; r.nj = r.nw; r.pitch = r.nj;   // the tensor-core partials carry no bias column
       r.glw = glw; r.glb = nullptr;
       if (glw != nullptr) {
         prof_before("bypass_wgrad_reduce", st);
@@ -911,12 +915,171 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
   if (rc != DENO_OK) return rc;
   WgradReduceParams r;
   r.partial = partial; r.ncta = c.ncta;
-  r.nw = s.CO * s.CI; r.nj = r.nw + s.CO;
+  r.nw = s.CO * s.CI; r.nj = r.nw + s.CO; r.pitch = r.nj;
   r.glw = glw; r.glb = glb;
   prof_before("bypass_wgrad_reduce", st);
   DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
   return check_launch("bypass_wgrad_reduce", st);
 }
+
+// ------------------------------------------------------------------------------------------
+// Point-wise ends of the stack (include/deno_fno.h, kernels in fno_pointwise.cuh)
+// ------------------------------------------------------------------------------------------
+struct FnoShape {
+  PointGeom g;
+  int ndim, B, C, Hd, Kx, ND, O;
+  int pdim[3];      // padded extents, outermost first (as in the descriptor)
+};
+
+bool proj_width_built(int C) {
+  switch (C) {
+    case 8: case 12: case 16: case 20: case 24: case 32: case 40: case 48: case 64: return true;
+    default: return false;
+  }
+}
+
+int parse_fno(const deno_fno_desc* d, FnoShape& f) {
+  if (d == nullptr) return fail(DENO_E_INVALID, "null descriptor");
+  if (d->ndim < 1 || d->ndim > 3) return fail(DENO_E_INVALID, "ndim must be 1, 2 or 3");
+  if (d->batch < 1 || d->width < 1 || d->hidden < 1 || d->in_feats < 1 || d->grid_feats < 0 || d->out_dim < 1)
+    return fail(DENO_E_INVALID, "batch/width/hidden/in_feats/out_dim must be positive");
+  if (d->padding < 0) return fail(DENO_E_INVALID, "padding must be non-negative");
+  int sdim[3] = {1, 1, 1};
+  long long npts = 1, nppts = 1;
+  for (int a = 0; a < d->ndim; ++a) {
+    if (d->spatial[a] < 1) return fail(DENO_E_INVALID, "spatial sizes must be positive");
+    sdim[3 - d->ndim + a] = d->spatial[a];
+    npts *= d->spatial[a];
+    nppts *= d->spatial[a] + d->padding;
+  }
+  if ((long long)d->batch * nppts * (d->hidden > d->width ? d->hidden : d->width) >= (1LL << 40) || nppts >= (1LL << 31))
+    return fail(DENO_E_UNSUPPORTED, "grid too large");
+  if (d->in_feats + d->grid_feats > kLiftMaxK) return fail(DENO_E_UNSUPPORTED, "more than 16 input features (x ++ grid)");
+  if (d->out_dim > kProjMaxO) return fail(DENO_E_UNSUPPORTED, "out_dim above 4");
+  if (!proj_width_built(d->width)) return fail(DENO_E_UNSUPPORTED, "width is not one of the built point-wise kernels (8..64, multiple of 4)");
+  if (d->hidden > 1024) return fail(DENO_E_UNSUPPORTED, "hidden above 1024");
+  f.ndim = d->ndim; f.B = d->batch; f.C = d->width; f.Hd = d->hidden; f.Kx = d->in_feats; f.ND = d->grid_feats; f.O = d->out_dim;
+  f.g.sx = sdim[0]; f.g.sy = sdim[1]; f.g.sz = sdim[2];
+  f.g.px = d->ndim >= 3 ? sdim[0] + d->padding : 1;
+  f.g.py = d->ndim >= 2 ? sdim[1] + d->padding : 1;
+  f.g.pz = sdim[2] + d->padding;
+  f.g.npts = (int)npts;
+  f.g.nppts = (int)nppts;
+  for (int a = 0; a < 3; ++a) f.pdim[a] = a < d->ndim ? d->spatial[a] + d->padding : 0;
+  return DENO_OK;
+}
+
+// The fc1 weight gradient is gW[j, c] = sum_{b, pts} gt[b, j, pt] h[b, c, pt]: the bypass-conv weight gradient of a
+// layer with CI = width, CO = hidden on the padded grid.
+Shape proj_wgrad_shape(const FnoShape& f) {
+  Shape s;
+  memset(&s, 0, sizeof(s));
+  s.ndim = 1; s.B = f.B; s.CI = f.C; s.CO = f.Hd;
+  s.X = 1; s.H = 1; s.W = f.g.nppts;                // one flat "plane": the bypass_wgrad kernels only see points
+  s.mX = s.mH = s.mW = 1;
+  s.KX = s.KH = s.MW = 1;
+  s.KX4 = s.KH4 = s.MWp = 4;
+  s.S = f.g.nppts;
+  s.Q = 1; s.M = 1; s.act = 0;
+  return s;
+}
+
+struct ProjBwdWs { size_t gt, small, wpart, total; int nblk, nsmall; };
+int proj_bwd_ws(const FnoShape& f, ProjBwdWs& w) {
+  WgradCfg wc;
+  const Shape s = proj_wgrad_shape(f);
+  int rc = wgrad_cfg(s, wc);
+  if (rc != DENO_OK) return rc;
+  const int per = kProjThreads * proj_bwd_pt(f.C);
+  w.nblk = f.B * ((f.g.nppts + per - 1) / per);
+  w.nsmall = f.Hd + f.O * f.Hd + f.O;
+  size_t off = 0;
+  w.gt = off;    off += align_up((size_t)f.B * f.Hd * ((f.g.nppts + 127) / 128 * 128) * 4);   // plain or 128-point blocks
+  w.small = off; off += align_up((size_t)w.nblk * w.nsmall * 4);
+  const size_t nparts = (size_t)(wc.ncta > kWgradTcMaxCtas ? wc.ncta : kWgradTcMaxCtas);
+  w.wpart = off; off += align_up(nparts * ((size_t)f.Hd * f.C + f.Hd) * 4);
+  w.total = off;
+  return DENO_OK;
+}
+
+struct LiftBwdWs { size_t partial, total; int nblk, nj; };
+void lift_bwd_ws(const FnoShape& f, LiftBwdWs& w) {
+  w.nblk = f.B * ((f.g.nppts + kLiftThreads - 1) / kLiftThreads);
+  w.nj = f.C * (f.Kx + f.ND + 1);
+  w.partial = 0;
+  w.total = align_up((size_t)w.nblk * w.nj * 4);
+}
+
+// Sums `nparts` partial rows (pitch floats apart) of nj columns in a fixed order; the first nw sums go to out_w, the rest to out_b.
+int launch_reduce(const float* partial, int nparts, int pitch, int nj, int nw, float* out_w, float* out_b, const char* label,
+                  cudaStream_t st) {
+  WgradReduceParams r;
+  r.partial = partial; r.ncta = nparts; r.pitch = pitch; r.nj = nj; r.nw = nw; r.glw = out_w; r.glb = out_b;
+  prof_before(label, st);
+  DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+  return check_launch(label, st);
+}
+
+#ifndef DENO_EMULATE
+// Tensor-core projection kernels (fno_proj_tc.cuh): 0 = launched, -1 = shape not covered, else an error code.
+tc::ProjTcParams proj_tc_params(const FnoShape& f) {
+  tc::ProjTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = f.g; p.B = f.B; p.O = f.O;
+  p.tiles_per_sample = (f.g.nppts + 127) / 128;
+  p.ntiles = f.B * p.tiles_per_sample;
+  return p;
+}
+
+template <int C>
+int launch_proj_fwd_tc(const tc::ProjTcParams& p, cudaStream_t st) {
+  using S = tc::ProjTcSmem<C, 128>;
+  int rc = allow_smem(tc::fno_proj_fwd_tc_kernel<C, 128>, (size_t)S::fwd_total, "fno_proj_fwd_tc");
+  if (rc != DENO_OK) return rc;
+  const int grid = p.ntiles < 148 ? p.ntiles : 148;
+  prof_before("fno_proj_fwd_tc", st);
+  tc::fno_proj_fwd_tc_kernel<C, 128><<<dim3(grid), dim3(tc::kPjFwdThreads), (size_t)S::fwd_total, st>>>(p);
+  return check_launch("fno_proj_fwd_tc", st);
+}
+
+int try_launch_proj_fwd_tc(const FnoShape& f, tc::ProjTcParams p, cudaStream_t st) {
+  if (path_pref() == PathPref::Simt || f.Hd != 128) return -1;
+  if (f.C == 32) return launch_proj_fwd_tc<32>(p, st);
+  if (f.C == 64) return launch_proj_fwd_tc<64>(p, st);
+  return -1;
+}
+
+constexpr int kProjTcCtas = 148;
+// The tensor-core backward writes gt in blocks of 128 points (strided 512-byte runs cost 2.4x in the store path,
+// profiles/r2m_phase_probe.txt), which only the tensor-core bypass_wgrad kernel reads: both or neither.
+bool proj_bwd_tc_eligible(const FnoShape& f) {
+  return path_pref() != PathPref::Simt && f.Hd == 128 && f.C == 32 && f.O == 1 && wgrad_tc_eligible(proj_wgrad_shape(f));
+}
+int launch_proj_bwd_tc(const tc::ProjTcParams& p, int& nparts, cudaStream_t st) {
+  using S = tc::ProjTcSmem<32, 128>;
+  int rc = allow_smem(tc::fno_proj_bwd_tc_kernel<32, 128>, (size_t)S::bwd_total, "fno_proj_bwd_tc");
+  if (rc != DENO_OK) return rc;
+  const int grid = p.ntiles < kProjTcCtas ? p.ntiles : kProjTcCtas;
+  nparts = grid;
+  prof_before("fno_proj_bwd_tc", st);
+  tc::fno_proj_bwd_tc_kernel<32, 128><<<dim3(grid), dim3(tc::kPjThreads), (size_t)S::bwd_total, st>>>(p);
+  return check_launch("fno_proj_bwd_tc", st);
+}
+#endif
+
+#define DENO_PROJ_DISPATCH(C_, CALL) \
+  switch (C_) {                      \
+    case 8: CALL(8) break;           \
+    case 12: CALL(12) break;         \
+    case 16: CALL(16) break;         \
+    case 20: CALL(20) break;         \
+    case 24: CALL(24) break;         \
+    case 32: CALL(32) break;         \
+    case 40: CALL(40) break;         \
+    case 48: CALL(48) break;         \
+    case 64: CALL(64) break;         \
+    default: return fail(DENO_E_UNSUPPORTED, "width not built"); \
+  }
 
 }  // namespace
 
@@ -1142,6 +1305,177 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
     if ((rc = launch_bypass_wgrad(s, gz, x, ghat, partial, glin_w, glin_b, bias_from_dc, st))) return rc;
   }
   return DENO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ deno_fno.h
+int deno_fno_supported(const deno_fno_desc* desc) {
+  FnoShape f;
+  return parse_fno(desc, f) == DENO_OK ? 1 : 0;
+}
+
+size_t deno_fno_workspace_bytes(const deno_fno_desc* desc, int which) {
+  FnoShape f;
+  if (parse_fno(desc, f) != DENO_OK) return 0;
+  if (which == DENO_FNO_WS_LIFT_BWD) {
+    LiftBwdWs w;
+    lift_bwd_ws(f, w);
+    return w.total;
+  }
+  if (which == DENO_FNO_WS_PROJ_BWD) {
+    ProjBwdWs w;
+    if (proj_bwd_ws(f, w) != DENO_OK) return 0;
+    return w.total;
+  }
+  fail(DENO_E_INVALID, "unknown workspace kind");
+  return 0;
+}
+
+int deno_fno_lift_fwd(const deno_fno_desc* desc, const float* x, const float* grid, const float* w0, const float* b0,
+                      float* h, void* stream) {
+  g_launches = 0;
+  FnoShape f;
+  int rc = parse_fno(desc, f);
+  if (rc != DENO_OK) return rc;
+  if (!x || !w0 || !b0 || !h || (f.ND > 0 && !grid)) return fail(DENO_E_INVALID, "deno_fno_lift_fwd: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LiftParams p;
+  p.g = f.g; p.C = f.C; p.Kx = f.Kx; p.ND = f.ND;
+  p.x = x; p.grid = grid; p.w0 = w0; p.b0 = b0; p.h = h;
+  p.chunks = (f.g.nppts + kLiftThreads - 1) / kLiftThreads;
+  const size_t smem = (size_t)f.C * (f.Kx + f.ND + 1) * sizeof(float);
+  prof_before("fno_lift", st);
+  DENO_LAUNCH(fno_lift_kernel, dim3((unsigned)(f.B * p.chunks)), dim3(kLiftThreads), smem, st, p);
+  return check_launch("fno_lift", st);
+}
+
+int deno_fno_lift_bwd(const deno_fno_desc* desc, const float* gh, const float* x, const float* grid, const float* w0,
+                      float* gx, float* gw0, float* gb0, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  FnoShape f;
+  int rc = parse_fno(desc, f);
+  if (rc != DENO_OK) return rc;
+  if (!gh || !x || !w0 || (f.ND > 0 && !grid) || !gw0 || !gb0) return fail(DENO_E_INVALID, "deno_fno_lift_bwd: null pointer argument");
+  LiftBwdWs w;
+  lift_bwd_ws(f, w);
+  if (workspace == nullptr || workspace_bytes < w.total) return fail(DENO_E_WORKSPACE, "deno_fno_lift_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LiftBwdParams p;
+  p.g = f.g; p.C = f.C; p.Kx = f.Kx; p.ND = f.ND;
+  p.gh = gh; p.x = x; p.grid = grid; p.w0 = w0; p.gx = gx;
+  p.partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.partial);
+  p.chunks = (f.g.nppts + kLiftThreads - 1) / kLiftThreads;
+  const size_t smem = lift_bwd_smem_bytes(f.C, f.Kx + f.ND);
+  rc = allow_smem(fno_lift_bwd_kernel, smem, "fno_lift_bwd");
+  if (rc != DENO_OK) return rc;
+  prof_before("fno_lift_bwd", st);
+  DENO_LAUNCH(fno_lift_bwd_kernel, dim3((unsigned)w.nblk), dim3(kLiftThreads), smem, st, p);
+  rc = check_launch("fno_lift_bwd", st);
+  if (rc != DENO_OK) return rc;
+  return launch_reduce(p.partial, w.nblk, w.nj, w.nj, f.C * (f.Kx + f.ND), gw0, gb0, "fno_lift_reduce", st);
+}
+
+int deno_fno_proj_fwd(const deno_fno_desc* desc, const float* h, const float* w1, const float* b1, const float* w2,
+                      const float* b2, float* y, void* stream) {
+  g_launches = 0;
+  FnoShape f;
+  int rc = parse_fno(desc, f);
+  if (rc != DENO_OK) return rc;
+  if (!h || !w1 || !b1 || !w2 || !b2 || !y) return fail(DENO_E_INVALID, "deno_fno_proj_fwd: null pointer argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProjParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = f.g; p.C = f.C; p.Hd = f.Hd; p.O = f.O;
+  p.h = h; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y = y;
+#ifndef DENO_EMULATE
+  {
+    tc::ProjTcParams tp = proj_tc_params(f);
+    tp.h = h; tp.w1 = w1; tp.b1 = b1; tp.w2 = w2; tp.b2 = b2; tp.y = y;
+    rc = try_launch_proj_fwd_tc(f, tp, st);
+    if (rc != -1) return rc;
+  }
+#endif
+  const int per = kProjThreads * proj_fwd_pt(f.C);
+  p.chunks = (f.g.nppts + per - 1) / per;
+  const size_t smem = proj_fwd_smem_bytes(f.C, f.Hd, f.O);
+  if (smem > (size_t)kMaxSmemBytes) return fail(DENO_E_UNSUPPORTED, "projection weights do not fit shared memory");
+#define DENO_PROJ_FWD(CV)                                                                                      \
+  {                                                                                                            \
+    auto kern = fno_proj_fwd_kernel<CV, proj_fwd_pt(CV)>;                                                      \
+    rc = allow_smem(kern, smem, "fno_proj_fwd");                                                               \
+    if (rc != DENO_OK) return rc;                                                                              \
+    prof_before("fno_proj_fwd", st);                                                                           \
+    DENO_LAUNCH(kern, dim3((unsigned)(f.B * p.chunks)), dim3(kProjThreads), smem, st, p);                      \
+  }
+  DENO_PROJ_DISPATCH(f.C, DENO_PROJ_FWD)
+#undef DENO_PROJ_FWD
+  return check_launch("fno_proj_fwd", st);
+}
+
+int deno_fno_proj_bwd(const deno_fno_desc* desc, const float* gy, const float* h, const float* w1, const float* b1,
+                      const float* w2, float* gh, float* gw1, float* gb1, float* gw2, float* gb2, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  FnoShape f;
+  int rc = parse_fno(desc, f);
+  if (rc != DENO_OK) return rc;
+  if (!gy || !h || !w1 || !b1 || !w2 || !gh || !gw1 || !gb1 || !gw2 || !gb2)
+    return fail(DENO_E_INVALID, "deno_fno_proj_bwd: null pointer argument");
+  ProjBwdWs w;
+  rc = proj_bwd_ws(f, w);
+  if (rc != DENO_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < w.total) return fail(DENO_E_WORKSPACE, "deno_fno_proj_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  ProjParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = f.g; p.C = f.C; p.Hd = f.Hd; p.O = f.O;
+  p.h = h; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = nullptr; p.gy = gy; p.gh = gh;
+  p.gt = reinterpret_cast<float*>(ws + w.gt);
+  p.partial = reinterpret_cast<float*>(ws + w.small);
+  int nparts = w.nblk;
+  bool done = false;
+#ifndef DENO_EMULATE
+  if (proj_bwd_tc_eligible(f)) {
+    tc::ProjTcParams tp = proj_tc_params(f);
+    tp.h = h; tp.w1 = w1; tp.b1 = b1; tp.w2 = w2; tp.gy = gy; tp.gh = gh; tp.gt = p.gt; tp.partial = p.partial;
+    rc = launch_proj_bwd_tc(tp, nparts, st);
+    if (rc != DENO_OK) return rc;
+    done = true;
+  }
+#endif
+  const int per = kProjThreads * proj_bwd_pt(f.C);
+  p.chunks = (f.g.nppts + per - 1) / per;
+  const size_t smem = proj_bwd_smem_bytes(f.C, f.Hd, f.O);
+  if (!done && smem > (size_t)kMaxSmemBytes) return fail(DENO_E_UNSUPPORTED, "projection weights do not fit shared memory");
+#define DENO_PROJ_BWD(CV)                                                                                      \
+  {                                                                                                            \
+    auto kern = fno_proj_bwd_kernel<CV, proj_bwd_pt(CV)>;                                                      \
+    rc = allow_smem(kern, smem, "fno_proj_bwd");                                                               \
+    if (rc != DENO_OK) return rc;                                                                              \
+    prof_before("fno_proj_bwd", st);                                                                           \
+    DENO_LAUNCH(kern, dim3((unsigned)w.nblk), dim3(kProjThreads), smem, st, p);                                \
+  }
+  if (!done) {
+    DENO_PROJ_DISPATCH(f.C, DENO_PROJ_BWD)
+    rc = check_launch("fno_proj_bwd", st);
+    if (rc != DENO_OK) return rc;
+  }
+#undef DENO_PROJ_BWD
+  // a partial row is gb1 | gw2 | gb2: two passes of the reduce kernel ("first nw columns / the rest") split it
+  rc = launch_reduce(p.partial, nparts, w.nsmall, f.Hd + f.O * f.Hd, f.Hd, gb1, gw2, "fno_proj_reduce", st);
+  if (rc != DENO_OK) return rc;
+  rc = launch_reduce(p.partial + f.Hd + f.O * f.Hd, nparts, w.nsmall, f.O, f.O, gb2, nullptr, "fno_proj_reduce", st);
+  if (rc != DENO_OK) return rc;
+  const Shape s = proj_wgrad_shape(f);
+  float* wpart = reinterpret_cast<float*>(ws + w.wpart);
+#ifndef DENO_EMULATE
+  if (done) {                                          // gt is blocked: tensor-core weight gradient only
+    const int np = try_launch_bypass_wgrad_tc(s, p.gt, h, wpart, st, (f.g.nppts + 127) / 128);
+    if (np <= 0) return np == -2 ? DENO_E_CUDA : fail(DENO_E_UNSUPPORTED, "bypass_wgrad_tc refused the projection shape");
+    return launch_reduce(wpart, np, f.Hd * f.C, f.Hd * f.C, f.Hd * f.C, gw1, nullptr, "bypass_wgrad_reduce", st);
+  }
+#endif
+  return launch_bypass_wgrad(s, p.gt, h, nullptr, wpart, gw1, nullptr, true, st);
 }
 
 }  // extern "C"

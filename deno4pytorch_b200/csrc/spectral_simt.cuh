@@ -672,6 +672,7 @@ __global__ void bypass_wgrad_partial_kernel(WgradParams p) {
 struct WgradReduceParams {
   const float* partial;
   int ncta, nj, nw;   // nj = CO*CI + CO outputs, the first nw go to glw, the rest to glb
+  int pitch;          // floats between consecutive partial rows (>= nj)
   float* glw;         // may be null
   float* glb;         // may be null
 };
@@ -689,7 +690,7 @@ __global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int c = c0 + 8 * u;
-        v[u] = ldg_ordered(p.partial + (long long)min(c, p.ncta - 1) * p.nj + j);
+        v[u] = ldg_ordered(p.partial + (long long)min(c, p.ncta - 1) * p.pitch + j);
         if (c >= p.ncta) v[u] = 0.f;
       }
       DENO_SCHED_FENCE();

@@ -1177,6 +1177,7 @@ struct WgradTcParams {
   int ntiles;            // ngroups * tiles_per_plane
   int nbatch;            // NB'
   int vec4;              // H*W % 4 == 0: 16-byte global loads are aligned
+  int gz_tps;            // > 0: gz is stored in blocks of 128 points, [batch][gz_tps blocks][CO][128] (fno_proj_bwd_tc)
 };
 
 constexpr int kWgradKT = 32;        // points per tile (two shared-memory stages of operand images)
@@ -1263,7 +1264,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
         const int ir = isg ? j * COs + r : j * CIs + (r - CO);
         const int off = (ir & 7) * 16 + (ir >> 3) * 128 + pq * (isg ? so.g_lbo : so.x_lbo);
         meta[it] = 0x80000000u | (isg ? 0x40000000u : 0u) | ((uint32_t)j << 28) | (uint32_t)off;
-        roff[it] = (int)((isg ? r : r - CO) * p.gx.sc) + pq * 4;
+        roff[it] = (isg && p.gz_tps > 0) ? r * 128 + pq * 4 : (int)((isg ? r : r - CO) * p.gx.sc) + pq * 4;
       }
     }
     float4 ra[NIT], rb[NIT];
@@ -1275,7 +1276,8 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int bp = min(grp * NS + j, p.nbatch - 1);
-        gb[j] = (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
+        gb[j] = p.gz_tps > 0 ? ((long long)bp * p.gz_tps + (p0 >> 7)) * p.CO * 128 + (p0 & 127)
+                             : (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
         xb[j] = plane_base(p.gx, bp, 0) + p0;
       }
 #pragma unroll

@@ -25,7 +25,8 @@ def _stale():
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".cu", ".cuh"))]
-    deps += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "deno_spectral.h")]
+    deps += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "deno_spectral.h"),
+             os.path.join(ROOT, "include", "deno_fno.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -110,3 +111,59 @@ class EmuLayer:
         _capi.check(lib, rc, "deno_spectral_bwd")
         self.bwd_launches = lib.deno_spectral_last_launch_count()
         return gx, gws, glw, glb
+
+
+class EmuEnds:
+    """Lift / projection calls (include/deno_fno.h) through the emulated C ABI; numpy in, numpy out."""
+
+    def __init__(self, batch, width, hidden, in_feats, grid_feats, out_dim, spatial, padding):
+        self.lib = load()
+        self.desc = _capi.make_fno_desc(batch, width, hidden, in_feats, grid_feats, out_dim, spatial, padding)
+        self.spatial = tuple(spatial)
+        self.padded = tuple(s + padding for s in spatial)
+        self.B, self.C, self.Hd, self.O = batch, width, hidden, out_dim
+
+    def supported(self):
+        return bool(self.lib.deno_fno_supported(C.byref(self.desc)))
+
+    def _ws(self, which):
+        n = self.lib.deno_fno_workspace_bytes(C.byref(self.desc), which)
+        return np.full(max(n, 1), 0xFF, dtype=np.uint8)   # NaN poison
+
+    def lift(self, x, grid, w0, b0):
+        x, grid, w0, b0 = (np.ascontiguousarray(a, dtype=np.float32) for a in (x, grid, w0, b0))
+        h = np.full((self.B, self.C) + self.padded, np.nan, dtype=np.float32)
+        _capi.check(self.lib, self.lib.deno_fno_lift_fwd(C.byref(self.desc), _ptr(x), _ptr(grid), _ptr(w0), _ptr(b0),
+                                                         _ptr(h), None), "lift_fwd")
+        return h
+
+    def lift_bwd(self, gh, x, grid, w0, want_gx=True):
+        gh, x, grid, w0 = (np.ascontiguousarray(a, dtype=np.float32) for a in (gh, x, grid, w0))
+        gx = np.full(x.shape, np.nan, dtype=np.float32) if want_gx else None
+        gw0 = np.full(w0.shape, np.nan, dtype=np.float32)
+        gb0 = np.full(w0.shape[0], np.nan, dtype=np.float32)
+        ws = self._ws(_capi.FNO_WS_LIFT_BWD)
+        _capi.check(self.lib, self.lib.deno_fno_lift_bwd(C.byref(self.desc), _ptr(gh), _ptr(x), _ptr(grid), _ptr(w0),
+                                                         _ptr(gx), _ptr(gw0), _ptr(gb0), _ptr(ws), ws.size, None),
+                    "lift_bwd")
+        return gx, gw0, gb0
+
+    def proj(self, h, w1, b1, w2, b2):
+        h, w1, b1, w2, b2 = (np.ascontiguousarray(a, dtype=np.float32) for a in (h, w1, b1, w2, b2))
+        y = np.full((self.B,) + self.spatial + (self.O,), np.nan, dtype=np.float32)
+        _capi.check(self.lib, self.lib.deno_fno_proj_fwd(C.byref(self.desc), _ptr(h), _ptr(w1), _ptr(b1), _ptr(w2),
+                                                         _ptr(b2), _ptr(y), None), "proj_fwd")
+        return y
+
+    def proj_bwd(self, gy, h, w1, b1, w2):
+        gy, h, w1, b1, w2 = (np.ascontiguousarray(a, dtype=np.float32) for a in (gy, h, w1, b1, w2))
+        gh = np.full(h.shape, np.nan, dtype=np.float32)
+        gw1 = np.full(w1.shape, np.nan, dtype=np.float32)
+        gb1 = np.full(b1.shape, np.nan, dtype=np.float32)
+        gw2 = np.full(w2.shape, np.nan, dtype=np.float32)
+        gb2 = np.full(w2.shape[0], np.nan, dtype=np.float32)
+        ws = self._ws(_capi.FNO_WS_PROJ_BWD)
+        _capi.check(self.lib, self.lib.deno_fno_proj_bwd(C.byref(self.desc), _ptr(gy), _ptr(h), _ptr(w1), _ptr(b1),
+                                                         _ptr(w2), _ptr(gh), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2),
+                                                         _ptr(ws), ws.size, None), "proj_bwd")
+        return gh, gw1, gb1, gw2, gb2

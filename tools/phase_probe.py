@@ -63,3 +63,28 @@ for which in ("fwd", "bwd"):
     wv = v[0:10]
     if wv[9]:
         print(f"[{which}] synthesis_ws slots:", wv)
+
+
+# projection kernels (fno_proj_tc.cuh), Darcy shapes
+from deno4pytorch_b200 import _capi  # noqa: E402
+from deno4pytorch_b200.FNOs import _ProjFn  # noqa: E402
+d = _capi.make_fno_desc(20, 32, 128, 1, 2, 1, (85, 85), 9)
+hp = torch.randn(20, 32, 94, 94, device=dev, requires_grad=True)
+w1 = (torch.randn(128, 32, device=dev) / 32 ** 0.5).requires_grad_(True)
+b1 = torch.zeros(128, device=dev, requires_grad=True)
+w2 = (torch.randn(1, 128, device=dev) / 128 ** 0.5).requires_grad_(True)
+b2 = torch.zeros(1, device=dev, requires_grad=True)
+gyp = torch.randn(20, 85, 85, 1, device=dev)
+for it in range(3):
+    L.deno_debug_read(buf, 64, 1)
+    yp = _ProjFn.apply(hp, w1, b1, w2, b2, d)
+    yp.backward(gyp)
+    torch.cuda.synchronize()
+    L.deno_debug_read(buf, 64, 0)
+v = list(buf)
+fn = ["wait GEMM1", "A1 store + prefetch", "epilogue math", "exchange + store"]
+nt = max(v[20], 1)
+print(f"proj_fwd_tc per tile (CTA 0, {v[20]} tiles):", {n: round(x_ / nt) for n, x_ in zip(fn, v[16:20])})
+bn = ["wait GEMM1", "chunk math + stores", "ring waits", "A1 store + prefetch", "wait GEMM2", "gh epilogue"]
+nt = max(v[27], 1)
+print(f"proj_bwd_tc per tile (CTA 0, {v[27]} tiles):", {n: round(x_ / nt) for n, x_ in zip(bn, v[21:27])})
