@@ -236,9 +236,18 @@ def layer_roofline(workload: str, device, hbm_peak: float, reps: int = 20):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     layer_bytes = 7 * A + 3 * Wb
     layer_gbs = layer_bytes / (layer_ms * 1e-3) / 1e9
+    traffic, traffic_note = None, None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of this kernel
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == workload and dom in tj["kernels"]:
+            traffic = tj["kernels"][dom]["dram_bytes_read"] + tj["kernels"][dom]["dram_bytes_write"]
+            traffic_note = tj["source"] + "; " + tj["note"]
+    except (OSError, ValueError, KeyError):
+        pass
     roof = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None,
+        "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_note,
         "algorithmic_bytes_per_launch": dom_bytes, "kernel_us": dom_ms * 1e3,
         "layer_fwd_bwd": {"algorithmic_bytes": layer_bytes, "us": layer_ms * 1e3, "achieved": layer_gbs,
                           "frac": layer_gbs / hbm_peak, "formula": "7A+3Wb (SURVEY 8d)"},

@@ -74,6 +74,11 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _grad_sink(param, like):
+    from .functional import grad_sink
+    return grad_sink(param, like)
+
+
 def _count_launches(L):
     from .functional import _LAUNCHES
     _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
@@ -84,9 +89,9 @@ class _LiftFn(torch.autograd.Function):
     include/deno_fno.h; /root/reference/Models/fno/FNOs.py:136-142)."""
 
     @staticmethod
-    def forward(ctx, x, grid, w0, b0, desc):
+    def forward(ctx, x, grid, w0_in, b0_in, desc):
         L = _lib()
-        x, grid, w0, b0 = x.contiguous(), grid.contiguous(), w0.contiguous(), b0.contiguous()
+        x, grid, w0, b0 = x.contiguous(), grid.contiguous(), w0_in.contiguous(), b0_in.contiguous()
         nd = desc.ndim
         padded = tuple(desc.spatial[a] + desc.padding for a in range(nd))
         h = torch.empty((desc.batch, desc.width) + padded, dtype=torch.float32, device=x.device)
@@ -96,6 +101,7 @@ class _LiftFn(torch.autograd.Function):
                                                b0.data_ptr(), h.data_ptr(), st), "deno_fno_lift_fwd")
         _count_launches(L)
         ctx.save_for_backward(x, grid, w0)
+        ctx.sinks = (_grad_sink(w0_in, w0), _grad_sink(b0_in, b0))
         ctx.desc = desc
         return h
 
@@ -106,8 +112,9 @@ class _LiftFn(torch.autograd.Function):
         desc = ctx.desc
         gh = gh.contiguous()
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        gw0 = torch.empty_like(w0)
-        gb0 = torch.empty(w0.shape[0], dtype=torch.float32, device=gh.device)
+        s_w0, s_b0 = ctx.sinks
+        gw0 = s_w0 if s_w0 is not None else torch.empty_like(w0)
+        gb0 = s_b0 if s_b0 is not None else torch.empty(w0.shape[0], dtype=torch.float32, device=gh.device)
         nws = L.deno_fno_workspace_bytes(_C.byref(desc), _capi.FNO_WS_LIFT_BWD)
         ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=gh.device)
         with torch.cuda.device(gh.device):
@@ -116,7 +123,7 @@ class _LiftFn(torch.autograd.Function):
                                                w0.data_ptr(), _ptr(gx), gw0.data_ptr(), gb0.data_ptr(),
                                                ws.data_ptr(), ws.numel(), st), "deno_fno_lift_bwd")
         _count_launches(L)
-        return gx, None, gw0, gb0, None
+        return gx, None, None if s_w0 is not None else gw0, None if s_b0 is not None else gb0, None
 
 
 class _ProjFn(torch.autograd.Function):
@@ -124,9 +131,9 @@ class _ProjFn(torch.autograd.Function):
     in the backward pass (``deno_fno_proj_fwd/_bwd``; FNOs.py:147-152 of the reference)."""
 
     @staticmethod
-    def forward(ctx, h, w1, b1, w2, b2, desc):
+    def forward(ctx, h, w1_in, b1_in, w2_in, b2_in, desc):
         L = _lib()
-        h, w1, b1, w2, b2 = (t.contiguous() for t in (h, w1, b1, w2, b2))
+        h, w1, b1, w2, b2 = (t.contiguous() for t in (h, w1_in, b1_in, w2_in, b2_in))
         nd = desc.ndim
         y = torch.empty((desc.batch,) + tuple(desc.spatial[a] for a in range(nd)) + (desc.out_dim,),
                         dtype=torch.float32, device=h.device)
@@ -136,6 +143,7 @@ class _ProjFn(torch.autograd.Function):
                                                w2.data_ptr(), b2.data_ptr(), y.data_ptr(), st), "deno_fno_proj_fwd")
         _count_launches(L)
         ctx.save_for_backward(h, w1, b1, w2)
+        ctx.sinks = tuple(_grad_sink(a, c) for a, c in ((w1_in, w1), (b1_in, b1), (w2_in, w2), (b2_in, b2)))
         ctx.desc = desc
         return y
 
@@ -147,8 +155,11 @@ class _ProjFn(torch.autograd.Function):
         gy = gy.contiguous()
         dev = gy.device
         gh = torch.empty_like(h)
-        gw1, gb1, gw2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
-        gb2 = torch.empty(w2.shape[0], dtype=torch.float32, device=dev)
+        sinks = ctx.sinks
+        gw1 = sinks[0] if sinks[0] is not None else torch.empty_like(w1)
+        gb1 = sinks[1] if sinks[1] is not None else torch.empty_like(b1)
+        gw2 = sinks[2] if sinks[2] is not None else torch.empty_like(w2)
+        gb2 = sinks[3] if sinks[3] is not None else torch.empty(w2.shape[0], dtype=torch.float32, device=dev)
         nws = L.deno_fno_workspace_bytes(_C.byref(desc), _capi.FNO_WS_PROJ_BWD)
         ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
@@ -158,7 +169,7 @@ class _ProjFn(torch.autograd.Function):
                                                gb1.data_ptr(), gw2.data_ptr(), gb2.data_ptr(), ws.data_ptr(),
                                                ws.numel(), st), "deno_fno_proj_bwd")
         _count_launches(L)
-        return gh, gw1, gb1, gw2, gb2, None
+        return (gh,) + tuple(None if sk is not None else g for sk, g in zip(sinks, (gw1, gb1, gw2, gb2))) + (None,)
 
 
 def _fused_ends_enabled() -> bool:

@@ -73,6 +73,20 @@ def _check_weight(w: torch.Tensor, cin: int, cout: int, modes: Tuple[int, ...], 
                        f"got {w.dtype} {tuple(w.shape)}")
 
 
+def grad_sink(param, like: Optional[torch.Tensor] = None):
+    """Where the backward kernels may write this parameter's gradient DIRECTLY: the ``.grad`` view registered by
+    ``parallel.FlatGradients.direct_writes()`` (one flat buffer for the optimiser and the all-reduce).  With a sink
+    the backward returns ``None`` for the parameter, so autograd launches no ``grad += new`` kernel for it.  Only
+    valid when the parameter is used once per backward pass (the registering side's responsibility)."""
+    s = getattr(param, "_deno_grad_sink", None)
+    if s is None or not s.is_contiguous():
+        return None
+    ref = param if like is None else like
+    if s.dtype != ref.dtype or tuple(s.shape) != tuple(ref.shape) or s.device != ref.device:
+        return None
+    return s
+
+
 class _SpectralConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, lin_w, lin_b, modes, act, *weights):
@@ -115,6 +129,8 @@ class _SpectralConvFn(torch.autograd.Function):
             _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
         if needs_grad:
             ctx.save_for_backward(xc, z, xhat, lw, *wc)
+            ctx.sinks = (grad_sink(lin_w, lw), None if lin_b is None else grad_sink(lin_b, lb),
+                         [grad_sink(w, c) for w, c in zip(weights, wc)])
             ctx.desc = d
             ctx.has_bias = lin_b is not None
             ctx.weight_meta = [(w.dtype, tuple(w.shape)) for w in weights]
@@ -134,9 +150,12 @@ class _SpectralConvFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             tw = _twiddles(d, dev)
             gx = torch.empty_like(xc) if need_x else None
-            gws = [torch.empty(shape, dtype=dtype, device=dev) for dtype, shape in ctx.weight_meta] if need_w else None
-            glw = torch.empty_like(lw) if need_lw else None
-            glb = torch.empty(lw.shape[0], dtype=torch.float32, device=dev) if (need_lb and ctx.has_bias) else None
+            s_lw, s_lb, s_w = ctx.sinks
+            gws = [sk if sk is not None else torch.empty(shape, dtype=dtype, device=dev)
+                   for sk, (dtype, shape) in zip(s_w, ctx.weight_meta)] if need_w else None
+            glw = (s_lw if s_lw is not None else torch.empty_like(lw)) if need_lw else None
+            glb = (s_lb if s_lb is not None else torch.empty(lw.shape[0], dtype=torch.float32, device=dev)) \
+                if (need_lb and ctx.has_bias) else None
             nws = L.deno_spectral_workspace_bytes(C.byref(d), 1)
             ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -148,8 +167,9 @@ class _SpectralConvFn(torch.autograd.Function):
                                      ws.data_ptr(), nws, stream)
             _capi.check(L, rc, "deno_spectral_bwd")
             _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
-        grads_w = tuple(gws) if gws is not None else (None,) * len(wc)
-        return (gx, glw, glb, None, None) + grads_w
+        # gradients written straight into a registered sink are not handed to autograd (nothing left to accumulate)
+        grads_w = tuple(None if sk is not None else g for sk, g in zip(s_w, gws)) if gws is not None else (None,) * len(wc)
+        return (gx, None if s_lw is not None else glw, None if s_lb is not None else glb, None, None) + grads_w
 
 
 def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor], lin_w: torch.Tensor,

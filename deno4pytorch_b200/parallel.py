@@ -79,6 +79,14 @@ class FlatGradients:
     def nbytes(self) -> int:
         return self.flat.numel() * 4
 
+    def direct_writes(self, enable: bool = True):
+        """Let the backward kernels write parameter gradients straight into this buffer (``functional.grad_sink``)
+        instead of returning them to autograd, which would launch one ``grad += new`` kernel per parameter.
+        Valid only while every parameter is used ONCE per backward pass (a plain model call; not a roll-out that
+        calls the model several times before ``backward``): a direct write overwrites, it does not accumulate."""
+        for p in self.params:
+            p._deno_grad_sink = p.grad if enable else None
+
     def zero(self):
         self.flat.zero_()
 

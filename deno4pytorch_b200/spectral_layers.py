@@ -101,6 +101,8 @@ class _SpectralConvNd(nn.Module):
         act_id = activation_kernel_id(self.activation)
         fused_act = act_id if act_id else "identity"
         weights = self._weights()
+        if self.return_freq:   # the weights are used a second time below: no direct gradient writes (functional.grad_sink)
+            weights = [w.view_as(w) for w in weights]
         lw, lb = self.linear.weight, self.linear.bias
         drop = self._dropout_in_forward and self.training and self.dropout.p > 0
         if not drop:

@@ -41,6 +41,8 @@ class TrainStep:
             self.grads = FlatGradients(model.parameters())
             self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
                                         capturable=use_graph, foreach=True)
+        # one model call per step: parameter gradients go straight into the flat buffer (no per-parameter add kernels)
+        self.grads.direct_writes(forward_fn is None and x.is_cuda)
         self.loss = torch.zeros((), device=x.device)
         self.use_graph = use_graph
         self._g_bwd = self._g_opt = None

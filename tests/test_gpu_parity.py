@@ -318,3 +318,30 @@ def test_bitwise_repeatability(shape):
         for a, b in zip(first, again):
             assert torch.equal(torch.view_as_real(a) if a.is_complex() else a,
                                torch.view_as_real(b) if b.is_complex() else b)
+
+
+def test_direct_gradient_writes_match_autograd_accumulation():
+    """parallel.FlatGradients.direct_writes(): the backward kernels write parameter gradients straight into the flat
+    buffer and return None to autograd.  Same numbers as the accumulate path, and no gradient is left unwritten."""
+    import deno4pytorch_b200 as d4
+    from deno4pytorch_b200.parallel import FlatGradients
+    dev = _dev()
+    torch.manual_seed(3)
+    model = d4.FNO2d(in_dim=1, out_dim=1, modes=(6, 6), width=32, depth=2, padding=3).to(dev)
+    x = torch.randn(4, 29, 31, 1, device=dev)
+    grid = torch.rand(4, 29, 31, 2, device=dev)
+    tgt = torch.randn(4, 29, 31, 1, device=dev)
+    fg = FlatGradients(model.parameters())
+    out = {}
+    for direct in (False, True):
+        fg.direct_writes(direct)
+        fg.flat.fill_(float("nan") if direct else 0.0)      # direct mode overwrites: it must not depend on zeroing
+        torch.nn.functional.mse_loss(model(x, grid), tgt).backward()
+        torch.cuda.synchronize()
+        out[direct] = [torch.view_as_real(p.grad).clone() if p.grad.is_complex() else p.grad.clone()
+                       for p in model.parameters()]
+    for a, b in zip(out[True], out[False]):
+        assert torch.isfinite(a).all()
+        assert rel_l2(a.cpu(), b.cpu()) < 1e-6
+    for p in model.parameters():
+        assert p.grad.data_ptr() >= fg.flat.data_ptr() and p.grad.data_ptr() < fg.flat.data_ptr() + fg.nbytes
