@@ -1268,27 +1268,30 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
       }
     }
     float4 ra[NIT], rb[NIT];
+    // Per tile and item only the batch entry's base offset changes: keep the address arithmetic to one or two
+    // 64-bit multiply-adds per item (an earlier version spent ~1200 instructions per warp and tile on integer
+    // divisions and selects and was issue-bound on them, profiles/r2n_ncu_C2_layer_kernels.csv).
+    const bool flat_batch = p.gx.NBI == 1;
+    const long long blk_stride = (long long)CO * 128;
     auto prefetch = [&](int n, float4 (&regs)[NIT]) {
       const int t = (int)blockIdx.x + n * (int)gridDim.x;
       const int grp = t / p.tiles_per_plane;
       const int p0 = (t - grp * p.tiles_per_plane) * kWgradKT;
-      long long gb[4], xb[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int bp = min(grp * NS + j, p.nbatch - 1);
-        gb[j] = p.gz_tps > 0 ? ((long long)bp * p.gz_tps + (p0 >> 7)) * p.CO * 128 + (p0 & 127)
-                             : (long long)(bp / p.gx.NBI) * p.sbo_g + (long long)(bp % p.gx.NBI) * p.gx.sbi + p0;
-        xb[j] = plane_base(p.gx, bp, 0) + p0;
-      }
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t m = meta[it];
-        const int j = (int)((m >> 28) & 3u);
-        if ((m & 0x80000000u) && grp * NS + j < p.nbatch) {
+        const int bp = grp * NS + (int)((m >> 28) & 3u);
+        if ((m & 0x80000000u) && bp < p.nbatch) {
           const bool isg = (m & 0x40000000u) != 0u;
-          const long long base = isg ? (j == 0 ? gb[0] : (j == 1 ? gb[1] : (j == 2 ? gb[2] : gb[3])))
-                                     : (j == 0 ? xb[0] : (j == 1 ? xb[1] : (j == 2 ? xb[2] : xb[3])));
+          int bo = bp, bi = 0;
+          if (!flat_batch) {
+            bo = bp / p.gx.NBI;
+            bi = bp - bo * p.gx.NBI;
+          }
+          long long base;
+          if (isg && p.gz_tps > 0) base = ((long long)bp * p.gz_tps + (p0 >> 7)) * blk_stride + (p0 & 127);
+          else base = (long long)bo * (isg ? p.sbo_g : p.gx.sbo) + (long long)bi * p.gx.sbi + p0;
           const float* src = (isg ? p.gz : p.x) + base + roff[it];
           const int pt = p0 + ((it * kWgradLoaders + tid) % QPR) * 4;
           if (p.vec4 && pt + 3 < HW) {
@@ -1305,7 +1308,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
     };
     auto publish = [&](int n, float4 (&regs)[NIT]) {
       const int st = n & 1;
+      const long long tp0 = clock64();
       mbar_wait(&bar_empty[st], (uint32_t)(((n >> 1) & 1) ^ 1));      // MMAs of tile n-2 are done with this stage
+      const long long tp1 = clock64();
+      if (warp == 1) DENO_DBG_ADD(10, tp1 - tp0);                      // slot 10: loaders waiting for a free stage
       unsigned char* base = smem + so.stage[st];
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
@@ -1324,15 +1330,20 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
       }
       fence_proxy_async();
       mbar_arrive(&bar_full[st]);
+      if (warp == 1) { DENO_DBG_ADD(11, clock64() - tp1); DENO_DBG_ADD(15, 1); }   // slots 11/15: wait for the data + split + stores, tiles
     };
     if (ntile_cta > 0) prefetch(0, ra);
     if (ntile_cta > 1) prefetch(1, rb);
-    for (int n = 0; n < ntile_cta; n += 2) {
+    for (int n = 0; n < ntile_cta; n += 2) {   // (a third register buffer issued ahead of publish() spilled and was slower)
       publish(n, ra);
+      long long tf0 = clock64();
       if (n + 2 < ntile_cta) prefetch(n + 2, ra);
+      if (warp == 1) DENO_DBG_ADD(12, clock64() - tf0);                // slot 12: address arithmetic + load issue
       if (n + 1 < ntile_cta) {
         publish(n + 1, rb);
+        tf0 = clock64();
         if (n + 3 < ntile_cta) prefetch(n + 3, rb);
+        if (warp == 1) DENO_DBG_ADD(12, clock64() - tf0);
       }
     }
   } else {
@@ -1343,8 +1354,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
     const uint64_t inc_g = (uint64_t)((2 * so.g_lbo) >> 4), inc_x = (uint64_t)((2 * so.x_lbo) >> 4);
     for (int n = 0; n < ntile_cta; ++n) {
       const int st = n & 1;
+      const long long tm0 = clock64();
       mbar_wait(&bar_full[st], (uint32_t)((n >> 1) & 1));
       fence_after_sync();
+      const long long tm1 = clock64();
       const uint32_t b0 = sbase + so.stage[st];
       uint64_t gh = make_desc(b0, so.g_lbo, 128), gl = make_desc(b0 + so.g_lo, so.g_lbo, 128);
       uint64_t xh = make_desc(b0 + so.x_hi, so.x_lbo, 128), xl = make_desc(b0 + so.x_lo, so.x_lbo, 128);
@@ -1360,6 +1373,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
       }
       if (leader) mma_commit(&bar_empty[st]);
       __syncwarp();
+      if (leader) { DENO_DBG_ADD(13, tm1 - tm0); DENO_DBG_ADD(14, clock64() - tm1); }   // slots 13/14: MMA warp waiting / issuing
     }
     if (leader) mma_commit(&bar_done);
     __syncwarp();

@@ -60,6 +60,11 @@ for which in ("fwd", "bwd"):
     xv = v[57:61]
     ch = max(xv[3], 1)
     print(f"[{which}] stage A detail: zero+twiddles {xv[0]} | per chunk: load {xv[1] // ch} compute {xv[2] // ch} chunks {xv[3]}")
+    gv = v[10:16]
+    if gv[5]:
+        print(f"[{which}] bypass_wgrad_tc per tile (CTA 0, {gv[5]} tiles):",
+              {n: round(x_ / gv[5]) for n, x_ in zip(["wait free stage", "wait data + split + sts", "addr + load issue",
+                                                      "mma wait full", "mma issue"], gv[:5])})
     wv = v[0:10]
     if wv[9]:
         print(f"[{which}] synthesis_ws slots:", wv)
