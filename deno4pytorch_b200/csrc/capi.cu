@@ -303,8 +303,14 @@ int wgrad_cfg(const Shape& s, WgradCfg& c) {
 // ------------------------------------------------------------------------------------------
 // Workspace carving
 // ------------------------------------------------------------------------------------------
-struct FwdWs { size_t xhat, yhat, t2, v, total; };
-struct BwdWs { size_t gz, ghat, gxhat, t2, v, partial, total; };
+struct FwdWs { size_t xhat, yhat, t2, v, urow, total; };
+struct BwdWs { size_t gz, ghat, gxhat, t2, v, partial, urow, total; };
+
+// pre-split row-synthesis images for the tensor-core synthesis kernel: [B*X][H][hi|lo][KE * C] floats
+size_t urow_bytes(const Shape& s, int channels) {
+  if (s.ndim < 2) return 0;
+  return align_up((size_t)s.B * s.X * s.H * 2 * (2 * (size_t)s.MWp) * channels * 4);
+}
 
 FwdWs fwd_ws(const Shape& s) {
   FwdWs w;
@@ -313,6 +319,7 @@ FwdWs fwd_ws(const Shape& s) {
   w.yhat = off; off += align_up((size_t)s.B * s.CO * s.M * 8);
   w.t2 = off;   off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
   w.v = off;    off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
+  w.urow = off; off += urow_bytes(s, s.CO);
   w.total = off;
   return w;
 }
@@ -329,6 +336,7 @@ int bwd_ws(const Shape& s, BwdWs& w) {
   w.v = off;       off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
   const size_t nparts = (size_t)(wc.ncta > kWgradTcMaxCtas ? wc.ncta : kWgradTcMaxCtas);   // either kernel's partial count
   w.partial = off; off += align_up(nparts * ((size_t)s.CO * s.CI + s.CO) * 4);
+  w.urow = off;    off += urow_bytes(s, s.CI);
   w.total = off;
   return DENO_OK;
 }
@@ -650,6 +658,7 @@ int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int
   p.tiles = (p.g.H + bestR - 1) / bestR;
   q.s = p;
   q.ae = tw.synth_ae;
+  q.urow = nullptr;
   q.KE = tl.KE;
   q.nchunks = tl.nchunks;
   q.tmem_cols = cols;
@@ -688,7 +697,7 @@ int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int
 // Bulk-synchronous variant (two CTAs per SM, every warp does every phase).  Measured faster than the
 // warp-specialised kernel at the Darcy shape (profiles/r1t_phase_probe.txt), so it is the default;
 // DENO_SYNTH_WS=1 selects the warp-specialised kernel.
-int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
+int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, float* urow, cudaStream_t st) {
   const int CI = p.g.C, CO = p.CO;
   if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;
   const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
@@ -719,6 +728,28 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   p.tiles = (p.g.H + bestR - 1) / bestR;
   q.s = p;
   q.ae = tw.synth_ae;
+  q.urow = nullptr;
+  if (urow != nullptr && p.g.H > 1) {                   // row-axis synthesis once per layer instead of once per tile
+    tc::RowSynthParams r;
+    r.spec = p.spec; r.twH = p.twH; r.cl = p.cl; r.u = urow; r.scale = p.scale; r.herm = p.herm;
+    r.H = p.g.H; r.KH = p.g.KH; r.KH4 = round_up(p.g.KH, 4); r.MW = p.g.MW; r.CO = CO; r.KE = tl.KE;
+    r.Qp = tc::row_synth_pitch(r.KH, r.MW, r.KE);
+    r.tiles = (r.H + tc::kRowSynthRows - 1) / tc::kRowSynthRows;
+    r.ocb = CO;   // whole spectrum per block (8-channel blocks with staged 128-byte stores measured slower: 22 vs 16 us)
+    r.ogroups = (CO + r.ocb - 1) / r.ocb;
+    const size_t rs_smem = tc::row_synth_smem_bytes(r.ocb, r.KH, r.MW, r.KE);
+    if (rs_smem <= (size_t)kMaxSmemBytes) {
+      int rrc = allow_smem(tc::row_synthesis_kernel, rs_smem, "row_synthesis");
+      if (rrc != DENO_OK) return rrc;
+      int threads = round_up(r.ocb * (tl.KE / 2), 32);
+      if (threads > 384) threads = 384;
+      prof_before("row_synthesis", st);
+      tc::row_synthesis_kernel<<<dim3((unsigned)(p.g.NBO * p.g.NBI * r.tiles * r.ogroups)), dim3(threads), rs_smem, st>>>(r);
+      rrc = check_launch("row_synthesis", st);
+      if (rrc != DENO_OK) return rrc;
+      q.urow = urow;
+    }
+  }
   q.KE = tl.KE;
   q.nchunks = tl.nchunks;
   int cols = 32;
@@ -756,17 +787,18 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   return check_launch("plane_synthesis_tc", st);
 }
 
-int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
+int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, float* urow,
+                            cudaStream_t st) {
   const char* e = getenv("DENO_SYNTH_WS");
   if (e != nullptr && e[0] == '1') return try_launch_synthesis_ws(s, p, tw, act, label, st);
-  return try_launch_synthesis_bulk(s, p, tw, act, label, st);
+  return try_launch_synthesis_bulk(s, p, tw, act, label, urow, st);
 }
 #endif
 
 // spec [B*X][CO][KH][MW] + bypass(u) -> y (, z)
 int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, const float* u, const float* lw,
                      long long lw_so, long long lw_si, const float* bias, float* y, float* z, const TwPtrs& tw,
-                     float scale, int herm, int act, cudaStream_t st) {
+                     float scale, int herm, int act, float* urow, cudaStream_t st) {
   SynthParams p;
   p.g = make_geom(s, cin);
   p.CO = cout;
@@ -785,7 +817,7 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
   const PathPref pref = path_pref();
   if (pref != PathPref::Simt) {
     const bool is_fwd = (bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr);
-    rc = try_launch_synthesis_tc(s, p, tw, act, is_fwd ? "plane_synthesis_tc" : "plane_synthesis_bwd_tc", st);
+    rc = try_launch_synthesis_tc(s, p, tw, act, is_fwd ? "plane_synthesis_tc" : "plane_synthesis_bwd_tc", urow, st);
     if (rc >= 0) return rc;
     if (pref == PathPref::Tc) return fail(DENO_E_UNSUPPORTED, "DENO_SPECTRAL_PATH=tc but the shape is outside the tcgen05 synthesis kernel");
   }
@@ -1239,12 +1271,12 @@ int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void
     if ((rc = launch_mix(s, false, xhat, yhat, w_blocks, st))) return rc;
     if ((rc = launch_outer(s, s.CO, false, yhat, v, tw, st))) return rc;
     return launch_synthesis(s, s.CI, s.CO, v, x, lin_w, s.CI, 1, lin_b, y, z_saved, tw, (float)(1.0 / (double)s.S), 1,
-                            s.act, st);
+                            s.act, reinterpret_cast<float*>(wsb + ws.urow), st);
   }
   if ((rc = launch_analysis(s, s.CI, x, nullptr, nullptr, xhat, tw, 1.0f, 0, st))) return rc;
   if ((rc = launch_mix(s, false, xhat, yhat, w_blocks, st))) return rc;
   return launch_synthesis(s, s.CI, s.CO, yhat, x, lin_w, s.CI, 1, lin_b, y, z_saved, tw, (float)(1.0 / (double)s.S), 1,
-                          s.act, st);
+                          s.act, reinterpret_cast<float*>(wsb + ws.urow), st);
 }
 
 int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const float* x,
@@ -1297,7 +1329,7 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
     }
     // gx = Re sum G^x e^{+i theta} + W_l^T gz   (channels swap roles: "input" = gz with CO channels)
     if ((rc = launch_synthesis(s, s.CO, s.CI, spec, gz, lin_w, 1, s.CI, nullptr, gx, nullptr, tw, 1.0f, 0,
-                               DENO_ACT_IDENTITY, st)))
+                               DENO_ACT_IDENTITY, reinterpret_cast<float*>(wsb + ws.urow), st)))
       return rc;
   }
   if (glin_w != nullptr || glin_b != nullptr) {

@@ -149,7 +149,143 @@ struct SynthTcParams {
   int KE;                 // 2 * MWp rounded up to a multiple of 8
   int nchunks;            // column chunks of 128 per row
   int tmem_cols;          // power of two >= 6 * CO (two row buffers x three split-pass tiles)
+  const float* urow;      // row-axis synthesis U, pre-split B operand images [NB'][H][hi|lo][KE * CO] (row_synthesis_kernel)
 };
+
+// ----------------------------------------------------------------------------------------------
+// row_synthesis: the row-axis half of the inverse transform, once per (batch entry, row) for the whole layer:
+//   U[x][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x)}
+// written as the tf32 hi / lo B operand images plane_synthesis_tc feeds to the last-axis GEMM
+// (element (n = o, k = 2l): Re, (o, 2l + 1): -Im), so that kernel's per-tile "stage A" is one bulk copy.
+// Doing this inside every synthesis CTA cost half of that kernel (profiles/r2m_phase_probe.txt: 26 k of 58 k
+// cycles): each CTA re-read the batch entry's whole spectrum for its 7 rows.
+// Block = (batch entry, kRowSynthRows rows); thread = (o, l) pair with all rows in registers.
+// ----------------------------------------------------------------------------------------------
+constexpr int kRowSynthRows = 8;
+struct RowSynthParams {
+  const float2* spec;    // [NB'][CO][KH][MW]
+  const float2* twH;     // [H][KH4]
+  const float* cl;
+  float* u;              // [NB'][H][hi|lo][KE * CO]
+  float scale;
+  int herm;
+  int H, KH, KH4, MW, CO, KE;
+  int Qp;                // padded per-channel pitch of the staged spectrum (bank-conflict-free (o, l) lanes)
+  int tiles;             // ceil(H / kRowSynthRows)
+  int ocb, ogroups;      // output channels per block, ceil(CO / ocb); gridDim.x = NB' * tiles * ogroups
+};
+
+__host__ __device__ inline int row_synth_pitch(int KH, int MW, int KE) {
+  int qp = KH * MW;
+  while ((qp - KE / 2) % 16 != 0) ++qp;
+  return qp;
+}
+__host__ __device__ inline size_t row_synth_smem_bytes(int ocb, int KH, int MW, int KE) {
+  return ((size_t)ocb * row_synth_pitch(KH, MW, KE) + (size_t)KH * kRowSynthRows) * sizeof(float2) +
+         (size_t)kRowSynthRows * 2 * (KE / 4) * 36 * sizeof(float);   // spectrum, row twiddles, output staging
+}
+
+__global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  float2* sps = reinterpret_cast<float2*>(rs_smem);                 // [ocb][Qp]
+  float2* twr = sps + (size_t)p.ocb * p.Qp;                         // [KH][kRowSynthRows]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  int bid = blockIdx.x;
+  const int og = bid % p.ogroups; bid /= p.ogroups;
+  const int bp = bid / p.tiles;
+  const int x0 = (bid - bp * p.tiles) * kRowSynthRows;
+  const int trows = min(kRowSynthRows, p.H - x0);
+  const int Q = p.KH * p.MW;
+  const int o0 = og * p.ocb, noc = min(p.ocb, p.CO - o0);
+  const float2* src = p.spec + ((long long)bp * p.CO + o0) * Q;
+  {  // the block's channels are one contiguous run of the spectrum: 16-byte loads, six in flight per thread
+    // (a plain load -> store loop ran one global-memory latency per element and WAS the kernel: 16 -> 27 us)
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    const int n4 = noc * Q / 2;                                     // Q = KH * MW is even (KH = 2 * modes)
+    for (int i0 = 0; i0 < n4; i0 += 6 * nthr) {
+      float4 tmp[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = min(i0 + u * nthr + tid, n4 - 1);
+        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(tmp[u].x), "=f"(tmp[u].y), "=f"(tmp[u].z), "=f"(tmp[u].w) : "l"(src4 + i));
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u * nthr + tid;
+        if (i < n4) {
+          const int ol = (2 * i) / Q, r = 2 * i - ol * Q;
+          *reinterpret_cast<float4*>(sps + ol * p.Qp + r) = tmp[u];
+        }
+      }
+    }
+  }
+  for (int idx = tid; idx < p.KH * kRowSynthRows; idx += nthr) {
+    const int k = idx / kRowSynthRows, rr = idx - k * kRowSynthRows;
+    twr[idx] = rr < trows ? p.twH[(x0 + rr) * p.KH4 + k] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int LH = p.KE / 2;                                          // (cos, sin) column pairs incl. zero padding
+  const size_t img = (size_t)p.KE * p.CO;                           // floats per hi (or lo) image
+  // A block of 8 channels owns, in every K-quad of every image, one contiguous 128-byte run (8 rows x 16 bytes of
+  // the K-major layout): results are staged in shared memory and leave as full 128-byte lines (direct 8-byte
+  // stores from the (o, l) threads were the bottleneck of the first version).
+  const bool staged = (p.ocb == 8);
+  float* stg = reinterpret_cast<float*>(twr + p.KH * kRowSynthRows);   // [row][hi|lo][KE/4][36]
+  for (int task = tid; task < noc * LH; task += nthr) {
+    const int ol = task / LH, l = task - ol * LH;
+    const int o = o0 + ol;
+    float ar[kRowSynthRows], ai[kRowSynthRows];
+#pragma unroll
+    for (int rr = 0; rr < kRowSynthRows; ++rr) ar[rr] = ai[rr] = 0.f;
+    float f = 0.f;
+    if (l < p.MW) {
+      const float2* sp = sps + ol * p.Qp + l;
+#pragma unroll 4
+      for (int k = 0; k < p.KH; ++k) {
+        const float2 sv = sp[k * p.MW];
+        const float4* e4 = reinterpret_cast<const float4*>(twr + k * kRowSynthRows);
+#pragma unroll
+        for (int r2 = 0; r2 < kRowSynthRows / 2; ++r2) {
+          const float4 e = e4[r2];                                  // two rows' twiddles per shared-memory load
+          ar[2 * r2] = fmaf(sv.x, e.x, fmaf(-sv.y, e.y, ar[2 * r2]));
+          ai[2 * r2] = fmaf(sv.x, e.y, fmaf(sv.y, e.x, ai[2 * r2]));
+          ar[2 * r2 + 1] = fmaf(sv.x, e.z, fmaf(-sv.y, e.w, ar[2 * r2 + 1]));
+          ai[2 * r2 + 1] = fmaf(sv.x, e.w, fmaf(sv.y, e.z, ai[2 * r2 + 1]));
+        }
+      }
+      f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+    }
+    const int off = kmajor_off(o, 2 * l, p.CO) / 4;                 // floats; columns 2l and 2l + 1 are adjacent
+    float* dst = p.u + ((size_t)bp * p.H + x0) * 2 * img + off;
+    const int soff = ((2 * l) >> 2) * 36 + ol * 4 + ((2 * l) & 3);   // chunk pitch 36 floats: the six K-quads land in different banks
+#pragma unroll
+    for (int rr = 0; rr < kRowSynthRows; ++rr) {
+      if (rr < trows) {
+        float h0, l0, h1, l1;
+        split_tf32(ar[rr] * f, h0, l0);
+        split_tf32(-ai[rr] * f, h1, l1);
+        if (staged) {
+          *reinterpret_cast<float2*>(stg + (rr * 2) * (p.KE / 4) * 36 + soff) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(stg + (rr * 2 + 1) * (p.KE / 4) * 36 + soff) = make_float2(l0, l1);
+        } else {
+          *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img + img) = make_float2(l0, l1);
+        }
+      }
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    const int nkq = p.KE / 4;
+    float* ubase = p.u + ((size_t)bp * p.H + x0) * 2 * img + (o0 >> 3) * 32;
+    const int w = tid & 31;
+    for (int c = tid >> 5; c < trows * 2 * nkq; c += nthr >> 5) {   // one 128-byte line per warp and step
+      const int ri = c / nkq, kq = c - ri * nkq;                    // ri = row * 2 + (hi | lo)
+      ubase[(size_t)ri * img + (size_t)kq * 4 * p.CO + w] = stg[c * 36 + w];
+    }
+  }
+}
 
 struct SynthTcSmem {
   int bw_hi, bw_lo, ae_hi, ae_lo, bu, ax_hi, ax_lo, bias, total;  // byte offsets
@@ -176,7 +312,7 @@ template <int ACT, int CIP>
 __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t mbar[2], mbar_u;
   const SynthParams& p = q.s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = p.CO;
@@ -200,7 +336,16 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   if (tid == 32) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
+    mbar_init(&mbar_u, 1);
     mbar_fence_init();
+    if (q.urow != nullptr) {   // stage A was done once per layer by row_synthesis_kernel: one bulk copy of this tile's images
+      const uint32_t bytes = (uint32_t)(trows * 2 * so.bu_one);
+      const float* usrc = q.urow + ((size_t)bp * H + x0) * 2 * (size_t)(so.bu_one / 4);
+      const uint32_t bar = smem_u32(&mbar_u);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(smem + so.bu)), "l"(usrc), "r"(bytes), "r"(bar) : "memory");
+    }
   }
 
   // ---- constant operands -------------------------------------------------------------------
@@ -243,9 +388,10 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   const long long tb1 = clock64();
   if (warp == 1) DENO_DBG_ADD(48, tb1 - tb0);          // slot 48: TMEM alloc, weight / twiddle images, first prefetch issue
   // ---- stage A: U[r][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0 + r)}, written as B operand images ----
-  // The packed spectrum of this batch entry is staged through the (still unused) A_X area in chunks of
-  // OC output channels with fully coalesced loads, so the k-loop below runs out of shared memory.
-  {
+  // Normally precomputed (q.urow, bulk copy issued above); the in-kernel version below is kept for callers without
+  // the workspace: the packed spectrum of this batch entry is staged through the (still unused) A_X area in chunks
+  // of OC output channels with fully coalesced loads, so the k-loop runs out of shared memory.
+  if (q.urow == nullptr) {
     unsigned char* bu = smem + so.bu;
     for (int idx = tid; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     float2* twr = reinterpret_cast<float2*>(smem + so.ax_hi);            // [trows][KH] row twiddles
@@ -321,6 +467,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  if (q.urow != nullptr) mbar_wait(&mbar_u, 0);        // the U images have landed (barrier initialised before the sync above)
   const long long tb2 = clock64();
   if (warp == 1) DENO_DBG_ADD(49, tb2 - tb1);          // slot 49: stage A
   const uint32_t tmem = tmem_slot;
