@@ -102,17 +102,27 @@ __device__ __forceinline__ void pj_store_a1(unsigned char* smem, int xrow, int w
 template <int C, int HD>
 __device__ __forceinline__ void pj_prologue(const ProjTcParams& p, unsigned char* smem, int tid) {
   using S = ProjTcSmem<C, HD>;
-  for (int i = tid; i < HD * (C / 4); i += (int)blockDim.x) {
-    const int j = i / (C / 4), q = i - j * (C / 4);
-    const float4 w = *reinterpret_cast<const float4*>(p.w1 + (long long)j * C + 4 * q);
-    float4 hi, lo;
-    split_tf32(w.x, hi.x, lo.x);
-    split_tf32(w.y, hi.y, lo.y);
-    split_tf32(w.z, hi.z, lo.z);
-    split_tf32(w.w, hi.w, lo.w);
-    const int off = (j & 7) * 16 + (j >> 3) * 128 + q * (16 * HD);
-    *reinterpret_cast<float4*>(smem + S::off_b1 + off) = hi;
-    *reinterpret_cast<float4*>(smem + S::off_b1 + S::b1_one + off) = lo;
+  const int nthr = (int)blockDim.x;
+  const float4* w4 = reinterpret_cast<const float4*>(p.w1);
+  for (int i0 = tid; i0 < HD * (C / 4); i0 += 4 * nthr) {         // four loads in flight per thread
+    float4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = __ldg(w4 + min(i0 + u * nthr, HD * (C / 4) - 1));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * nthr;
+      if (i < HD * (C / 4)) {
+        const int j = i / (C / 4), q = i - j * (C / 4);
+        float4 hi, lo;
+        split_tf32(w[u].x, hi.x, lo.x);
+        split_tf32(w[u].y, hi.y, lo.y);
+        split_tf32(w[u].z, hi.z, lo.z);
+        split_tf32(w[u].w, hi.w, lo.w);
+        const int off = (j & 7) * 16 + (j >> 3) * 128 + q * (16 * HD);
+        *reinterpret_cast<float4*>(smem + S::off_b1 + off) = hi;
+        *reinterpret_cast<float4*>(smem + S::off_b1 + S::b1_one + off) = lo;
+      }
+    }
   }
   float* b1s = reinterpret_cast<float*>(smem + S::off_small);
   float* w2s = b1s + HD;
@@ -270,14 +280,31 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
     mbar_fence_init();
   }
   pj_prologue<C, HD>(p, smem, tid);
-  // w1^T as the B operand of GEMM 2: rows c (hi) and C + c (lo), K = hidden unit j
-  for (int i = tid; i < HD * C; i += kPjThreads) {
-    const int j = i / C, c = i - j * C;
-    float hi, lo;
-    split_tf32(p.w1[i], hi, lo);
-    const int koff = (j & 3) * 4 + (j >> 2) * S::b2_lbo;
-    *reinterpret_cast<float*>(smem + S::off_b2 + (c & 7) * 16 + (c >> 3) * 128 + koff) = hi;
-    *reinterpret_cast<float*>(smem + S::off_b2 + ((C + c) & 7) * 16 + ((C + c) >> 3) * 128 + koff) = lo;
+  // w1^T as the B operand of GEMM 2: rows c (hi) and C + c (lo), K = hidden unit j; 16-byte loads, four in flight
+  {
+    const float4* w4 = reinterpret_cast<const float4*>(p.w1);
+    for (int i0 = tid; i0 < HD * (C / 4); i0 += 4 * kPjThreads) {
+      float4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = __ldg(w4 + min(i0 + u * kPjThreads, HD * (C / 4) - 1));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kPjThreads;
+        if (i < HD * (C / 4)) {
+          const int j = i / (C / 4), c0 = (i - j * (C / 4)) * 4;
+          const int koff = (j & 3) * 4 + (j >> 2) * S::b2_lbo;
+          const float wv[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + e;
+            float hi, lo;
+            split_tf32(wv[e], hi, lo);
+            *reinterpret_cast<float*>(smem + S::off_b2 + (c & 7) * 16 + (c >> 3) * 128 + koff) = hi;
+            *reinterpret_cast<float*>(smem + S::off_b2 + ((C + c) & 7) * 16 + ((C + c) >> 3) * 128 + koff) = lo;
+          }
+        }
+      }
+    }
   }
   fence_proxy_async();
   fence_before_sync();

@@ -38,6 +38,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   }
 }
+// one bulk async copy global -> shared (multiple of 16 bytes, 16-byte aligned both sides); completion on an mbarrier
+// that was armed with mbarrier.arrive.expect_tx for at least these bytes
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -338,31 +347,38 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     mbar_init(&mbar[1], 1);
     mbar_init(&mbar_u, 1);
     mbar_fence_init();
-    if (q.urow != nullptr) {   // stage A was done once per layer by row_synthesis_kernel: one bulk copy of this tile's images
-      const uint32_t bytes = (uint32_t)(trows * 2 * so.bu_one);
-      const float* usrc = q.urow + ((size_t)bp * H + x0) * 2 * (size_t)(so.bu_one / 4);
-      const uint32_t bar = smem_u32(&mbar_u);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_u32(smem + so.bu)), "l"(usrc), "r"(bytes), "r"(bar) : "memory");
-    }
+    // constant twiddle images (final layout in global memory) and, when row_synthesis_kernel ran (q.urow), this
+    // tile's U images: bulk async copies, so the prologue costs one memory round trip instead of one per loop trip
+    const uint32_t ae_bytes = (uint32_t)(2 * KE * 128 * 4);
+    const uint32_t u_bytes = q.urow != nullptr ? (uint32_t)(trows * 2 * so.bu_one) : 0u;
+    mbar_expect_tx(&mbar_u, ae_bytes + u_bytes);
+    bulk_g2s(smem + so.ae_hi, q.ae + (long long)chunk * 2 * KE * 128, ae_bytes, &mbar_u);
+    if (q.urow != nullptr)
+      bulk_g2s(smem + so.bu, q.urow + ((size_t)bp * H + x0) * 2 * (size_t)(so.bu_one / 4), u_bytes, &mbar_u);
   }
 
   // ---- constant operands -------------------------------------------------------------------
-  // bypass weight image B_W[n = o][k = i], split on the fly
-  for (int idx = tid; idx < CO * CIP; idx += 256) {
-    const int o = idx / CIP, i = idx - o * CIP;
-    const float w = (i < CI) ? p.lw[(long long)o * p.lw_so + (long long)i * p.lw_si] : 0.f;
-    float hi, lo;
-    split_tf32(w, hi, lo);
-    const int off = kmajor_off(o, i, CO);
-    *reinterpret_cast<float*>(smem + so.bw_hi + off) = hi;
-    *reinterpret_cast<float*>(smem + so.bw_lo + off) = lo;
-  }
-  {  // twiddle images are stored in their final layout: straight 16-byte copies (hi and lo are adjacent)
-    const float4* src = reinterpret_cast<const float4*>(q.ae + (long long)chunk * 2 * KE * 128);
-    float4* dst = reinterpret_cast<float4*>(smem + so.ae_hi);
-    for (int idx = tid; idx < 2 * KE * 128 / 4; idx += 256) dst[idx] = src[idx];
+  // bypass weight image B_W[n = o][k = i], split on the fly; four loads in flight per thread
+  for (int idx0 = tid; idx0 < CO * CIP; idx0 += 4 * 256) {
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = min(idx0 + u * 256, CO * CIP - 1);
+      const int o = idx / CIP, i = idx - o * CIP;
+      wv[u] = (i < CI) ? ldg_ordered(p.lw + (long long)o * p.lw_so + (long long)i * p.lw_si) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * 256;
+      if (idx < CO * CIP) {
+        const int o = idx / CIP, i = idx - o * CIP;
+        float hi, lo;
+        split_tf32(wv[u], hi, lo);
+        const int off = kmajor_off(o, i, CO);
+        *reinterpret_cast<float*>(smem + so.bw_hi + off) = hi;
+        *reinterpret_cast<float*>(smem + so.bw_lo + off) = lo;
+      }
+    }
   }
   float* bias_s = reinterpret_cast<float*>(smem + so.bias);
   for (int o = tid; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  if (q.urow != nullptr) mbar_wait(&mbar_u, 0);        // the U images have landed (barrier initialised before the sync above)
+  mbar_wait(&mbar_u, 0);                               // twiddle (and U) images have landed (barrier initialised before the sync above)
   const long long tb2 = clock64();
   if (warp == 1) DENO_DBG_ADD(49, tb2 - tb1);          // slot 49: stage A
   const uint32_t tmem = tmem_slot;
@@ -998,7 +1014,7 @@ template <bool FUSE_GZ>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar[2], bar_stage;
+  __shared__ __align__(8) uint64_t mbar[2], bar_stage, bar_const;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
   const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
@@ -1012,20 +1028,17 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     mbar_init(&bar_stage, 1);
+    mbar_init(&bar_const, 1);
     mbar_fence_init();
+    // constant operand images (final layout in global memory): two bulk async copies
+    mbar_expect_tx(&bar_const, (uint32_t)(so.e1_bytes + 2 * so.a2_one));
+    bulk_g2s(smem + so.e1, p.e1, (uint32_t)so.e1_bytes, &bar_const);
+    bulk_g2s(smem + so.a2, p.a2, (uint32_t)(2 * so.a2_one), &bar_const);
   }
-  {  // constant operand images (final layout in global memory): straight copies
-    const float4* s1 = reinterpret_cast<const float4*>(p.e1);
-    float4* d1 = reinterpret_cast<float4*>(smem + so.e1);
-    for (int i = tid; i < so.e1_bytes / 16; i += kAnThreads) d1[i] = s1[i];
-    const float4* s2 = reinterpret_cast<const float4*>(p.a2);
-    float4* d2 = reinterpret_cast<float4*>(smem + so.a2);
-    for (int i = tid; i < 2 * so.a2_one / 16; i += kAnThreads) d2[i] = s2[i];
-  }
-  fence_proxy_async();
   fence_before_sync();
-  __syncthreads();                                     // barriers initialised, TMEM allocated, constant images stored
+  __syncthreads();                                     // barriers initialised, TMEM allocated
   fence_after_sync();
+  mbar_wait(&bar_const, 0);                            // constant images stored
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // [hi*hi | hi*lo | lo*hi] tiles per stage
   const uint32_t idesc_n2 = make_idesc_tf32(128, 2 * N1), idesc_n1 = make_idesc_tf32(128, N1);
