@@ -491,12 +491,12 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
     rc = allow_smem(tc::plane_analysis_tc_kernel<true>, (size_t)sm.total, "plane_analysis_tc");
     if (rc != DENO_OK) return rc;
     prof_before("plane_analysis_gz_tc", st);
-    tc::plane_analysis_tc_kernel<true><<<dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st>>>(p);
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<true>), dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st, p);
   } else {
     rc = allow_smem(tc::plane_analysis_tc_kernel<false>, (size_t)sm.total, "plane_analysis_tc");
     if (rc != DENO_OK) return rc;
     prof_before("plane_analysis_tc", st);
-    tc::plane_analysis_tc_kernel<false><<<dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st>>>(p);
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<false>), dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st, p);
   }
   return check_launch("plane_analysis_tc", st);
 }
@@ -671,7 +671,7 @@ int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int
     rc = allow_smem(tc::plane_synthesis_ws_kernel<ACT, CIPV>, smem, "plane_synthesis_ws");          \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    tc::plane_synthesis_ws_kernel<ACT, CIPV><<<dim3(grid), dim3(tc::kWsThreads), smem, st>>>(q);    \
+    DENO_LAUNCH((tc::plane_synthesis_ws_kernel<ACT, CIPV>), dim3(grid), dim3(tc::kWsThreads), smem, st, q);    \
   }
 #define DENO_TC_CASE(ACT)                                                                           \
   case ACT:                                                                                         \
@@ -744,7 +744,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
       int threads = round_up(r.ocb * (tl.KE / 2), 32);
       if (threads > 384) threads = 384;
       prof_before("row_synthesis", st);
-      tc::row_synthesis_kernel<<<dim3((unsigned)(p.g.NBO * p.g.NBI * r.tiles * r.ogroups)), dim3(threads), rs_smem, st>>>(r);
+      DENO_LAUNCH((tc::row_synthesis_kernel), dim3((unsigned)(p.g.NBO * p.g.NBI * r.tiles * r.ogroups)), dim3(threads), rs_smem, st, r);
       rrc = check_launch("row_synthesis", st);
       if (rrc != DENO_OK) return rrc;
       q.urow = urow;
@@ -764,7 +764,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
     rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV>, smem, "plane_synthesis_tc");          \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    tc::plane_synthesis_tc_kernel<ACT, CIPV><<<dim3(grid), dim3(256), smem, st>>>(q);               \
+    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV>), dim3(grid), dim3(256), smem, st, q);               \
   }
 #define DENO_TC_CASE(ACT)                                                                           \
   case ACT:                                                                                         \
@@ -875,7 +875,7 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
     rc = allow_smem(tc::bypass_wgrad_tc_kernel<NITV>, (size_t)sm.total, "bypass_wgrad_tc");        \
     if (rc != DENO_OK) return -2;                                                                  \
     prof_before("bypass_wgrad_tc", st);                                                            \
-    tc::bypass_wgrad_tc_kernel<NITV><<<dim3(grid), dim3(tc::kWgradThreads), (size_t)sm.total, st>>>(p);          \
+    DENO_LAUNCH((tc::bypass_wgrad_tc_kernel<NITV>), dim3(grid), dim3(tc::kWgradThreads), (size_t)sm.total, st, p);          \
   }
   if (need <= 2) DENO_WG_CASE(2)
   else if (need <= 4) DENO_WG_CASE(4)
@@ -926,7 +926,7 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
         tc::BiasDcParams bp;
         bp.ghat = ghat; bp.glb = glb; bp.B = s.B; bp.CO = s.CO; bp.M = s.M; bp.s_total = (float)s.S;
         prof_before("bias_from_dc", st);
-        tc::bias_from_dc_kernel<<<dim3((s.CO + 127) / 128), dim3(128), 0, st>>>(bp);
+        DENO_LAUNCH((tc::bias_from_dc_kernel), dim3((s.CO + 127) / 128), dim3(128), 0, st, bp);
         rc = check_launch("bias_from_dc", st);
       }
       return rc;
@@ -1070,7 +1070,7 @@ int launch_proj_fwd_tc(const tc::ProjTcParams& p, cudaStream_t st) {
   if (rc != DENO_OK) return rc;
   const int grid = p.ntiles < 148 ? p.ntiles : 148;
   prof_before("fno_proj_fwd_tc", st);
-  tc::fno_proj_fwd_tc_kernel<C, 128><<<dim3(grid), dim3(tc::kPjFwdThreads), (size_t)S::fwd_total, st>>>(p);
+  DENO_LAUNCH((tc::fno_proj_fwd_tc_kernel<C, 128>), dim3(grid), dim3(tc::kPjFwdThreads), (size_t)S::fwd_total, st, p);
   return check_launch("fno_proj_fwd_tc", st);
 }
 
@@ -1094,7 +1094,7 @@ int launch_proj_bwd_tc(const tc::ProjTcParams& p, int& nparts, cudaStream_t st) 
   const int grid = p.ntiles < kProjTcCtas ? p.ntiles : kProjTcCtas;
   nparts = grid;
   prof_before("fno_proj_bwd_tc", st);
-  tc::fno_proj_bwd_tc_kernel<32, 128><<<dim3(grid), dim3(tc::kPjThreads), (size_t)S::bwd_total, st>>>(p);
+  DENO_LAUNCH((tc::fno_proj_bwd_tc_kernel<32, 128>), dim3(grid), dim3(tc::kPjThreads), (size_t)S::bwd_total, st, p);
   return check_launch("fno_proj_bwd_tc", st);
 }
 #endif

@@ -52,6 +52,7 @@ struct LiftParams {
 };
 
 __global__ void __launch_bounds__(kLiftThreads) fno_lift_kernel(LiftParams p) {
+  DENO_PDL_SYNC();   // first kernel after the optimiser step: even the weights need the predecessor
   DENO_DYN_SMEM(smem_raw);
   float* w0s = reinterpret_cast<float*>(smem_raw);     // [C][K] then b0 [C]
   const int K = p.Kx + p.ND;
@@ -107,6 +108,7 @@ __host__ __device__ inline size_t lift_bwd_smem_bytes(int C, int K) {
 }
 
 __global__ void __launch_bounds__(kLiftThreads) fno_lift_bwd_kernel(LiftBwdParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   const int K = p.Kx + p.ND, K1 = K + 1;
   float* s_g = reinterpret_cast<float*>(smem_raw);                 // [C][257]
@@ -207,6 +209,7 @@ __device__ __forceinline__ void proj_load_weights(const ProjParams& p, float* w1
 // stay coalesced) and keeps the weight row of the current hidden unit in registers for all of them.
 template <int C, int PT>
 __global__ void __launch_bounds__(kProjThreads) fno_proj_fwd_kernel(ProjParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   float* w1s = reinterpret_cast<float*>(smem_raw);     // [Hd][C]
   float* b1s = w1s + p.Hd * C;
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(kProjThreads) fno_proj_fwd_kernel(ProjParams p
 
 template <int C, int PT>
 __global__ void __launch_bounds__(kProjThreads) fno_proj_bwd_kernel(ProjParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   const int R = (1 + p.O) * kProjJC;                   // reduction rows per round: gt, then gy_o * a per output
   float* w1s = reinterpret_cast<float*>(smem_raw);

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  DENO_PDL_SYNC();   // everything above read weights only; h (and gy) come from the predecessor
   const uint32_t tmem = tmem_slot;
   const uint32_t sbase = smem_u32(smem);
   const int nmine = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  DENO_PDL_SYNC();   // everything above read weights only; h and gy come from the predecessor
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + HD;    // D2: [hi*hi | hi*lo | lo*hi], C columns each
   const uint32_t sbase = smem_u32(smem);

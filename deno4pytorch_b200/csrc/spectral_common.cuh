@@ -9,9 +9,39 @@
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <utility>
 #define DENO_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+namespace deno {
+// Every kernel of the library can be launched with programmatic dependent launch (PDL, DENO_PDL=1): the next kernel's
+// CTAs may be scheduled while this one is still running, run their input-independent prologue (TMEM allocation, barrier
+// initialisation, constant / weight operand images) and then block in DENO_PDL_SYNC() until the predecessor has
+// completed and flushed.  OFF by default: inside the CUDA-graph replay of the training step it measured 19 712 vs
+// 19 735 samples/s without (round 1, profiles/r2w note in DESIGN.md) - the graph already removes the launch gaps and
+// the kernels fill the SMs to their end - so the default launch stays the plain, fully serialised one.  Rules every kernel follows: (1) nothing the IMMEDIATE predecessor may write is read, and no
+// global memory is written, before DENO_PDL_SYNC(); (2) DENO_PDL_SYNC() also releases the successor
+// (launch_dependents), i.e. only after this kernel has seen its own predecessor complete - so completion is
+// transitive and weights / constants written several kernels earlier are safe to read in the prologue.
+// Without the attribute the wait returns immediately.
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DENO_PDL"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}  // namespace deno
 #define DENO_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+  (void)deno::launch_pdl((kernel), (grid), (block), (smem), (stream), __VA_ARGS__)
+#define DENO_PDL_SYNC() do { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
 #endif
 
 #include <stdint.h>

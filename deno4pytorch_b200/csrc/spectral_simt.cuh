@@ -66,6 +66,7 @@ __host__ __device__ inline AnalysisSmem analysis_smem(const AnalysisParams& p) {
 
 template <bool FUSE_GZ>
 __global__ void plane_analysis_kernel(AnalysisParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -195,6 +196,7 @@ struct OuterParams {
 
 // out[b][c][k][q] = sum_x (cos - i sin)(k,x) * in[b][x][c][q];  thread = (q, k quad, c, b)
 __global__ void outer_analysis_kernel(OuterParams p) {
+  DENO_PDL_SYNC();
   const int KX4 = round_up(p.KX, 4), KQ = KX4 / 4;
   const long long total = (long long)p.B * p.C * KQ * p.Q;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -225,6 +227,7 @@ __global__ void outer_analysis_kernel(OuterParams p) {
 
 // out[b][x][c][q] = sum_k (cos + i sin)(k,x) * in[b][c][k][q];  thread = (q, x quad, c, b)
 __global__ void outer_synthesis_kernel(OuterParams p) {
+  DENO_PDL_SYNC();
   const int KX4 = round_up(p.KX, 4);
   const int XQ = (p.X + 3) / 4;
   const long long total = (long long)p.B * p.C * XQ * p.Q;
@@ -319,7 +322,10 @@ __device__ __forceinline__ void mode_mix_body(const MixParams& p, int bx, int by
     if (b0 + j < p.B) p.out[((long long)(b0 + j) * p.CO + co) * M + pm] = make_float2(ar[j], ai[j]);
 }
 
-__global__ void mode_mix_kernel(MixParams p) { mode_mix_body(p, blockIdx.x, blockIdx.y, blockIdx.z); }
+__global__ void mode_mix_kernel(MixParams p) {
+  DENO_PDL_SYNC();
+  mode_mix_body(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
 
 // gW[i,o,p] = sum_b conj(xhat[b,i,p]) * ghat[b,o,p]
 struct MixWgradParams {
@@ -375,7 +381,10 @@ __device__ __forceinline__ void mode_mix_wgrad_body(const MixWgradParams& p, int
     if (oq * kMixWgradOut + j < p.CO) dst[(long long)(oq * kMixWgradOut + j) * p.md.Mblk] = make_float2(ar[j], ai[j]);
 }
 
-__global__ void mode_mix_wgrad_kernel(MixWgradParams p) { mode_mix_wgrad_body(p, blockIdx.x, blockIdx.y, blockIdx.z); }
+__global__ void mode_mix_wgrad_kernel(MixWgradParams p) {
+  DENO_PDL_SYNC();
+  mode_mix_wgrad_body(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
 
 // One launch for the three small consumers of the packed gradient spectrum G^ in the backward pass:
 //   blocks [0, nA)        G^x = conj(W) G^            (mode_mix_body)
@@ -395,6 +404,7 @@ struct MixBwdFusedParams {
 };
 
 __global__ void mode_mix_bwd_fused_kernel(MixBwdFusedParams f) {
+  DENO_PDL_SYNC();
   int id = blockIdx.x;
   const int nA = f.ax * f.ay * f.az, nB = f.bx * f.by * f.bz;
   if (id < nA) {
@@ -472,6 +482,7 @@ __host__ __device__ inline SynthSmem synth_smem(const SynthParams& p) {
 
 template <int ACT>
 __global__ void plane_synthesis_kernel(SynthParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -599,6 +610,7 @@ __host__ __device__ inline int wgrad_smem_floats(const WgradParams& p) {
 }
 
 __global__ void bypass_wgrad_partial_kernel(WgradParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   float* smem = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -679,6 +691,7 @@ struct WgradReduceParams {
 
 // blockDim = (32 outputs, 8 slices); grid = ceil(nj / 32).  Fixed summation order -> deterministic.
 __global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
+  DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
   float* red = reinterpret_cast<float*>(smem_raw);  // [8][32]
   const int j = blockIdx.x * 32 + threadIdx.x;
@@ -728,6 +741,7 @@ struct AdamParams {
 };
 
 __global__ void adam_flat_kernel(AdamParams a) {
+  DENO_PDL_SYNC();
   const float t = a.step[0];
   const float bc1 = 1.0f - powf(a.beta1, t);
   const float bc2 = 1.0f - powf(a.beta2, t);

@@ -195,6 +195,7 @@ __host__ __device__ inline size_t row_synth_smem_bytes(int ocb, int KH, int MW, 
 }
 
 __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
+  DENO_PDL_SYNC();
   extern __shared__ __align__(16) unsigned char rs_smem[];
   float2* sps = reinterpret_cast<float2*>(rs_smem);                 // [ocb][Qp]
   float2* twr = sps + (size_t)p.ocb * p.Qp;                         // [KH][kRowSynthRows]
@@ -353,8 +354,6 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     const uint32_t u_bytes = q.urow != nullptr ? (uint32_t)(trows * 2 * so.bu_one) : 0u;
     mbar_expect_tx(&mbar_u, ae_bytes + u_bytes);
     bulk_g2s(smem + so.ae_hi, q.ae + (long long)chunk * 2 * KE * 128, ae_bytes, &mbar_u);
-    if (q.urow != nullptr)
-      bulk_g2s(smem + so.bu, q.urow + ((size_t)bp * H + x0) * 2 * (size_t)(so.bu_one / 4), u_bytes, &mbar_u);
   }
 
   // ---- constant operands -------------------------------------------------------------------
@@ -382,6 +381,12 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   }
   float* bias_s = reinterpret_cast<float*>(smem + so.bias);
   for (int o = tid; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
+
+  // Everything above depends on constants and weights only.  The U images come from the immediate predecessor
+  // (row_synthesis_kernel) and x / gz from earlier kernels: from here on the predecessor must have completed.
+  DENO_PDL_SYNC();
+  if (tid == 32 && q.urow != nullptr)
+    bulk_g2s(smem + so.bu, q.urow + ((size_t)bp * H + x0) * 2 * (size_t)(so.bu_one / 4), (uint32_t)(trows * 2 * so.bu_one), &mbar_u);
 
   // ---- x row prefetch (registers) ------------------------------------------------------------
   float xr[NIT][4];
@@ -653,6 +658,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
   const SynthWsSmem so = synth_ws_smem(CIP, CO, KE, R);
   constexpr int NCQ = CIP / 4;            // channel quads per point (one loader thread = one point)
 
+  DENO_PDL_SYNC();
   if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)q.tmem_cols);
   if (tid == 32) {
     for (int s = 0; s < 2; ++s) {
@@ -1038,6 +1044,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   fence_before_sync();
   __syncthreads();                                     // barriers initialised, TMEM allocated
   fence_after_sync();
+  DENO_PDL_SYNC();                                     // the planes (and act'(z)) come from the predecessor
   mbar_wait(&bar_const, 0);                            // constant images stored
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + (uint32_t)(3 * N1);   // [hi*hi | hi*lo | lo*hi] tiles per stage
@@ -1402,6 +1409,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  DENO_PDL_SYNC();                                     // gz and x come from earlier kernels
   const uint32_t tmem = tmem_slot;
   // tiles of this CTA: t = blockIdx.x + n * gridDim.x
   const int ntile_cta = (p.ntiles > (int)blockIdx.x) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -1570,6 +1578,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
 // glb[o] = S * sum_b Re G^[b, o, mode 0]  (the DC mode of the scaled spectrum is sum_pt gz / S)
 struct BiasDcParams { const float2* ghat; float* glb; int B, CO, M; float s_total; };
 __global__ void bias_from_dc_kernel(BiasDcParams p) {
+  DENO_PDL_SYNC();
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= p.CO) return;
   float acc = 0.f;

@@ -70,6 +70,12 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._g_bwd = torch.cuda.CUDAGraph()
+        if self.world == 1:
+            # no collective between backward and optimiser: the whole step is one graph launch
+            with torch.cuda.graph(self._g_bwd):
+                self._forward_backward()
+                self.opt.step()
+            return
         with torch.cuda.graph(self._g_bwd):
             self._forward_backward()
         self._g_opt = torch.cuda.CUDAGraph()
@@ -91,8 +97,9 @@ class TrainStep:
         self.load(x, grid, target)
         if self.use_graph:
             self._g_bwd.replay()
-            self.grads.all_reduce_mean(self.group)
-            self._g_opt.replay()
+            if self._g_opt is not None:
+                self.grads.all_reduce_mean(self.group)
+                self._g_opt.replay()
         else:
             self._forward_backward()
             self.grads.all_reduce_mean(self.group)

@@ -155,6 +155,7 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 
+#define DENO_PDL_SYNC() do { } while (0)
 #define DENO_DYN_SMEM(name) unsigned char* name = emu::g_dyn_smem
 #define DENO_LAUNCH(kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })

@@ -76,6 +76,7 @@ CASES = [
     ((94, 94), (12, 12), 1, 32, 32, "gelu"),    # the Darcy (C2) layer's launch geometry, batch 1
     ((1026,), (16,), 2, 64, 64, "gelu"),        # the Burgers (C1) layer's launch geometry, batch 2
     ((10, 70, 46), (2, 8, 8), 1, 32, 32, "gelu"),  # the C5 plane geometry (70x46 planes), short X
+    ((128, 40), (64, 16), 2, 6, 6, "tanh"),     # every row mode retained (2 * modes == H), the Airfoil/Pipe mode counts
 ]
 
 

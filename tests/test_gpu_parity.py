@@ -106,11 +106,15 @@ def test_layer_matches_cpu_oracle_at_config_shapes(shape):
     lb = torch.randn(cout, generator=gen)
     cot = torch.randn((B, cout) + spatial, generator=gen)
 
-    xr = x.clone().requires_grad_(True)
-    wr = [w.clone().requires_grad_(True) for w in ws]
-    lwr, lbr = lw.clone().requires_grad_(True), lb.clone().requires_grad_(True)
+    # The oracle is evaluated in float64.  With the fp32 evaluation a 1-2e-5 excursion of gx on the (128, 40) case was
+    # seen twice in ~40 suite runs; its origin is not isolated - the GPU side is bitwise identical over 180
+    # repetitions of that case (tools/repro_case.py, tools/flaky_hunt.py) and so is the fp32 oracle when repeated on
+    # its own - so the float64 evaluation at least takes the fp32 CPU FFT out of the comparison.
+    xr = x.double().requires_grad_(True)
+    wr = [w.to(torch.complex128).requires_grad_(True) for w in ws]
+    lwr, lbr = lw.double().requires_grad_(True), lb.double().requires_grad_(True)
     ref = fno_port.spectral_conv(xr, wr, lwr, lbr, modes, activation=act)
-    (ref * cot).sum().backward()
+    (ref * cot.double()).sum().backward()
 
     y, gx, gws, glw, glb = _run_layer(x, ws, lw, lb, modes, act, cot)
     assert rel_l2(y.cpu(), ref) < TOL
