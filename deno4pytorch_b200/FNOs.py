@@ -211,8 +211,16 @@ class _FNONd(nn.Module):
             h = h.movedim(-1, 1)
             if self.padding != 0:
                 h = F.pad(h, [0, self.padding] * nd)
-        for layer in self.convs:
+        # ``_stage_done(i)`` (set by training.TrainStep for data-parallel runs) is called from the backward pass as soon
+        # as the gradient wrt the INPUT of stage i exists, i.e. stage i's own parameter gradients have been enqueued:
+        # stage i < depth is convs[i], stage depth is the projection.  The lift finishes with backward() itself.
+        notify = getattr(self, "_stage_done", None) if torch.is_grad_enabled() else None
+        for i, layer in enumerate(self.convs):
+            if notify is not None and h.requires_grad:
+                h.register_hook(lambda g, i=i: notify(i))
             h = layer(h)
+        if notify is not None and h.requires_grad:
+            h.register_hook(lambda g, i=len(self.convs): notify(i))
         if desc is not None:
             return _ProjFn.apply(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, desc)
         if self.padding != 0:

@@ -65,8 +65,10 @@ class FlatGradients:
             n = p.numel() * (2 if p.is_complex() else 1)
             sizes.append((n + 3) // 4 * 4)  # keep every view 16-byte aligned
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self.spans = {}            # id(param) -> (offset, padded length) inside ``flat``
         off = 0
         for p, n in zip(self.params, sizes):
+            self.spans[id(p)] = (off, n)
             real_n = p.numel() * (2 if p.is_complex() else 1)
             seg = self.flat[off:off + real_n]
             if p.is_complex():
@@ -89,6 +91,16 @@ class FlatGradients:
 
     def zero(self):
         self.flat.zero_()
+
+    def span_of(self, params: Iterable[torch.nn.Parameter]) -> torch.Tensor:
+        """The contiguous slice of the flat buffer covering ``params`` (which must be adjacent in it)."""
+        spans = sorted(self.spans[id(p)] for p in params if id(p) in self.spans)
+        if not spans:
+            return self.flat[:0]
+        for (o0, n0), (o1, _) in zip(spans, spans[1:]):
+            if o0 + n0 != o1:
+                raise ValueError("parameters are not adjacent in the flat gradient buffer")
+        return self.flat[spans[0][0]:spans[-1][0] + spans[-1][1]]
 
     def all_reduce_mean(self, group=None, async_op: bool = False):
         """Sum over ranks then divide by world size (DDP's gradient averaging)."""

@@ -9,6 +9,7 @@ backward graph and the optimiser graph on the same stream.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -18,11 +19,32 @@ import torch.nn.functional as F
 from .parallel import FlatAdam, FlatGradients, FlatParameters
 
 
+def _all_gradients_direct(model, x, grid) -> bool:
+    """True when every parameter gradient of ``model`` is written by this library's backward kernels themselves
+    (``functional.grad_sink``), i.e. is complete the moment a stage's backward function returns.  Gradients that
+    still go through autograd's AccumulateGrad nodes (op-by-op ends, the dropout / return_freq branches of the layer)
+    have no such ordering, and the per-stage all-reduce must not be used."""
+    if not (hasattr(model, "convs") and hasattr(model, "_ends_desc")):
+        return False
+    if model._ends_desc(x, grid) is None:
+        return False
+    for layer in model.convs:
+        if getattr(layer, "return_freq", False):
+            return False
+        drop = getattr(layer, "dropout", None)
+        if getattr(layer, "_dropout_in_forward", False) and drop is not None and getattr(drop, "p", 0.0) > 0:
+            return False
+        if not callable(getattr(layer, "_weights", None)):
+            return False
+    return True
+
+
 class TrainStep:
     def __init__(self, model: torch.nn.Module, x: torch.Tensor, grid: torch.Tensor, target: torch.Tensor, *,
                  lr: float = 1e-3, betas=(0.7, 0.9), weight_decay: float = 1e-4,
                  loss_fn: Callable = F.mse_loss, forward_fn: Optional[Callable] = None,
-                 use_graph: bool = True, warmup: int = 3, group=None, fused_adam: bool = True):
+                 use_graph: bool = True, warmup: int = 3, group=None, fused_adam: bool = True,
+                 overlap_allreduce: Optional[bool] = None):
         """``x``/``grid``/``target`` are example device tensors fixing the shapes; later calls copy new
         data into static buffers.  ``forward_fn(model, x, grid, target) -> loss`` overrides the default
         single model call (e.g. the 10-step autoregressive rollout of Demo/Turbulence_2d+t)."""
@@ -43,6 +65,23 @@ class TrainStep:
                                         capturable=use_graph, foreach=True)
         # one model call per step: parameter gradients go straight into the flat buffer (no per-parameter add kernels)
         self.grads.direct_writes(forward_fn is None and x.is_cuda)
+        # Data parallel on GPUs with the stock single-call step: the gradient all-reduce is issued per stage from inside
+        # the backward pass on a side stream (projection first, then the spectral layers last to first, the lift after
+        # backward() returns), so it overlaps the rest of the backward, and the whole step is ONE captured graph.
+        if overlap_allreduce is None:     # opt-in (DENO_DP_OVERLAP=1) until it has been proven under graph capture on NCCL
+            overlap_allreduce = os.environ.get("DENO_DP_OVERLAP", "0") == "1"
+        self._overlap = bool(overlap_allreduce and self.world > 1 and x.is_cuda and forward_fn is None
+                             and dist.get_backend(group) == "nccl" and _all_gradients_direct(model, x, grid))
+        self._ar_stream = torch.cuda.Stream() if self._overlap else None
+        if self._overlap:
+            stages = [list(layer.parameters()) for layer in model.convs]
+            stages.append(list(model.fc1.parameters()) + list(model.fc2.parameters()))
+            self._stage_grads = [self.grads.span_of(ps) for ps in stages]
+            self._lift_grads = self.grads.span_of(list(model.fc0.parameters()))
+            covered = sum(t.numel() for t in self._stage_grads) + self._lift_grads.numel()
+            if covered != self.grads.flat.numel():
+                raise RuntimeError("stage buckets do not cover the flat gradient buffer")
+            model._stage_done = self._reduce_stage
         self.loss = torch.zeros((), device=x.device)
         self.use_graph = use_graph
         self._g_bwd = self._g_opt = None
@@ -50,6 +89,17 @@ class TrainStep:
             self._capture(warmup)
 
     # ------------------------------------------------------------------------------------
+    def _reduce_bucket(self, t: torch.Tensor):
+        """Average ``t`` over the ranks on the side stream, ordered after everything enqueued so far on this one."""
+        if t.numel() == 0:
+            return
+        self._ar_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._ar_stream):
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+
+    def _reduce_stage(self, i: int):
+        self._reduce_bucket(self._stage_grads[i])
+
     def _forward_backward(self):
         self.grads.zero()
         if self.forward_fn is not None:
@@ -57,6 +107,9 @@ class TrainStep:
         else:
             loss = self.loss_fn(self.model(self.sx, self.sg), self.st)
         loss.backward()
+        if self._overlap:
+            self._reduce_bucket(self._lift_grads)
+            torch.cuda.current_stream().wait_stream(self._ar_stream)
         self.loss.copy_(loss.detach())
 
     def _capture(self, warmup: int):
@@ -65,13 +118,14 @@ class TrainStep:
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):   # also fills the twiddle cache and cuBLAS workspaces
                 self._forward_backward()
-                self.grads.all_reduce_mean(self.group)
+                if not self._overlap:
+                    self.grads.all_reduce_mean(self.group)
                 self.opt.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._g_bwd = torch.cuda.CUDAGraph()
-        if self.world == 1:
-            # no collective between backward and optimiser: the whole step is one graph launch
+        if self.world == 1 or self._overlap:
+            # no separate collective between backward and optimiser: the whole step is one graph launch
             with torch.cuda.graph(self._g_bwd):
                 self._forward_backward()
                 self.opt.step()
@@ -102,6 +156,7 @@ class TrainStep:
                 self._g_opt.replay()
         else:
             self._forward_backward()
-            self.grads.all_reduce_mean(self.group)
+            if not self._overlap:
+                self.grads.all_reduce_mean(self.group)
             self.opt.step()
         return self.loss
