@@ -258,6 +258,9 @@ def layer_roofline(workload: str, device, hbm_peak: float, reps: int = 20):
     return roof
 
 
+_OPEN_STEPS = []
+
+
 def run_own(args):
     from deno4pytorch_b200 import parallel
     from deno4pytorch_b200.functional import launch_count
@@ -282,6 +285,7 @@ def run_own(args):
 
     before = launch_count()
     step = TrainStep(model, dx, dg, dt_, use_graph=not args.eager, warmup=3)
+    _OPEN_STEPS.append(step)
     # kernels of ours per step = launches recorded while one eager step / one capture ran
     probe_before = launch_count()
     if args.eager:
@@ -370,6 +374,8 @@ def run_own(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT.get(args.workload, args.workload), "global_batch": world * batch,
                    "parallelism": f"dp{world}", "parameters": nparams, "cuda_graph": not args.eager,
+                   "allreduce": ("per stage, overlapped with the backward, inside the graph" if step._overlap else
+                                 ("one flat all-reduce between the backward and the optimiser graph" if world > 1 else "none")),
                    "l2": f"no explicit flush: saved activations per step ~{act_mb:.0f} MB > 126 MB L2 "
                          "(inputs larger than L2)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -403,6 +409,8 @@ def main():
     try:
         run_own(args)
     finally:
+        for st in _OPEN_STEPS:          # captured graphs may reference NCCL kernels: drop them before the communicator
+            st.close()
         if dist.is_initialized():
             dist.destroy_process_group()
 

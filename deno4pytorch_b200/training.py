@@ -136,6 +136,13 @@ class TrainStep:
         with torch.cuda.graph(self._g_opt):
             self.opt.step()
 
+    def close(self):
+        """Drop the captured graphs.  Needed before ``dist.destroy_process_group()`` when the all-reduce was captured
+        (a live graph keeps NCCL kernels referenced and communicator teardown waits for them forever)."""
+        torch.cuda.synchronize()
+        self._g_bwd = self._g_opt = None
+        self.use_graph = False
+
     # ------------------------------------------------------------------------------------
     def load(self, x=None, grid=None, target=None, non_blocking: bool = True):
         """Copy a new batch (host or device tensors) into the static buffers."""

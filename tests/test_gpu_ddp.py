@@ -33,6 +33,10 @@ def _worker(rank, world, port, out_path):
     import torch.distributed as dist
     from deno4pytorch_b200.training import TrainStep
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if os.environ.get("DENO_DDP_DEBUG") == "1":      # where does a hung rank sit?
+        import faulthandler
+        import sys
+        faulthandler.dump_traceback_later(45, exit=True, file=sys.stderr)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -48,6 +52,7 @@ def _worker(rank, world, port, out_path):
     if rank == 0:
         torch.save({"losses": losses, "start": {k: v.cpu() for k, v in start.items()},
                     "end": {k: v.detach().cpu() for k, v in model.state_dict().items()}}, out_path)
+    step.close()
     dist.barrier()
     dist.destroy_process_group()
 
