@@ -83,6 +83,10 @@ class TrainStep:
                 raise RuntimeError("stage buckets do not cover the flat gradient buffer")
             model._stage_done = self._reduce_stage
         self.loss = torch.zeros((), device=x.device)
+        self._copy_stream = None          # input pipeline (prefetch): created on first use
+        self._staged = None
+        self._loss_slots = None           # pipelined loss read-back (enable_loss_readback)
+        self._nsteps = 0
         self.use_graph = use_graph
         self._g_bwd = self._g_opt = None
         if use_graph:
@@ -153,9 +157,55 @@ class TrainStep:
         if target is not None:
             self.st.copy_(target, non_blocking=non_blocking)
 
+    def prefetch(self, x, grid, target):
+        """Input pipeline: start the host-to-device copy of the NEXT batch (pinned host tensors) on a copy stream
+        into staging buffers, so it overlaps the step that is running; the next ``step()`` without arguments
+        moves the staged batch into the graph's static buffers (device-to-device) and runs on it."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_bufs = (torch.empty_like(self.sx), torch.empty_like(self.sg), torch.empty_like(self.st))
+            self._staged_ready = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        self._copy_stream.wait_event(self._stage_free)      # the previous staged batch has been consumed
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage_bufs, (x, grid, target)):
+                dst.copy_(src, non_blocking=True)
+            self._staged_ready.record()
+        self._staged = True
+
+    def enable_loss_readback(self):
+        """Every step additionally copies its loss to pinned host memory (asynchronously, two slots);
+        ``read_loss(lag)`` then returns the loss of the step ``lag`` calls back after waiting for THAT copy only, so a
+        training loop can log step k - 1 while step k is already running (no GPU idle time between steps)."""
+        if self._loss_slots is None:
+            self._loss_slots = [(torch.zeros((), dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+
+    def read_loss(self, lag: int = 0) -> float:
+        """Host value of the loss of the step ``lag`` calls back (0: the latest; 1: the one before).  Needs
+        ``enable_loss_readback()``; waits only for that step's device-to-host copy."""
+        if self._loss_slots is None or lag not in (0, 1) or self._nsteps - 1 - lag < 0:
+            raise RuntimeError("read_loss: enable_loss_readback() first; lag must be 0 or 1 with enough steps run")
+        buf, ev = self._loss_slots[(self._nsteps - 1 - lag) % 2]
+        ev.synchronize()
+        return float(buf)
+
+    def _consume_staged(self):
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged_ready)
+        self.sx.copy_(self._stage_bufs[0])
+        self.sg.copy_(self._stage_bufs[1])
+        self.st.copy_(self._stage_bufs[2])
+        self._stage_free.record(cur)
+        self._staged = None
+
     def __call__(self, x=None, grid=None, target=None) -> torch.Tensor:
-        """Runs one optimiser step; returns the (device) loss of this rank's shard."""
-        self.load(x, grid, target)
+        """Runs one optimiser step; returns the (device) loss of this rank's shard.  Without arguments it runs on
+        the batch staged by ``prefetch`` (if any), else on the batch already in the static buffers."""
+        if x is None and grid is None and target is None and self._staged:
+            self._consume_staged()
+        else:
+            self.load(x, grid, target)
         if self.use_graph:
             self._g_bwd.replay()
             if self._g_opt is not None:
@@ -166,4 +216,9 @@ class TrainStep:
             if not self._overlap:
                 self.grads.all_reduce_mean(self.group)
             self.opt.step()
+        if self._loss_slots is not None:
+            buf, ev = self._loss_slots[self._nsteps % 2]
+            buf.copy_(self.loss, non_blocking=True)
+            ev.record()
+        self._nsteps += 1
         return self.loss

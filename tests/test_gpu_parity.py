@@ -349,3 +349,53 @@ def test_direct_gradient_writes_match_autograd_accumulation():
         assert rel_l2(a.cpu(), b.cpu()) < 1e-6
     for p in model.parameters():
         assert p.grad.data_ptr() >= fg.flat.data_ptr() and p.grad.data_ptr() < fg.flat.data_ptr() + fg.nbytes
+
+
+def test_prefetch_input_pipeline_matches_direct_load():
+    """TrainStep.prefetch() (H2D of the next batch on a copy stream) feeds the same numbers as passing the batch to the
+    step call: identical loss sequence over different batches."""
+    import deno4pytorch_b200 as d4
+    from deno4pytorch_b200.training import TrainStep
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(4, 29, 31, 1, generator=g).pin_memory(), torch.rand(4, 29, 31, 2, generator=g).pin_memory(),
+                torch.randn(4, 29, 31, 1, generator=g).pin_memory()) for _ in range(4)]
+    losses = {}
+    for mode in ("direct", "prefetch"):
+        torch.manual_seed(3)
+        model = d4.FNO2d(in_dim=1, out_dim=1, modes=(6, 6), width=32, depth=2, padding=3).to(dev)
+        x0, g0, t0 = (t.to(dev) for t in batches[0])
+        step = TrainStep(model, x0, g0, t0, lr=1e-3, warmup=1)
+        out = []
+        if mode == "direct":
+            for b in batches:
+                out.append(float(step(*b)))
+        else:
+            step.prefetch(*batches[0])
+            for i in range(len(batches)):
+                lt = step()
+                if i + 1 < len(batches):
+                    step.prefetch(*batches[i + 1])
+                out.append(float(lt))
+        losses[mode] = out
+    assert losses["direct"] == losses["prefetch"]
+
+
+def test_pipelined_loss_readback_returns_each_steps_loss():
+    import deno4pytorch_b200 as d4
+    from deno4pytorch_b200.training import TrainStep
+    dev = _dev()
+    torch.manual_seed(4)
+    model = d4.FNO2d(in_dim=1, out_dim=1, modes=(6, 6), width=32, depth=2, padding=3).to(dev)
+    x = torch.randn(4, 29, 31, 1, device=dev)
+    grid = torch.rand(4, 29, 31, 2, device=dev)
+    tgt = torch.randn(4, 29, 31, 1, device=dev)
+    step = TrainStep(model, x, grid, tgt, lr=1e-3, warmup=1)
+    step.enable_loss_readback()
+    direct, lagged = [], []
+    for k in range(5):
+        direct.append(float(step()))
+        assert step.read_loss(lag=0) == direct[-1]
+        if k > 0:
+            lagged.append(step.read_loss(lag=1))
+    assert lagged == direct[:-1]
