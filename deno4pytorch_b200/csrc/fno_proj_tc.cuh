@@ -227,13 +227,17 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
         float v[16];
         tmem_ld16(td + c0, v);
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
+        for (int jj = 0; jj < 16; jj += 2) {            // two hidden units per packed fp32x2 evaluation
           const int j = wg * (HD / 4) + c0 + jj;
-          float a, da;
-          gelu_fast(v[jj] + b1s[j], a, da);
+          const float2 bb = *reinterpret_cast<const float2*>(b1s + j);
+          float2 a, da;
+          gelu_fast2(__fadd2_rn(make_float2(v[jj], v[jj + 1]), bb), a, da);
 #pragma unroll
           for (int o = 0; o < 4; ++o)
-            if (o < p.O) yo[o] = fmaf(w2s[o * HD + j], a, yo[o]);
+            if (o < p.O) {
+              const float2 ww = *reinterpret_cast<const float2*>(w2s + o * HD + j);
+              yo[o] = fmaf(ww.y, a.y, fmaf(ww.x, a.x, yo[o]));
+            }
         }
       }
       fence_before_sync();                               // D1 reads ordered before the next hand-off
@@ -402,16 +406,23 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
         const int slot = c & 1;
         float v[16];
         tmem_ld16(tmem_d1 + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * (HD / 2) + c * 16), v);
+        const float2 gy2 = make_float2(gy_cur, gy_cur);
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
+        for (int jj = 0; jj < 16; jj += 2) {            // two hidden units per packed fp32x2 evaluation
           const int j = wg * (HD / 2) + c * 16 + jj;
-          float a, da;
-          gelu_fast(v[jj] + b1s[j], a, da);
-          const float gt = gy_cur * w2s[j] * da;         // zero for padding lanes: their gy is zero
-          acc_b1[c * 16 + jj] += gt;
-          acc_w2[c * 16 + jj] = fmaf(gy_cur, a, acc_w2[c * 16 + jj]);
-          v[jj] = gt;
-          gt_dst[(c * 16 + jj) * 128] = gt;
+          const float2 bb = *reinterpret_cast<const float2*>(b1s + j);
+          const float2 ww = *reinterpret_cast<const float2*>(w2s + j);
+          float2 a, da;
+          gelu_fast2(__fadd2_rn(make_float2(v[jj], v[jj + 1]), bb), a, da);
+          const float2 gt = __fmul2_rn(__fmul2_rn(gy2, ww), da);   // zero for padding lanes: their gy is zero
+          acc_b1[c * 16 + jj] += gt.x;
+          acc_b1[c * 16 + jj + 1] += gt.y;
+          acc_w2[c * 16 + jj] = fmaf(gy_cur, a.x, acc_w2[c * 16 + jj]);
+          acc_w2[c * 16 + jj + 1] = fmaf(gy_cur, a.y, acc_w2[c * 16 + jj + 1]);
+          v[jj] = gt.x;
+          v[jj + 1] = gt.y;
+          gt_dst[(c * 16 + jj) * 128] = gt.x;
+          gt_dst[(c * 16 + jj + 1) * 128] = gt.y;
         }
         if (c >= 2) {                                    // the slot's previous chunk has been consumed by the tensor core
           const long long ts = clock64();

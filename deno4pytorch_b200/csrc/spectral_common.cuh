@@ -116,6 +116,35 @@ __device__ __forceinline__ void gelu_fast(float z, float& y, float& d) {
   d = fmaf(z * e, 0.39894228040143267794f, cdf);
 }
 
+// Two GELUs at once on the packed fp32x2 pipe of sm_100 (fma.rn.f32x2 and friends: two IEEE fp32 operations per issue
+// slot).  Same formula as gelu_fast; only exp2 / rcp / abs / copysign stay scalar.  The epilogues that evaluate 32-64
+// GELUs per thread and tile are issue-bound, so this is where their time goes.
+__device__ __forceinline__ void gelu_fast2(float2 z, float2& y, float2& d) {
+#ifdef DENO_EMULATE
+  gelu_fast(z.x, y.x, d.x);
+  gelu_fast(z.y, y.y, d.y);
+#else
+  const float2 ax = __fmul2_rn(make_float2(fabsf(z.x), fabsf(z.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 earg = __fmul2_rn(__fmul2_rn(ax, ax), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e, t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(earg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(earg.y));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  // q = -poly(t): coefficients negated so that erf_abs = q * t * e + 1
+  float2 q = __ffma2_rn(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
+  q = __ffma2_rn(q, t, make_float2(-1.421413741f, -1.421413741f));
+  q = __ffma2_rn(q, t, make_float2(0.284496736f, 0.284496736f));
+  q = __ffma2_rn(q, t, make_float2(-0.254829592f, -0.254829592f));
+  const float2 erf_abs = __ffma2_rn(__fmul2_rn(q, t), e, make_float2(1.0f, 1.0f));
+  const float2 erf_s = make_float2(copysignf(erf_abs.x, z.x), copysignf(erf_abs.y, z.y));
+  const float2 cdf = __ffma2_rn(make_float2(0.5f, 0.5f), erf_s, make_float2(0.5f, 0.5f));
+  y = __fmul2_rn(z, cdf);
+  d = __ffma2_rn(__fmul2_rn(z, e), make_float2(0.39894228040143267794f, 0.39894228040143267794f), cdf);
+#endif
+}
+
 __device__ __forceinline__ float act_apply(int act, float z) {
   switch (act) {
     case ACT_GELU: {

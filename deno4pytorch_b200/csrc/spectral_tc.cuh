@@ -511,18 +511,37 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       tmem_ld16(tb + CO + c0, v1);
       tmem_ld16(tb + 2 * CO + c0, v2);
       if (yl < ny) {
+        if (ACT == ACT_GELU) {                           // two channels per packed fp32x2 GELU evaluation
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int o = wg * ncol_half + c0 + j;
-          const float zz = (v[j] + bias_s[o]) + (v1[j] + v2[j]);
-          const long long a = pbase + (long long)o * p.g.sc;
-          if (p.z != nullptr) {
-            float yv, dv;
-            act_apply_grad(ACT, zz, yv, dv);
-            p.z[a] = dv;
-            p.y[a] = yv;
-          } else {
-            p.y[a] = act_apply(ACT, zz);
+          for (int j = 0; j < 16; j += 2) {
+            const int o = wg * ncol_half + c0 + j;
+            const float2 bb = *reinterpret_cast<const float2*>(bias_s + o);
+            const float2 zz = __fadd2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), bb),
+                                         __fadd2_rn(make_float2(v1[j], v1[j + 1]), make_float2(v2[j], v2[j + 1])));
+            float2 yv, dv;
+            gelu_fast2(zz, yv, dv);
+            const long long a = pbase + (long long)o * p.g.sc;
+            if (p.z != nullptr) {
+              p.z[a] = dv.x;
+              p.z[a + p.g.sc] = dv.y;
+            }
+            p.y[a] = yv.x;
+            p.y[a + p.g.sc] = yv.y;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int o = wg * ncol_half + c0 + j;
+            const float zz = (v[j] + bias_s[o]) + (v1[j] + v2[j]);
+            const long long a = pbase + (long long)o * p.g.sc;
+            if (p.z != nullptr) {
+              float yv, dv;
+              act_apply_grad(ACT, zz, yv, dv);
+              p.z[a] = dv;
+              p.y[a] = yv;
+            } else {
+              p.y[a] = act_apply(ACT, zz);
+            }
           }
         }
       }
