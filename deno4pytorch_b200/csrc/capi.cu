@@ -557,6 +557,34 @@ int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, 
   return check_launch(analysis ? "outer_analysis" : "outer_synthesis", st);
 }
 
+// Tiled per-mode products (mode_mix_tile_kernel / mode_mix_bwd_tile_kernel): picks the modes per block so that the grid
+// is about one block per SM and the staged operands fit shared memory; false when even one mode per block does not fit.
+bool mix_tile_cfg(const Shape& s, bool backward, MixTileParams& p, size_t& smem_bytes, int& grid) {
+  const char* e = getenv("DENO_MIX_TILE");
+  if (e != nullptr && e[0] == '0') return false;
+  p.md = make_decode(s);
+  p.B = s.B; p.CI = s.CI; p.CO = s.CO;
+  int TM = 4;
+  while (TM > 1 && (s.M + TM - 1) / TM < 140) TM /= 2;
+  if (const char* t = getenv("DENO_MIX_TM")) { const int v = atoi(t); if (v == 1 || v == 2 || v == 4) TM = v; }   // experiments
+  while (TM > 1 && (size_t)mix_tile_smem(s.B, s.CI, s.CO, TM, backward).total * 8 > (size_t)kMaxSmemBytes - 2048) TM /= 2;
+  if ((size_t)mix_tile_smem(s.B, s.CI, s.CO, TM, backward).total * 8 > (size_t)kMaxSmemBytes - 2048) return false;
+  p.TM = TM;
+  const int rmax = s.CI > s.CO ? s.CI : s.CO;
+  const int slots = kMixTileThreads / TM, nr2 = (rmax + 1) / 2;
+  const int groups = slots / nr2 > 0 ? slots / nr2 : 1;
+  int bper = (s.B + groups - 1) / groups;
+  if (bper > kMixTileB) bper = kMixTileB;
+  if (bper < 1) bper = 1;
+  p.bper = bper;
+  int cit = 4;
+  while (cit > 1 && ((s.CI + cit - 1) / cit) * ((s.CO + 3) / 4) * TM < kMixTileThreads) cit /= 2;
+  p.cit = cit;
+  smem_bytes = (size_t)mix_tile_smem(s.B, s.CI, s.CO, TM, backward).total * 8 + 64;   // + the decoded weight offsets
+  grid = (s.M + TM - 1) / TM;
+  return true;
+}
+
 int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks,
                cudaStream_t st) {
   MixParams p;
@@ -573,6 +601,24 @@ int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, con
     p.CI = s.CO; p.CO = s.CI;
     p.w_sci = p.md.Mblk; p.w_sco = (long long)s.CO * p.md.Mblk;
     p.conj_w = 1;
+  }
+  // The forward product alone is too little work per block for the tiled kernel (18.7 us vs 13.3 us for the
+  // thread-per-output kernel at the Darcy shape, which fills every SM with warps); DENO_MIX_TILE=2 forces it.
+  const char* tile_env = getenv("DENO_MIX_TILE");
+  if (!backward && tile_env != nullptr && tile_env[0] == '2') {
+    MixTileParams t;
+    memset(&t, 0, sizeof(t));
+    size_t tsm = 0;
+    int tgrid = 0;
+    if (mix_tile_cfg(s, false, t, tsm, tgrid)) {
+      t.xhat = in; t.yhat = out;
+      for (int j = 0; j < 4; ++j) t.w[j] = p.w[j];
+      int rc = allow_smem(mode_mix_tile_kernel, tsm, "mode_mix_tile");
+      if (rc != DENO_OK) return rc;
+      prof_before("mode_mix", st);
+      DENO_LAUNCH(mode_mix_tile_kernel, dim3(tgrid), dim3(kMixTileThreads), tsm, st, t);
+      return check_launch("mode_mix_tile", st);
+    }
   }
   dim3 block(32, 8);
   dim3 grid((s.M + 31) / 32, (p.CO + 7) / 8, (s.B + kMixBatchTile - 1) / kMixBatchTile);
@@ -598,9 +644,28 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
 // Fused launch of the backward consumers of G^ (see mode_mix_bwd_fused_kernel).  Any role may be disabled.
 int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat, float2* gxhat, const void* const* w_blocks,
                          void* const* gw_blocks, float* glb_from_dc, cudaStream_t st) {
+  const int nblk = 1 << (s.ndim - 1);
+  {
+    MixTileParams t;
+    memset(&t, 0, sizeof(t));
+    size_t tsm = 0;
+    int tgrid = 0;
+    if ((gxhat != nullptr || gw_blocks != nullptr || glb_from_dc != nullptr) && mix_tile_cfg(s, true, t, tsm, tgrid)) {
+      t.xhat = xhat; t.ghat = ghat; t.gxhat = gxhat;
+      for (int j = 0; j < 4; ++j) {
+        t.w[j] = (gxhat != nullptr && w_blocks != nullptr) ? static_cast<const float2*>(w_blocks[j < nblk ? j : 0]) : nullptr;
+        t.gw[j] = gw_blocks != nullptr ? static_cast<float2*>(gw_blocks[j < nblk ? j : 0]) : nullptr;
+      }
+      t.glb = glb_from_dc; t.s_total = (float)s.S;
+      int rc = allow_smem(mode_mix_bwd_tile_kernel, tsm, "mode_mix_bwd_tile");
+      if (rc != DENO_OK) return rc;
+      prof_before("mode_mix_bwd_fused", st);
+      DENO_LAUNCH(mode_mix_bwd_tile_kernel, dim3(tgrid), dim3(kMixTileThreads), tsm, st, t);
+      return check_launch("mode_mix_bwd_tile", st);
+    }
+  }
   MixBwdFusedParams f;
   memset(&f, 0, sizeof(f));
-  const int nblk = 1 << (s.ndim - 1);
   f.mix.md = make_decode(s);
   f.wg.md = f.mix.md;
   if (gxhat != nullptr) {

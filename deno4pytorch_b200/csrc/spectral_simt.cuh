@@ -437,6 +437,240 @@ __global__ void mode_mix_bwd_fused_kernel(MixBwdFusedParams f) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Tiled per-mode products.  mode_mix / mode_mix_bwd_fused above give every (mode, channel, batch) output its own
+// thread and read both operands straight from L2 with no reuse: 94 MB of L2 -> SM traffic for 5 MB of data at the
+// Darcy shape, 13 / 29 us.  Here a block owns TM consecutive packed modes, stages X^ (and G^) and W of those modes in
+// shared memory once, and register-tiles the small complex GEMMs:
+//   forward   Y^[b, o]  = sum_i X^[b, i] W[i, o]                thread tile: up to 5 batch entries x 2 outputs
+//   backward  G^x[b, i] = sum_o conj(W[i, o]) G^[b, o]          thread tile: up to 5 batch entries x 2 inputs
+//             gW[i, o]  = sum_b conj(X^[b, i]) G^[b, o]         thread tile: up to 4 inputs x 4 outputs
+//             glb[o]    = S * sum_b Re G^[b, o, mode 0]         (block of mode 0)
+// Shared-memory pitches are padded so that the lanes of a warp (TM modes x 8 channel tiles) hit distinct banks.
+// ----------------------------------------------------------------------------------------------
+constexpr int kMixTileThreads = 256;
+constexpr int kMixTileB = 5;       // batch entries per thread tile (register array size)
+
+struct MixTileParams {
+  const float2* xhat;    // [B][CI][M]
+  const float2* ghat;    // backward: [B][CO][M]
+  float2* yhat;          // forward:  [B][CO][M]
+  float2* gxhat;         // backward: [B][CI][M], may be null
+  const float2* w[4];    // weight blocks [CI][CO][Mblk]
+  float2* gw[4];         // backward: may be null (gw[0] == nullptr)
+  float* glb;            // backward: bias gradient from the DC mode, may be null
+  float s_total;
+  ModeDecode md;
+  int B, CI, CO, TM;
+  int bper;              // batch entries per thread tile (<= kMixTileB)
+  int cit;               // input channels per thread tile of the gW role (<= 4)
+};
+
+struct MixTileSmem { int x, g, w, chp, wip, total; };   // float2 offsets; channel pitch; ci pitch of W
+__host__ __device__ inline MixTileSmem mix_tile_smem(int B, int CI, int CO, int TM, bool backward) {
+  MixTileSmem m;
+  m.chp = TM + 1;                                  // one complex of padding per (., channel) row
+  m.wip = CO * m.chp + 2;                          // ... and two per input-channel slab of W
+  m.x = 0;
+  int off = B * CI * m.chp;
+  m.g = off;
+  if (backward) off += B * CO * m.chp;
+  m.w = off;
+  off += CI * m.wip;
+  m.total = off;
+  return m;
+}
+
+// Staging loops keep eight global loads in flight per thread: a plain load -> store loop costs one memory round trip
+// per trip, which for these small tiles IS the kernel (first version: 22 us for the forward product).
+constexpr int kMixStageBatch = 8;
+
+// stage [rows][TM] complex of a (B, C, M) spectrum tensor: rows = B * C, channel pitch chp
+__device__ __forceinline__ void mix_tile_stage(float2* dst, const float2* src, int rows, int M, int pm0, int TM, int chp) {
+  const int n = rows * TM;
+  for (int idx0 = threadIdx.x; idx0 < n; idx0 += kMixStageBatch * kMixTileThreads) {
+    float2 v[kMixStageBatch];
+#pragma unroll
+    for (int u = 0; u < kMixStageBatch; ++u) {
+      const int idx = min(idx0 + u * kMixTileThreads, n - 1);
+      const int r = idx / TM, t = idx - r * TM;
+      v[u] = ldg_ordered(src + (long long)r * M + min(pm0 + t, M - 1));
+    }
+    DENO_SCHED_FENCE();
+#pragma unroll
+    for (int u = 0; u < kMixStageBatch; ++u) {
+      const int idx = idx0 + u * kMixTileThreads;
+      if (idx < n) {
+        const int r = idx / TM, t = idx - r * TM;
+        dst[r * chp + t] = (pm0 + t < M) ? v[u] : make_float2(0.f, 0.f);
+      }
+    }
+  }
+}
+
+// stage the TM modes' weights [CI][CO][TM]; the (block, offset) of each mode is decoded once per block (woff, smem)
+__device__ __forceinline__ void mix_tile_stage_w(const MixTileParams& p, float2* ws, const MixTileSmem& so, int pm0, const int* woff) {
+  const int TM = p.TM, n = p.CI * p.CO * TM;
+  for (int idx0 = threadIdx.x; idx0 < n; idx0 += kMixStageBatch * kMixTileThreads) {
+    float2 v[kMixStageBatch];
+#pragma unroll
+    for (int u = 0; u < kMixStageBatch; ++u) {
+      const int idx = min(idx0 + u * kMixTileThreads, n - 1);
+      const int r = idx / TM, t = idx - r * TM;            // r = ci * CO + co
+      const int wo = woff[t];                              // (blk << 28) | off
+      const int blk = wo >> 28;
+      const float2* wb = blk == 0 ? p.w[0] : (blk == 1 ? p.w[1] : (blk == 2 ? p.w[2] : p.w[3]));
+      v[u] = ldg_ordered(wb + (long long)r * p.md.Mblk + (wo & 0x0FFFFFFF));
+    }
+    DENO_SCHED_FENCE();
+#pragma unroll
+    for (int u = 0; u < kMixStageBatch; ++u) {
+      const int idx = idx0 + u * kMixTileThreads;
+      if (idx < n) {
+        const int r = idx / TM, t = idx - r * TM;
+        const int co = r % p.CO, ci = r / p.CO;
+        ws[ci * so.wip + co * so.chp + t] = (pm0 + t < p.md.M) ? v[u] : make_float2(0.f, 0.f);
+      }
+    }
+  }
+}
+
+// (block, offset) of the block's modes, decoded once: woff[t] = (blk << 28) | off
+__device__ __forceinline__ void mix_tile_decode(const MixTileParams& p, int pm0, int* woff) {
+  if ((int)threadIdx.x < p.TM) {
+    int blk, off;
+    decode_mode(p.md, min(pm0 + (int)threadIdx.x, p.md.M - 1), blk, off);
+    woff[threadIdx.x] = (blk << 28) | off;
+  }
+  __syncthreads();
+}
+
+// out[b][r][t] = sum_c A[b][c][t] * (conj?) W(c, r)[t] for the block's modes; W(c, r) = ws[c * cstride + r * rstride]
+__device__ __forceinline__ void mix_tile_product(const float2* as, const float2* ws, float2* out, int B, int C, int R, int M,
+                                                 int pm0, int TM, int chp, int w_cstride, int w_rstride, int bper, bool conj_w) {
+  const int t = threadIdx.x % TM;
+  const int nr2 = (R + 1) / 2;
+  const int nbg = (B + bper - 1) / bper;
+  for (int item = threadIdx.x / TM; item < nbg * nr2; item += kMixTileThreads / TM) {
+    const int r2 = item % nr2, bg = item / nr2;
+    const int r0 = 2 * r2, r1 = min(2 * r2 + 1, R - 1);
+    const int b0 = bg * bper;
+    float ar[kMixTileB][2], ai[kMixTileB][2];
+#pragma unroll
+    for (int j = 0; j < kMixTileB; ++j) ar[j][0] = ai[j][0] = ar[j][1] = ai[j][1] = 0.f;
+    const float sgn = conj_w ? -1.0f : 1.0f;
+    for (int c = 0; c < C; ++c) {
+      const float2 w0 = ws[c * w_cstride + r0 * w_rstride + t], w1 = ws[c * w_cstride + r1 * w_rstride + t];
+      const float w0i = w0.y * sgn, w1i = w1.y * sgn;
+#pragma unroll
+      for (int j = 0; j < kMixTileB; ++j) {
+        if (j < bper) {
+          const float2 a = as[(min(b0 + j, B - 1) * C + c) * chp + t];
+          ar[j][0] = fmaf(a.x, w0.x, fmaf(-a.y, w0i, ar[j][0]));
+          ai[j][0] = fmaf(a.x, w0i, fmaf(a.y, w0.x, ai[j][0]));
+          ar[j][1] = fmaf(a.x, w1.x, fmaf(-a.y, w1i, ar[j][1]));
+          ai[j][1] = fmaf(a.x, w1i, fmaf(a.y, w1.x, ai[j][1]));
+        }
+      }
+    }
+    if (pm0 + t < M) {
+#pragma unroll
+      for (int j = 0; j < kMixTileB; ++j) {
+        if (j < bper && b0 + j < B) {
+          out[((long long)(b0 + j) * R + r0) * M + pm0 + t] = make_float2(ar[j][0], ai[j][0]);
+          if (2 * r2 + 1 < R) out[((long long)(b0 + j) * R + r0 + 1) * M + pm0 + t] = make_float2(ar[j][1], ai[j][1]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMixTileThreads) mode_mix_tile_kernel(MixTileParams p) {
+  DENO_PDL_SYNC();
+  DENO_DYN_SMEM(smem_raw);
+  float2* sm = reinterpret_cast<float2*>(smem_raw);
+  const MixTileSmem so = mix_tile_smem(p.B, p.CI, p.CO, p.TM, false);
+  const int pm0 = blockIdx.x * p.TM;
+  int* woff = reinterpret_cast<int*>(sm + so.total);
+  mix_tile_decode(p, pm0, woff);
+  mix_tile_stage(sm + so.x, p.xhat, p.B * p.CI, p.md.M, pm0, p.TM, so.chp);
+  mix_tile_stage_w(p, sm + so.w, so, pm0, woff);
+  __syncthreads();
+  // contraction over ci: W(ci, co) = ws[ci * wip + co * chp]
+  mix_tile_product(sm + so.x, sm + so.w, p.yhat, p.B, p.CI, p.CO, p.md.M, pm0, p.TM, so.chp, so.wip, so.chp, p.bper, false);
+}
+
+__global__ void __launch_bounds__(kMixTileThreads) mode_mix_bwd_tile_kernel(MixTileParams p) {
+  DENO_PDL_SYNC();
+  DENO_DYN_SMEM(smem_raw);
+  float2* sm = reinterpret_cast<float2*>(smem_raw);
+  const MixTileSmem so = mix_tile_smem(p.B, p.CI, p.CO, p.TM, true);
+  const int pm0 = blockIdx.x * p.TM, TM = p.TM, M = p.md.M;
+  float2* xs = sm + so.x;
+  float2* gs = sm + so.g;
+  float2* ws = sm + so.w;
+  int* woff = reinterpret_cast<int*>(sm + so.total);
+  mix_tile_decode(p, pm0, woff);
+  if (p.gw[0] != nullptr) mix_tile_stage(xs, p.xhat, p.B * p.CI, M, pm0, TM, so.chp);
+  mix_tile_stage(gs, p.ghat, p.B * p.CO, M, pm0, TM, so.chp);
+  if (p.gxhat != nullptr) mix_tile_stage_w(p, ws, so, pm0, woff);
+  __syncthreads();
+  // G^x: contraction over co of conj(W(ci, co)): W as seen from (c = co, r = ci) is ws[r * wip + c * chp]
+  if (p.gxhat != nullptr)
+    mix_tile_product(gs, ws, p.gxhat, p.B, p.CO, p.CI, M, pm0, TM, so.chp, so.chp, so.wip, p.bper, true);
+  // gW[i, o] = sum_b conj(X^[b, i]) G^[b, o]
+  if (p.gw[0] != nullptr) {
+    const int t = threadIdx.x % TM;
+    const int cit = p.cit;
+    const int nci = (p.CI + cit - 1) / cit, nco = (p.CO + 3) / 4;
+    for (int item = threadIdx.x / TM; item < nci * nco; item += kMixTileThreads / TM) {
+      const int oq = item % nco, iq = item / nco;
+      const int i0 = iq * cit, o0 = oq * 4;
+      float ar[4][4], ai[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ar[a][b] = ai[a][b] = 0.f;
+      for (int b = 0; b < p.B; ++b) {
+        float2 xv[4], gv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) xv[a] = xs[(b * p.CI + min(i0 + a, p.CI - 1)) * so.chp + t];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gv[c] = gs[(b * p.CO + min(o0 + c, p.CO - 1)) * so.chp + t];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          if (a < cit) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
+              ar[a][c] = fmaf(xv[a].x, gv[c].x, fmaf(xv[a].y, gv[c].y, ar[a][c]));
+              ai[a][c] = fmaf(xv[a].x, gv[c].y, fmaf(-xv[a].y, gv[c].x, ai[a][c]));
+            }
+          }
+        }
+      }
+      if (pm0 + t < M) {
+        const int blk = woff[t] >> 28, off = woff[t] & 0x0FFFFFFF;
+        float2* gb = blk == 0 ? p.gw[0] : (blk == 1 ? p.gw[1] : (blk == 2 ? p.gw[2] : p.gw[3]));
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (a < cit && i0 + a < p.CI && o0 + c < p.CO)
+              gb[((long long)(i0 + a) * p.CO + o0 + c) * p.md.Mblk + off] = make_float2(ar[a][c], ai[a][c]);
+      }
+    }
+  }
+  // bias gradient of the bypass conv from the DC mode (packed mode 0 lives in block 0, column 0)
+  if (p.glb != nullptr && blockIdx.x == 0) {
+    for (int o = threadIdx.x; o < p.CO; o += kMixTileThreads) {
+      float acc = 0.f;
+      for (int b = 0; b < p.B; ++b) acc += gs[(b * p.CO + o) * so.chp].x;
+      p.glb[o] = acc * p.s_total;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // plane_synthesis: y = act( scale * sum_{k,l} c_l Re(spec e^{+i theta}) + sum_i W[o,i] u[i] + bias[o] )
 // ----------------------------------------------------------------------------------------------
 struct SynthParams {
