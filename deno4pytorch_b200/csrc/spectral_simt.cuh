@@ -544,42 +544,113 @@ __device__ __forceinline__ void mix_tile_decode(const MixTileParams& p, int pm0,
   __syncthreads();
 }
 
-// out[b][r][t] = sum_c A[b][c][t] * (conj?) W(c, r)[t] for the block's modes; W(c, r) = ws[c * cstride + r * rstride]
+// out[b][r][t] = sum_c A[b][c][t] * (conj?) W(c, r)[t] for the block's modes; W(c, r) = ws[c * cstride + r * rstride].
+// BPER (batch entries per thread tile) is a template argument and every address is a base pointer plus c * stride, so
+// the inner loop is loads + FMAs only (the first version spent 60 % of its instructions on index arithmetic and guards).
+template <int BPER>
 __device__ __forceinline__ void mix_tile_product(const float2* as, const float2* ws, float2* out, int B, int C, int R, int M,
-                                                 int pm0, int TM, int chp, int w_cstride, int w_rstride, int bper, bool conj_w) {
+                                                 int pm0, int TM, int chp, int w_cstride, int w_rstride, bool conj_w) {
   const int t = threadIdx.x % TM;
   const int nr2 = (R + 1) / 2;
-  const int nbg = (B + bper - 1) / bper;
+  const int nbg = (B + BPER - 1) / BPER;
+  const float sgn = conj_w ? -1.0f : 1.0f;
   for (int item = threadIdx.x / TM; item < nbg * nr2; item += kMixTileThreads / TM) {
     const int r2 = item % nr2, bg = item / nr2;
     const int r0 = 2 * r2, r1 = min(2 * r2 + 1, R - 1);
-    const int b0 = bg * bper;
-    float ar[kMixTileB][2], ai[kMixTileB][2];
+    const int b0 = bg * BPER;
+    float ar[BPER][2], ai[BPER][2];
+    const float2* ap[BPER];
 #pragma unroll
-    for (int j = 0; j < kMixTileB; ++j) ar[j][0] = ai[j][0] = ar[j][1] = ai[j][1] = 0.f;
-    const float sgn = conj_w ? -1.0f : 1.0f;
+    for (int j = 0; j < BPER; ++j) {
+      ar[j][0] = ai[j][0] = ar[j][1] = ai[j][1] = 0.f;
+      ap[j] = as + (min(b0 + j, B - 1) * C) * chp + t;
+    }
+    const float2* w0p = ws + r0 * w_rstride + t;
+    const float2* w1p = ws + r1 * w_rstride + t;
+#pragma unroll 4
     for (int c = 0; c < C; ++c) {
-      const float2 w0 = ws[c * w_cstride + r0 * w_rstride + t], w1 = ws[c * w_cstride + r1 * w_rstride + t];
+      const float2 w0 = w0p[c * w_cstride], w1 = w1p[c * w_cstride];
       const float w0i = w0.y * sgn, w1i = w1.y * sgn;
 #pragma unroll
-      for (int j = 0; j < kMixTileB; ++j) {
-        if (j < bper) {
-          const float2 a = as[(min(b0 + j, B - 1) * C + c) * chp + t];
-          ar[j][0] = fmaf(a.x, w0.x, fmaf(-a.y, w0i, ar[j][0]));
-          ai[j][0] = fmaf(a.x, w0i, fmaf(a.y, w0.x, ai[j][0]));
-          ar[j][1] = fmaf(a.x, w1.x, fmaf(-a.y, w1i, ar[j][1]));
-          ai[j][1] = fmaf(a.x, w1i, fmaf(a.y, w1.x, ai[j][1]));
-        }
+      for (int j = 0; j < BPER; ++j) {
+        const float2 a = ap[j][c * chp];
+        ar[j][0] = fmaf(a.x, w0.x, fmaf(-a.y, w0i, ar[j][0]));
+        ai[j][0] = fmaf(a.x, w0i, fmaf(a.y, w0.x, ai[j][0]));
+        ar[j][1] = fmaf(a.x, w1.x, fmaf(-a.y, w1i, ar[j][1]));
+        ai[j][1] = fmaf(a.x, w1i, fmaf(a.y, w1.x, ai[j][1]));
       }
     }
     if (pm0 + t < M) {
 #pragma unroll
-      for (int j = 0; j < kMixTileB; ++j) {
-        if (j < bper && b0 + j < B) {
+      for (int j = 0; j < BPER; ++j) {
+        if (b0 + j < B) {
           out[((long long)(b0 + j) * R + r0) * M + pm0 + t] = make_float2(ar[j][0], ai[j][0]);
           if (2 * r2 + 1 < R) out[((long long)(b0 + j) * R + r0 + 1) * M + pm0 + t] = make_float2(ar[j][1], ai[j][1]);
         }
       }
+    }
+  }
+}
+
+__device__ __forceinline__ void mix_tile_product_any(int bper, const float2* as, const float2* ws, float2* out, int B, int C, int R,
+                                                     int M, int pm0, int TM, int chp, int w_cstride, int w_rstride, bool conj_w) {
+  switch (bper) {
+    case 1: mix_tile_product<1>(as, ws, out, B, C, R, M, pm0, TM, chp, w_cstride, w_rstride, conj_w); break;
+    case 2: mix_tile_product<2>(as, ws, out, B, C, R, M, pm0, TM, chp, w_cstride, w_rstride, conj_w); break;
+    case 3: mix_tile_product<3>(as, ws, out, B, C, R, M, pm0, TM, chp, w_cstride, w_rstride, conj_w); break;
+    case 4: mix_tile_product<4>(as, ws, out, B, C, R, M, pm0, TM, chp, w_cstride, w_rstride, conj_w); break;
+    default: mix_tile_product<5>(as, ws, out, B, C, R, M, pm0, TM, chp, w_cstride, w_rstride, conj_w); break;
+  }
+}
+
+// gW[i, o] = sum_b conj(X^[b, i]) G^[b, o] for the block's modes; thread tile CIT inputs x 4 outputs
+template <int CIT>
+__device__ __forceinline__ void mix_tile_wgrad(const MixTileParams& p, const float2* xs, const float2* gs, int chp, int pm0,
+                                               const int* woff) {
+  const int TM = p.TM, M = p.md.M;
+  const int t = threadIdx.x % TM;
+  const int nci = (p.CI + CIT - 1) / CIT, nco = (p.CO + 3) / 4;
+  const int xstep = p.CI * chp, gstep = p.CO * chp;
+  for (int item = threadIdx.x / TM; item < nci * nco; item += kMixTileThreads / TM) {
+    const int oq = item % nco, iq = item / nco;
+    const int i0 = iq * CIT, o0 = oq * 4;
+    float ar[CIT][4], ai[CIT][4];
+    const float2* xp[CIT];
+    const float2* gp[4];
+#pragma unroll
+    for (int a = 0; a < CIT; ++a) {
+      xp[a] = xs + min(i0 + a, p.CI - 1) * chp + t;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ar[a][c] = ai[a][c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) gp[c] = gs + min(o0 + c, p.CO - 1) * chp + t;
+#pragma unroll 2
+    for (int b = 0; b < p.B; ++b) {
+      float2 xv[CIT], gv[4];
+#pragma unroll
+      for (int a = 0; a < CIT; ++a) xv[a] = xp[a][b * xstep];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) gv[c] = gp[c][b * gstep];
+#pragma unroll
+      for (int a = 0; a < CIT; ++a) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
+          ar[a][c] = fmaf(xv[a].x, gv[c].x, fmaf(xv[a].y, gv[c].y, ar[a][c]));
+          ai[a][c] = fmaf(xv[a].x, gv[c].y, fmaf(-xv[a].y, gv[c].x, ai[a][c]));
+        }
+      }
+    }
+    if (pm0 + t < M) {
+      const int blk = woff[t] >> 28, off = woff[t] & 0x0FFFFFFF;
+      float2* gb = blk == 0 ? p.gw[0] : (blk == 1 ? p.gw[1] : (blk == 2 ? p.gw[2] : p.gw[3]));
+#pragma unroll
+      for (int a = 0; a < CIT; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (i0 + a < p.CI && o0 + c < p.CO)
+            gb[((long long)(i0 + a) * p.CO + o0 + c) * p.md.Mblk + off] = make_float2(ar[a][c], ai[a][c]);
     }
   }
 }
@@ -596,7 +667,7 @@ __global__ void __launch_bounds__(kMixTileThreads) mode_mix_tile_kernel(MixTileP
   mix_tile_stage_w(p, sm + so.w, so, pm0, woff);
   __syncthreads();
   // contraction over ci: W(ci, co) = ws[ci * wip + co * chp]
-  mix_tile_product(sm + so.x, sm + so.w, p.yhat, p.B, p.CI, p.CO, p.md.M, pm0, p.TM, so.chp, so.wip, so.chp, p.bper, false);
+  mix_tile_product_any(p.bper, sm + so.x, sm + so.w, p.yhat, p.B, p.CI, p.CO, p.md.M, pm0, p.TM, so.chp, so.wip, so.chp, false);
 }
 
 __global__ void __launch_bounds__(kMixTileThreads) mode_mix_bwd_tile_kernel(MixTileParams p) {
@@ -616,49 +687,12 @@ __global__ void __launch_bounds__(kMixTileThreads) mode_mix_bwd_tile_kernel(MixT
   __syncthreads();
   // G^x: contraction over co of conj(W(ci, co)): W as seen from (c = co, r = ci) is ws[r * wip + c * chp]
   if (p.gxhat != nullptr)
-    mix_tile_product(gs, ws, p.gxhat, p.B, p.CO, p.CI, M, pm0, TM, so.chp, so.chp, so.wip, p.bper, true);
+    mix_tile_product_any(p.bper, gs, ws, p.gxhat, p.B, p.CO, p.CI, M, pm0, TM, so.chp, so.chp, so.wip, true);
   // gW[i, o] = sum_b conj(X^[b, i]) G^[b, o]
   if (p.gw[0] != nullptr) {
-    const int t = threadIdx.x % TM;
-    const int cit = p.cit;
-    const int nci = (p.CI + cit - 1) / cit, nco = (p.CO + 3) / 4;
-    for (int item = threadIdx.x / TM; item < nci * nco; item += kMixTileThreads / TM) {
-      const int oq = item % nco, iq = item / nco;
-      const int i0 = iq * cit, o0 = oq * 4;
-      float ar[4][4], ai[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) ar[a][b] = ai[a][b] = 0.f;
-      for (int b = 0; b < p.B; ++b) {
-        float2 xv[4], gv[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) xv[a] = xs[(b * p.CI + min(i0 + a, p.CI - 1)) * so.chp + t];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) gv[c] = gs[(b * p.CO + min(o0 + c, p.CO - 1)) * so.chp + t];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          if (a < cit) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              // conj(x) * g = (xr gr + xi gi) + i (xr gi - xi gr)
-              ar[a][c] = fmaf(xv[a].x, gv[c].x, fmaf(xv[a].y, gv[c].y, ar[a][c]));
-              ai[a][c] = fmaf(xv[a].x, gv[c].y, fmaf(-xv[a].y, gv[c].x, ai[a][c]));
-            }
-          }
-        }
-      }
-      if (pm0 + t < M) {
-        const int blk = woff[t] >> 28, off = woff[t] & 0x0FFFFFFF;
-        float2* gb = blk == 0 ? p.gw[0] : (blk == 1 ? p.gw[1] : (blk == 2 ? p.gw[2] : p.gw[3]));
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (a < cit && i0 + a < p.CI && o0 + c < p.CO)
-              gb[((long long)(i0 + a) * p.CO + o0 + c) * p.md.Mblk + off] = make_float2(ar[a][c], ai[a][c]);
-      }
-    }
+    if (p.cit >= 4) mix_tile_wgrad<4>(p, xs, gs, so.chp, pm0, woff);
+    else if (p.cit == 2) mix_tile_wgrad<2>(p, xs, gs, so.chp, pm0, woff);
+    else mix_tile_wgrad<1>(p, xs, gs, so.chp, pm0, woff);
   }
   // bias gradient of the bypass conv from the DC mode (packed mode 0 lives in block 0, column 0)
   if (p.glb != nullptr && blockIdx.x == 0) {
