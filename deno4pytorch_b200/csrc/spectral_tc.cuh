@@ -208,20 +208,27 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
   const int Q = p.KH * p.MW;
   const int o0 = og * p.ocb, noc = min(p.ocb, p.CO - o0);
   const float2* src = p.spec + ((long long)bp * p.CO + o0) * Q;
-  {  // the block's channels are one contiguous run of the spectrum: 16-byte loads, six in flight per thread
-    // (a plain load -> store loop ran one global-memory latency per element and WAS the kernel: 16 -> 27 us)
+  {  // The block's channels are one contiguous run of the spectrum.  ALL global loads of the prologue (one row
+    // twiddle and up to twelve 16-byte spectrum loads per thread) are issued before the first one is consumed: the
+    // kernel is latency-bound and every extra round trip is ~1 us of its ~12.
+    const int ntw = p.KH * kRowSynthRows;
+    float2 twv = make_float2(0.f, 0.f);
+    if (tid < ntw) {
+      const int k = tid / kRowSynthRows, rr = tid - k * kRowSynthRows;
+      if (rr < trows) twv = ldg_ordered(p.twH + (x0 + rr) * p.KH4 + k);
+    }
     const float4* src4 = reinterpret_cast<const float4*>(src);
     const int n4 = noc * Q / 2;                                     // Q = KH * MW is even (KH = 2 * modes)
-    for (int i0 = 0; i0 < n4; i0 += 6 * nthr) {
-      float4 tmp[6];
+    for (int i0 = 0; i0 < n4; i0 += 12 * nthr) {
+      float4 tmp[12];
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
+      for (int u = 0; u < 12; ++u) {
         const int i = min(i0 + u * nthr + tid, n4 - 1);
         asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(tmp[u].x), "=f"(tmp[u].y), "=f"(tmp[u].z), "=f"(tmp[u].w) : "l"(src4 + i));
       }
 #pragma unroll
-      for (int u = 0; u < 6; ++u) {
+      for (int u = 0; u < 12; ++u) {
         const int i = i0 + u * nthr + tid;
         if (i < n4) {
           const int ol = (2 * i) / Q, r = 2 * i - ol * Q;
@@ -229,10 +236,11 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
         }
       }
     }
-  }
-  for (int idx = tid; idx < p.KH * kRowSynthRows; idx += nthr) {
-    const int k = idx / kRowSynthRows, rr = idx - k * kRowSynthRows;
-    twr[idx] = rr < trows ? p.twH[(x0 + rr) * p.KH4 + k] : make_float2(0.f, 0.f);
+    if (tid < ntw) twr[tid] = twv;
+    for (int idx = tid + nthr; idx < ntw; idx += nthr) {            // more twiddles than threads (small blocks only)
+      const int k = idx / kRowSynthRows, rr = idx - k * kRowSynthRows;
+      twr[idx] = rr < trows ? p.twH[(x0 + rr) * p.KH4 + k] : make_float2(0.f, 0.f);
+    }
   }
   __syncthreads();
   const int LH = p.KE / 2;                                          // (cos, sin) column pairs incl. zero padding
