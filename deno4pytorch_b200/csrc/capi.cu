@@ -829,7 +829,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
     rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV>, smem, "plane_synthesis_tc");          \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV>), dim3(grid), dim3(256), smem, st, q);               \
+    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);               \
   }
 #define DENO_TC_CASE(ACT)                                                                           \
   case ACT:                                                                                         \

@@ -47,6 +47,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// named barriers: producers arrive without blocking, the consumer warp syncs (count = all participating threads)
+__device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -326,13 +329,18 @@ __host__ __device__ inline SynthTcSmem synth_tc_smem(int CIP, int CO, int KE, in
   return m;
 }
 
+constexpr int kSynThreads = 256 + 32;   // 8 worker warps + the MMA-issuing warp
+constexpr int kSynBarAx = 2;            // A_X images of a row stored (workers arrive, MMA warp syncs)
+
 template <int ACT, int CIP>
-__global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParams q) {
+__global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(SynthTcParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t mbar[2], mbar_u;
   const SynthParams& p = q.s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_mma = warp == 8;             // ninth warp: issues the MMAs, takes no part in the SIMT work
+  const int wt = is_mma ? (1 << 28) : tid;     // loop start of the 256 worker threads (beyond every bound for the MMA warp)
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = p.CO;
   const int KH4 = round_up(KH, 4);
   const int KE = q.KE, R = p.R;
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
 
   // ---- constant operands -------------------------------------------------------------------
   // bypass weight image B_W[n = o][k = i], split on the fly; four loads in flight per thread
-  for (int idx0 = tid; idx0 < CO * CIP; idx0 += 4 * 256) {
+  for (int idx0 = wt; idx0 < CO * CIP; idx0 += 4 * 256) {
     float wv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     }
   }
   float* bias_s = reinterpret_cast<float*>(smem + so.bias);
-  for (int o = tid; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
+  for (int o = wt; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
 
   // Everything above depends on constants and weights only.  The U images come from the immediate predecessor
   // (row_synthesis_kernel) and x / gz from earlier kernels: from here on the predecessor must have completed.
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       }
     }
   };
-  prefetch(0);
+  if (!is_mma) prefetch(0);
 
   const long long tb1 = clock64();
   if (warp == 1) DENO_DBG_ADD(48, tb1 - tb0);          // slot 48: TMEM alloc, weight / twiddle images, first prefetch issue
@@ -422,14 +430,14 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
   // of OC output channels with fully coalesced loads, so the k-loop runs out of shared memory.
   if (q.urow == nullptr) {
     unsigned char* bu = smem + so.bu;
-    for (int idx = tid; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = wt; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     float2* twr = reinterpret_cast<float2*>(smem + so.ax_hi);            // [trows][KH] row twiddles
     float2* sps = twr + round_up(kSynthMaxRows * KH, 2);                 // [OC][KH*MW] spectrum chunk
     const int Q = KH * MW;
     const int avail = 2 * CIP * 128 * 4 - round_up(kSynthMaxRows * KH, 2) * 8;
     int OC = avail / (Q * 8);
     if (OC > CO) OC = CO;
-    for (int idx = tid; idx < trows * KH; idx += 256) {
+    for (int idx = wt; idx < trows * KH; idx += 256) {
       const int rr = idx / KH, k = idx - rr * KH;
       twr[idx] = p.twH[(x0 + rr) * KH4 + k];
     }
@@ -442,10 +450,10 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       for (int idx0 = 0; idx0 < oc * Q; idx0 += 8 * 256) {     // eight independent loads in flight per thread
         float2 tmp[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) tmp[u] = ldg_ordered(src + min(idx0 + u * 256 + tid, oc * Q - 1));
+        for (int u = 0; u < 8; ++u) tmp[u] = ldg_ordered(src + min(idx0 + u * 256 + (tid & 255), oc * Q - 1));
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int idx = idx0 + u * 256 + tid;
+          const int idx = idx0 + u * 256 + wt;
           if (idx < oc * Q) sps[idx] = tmp[u];
         }
       }
@@ -453,7 +461,7 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       const long long tc1 = clock64();
       if (warp == 1) DENO_DBG_ADD(58, tc1 - tc0);       // slot 58: spectrum chunk load (incl. barriers)
       // task = (row half, output channel, mode): two threads share an (o, l) pair, four rows each
-      for (int task = tid; task < 2 * oc * MW; task += 256) {
+      for (int task = wt; task < 2 * oc * MW; task += 256) {
         const int half = task / (oc * MW), t2 = task - half * (oc * MW);
         const int ol = t2 / MW, l = t2 - ol * MW;
         const int o = o0 + ol;
@@ -556,41 +564,18 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
     }
   };
 
-  for (int rr = 0; rr < trows; ++rr) {
-    const long long tr0 = clock64();
-    if (rr > 0) mbar_wait(&mbar[(rr - 1) & 1], ((rr - 1) >> 1) & 1);   // MMA(rr-1) done: A_X free, D(rr-1) ready
-    const long long tr1 = clock64();
-    if (warp == 1) DENO_DBG_ADD(50, tr1 - tr0);        // slot 50: wait for the previous row's MMAs
-    // registers -> A_X images (hi / lo)
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int item = it * 256 + tid;
-      const int pt = item & 127, cq = item >> 7;
-      float4 hi, lo;
-      split_tf32(xr[it][0], hi.x, lo.x);
-      split_tf32(xr[it][1], hi.y, lo.y);
-      split_tf32(xr[it][2], hi.z, lo.z);
-      split_tf32(xr[it][3], hi.w, lo.w);
-      const int off = kmajor_off(pt, cq * 4, 128);
-      *reinterpret_cast<float4*>(smem + so.ax_hi + off) = hi;
-      *reinterpret_cast<float4*>(smem + so.ax_lo + off) = lo;
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    const long long tr2 = clock64();
-    __syncthreads();
-    const long long tr3 = clock64();
-    if (warp == 1) { DENO_DBG_ADD(51, tr2 - tr1); DENO_DBG_ADD(52, tr3 - tr2); }   // slots 51/52: split + store, barrier
-    if (warp == 0) {
+  if (is_mma) {
+    // ---- MMA warp: per row, wait until the 256 workers have stored the A_X images, issue, commit ----
+    const bool leader = elect_one();   // warp-uniform loop (descriptors in uniform registers); one lane issues
+    const uint64_t inc_m = (uint64_t)((2 * lbo_m) >> 4), inc_n = (uint64_t)((2 * lbo_n) >> 4);
+    for (int rr = 0; rr < trows; ++rr) {
+      nbar_sync(kSynBarAx, kSynThreads);
       fence_after_sync();
-      const bool leader = elect_one();   // warp-uniform loop (descriptors in uniform registers); one lane issues
-      // Back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency (measured ~120
-      // cycles each at N = 32), so the three split passes (hi*hi, lo*hi, hi*lo) accumulate into three
-      // separate TMEM tiles and are issued round-robin; the epilogue adds the tiles.
-      // The issuing thread is the critical path (a single lane, nothing to hide ALU latency behind):
-      // descriptors are built once and advanced by a constant per K step.
+      const long long tr3 = clock64();
+      // Back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency (measured ~120 cycles each at
+      // N = 32), so the three split passes (hi*hi, lo*hi, hi*lo) accumulate into three separate TMEM tiles and are
+      // issued round-robin; the epilogue adds the tiles.  Descriptors are built once and advanced by a constant.
       const uint32_t d = tmem + (uint32_t)((rr & 1) * 3 * CO);
-      const uint64_t inc_m = (uint64_t)((2 * lbo_m) >> 4), inc_n = (uint64_t)((2 * lbo_n) >> 4);
       uint64_t axh = make_desc(sbase + so.ax_hi, lbo_m, 128), axl = make_desc(sbase + so.ax_lo, lbo_m, 128);
       uint64_t bwh = make_desc(sbase + so.bw_hi, lbo_n, 128), bwl = make_desc(sbase + so.bw_lo, lbo_n, 128);
 #pragma unroll
@@ -616,20 +601,48 @@ __global__ void __launch_bounds__(256, 2) plane_synthesis_tc_kernel(SynthTcParam
       }
       if (leader) mma_commit(&mbar[rr & 1]);
       __syncwarp();
-      DENO_DBG_ADD(53, clock64() - tr3);               // slot 53: MMA issue (warp 0)
+      if (leader) DENO_DBG_ADD(53, clock64() - tr3);   // slot 53: MMA issue
     }
-    const long long tr4 = clock64();
-    if (rr + 1 < trows) prefetch(rr + 1);
-    const long long tr5 = clock64();
-    if (rr > 0) {
-      fence_after_sync();
-      epilogue(rr - 1);
+  } else {
+    // ---- workers: A_X images of row rr, then (while the tensor core works on it) the epilogue of row rr - 1 ----
+    for (int rr = 0; rr < trows; ++rr) {
+      const long long tr0 = clock64();
+      if (rr > 0) mbar_wait(&mbar[(rr - 1) & 1], ((rr - 1) >> 1) & 1);   // MMA(rr-1) done: A_X free, D(rr-1) ready
+      const long long tr1 = clock64();
+      if (warp == 1) DENO_DBG_ADD(50, tr1 - tr0);        // slot 50: wait for the previous row's MMAs
+      // registers -> A_X images (hi / lo)
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int item = it * 256 + tid;
+        const int pt = item & 127, cq = item >> 7;
+        float4 hi, lo;
+        split_tf32(xr[it][0], hi.x, lo.x);
+        split_tf32(xr[it][1], hi.y, lo.y);
+        split_tf32(xr[it][2], hi.z, lo.z);
+        split_tf32(xr[it][3], hi.w, lo.w);
+        const int off = kmajor_off(pt, cq * 4, 128);
+        *reinterpret_cast<float4*>(smem + so.ax_hi + off) = hi;
+        *reinterpret_cast<float4*>(smem + so.ax_lo + off) = lo;
+      }
+      fence_proxy_async();
+      fence_before_sync();                               // also orders the D reads of epilogue(rr - 2) before the hand-off
+      nbar_arrive(kSynBarAx, kSynThreads);
+      const long long tr4 = clock64();
+      if (warp == 1) DENO_DBG_ADD(51, tr4 - tr1);        // slot 51: split + store + hand-off
+      if (rr + 1 < trows) prefetch(rr + 1);
+      const long long tr5 = clock64();
+      if (rr > 0) {
+        fence_after_sync();
+        epilogue(rr - 1);
+      }
+      if (warp == 1) { DENO_DBG_ADD(54, tr5 - tr4); DENO_DBG_ADD(55, clock64() - tr5); DENO_DBG_ADD(56, 1); }  // prefetch issue, epilogue, rows
     }
-    if (warp == 1) { DENO_DBG_ADD(54, tr5 - tr4); DENO_DBG_ADD(55, clock64() - tr5); DENO_DBG_ADD(56, 1); }  // prefetch issue, epilogue, rows
   }
-  mbar_wait(&mbar[(trows - 1) & 1], ((trows - 1) >> 1) & 1);
-  fence_after_sync();
-  epilogue(trows - 1);
+  if (!is_mma) {
+    mbar_wait(&mbar[(trows - 1) & 1], ((trows - 1) >> 1) & 1);
+    fence_after_sync();
+    epilogue(trows - 1);
+  }
 
   fence_before_sync();
   __syncthreads();
@@ -1035,8 +1048,6 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 constexpr int kAnBarA = 2;         // A images stored (workers arrive, MMA warp syncs)
 constexpr int kAnBarEpi0 = 8;      // 8..11: sin rows exchanged, one barrier per worker warp group
