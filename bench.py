@@ -385,7 +385,8 @@ def run_own(args):
         "config": {"workload": WORKLOAD_TEXT.get(args.workload, args.workload), "global_batch": world * batch,
                    "parallelism": f"dp{world}", "parameters": nparams, "cuda_graph": not args.eager,
                    "allreduce": ("per stage, overlapped with the backward, inside the graph" if step._overlap else
-                                 ("one flat all-reduce between the backward and the optimiser graph" if world > 1 else "none")),
+                                 ("one flat averaged all-reduce inside the step graph" if getattr(step, "_ingraph", False) else
+                                  ("one flat all-reduce between the backward and the optimiser graph" if world > 1 else "none"))),
                    "l2": f"no explicit flush: saved activations per step ~{act_mb:.0f} MB > 126 MB L2 "
                          "(inputs larger than L2)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

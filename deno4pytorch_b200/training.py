@@ -73,6 +73,10 @@ class TrainStep:
         self._overlap = bool(overlap_allreduce and self.world > 1 and x.is_cuda and forward_fn is None
                              and dist.get_backend(group) == "nccl" and _all_gradients_direct(model, x, grid))
         self._ar_stream = torch.cuda.Stream() if self._overlap else None
+        # NCCL without the per-stage overlap: ONE averaged all-reduce of the flat buffer, captured in the same graph as
+        # the backward and the optimiser (DENO_DP_INGRAPH=0 keeps it between two graphs, as gloo / eager runs do)
+        self._ingraph = bool(not self._overlap and self.world > 1 and x.is_cuda and use_graph
+                             and dist.get_backend(group) == "nccl" and os.environ.get("DENO_DP_INGRAPH", "1") == "1")
         if self._overlap:
             stages = [list(layer.parameters()) for layer in model.convs]
             stages.append(list(model.fc1.parameters()) + list(model.fc2.parameters()))
@@ -114,6 +118,8 @@ class TrainStep:
         if self._overlap:
             self._reduce_bucket(self._lift_grads)
             torch.cuda.current_stream().wait_stream(self._ar_stream)
+        elif self._ingraph:
+            dist.all_reduce(self.grads.flat, op=dist.ReduceOp.AVG, group=self.group)
         self.loss.copy_(loss.detach())
 
     def _capture(self, warmup: int):
@@ -122,13 +128,13 @@ class TrainStep:
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):   # also fills the twiddle cache and cuBLAS workspaces
                 self._forward_backward()
-                if not self._overlap:
+                if not (self._overlap or self._ingraph):
                     self.grads.all_reduce_mean(self.group)
                 self.opt.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._g_bwd = torch.cuda.CUDAGraph()
-        if self.world == 1 or self._overlap:
+        if self.world == 1 or self._overlap or self._ingraph:
             # no separate collective between backward and optimiser: the whole step is one graph launch
             with torch.cuda.graph(self._g_bwd):
                 self._forward_backward()
@@ -213,7 +219,7 @@ class TrainStep:
                 self._g_opt.replay()
         else:
             self._forward_backward()
-            if not self._overlap:
+            if not (self._overlap or self._ingraph):
                 self.grads.all_reduce_mean(self.group)
             self.opt.step()
         if self._loss_slots is not None:
