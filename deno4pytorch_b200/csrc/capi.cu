@@ -983,7 +983,7 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
       r.glw = glw; r.glb = nullptr;
       if (glw != nullptr) {
         prof_before("bypass_wgrad_reduce", st);
-        DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+        DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, kReduceSlices), kReduceSlices * 32 * sizeof(float), st, r);
         rc = check_launch("bypass_wgrad_reduce", st);
         if (rc != DENO_OK) return rc;
       }
@@ -1015,7 +1015,7 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
   r.nw = s.CO * s.CI; r.nj = r.nw + s.CO; r.pitch = r.nj;
   r.glw = glw; r.glb = glb;
   prof_before("bypass_wgrad_reduce", st);
-  DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+  DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((r.nj + 31) / 32), dim3(32, kReduceSlices), kReduceSlices * 32 * sizeof(float), st, r);
   return check_launch("bypass_wgrad_reduce", st);
 }
 
@@ -1113,7 +1113,7 @@ int launch_reduce(const float* partial, int nparts, int pitch, int nj, int nw, f
   WgradReduceParams r;
   r.partial = partial; r.ncta = nparts; r.pitch = pitch; r.nj = nj; r.nw = nw; r.glw = out_w; r.glb = out_b;
   prof_before(label, st);
-  DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((nj + 31) / 32), dim3(32, 8), 8 * 32 * sizeof(float), st, r);
+  DENO_LAUNCH(bypass_wgrad_reduce_kernel, dim3((nj + 31) / 32), dim3(32, kReduceSlices), kReduceSlices * 32 * sizeof(float), st, r);
   return check_launch(label, st);
 }
 

@@ -957,20 +957,23 @@ struct WgradReduceParams {
   float* glb;         // may be null
 };
 
-// blockDim = (32 outputs, 8 slices); grid = ceil(nj / 32).  Fixed summation order -> deterministic.
-__global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
+// blockDim = (32 outputs, kReduceSlices slices); grid = ceil(nj / 32).  Fixed summation order -> deterministic.
+// 32 slices x 8 loads in flight: the ~600 partial rows of a layer's weight gradient are three memory round trips
+// (with 8 slices it was ten, ~10 us per launch, eight launches per training step).
+constexpr int kReduceSlices = 32;
+__global__ void __launch_bounds__(32 * kReduceSlices) bypass_wgrad_reduce_kernel(WgradReduceParams p) {
   DENO_PDL_SYNC();
   DENO_DYN_SMEM(smem_raw);
-  float* red = reinterpret_cast<float*>(smem_raw);  // [8][32]
+  float* red = reinterpret_cast<float*>(smem_raw);  // [kReduceSlices][32]
   const int j = blockIdx.x * 32 + threadIdx.x;
   const int slice = threadIdx.y;
   float s = 0.f;
   if (j < p.nj) {
-    for (int c0 = slice; c0 < p.ncta; c0 += 64) {   // eight loads in flight per thread
+    for (int c0 = slice; c0 < p.ncta; c0 += 8 * kReduceSlices) {   // eight loads in flight per thread
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int c = c0 + 8 * u;
+        const int c = c0 + kReduceSlices * u;
         v[u] = ldg_ordered(p.partial + (long long)min(c, p.ncta - 1) * p.pitch + j);
         if (c >= p.ncta) v[u] = 0.f;
       }
@@ -983,7 +986,7 @@ __global__ void bypass_wgrad_reduce_kernel(WgradReduceParams p) {
   __syncthreads();
   if (slice == 0 && j < p.nj) {
     float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += red[k * 32 + threadIdx.x];
+    for (int k = 0; k < kReduceSlices; ++k) t += red[k * 32 + threadIdx.x];
     if (j < p.nw) {
       if (p.glw != nullptr) p.glw[j] = t;
     } else if (p.glb != nullptr) {
