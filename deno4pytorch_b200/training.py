@@ -65,6 +65,8 @@ class TrainStep:
                                         capturable=use_graph, foreach=True)
         # one model call per step: parameter gradients go straight into the flat buffer (no per-parameter add kernels)
         self.grads.direct_writes(forward_fn is None and x.is_cuda)
+        # ... and when EVERY gradient is written that way the flat buffer is fully overwritten each step: no memset
+        self._skip_zero = bool(forward_fn is None and x.is_cuda and _all_gradients_direct(model, x, grid))
         # Data parallel on GPUs with the stock single-call step: the gradient all-reduce is issued per stage from inside
         # the backward pass on a side stream (projection first, then the spectral layers last to first, the lift after
         # backward() returns), so it overlaps the rest of the backward, and the whole step is ONE captured graph.
@@ -109,7 +111,8 @@ class TrainStep:
         self._reduce_bucket(self._stage_grads[i])
 
     def _forward_backward(self):
-        self.grads.zero()
+        if not self._skip_zero:
+            self.grads.zero()
         if self.forward_fn is not None:
             loss = self.forward_fn(self.model, self.sx, self.sg, self.st)
         else:
