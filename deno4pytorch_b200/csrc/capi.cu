@@ -212,7 +212,7 @@ void fill_axis(float* dst, int n, int nfreq, int pitch, int m, bool half) {
 // ------------------------------------------------------------------------------------------
 // Launch-geometry heuristics (pure functions of the shape so that workspace sizing agrees)
 // ------------------------------------------------------------------------------------------
-struct AnalysisCfg { int G, RT, RTP, YC, RS, threads; size_t smem; };
+struct AnalysisCfg { int G, RT, RTP, YC, RS, CS, threads; size_t smem; };
 
 int analysis_cfg(const PlaneGeom& g, AnalysisCfg& c) {
   const int MWp = round_up(g.MW, 4), NLG = MWp / 4, KQ = round_up(g.KH, 4) / 4;
@@ -223,7 +223,11 @@ int analysis_cfg(const PlaneGeom& g, AnalysisCfg& c) {
   const int ntiles = (rows + rtcap - 1) / rtcap;
   c.RT = (rows + ntiles - 1) / ntiles;
   c.RTP = c.RT < 32 ? c.RT : round_up(c.RT, 32);
-  c.threads = round_up(c.RTP * NLG, 32);
+  // few rows per tile (1-D layers: 8 single-row planes per CTA): split the columns of stage 1 over up to 8 thread
+  // slices, otherwise a CTA is one busy warp walking 1 000 columns (178 us for the Burgers layer)
+  c.CS = 1;
+  while (c.CS < 8 && c.RTP * NLG * c.CS * 2 <= 256) c.CS *= 2;
+  c.threads = round_up(c.RTP * NLG * c.CS, 32);
   if (c.threads < 64) c.threads = 64;
   if (c.threads > 1024) return fail(DENO_E_UNSUPPORTED, "too many retained modes on the last axis for plane_analysis");
   const int nchunks = (g.W + 127) / 128;
@@ -233,7 +237,7 @@ int analysis_cfg(const PlaneGeom& g, AnalysisCfg& c) {
   if (c.RS < 1) c.RS = 1;
   if (c.RS > 8) c.RS = 8;
   AnalysisParams p;
-  p.g = g; p.G = c.G; p.RT = c.RT; p.YC = c.YC; p.RS = c.RS;
+  p.g = g; p.G = c.G; p.RT = c.RT; p.YC = c.YC; p.RS = c.RS; p.CS = c.CS;
   c.smem = (size_t)analysis_smem(p).total * sizeof(float);
   if (c.smem > (size_t)kMaxSmemBytes) return fail(DENO_E_UNSUPPORTED, "plane_analysis tile does not fit shared memory");
   return DENO_OK;
@@ -523,7 +527,7 @@ int launch_analysis(const Shape& s, int channels, const float* u, const float* z
   p.twW = tw.last; p.twH = tw.mid; p.cl = tw.cl;
   p.scale = scale; p.herm = herm; p.act = s.act;
   p.nplanes = s.B * s.X * channels;
-  p.G = c.G; p.RT = c.RT; p.RTP = c.RTP; p.YC = c.YC; p.RS = c.RS;
+  p.G = c.G; p.RT = c.RT; p.RTP = c.RTP; p.YC = c.YC; p.RS = c.RS; p.CS = c.CS;
   const int grid = (p.nplanes + c.G - 1) / c.G;
   if (z != nullptr) {
     rc = allow_smem(plane_analysis_kernel<true>, c.smem, "plane_analysis");

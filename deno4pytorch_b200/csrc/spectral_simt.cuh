@@ -45,6 +45,7 @@ struct AnalysisParams {
   int RTP;             // thread mapping: r = tid % RTP, lq = tid / RTP
   int YC;              // columns per chunk
   int RS;              // row split of stage 2
+  int CS;              // column split of stage 1: thread = (row, mode quad, column slice); 1 except for few-row tiles
 };
 
 struct AnalysisSmem {
@@ -57,7 +58,7 @@ __host__ __device__ inline AnalysisSmem analysis_smem(const AnalysisParams& p) {
   int off = 0;
   s.xs = off;  off += round_up(p.RT * (p.YC + 1), 4);
   s.tws = off; off += p.YC * MWp * 2;
-  s.ts = off;  off += p.RT * MWp * 2;
+  s.ts = off;  off += p.RT * MWp * 2 * (p.CS > 1 ? p.CS : 1);   // per column slice, reduced in place
   s.twh = off; off += p.g.H * KH4 * 2;
   s.acc = off; off += p.RS * p.G * KH4 * p.g.MW * 2;
   s.total = off;
@@ -88,13 +89,13 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
   for (int i = tid; i < H * KH4; i += nt) twHs[i] = p.twH[i];
   for (int i = tid; i < p.RS * acc_stride; i += nt) acc2[i] = make_float2(0.f, 0.f);
 
-  const int r = tid % p.RTP, lq = tid / p.RTP;
+  const int r = tid % p.RTP, lq = (tid / p.RTP) % NLG, cs = tid / (p.RTP * NLG);   // cs < CS (launch geometry)
   const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
   const int ntask2 = p.G * KQ * MW;
 
   for (int tile0 = 0; tile0 < rows; tile0 += p.RT) {
     const int trows = min(p.RT, rows - tile0);
-    const bool active = (r < trows) && (lq < NLG);
+    const bool active = (r < trows) && (cs < p.CS);
     float re0 = 0.f, re1 = 0.f, re2 = 0.f, re3 = 0.f, im0 = 0.f, im1 = 0.f, im2 = 0.f, im3 = 0.f;
 
     for (int y0 = 0; y0 < W; y0 += p.YC) {
@@ -121,7 +122,7 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
         const float4* t4 = reinterpret_cast<const float4*>(tws) + lq * 2;
         const int step = MWp / 2;
 #pragma unroll 4
-        for (int j = 0; j < yc; ++j) {
+        for (int j = cs; j < yc; j += p.CS) {
           const float xv = xrow[j];
           const float4 a = t4[j * step], b = t4[j * step + 1];
           re0 = fmaf(xv, a.x, re0); im0 = fmaf(-xv, a.y, im0);
@@ -132,13 +133,25 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
       }
     }
     if (active) {
-      float2* t = Ts + r * MWp + lq * 4;
+      float2* t = Ts + (cs * p.RT + r) * MWp + lq * 4;
       t[0] = make_float2(re0, im0);
       t[1] = make_float2(re1, im1);
       t[2] = make_float2(re2, im2);
       t[3] = make_float2(re3, im3);
     }
     __syncthreads();
+    if (p.CS > 1) {                       // sum the column slices into slice 0 (fixed order)
+      for (int i = tid; i < trows * MWp; i += nt) {
+        float2 a = Ts[i];
+        for (int c2 = 1; c2 < p.CS; ++c2) {
+          const float2 b = Ts[c2 * p.RT * MWp + i];
+          a.x += b.x;
+          a.y += b.y;
+        }
+        Ts[i] = a;
+      }
+      __syncthreads();
+    }
     // stage 2: contract the rows of each plane against e^{-i phi(k, x)}; thread = (row split, plane, k quad, l)
     for (int tt = tid; tt < ntask2 * p.RS; tt += nt) {
       const int rs = tt / ntask2, task = tt - rs * ntask2;
