@@ -1144,7 +1144,7 @@ int launch_proj_fwd_tc(const tc::ProjTcParams& p, cudaStream_t st) {
 }
 
 int try_launch_proj_fwd_tc(const FnoShape& f, tc::ProjTcParams p, cudaStream_t st) {
-  if (path_pref() == PathPref::Simt || f.Hd != 128) return -1;
+  if (path_pref() == PathPref::Simt || f.Hd != 128 || p.tiles_per_sample > 4096 || f.B >= (1 << 19)) return -1;
   if (f.C == 32) return launch_proj_fwd_tc<32>(p, st);
   if (f.C == 64) return launch_proj_fwd_tc<64>(p, st);
   return -1;
@@ -1154,7 +1154,8 @@ constexpr int kProjTcCtas = 148;
 // The tensor-core backward writes gt in blocks of 128 points (strided 512-byte runs cost 2.4x in the store path,
 // profiles/r2m_phase_probe.txt), which only the tensor-core bypass_wgrad kernel reads: both or neither.
 bool proj_bwd_tc_eligible(const FnoShape& f) {
-  return path_pref() != PathPref::Simt && f.Hd == 128 && f.C == 32 && f.O == 1 && wgrad_tc_eligible(proj_wgrad_shape(f));
+  return path_pref() != PathPref::Simt && f.Hd == 128 && f.C == 32 && f.O == 1 && (f.g.nppts + 127) / 128 <= 4096 &&
+         f.B < (1 << 19) && wgrad_tc_eligible(proj_wgrad_shape(f));
 }
 int launch_proj_bwd_tc(const tc::ProjTcParams& p, int& nparts, cudaStream_t st) {
   using S = tc::ProjTcSmem<32, 128>;

@@ -29,10 +29,13 @@ struct PointGeom {
 
 // Padded point index -> cropped point index; false inside the padding.
 __device__ __forceinline__ bool padded_to_cropped(const PointGeom& g, int pp, int& pc) {
-  const int z = pp % g.pz;
   const int r = pp / g.pz;
-  const int y = r % g.py;
-  const int x = r / g.py;
+  const int z = pp - r * g.pz;
+  int x = 0, y = r;
+  if (g.px > 1) {                      // one integer division for 1-D / 2-D grids, two for 3-D
+    x = r / g.py;
+    y = r - x * g.py;
+  }
   pc = (x * g.sy + y) * g.sz + z;
   return z < g.sz && y < g.sy && x < g.sx;
 }

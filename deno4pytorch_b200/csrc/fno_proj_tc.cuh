@@ -69,8 +69,9 @@ struct ProjTcSmem {
 template <int C, int NG>
 __device__ __forceinline__ void pj_load_tile(const ProjTcParams& p, int tile, int xrow, int wg, float (&hr)[C / NG], bool& inside,
                                              bool& valid, int& b, int& pp, int& pc) {
-  b = tile / p.tiles_per_sample;
-  pp = (tile - b * p.tiles_per_sample) * 128 + xrow;
+  // `tile` is passed as (sample, tile inside the sample) packed by PjTileIter: no division here
+  b = tile >> 12;
+  pp = (tile & 4095) * 128 + xrow;
   inside = pp < p.g.nppts;
   pc = 0;
   valid = inside && padded_to_cropped(p.g, pp, pc);
@@ -78,6 +79,19 @@ __device__ __forceinline__ void pj_load_tile(const ProjTcParams& p, int tile, in
 #pragma unroll
   for (int i = 0; i < C / NG; ++i) hr[i] = valid ? __ldg(src + (long long)i * p.g.nppts) : 0.f;
 }
+
+// The tiles of a CTA are blockIdx.x + k * gridDim.x; (sample, tile inside the sample) advance by addition and compare
+// instead of a division per tile and thread.  Packed as (sample << 12) | tile_in_sample (tiles_per_sample <= 4096,
+// checked on the host).
+struct PjTileIter {
+  int b, t, step, tps;
+  __device__ __forceinline__ PjTileIter(int first, int step_, int tps_) : b(first / tps_), t(first % tps_), step(step_), tps(tps_) {}
+  __device__ __forceinline__ int packed() const { return (b << 12) | t; }
+  __device__ __forceinline__ void next() {
+    t += step;
+    while (t >= tps) { t -= tps; ++b; }
+  }
+};
 
 template <int C, int HD, int NG>
 __device__ __forceinline__ void pj_store_a1(unsigned char* smem, int xrow, int wg, const float (&hr)[C / NG]) {
@@ -194,13 +208,18 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
     bool inside, valid, valid_cur = false;
     int b, pp, pc, b_cur = 0, pc_cur = 0;
     uint32_t phase = 0;
+    PjTileIter it((int)blockIdx.x, (int)gridDim.x, p.tiles_per_sample);   // tile of the NEXT load
     if (nmine > 0) {
-      pj_load_tile<C, 4>(p, blockIdx.x, xrow, wg, hr, inside, valid, b, pp, pc);
+      pj_load_tile<C, 4>(p, it.packed(), xrow, wg, hr, inside, valid, b, pp, pc);
+      it.next();
       pj_store_a1<C, HD, 4>(smem, xrow, wg, hr);
       fence_proxy_async();
       nbar_arrive(kPjBarA1, kPjFwdThreads);
       valid_cur = valid; b_cur = b; pc_cur = pc;
-      if (nmine > 1) pj_load_tile<C, 4>(p, blockIdx.x + gridDim.x, xrow, wg, hr, inside, valid, b, pp, pc);
+      if (nmine > 1) {
+        pj_load_tile<C, 4>(p, it.packed(), xrow, wg, hr, inside, valid, b, pp, pc);
+        it.next();
+      }
     }
     for (int k = 0; k < nmine; ++k) {
       const long long t0 = clock64();
@@ -216,7 +235,10 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
         fence_proxy_async();
         nbar_arrive(kPjBarA1, kPjFwdThreads);
         valid_cur = valid; b_cur = b; pc_cur = pc;
-        if (k + 2 < nmine) pj_load_tile<C, 4>(p, blockIdx.x + (k + 2) * gridDim.x, xrow, wg, hr, inside, valid, b, pp, pc);
+        if (k + 2 < nmine) {
+          pj_load_tile<C, 4>(p, it.packed(), xrow, wg, hr, inside, valid, b, pp, pc);
+          it.next();
+        }
       }
       const long long t2 = clock64();
       if (warp == 1) DENO_DBG_ADD(17, t2 - t1);          // slot 17: A1 image of the next tile + prefetch issue
@@ -377,15 +399,18 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
     int b, pp, pc, b_cur = 0, pp_cur = 0;
     float gy_next = 0.f, gy_cur = 0.f;
     uint32_t phase = 0, slot_phase[2] = {0u, 0u};
+    PjTileIter it((int)blockIdx.x, (int)gridDim.x, p.tiles_per_sample);   // tile of the NEXT load
     if (nmine > 0) {
-      pj_load_tile<C, 2>(p, blockIdx.x, xrow, wg, hr, inside, valid, b, pp, pc);
+      pj_load_tile<C, 2>(p, it.packed(), xrow, wg, hr, inside, valid, b, pp, pc);
+      it.next();
       gy_cur = valid ? __ldg(p.gy + (long long)b * p.g.npts + pc) : 0.f;
       pj_store_a1<C, HD, 2>(smem, xrow, wg, hr);
       fence_proxy_async();
       nbar_arrive(kPjBarA1, kPjThreads);
       inside_cur = inside; b_cur = b; pp_cur = pp;
       if (nmine > 1) {
-        pj_load_tile<C, 2>(p, blockIdx.x + gridDim.x, xrow, wg, hr, inside, valid, b, pp, pc);
+        pj_load_tile<C, 2>(p, it.packed(), xrow, wg, hr, inside, valid, b, pp, pc);
+        it.next();
         gy_next = valid ? __ldg(p.gy + (long long)b * p.g.npts + pc) : 0.f;
       }
     }
@@ -455,7 +480,8 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
         nbar_arrive(kPjBarA1, kPjThreads);
         inside_cur = inside; b_cur = b; pp_cur = pp; gy_cur = gy_next;
         if (k + 2 < nmine) {
-          pj_load_tile<C, 2>(p, blockIdx.x + (k + 2) * gridDim.x, xrow, wg, hr, inside, valid, b, pp, pc);
+          pj_load_tile<C, 2>(p, it.packed(), xrow, wg, hr, inside, valid, b, pp, pc);
+          it.next();
           gy_next = valid ? __ldg(p.gy + (long long)b * p.g.npts + pc) : 0.f;
         }
       }
