@@ -85,10 +85,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, extra_steps: int = 0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if not self.rows:
+            time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -106,7 +107,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "window": f"timed region + {extra_steps} further untimed steps of the same workload (100 ms nvidia-smi period)"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -323,7 +325,21 @@ def run_own(args):
     torch.cuda.synchronize()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    # nvidia-smi reports every 100 ms and the timed region is tens of milliseconds: keep the SAME load running
+    # (untimed) until about half a second has been sampled, so the clocks line describes the GPU under this workload
+    # and not the idle moment after it.
+    extra_steps = 0
+    if rank == 0:
+        per_step_ms = max(elapsed_ms / max(args.steps, 1), 1e-3)
+        extra_steps = int(max(0.0, 500.0 - elapsed_ms) / per_step_ms)
+    if world > 1:
+        t = torch.tensor([extra_steps], device=device)
+        dist.broadcast(t, src=0)
+        extra_steps = int(t.item())
+    for _ in range(extra_steps):
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop(extra_steps) if rank == 0 else None
     if world > 1:
         t = torch.tensor([elapsed_ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
