@@ -193,8 +193,7 @@ __host__ __device__ inline int row_synth_pitch(int KH, int MW, int KE) {
   return qp;
 }
 __host__ __device__ inline size_t row_synth_smem_bytes(int ocb, int KH, int MW, int KE) {
-  return ((size_t)ocb * row_synth_pitch(KH, MW, KE) + (size_t)KH * kRowSynthRows) * sizeof(float2) +
-         (size_t)kRowSynthRows * 2 * (KE / 4) * 36 * sizeof(float);   // spectrum, row twiddles, output staging
+  return ((size_t)ocb * row_synth_pitch(KH, MW, KE) + (size_t)KH * kRowSynthRows) * sizeof(float2);   // spectrum, row twiddles
 }
 
 __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
@@ -248,11 +247,8 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
   __syncthreads();
   const int LH = p.KE / 2;                                          // (cos, sin) column pairs incl. zero padding
   const size_t img = (size_t)p.KE * p.CO;                           // floats per hi (or lo) image
-  // A block of 8 channels owns, in every K-quad of every image, one contiguous 128-byte run (8 rows x 16 bytes of
-  // the K-major layout): results are staged in shared memory and leave as full 128-byte lines (direct 8-byte
-  // stores from the (o, l) threads were the bottleneck of the first version).
-  const bool staged = (p.ocb == 8);
-  float* stg = reinterpret_cast<float*>(twr + p.KH * kRowSynthRows);   // [row][hi|lo][KE/4][36]
+  // (8-channel blocks that stage their results in shared memory and store full 128-byte lines were tried and measured
+  // slower - 22 vs 16 us - as were lane pairs splitting the k range)
   for (int task = tid; task < noc * LH; task += nthr) {
     const int ol = task / LH, l = task - ol * LH;
     const int o = o0 + ol;
@@ -279,31 +275,15 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
     }
     const int off = kmajor_off(o, 2 * l, p.CO) / 4;                 // floats; columns 2l and 2l + 1 are adjacent
     float* dst = p.u + ((size_t)bp * p.H + x0) * 2 * img + off;
-    const int soff = ((2 * l) >> 2) * 36 + ol * 4 + ((2 * l) & 3);   // chunk pitch 36 floats: the six K-quads land in different banks
 #pragma unroll
     for (int rr = 0; rr < kRowSynthRows; ++rr) {
       if (rr < trows) {
         float h0, l0, h1, l1;
         split_tf32(ar[rr] * f, h0, l0);
         split_tf32(-ai[rr] * f, h1, l1);
-        if (staged) {
-          *reinterpret_cast<float2*>(stg + (rr * 2) * (p.KE / 4) * 36 + soff) = make_float2(h0, h1);
-          *reinterpret_cast<float2*>(stg + (rr * 2 + 1) * (p.KE / 4) * 36 + soff) = make_float2(l0, l1);
-        } else {
-          *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img) = make_float2(h0, h1);
-          *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img + img) = make_float2(l0, l1);
-        }
+        *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img) = make_float2(h0, h1);
+        *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img + img) = make_float2(l0, l1);
       }
-    }
-  }
-  if (staged) {
-    __syncthreads();
-    const int nkq = p.KE / 4;
-    float* ubase = p.u + ((size_t)bp * p.H + x0) * 2 * img + (o0 >> 3) * 32;
-    const int w = tid & 31;
-    for (int c = tid >> 5; c < trows * 2 * nkq; c += nthr >> 5) {   // one 128-byte line per warp and step
-      const int ri = c / nkq, kq = c - ri * nkq;                    // ri = row * 2 + (hi | lo)
-      ubase[(size_t)ri * img + (size_t)kq * 4 * p.CO + w] = stg[c * 36 + w];
     }
   }
 }
