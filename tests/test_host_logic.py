@@ -195,3 +195,28 @@ def test_flat_gradient_allreduce_two_ranks_gloo(tmp_path):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and "dp-ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_flat_gradient_spans_and_direct_write_registration():
+    """Host-side bookkeeping of parallel.FlatGradients (no kernels involved): per-stage slices of the flat buffer and
+    the gradient-sink registration the backward kernels look up (functional.grad_sink)."""
+    import torch
+    from deno4pytorch_b200.functional import grad_sink
+    from deno4pytorch_b200.parallel import FlatGradients
+    a = torch.nn.Parameter(torch.zeros(3, 5))
+    b = torch.nn.Parameter(torch.zeros(7, dtype=torch.complex64))
+    c = torch.nn.Parameter(torch.zeros(2))
+    fg = FlatGradients([a, b, c])
+    assert fg.flat.numel() == 16 + 16 + 4                      # every span padded to a multiple of 4 floats
+    assert fg.span_of([a, b]).numel() == 32 and fg.span_of([c]).numel() == 4
+    assert fg.span_of([a, b]).data_ptr() == fg.flat.data_ptr()
+    with pytest.raises(ValueError):
+        fg.span_of([a, c])                                     # not adjacent
+    assert grad_sink(a) is None
+    fg.direct_writes(True)
+    assert grad_sink(a) is a.grad and grad_sink(b) is b.grad
+    assert grad_sink(a, like=torch.zeros(5, 3)) is None         # shape mismatch: no sink
+    b.grad.real.fill_(2.0)
+    assert float(fg.flat[16:30:2].sum()) == 14.0                # complex gradients live in the flat buffer as (re, im)
+    fg.direct_writes(False)
+    assert grad_sink(a) is None
