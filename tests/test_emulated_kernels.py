@@ -77,6 +77,8 @@ CASES = [
     ((1026,), (16,), 2, 64, 64, "gelu"),        # the Burgers (C1) layer's launch geometry, batch 2
     ((10, 70, 46), (2, 8, 8), 1, 32, 32, "gelu"),  # the C5 plane geometry (70x46 planes), short X
     ((128, 40), (64, 16), 2, 6, 6, "tanh"),     # every row mode retained (2 * modes == H), the Airfoil/Pipe mode counts
+    ((34,), (17,), 7, 9, 2, "tanh"),            # 1-D with all N/2+1 modes, cin > cout, odd batch (tiled mix thread tiles ragged)
+    ((20, 12), (10, 7), 6, 10, 6, "leakyrelu"),  # 2 * modes == H and all modes on the last axis, 10 -> 6 channels
 ]
 
 
