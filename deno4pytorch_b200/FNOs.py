@@ -75,8 +75,21 @@ def _ptr(t):
 
 
 def _grad_sink(param, like):
-    from .functional import grad_sink
-    return grad_sink(param, like)
+    from .functional import _claim_sink
+    return _claim_sink(param, like)
+
+
+def _resolve_sinks(owners, sinks):
+    from .functional import _release_sink, _resolve_sink
+    out = tuple(_resolve_sink(o, s) for o, s in zip(owners, sinks))
+    for o in owners:
+        _release_sink(o)
+    return out
+
+
+def _poison(*tensors):
+    from .functional import _poison as poison
+    poison(*tensors)
 
 
 def _count_launches(L):
@@ -89,19 +102,23 @@ class _LiftFn(torch.autograd.Function):
     include/deno_fno.h; /root/reference/Models/fno/FNOs.py:136-142)."""
 
     @staticmethod
-    def forward(ctx, x, grid, w0_in, b0_in, desc):
+    def forward(ctx, x, grid, w0_in, b0_in, desc, save=True):
         L = _lib()
         x, grid, w0, b0 = x.contiguous(), grid.contiguous(), w0_in.contiguous(), b0_in.contiguous()
         nd = desc.ndim
         padded = tuple(desc.spatial[a] + desc.padding for a in range(nd))
         h = torch.empty((desc.batch, desc.width) + padded, dtype=torch.float32, device=x.device)
+        _poison(h)
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream(x.device).cuda_stream
             _capi.check(L, L.deno_fno_lift_fwd(_C.byref(desc), x.data_ptr(), grid.data_ptr(), w0.data_ptr(),
                                                b0.data_ptr(), h.data_ptr(), st), "deno_fno_lift_fwd")
         _count_launches(L)
+        if not save:          # caller is under torch.no_grad(): nothing to save, no gradient sink to claim
+            return h
         ctx.save_for_backward(x, grid, w0)
         ctx.sinks = (_grad_sink(w0_in, w0), _grad_sink(b0_in, b0))
+        ctx.sink_owners = (w0_in, b0_in)
         ctx.desc = desc
         return h
 
@@ -112,18 +129,19 @@ class _LiftFn(torch.autograd.Function):
         desc = ctx.desc
         gh = gh.contiguous()
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        s_w0, s_b0 = ctx.sinks
+        s_w0, s_b0 = _resolve_sinks(ctx.sink_owners, ctx.sinks)
         gw0 = s_w0 if s_w0 is not None else torch.empty_like(w0)
         gb0 = s_b0 if s_b0 is not None else torch.empty(w0.shape[0], dtype=torch.float32, device=gh.device)
         nws = L.deno_fno_workspace_bytes(_C.byref(desc), _capi.FNO_WS_LIFT_BWD)
         ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=gh.device)
+        _poison(ws, gx, gw0 if s_w0 is None else None, gb0 if s_b0 is None else None)
         with torch.cuda.device(gh.device):
             st = torch.cuda.current_stream(gh.device).cuda_stream
             _capi.check(L, L.deno_fno_lift_bwd(_C.byref(desc), gh.data_ptr(), x.data_ptr(), grid.data_ptr(),
                                                w0.data_ptr(), _ptr(gx), gw0.data_ptr(), gb0.data_ptr(),
                                                ws.data_ptr(), ws.numel(), st), "deno_fno_lift_bwd")
         _count_launches(L)
-        return gx, None, None if s_w0 is not None else gw0, None if s_b0 is not None else gb0, None
+        return gx, None, None if s_w0 is not None else gw0, None if s_b0 is not None else gb0, None, None
 
 
 class _ProjFn(torch.autograd.Function):
@@ -131,19 +149,23 @@ class _ProjFn(torch.autograd.Function):
     in the backward pass (``deno_fno_proj_fwd/_bwd``; FNOs.py:147-152 of the reference)."""
 
     @staticmethod
-    def forward(ctx, h, w1_in, b1_in, w2_in, b2_in, desc):
+    def forward(ctx, h, w1_in, b1_in, w2_in, b2_in, desc, save=True):
         L = _lib()
         h, w1, b1, w2, b2 = (t.contiguous() for t in (h, w1_in, b1_in, w2_in, b2_in))
         nd = desc.ndim
         y = torch.empty((desc.batch,) + tuple(desc.spatial[a] for a in range(nd)) + (desc.out_dim,),
                         dtype=torch.float32, device=h.device)
+        _poison(y)
         with torch.cuda.device(h.device):
             st = torch.cuda.current_stream(h.device).cuda_stream
             _capi.check(L, L.deno_fno_proj_fwd(_C.byref(desc), h.data_ptr(), w1.data_ptr(), b1.data_ptr(),
                                                w2.data_ptr(), b2.data_ptr(), y.data_ptr(), st), "deno_fno_proj_fwd")
         _count_launches(L)
+        if not save:
+            return y
         ctx.save_for_backward(h, w1, b1, w2)
         ctx.sinks = tuple(_grad_sink(a, c) for a, c in ((w1_in, w1), (b1_in, b1), (w2_in, w2), (b2_in, b2)))
+        ctx.sink_owners = (w1_in, b1_in, w2_in, b2_in)
         ctx.desc = desc
         return y
 
@@ -155,13 +177,14 @@ class _ProjFn(torch.autograd.Function):
         gy = gy.contiguous()
         dev = gy.device
         gh = torch.empty_like(h)
-        sinks = ctx.sinks
+        sinks = _resolve_sinks(ctx.sink_owners, ctx.sinks)
         gw1 = sinks[0] if sinks[0] is not None else torch.empty_like(w1)
         gb1 = sinks[1] if sinks[1] is not None else torch.empty_like(b1)
         gw2 = sinks[2] if sinks[2] is not None else torch.empty_like(w2)
         gb2 = sinks[3] if sinks[3] is not None else torch.empty(w2.shape[0], dtype=torch.float32, device=dev)
         nws = L.deno_fno_workspace_bytes(_C.byref(desc), _capi.FNO_WS_PROJ_BWD)
         ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+        _poison(ws, gh, *[g for g, sk in zip((gw1, gb1, gw2, gb2), sinks) if sk is None])
         with torch.cuda.device(dev):
             st = torch.cuda.current_stream(dev).cuda_stream
             _capi.check(L, L.deno_fno_proj_bwd(_C.byref(desc), gy.data_ptr(), h.data_ptr(), w1.data_ptr(),
@@ -169,7 +192,7 @@ class _ProjFn(torch.autograd.Function):
                                                gb1.data_ptr(), gw2.data_ptr(), gb2.data_ptr(), ws.data_ptr(),
                                                ws.numel(), st), "deno_fno_proj_bwd")
         _count_launches(L)
-        return (gh,) + tuple(None if sk is not None else g for sk, g in zip(sinks, (gw1, gb1, gw2, gb2))) + (None,)
+        return (gh,) + tuple(None if sk is not None else g for sk, g in zip(sinks, (gw1, gb1, gw2, gb2))) + (None, None)
 
 
 def _fused_ends_enabled() -> bool:
@@ -205,7 +228,7 @@ class _FNONd(nn.Module):
         nd = self.ndim
         desc = self._ends_desc(x, grid)
         if desc is not None:
-            h = _LiftFn.apply(x, grid, self.fc0.weight, self.fc0.bias, desc)
+            h = _LiftFn.apply(x, grid, self.fc0.weight, self.fc0.bias, desc, torch.is_grad_enabled())
         else:
             h = _tall_linear(torch.cat((x, grid), dim=-1), self.fc0)
             h = h.movedim(-1, 1)
@@ -222,7 +245,8 @@ class _FNONd(nn.Module):
         if notify is not None and h.requires_grad:
             h.register_hook(lambda g, i=len(self.convs): notify(i))
         if desc is not None:
-            return _ProjFn.apply(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, desc)
+            return _ProjFn.apply(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, desc,
+                                 torch.is_grad_enabled())
         if self.padding != 0:
             h = h[(Ellipsis,) + (slice(None, -self.padding),) * nd]
         h = h.movedim(1, -1)

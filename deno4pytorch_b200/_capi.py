@@ -83,6 +83,7 @@ _PP = C.POINTER(C.c_void_p)
 _PROTOTYPES = {
     "deno_spectral_abi_version": (C.c_int, []),
     "deno_last_error": (C.c_char_p, []),
+    "deno_reload_env": (C.c_int, []),
     "deno_spectral_last_launch_count": (C.c_int, []),
     "deno_profile_begin": (C.c_int, []),
     "deno_profile_end": (C.c_int, [C.POINTER(ProfileRecord), C.c_int]),

@@ -38,6 +38,7 @@ int fail(int code, const std::string& msg) {
 constexpr size_t kAlign = 256;
 constexpr int kWgradTcMaxCtas = 4 * 148;   // partials of bypass_wgrad_tc: 148 persistent CTAs x up to 4 stacked batch entries
 constexpr int kMaxSmemBytes = 227 * 1024;
+constexpr int kProjTcCtas = 148;           // persistent CTAs of fno_proj_bwd_tc (one partial row each)
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 // ------------------------------------------------------------------------------------------
@@ -462,15 +463,42 @@ TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   return p;
 }
 
-// DENO_SPECTRAL_PATH = auto (default) | simt | tc : which kernels serve the stages both paths implement.
+// Process-wide switches, read from the environment ONCE (first use) and again only on deno_reload_env():
+//   DENO_SPECTRAL_PATH = auto (default) | simt | tc : which kernels serve the stages both paths implement
+//   DENO_MIX_TILE      = 0: never the tiled mix kernels, 2: tiled forward mix too      (experiments)
+//   DENO_MIX_TM        = 1 | 2 | 4: modes per block of the tiled mix kernels            (experiments)
+//   DENO_SYNTH_WS      = 1: warp-specialised synthesis kernel instead of the bulk one   (experiments)
 enum class PathPref { Auto, Simt, Tc };
-PathPref path_pref() {
-  const char* e = getenv("DENO_SPECTRAL_PATH");
-  if (e == nullptr) return PathPref::Auto;
-  if (strcmp(e, "simt") == 0) return PathPref::Simt;
-  if (strcmp(e, "tc") == 0) return PathPref::Tc;
-  return PathPref::Auto;
+struct Options {
+  PathPref path = PathPref::Auto;
+  int mix_tile = 1;      // 0 / 1 (default) / 2
+  int mix_tm = 0;        // 0 = heuristic
+  bool synth_ws = false;
+  bool wgrad_tma = true; // DENO_WGRAD_TMA=0: the register-staged bypass_wgrad_tc kernel instead of the TMA one
+  bool an_tma = true;    // DENO_ANALYSIS_TMA=0: the bulk-copy + SIMT-transform analysis kernel instead of the TMA one
+};
+Options read_options() {
+  Options o;
+  if (const char* e = getenv("DENO_SPECTRAL_PATH")) {
+    if (strcmp(e, "simt") == 0) o.path = PathPref::Simt;
+    else if (strcmp(e, "tc") == 0) o.path = PathPref::Tc;
+  }
+  if (const char* e = getenv("DENO_MIX_TILE")) { if (e[0] == '0') o.mix_tile = 0; else if (e[0] == '2') o.mix_tile = 2; }
+  if (const char* e = getenv("DENO_MIX_TM")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) o.mix_tm = v; }
+  if (const char* e = getenv("DENO_SYNTH_WS")) o.synth_ws = e[0] == '1';
+  if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] != '0';
+  if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] != '0';
+  return o;
 }
+std::mutex g_opt_mutex;
+Options g_options;
+bool g_options_read = false;
+Options options() {
+  std::lock_guard<std::mutex> lock(g_opt_mutex);
+  if (!g_options_read) { g_options = read_options(); g_options_read = true; }
+  return g_options;
+}
+PathPref path_pref() { return options().path; }
 
 #ifndef DENO_EMULATE
 // Tensor-core analysis; -1 when the shape is outside the kernel's coverage.
@@ -564,13 +592,13 @@ int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, 
 // Tiled per-mode products (mode_mix_tile_kernel / mode_mix_bwd_tile_kernel): picks the modes per block so that the grid
 // is about one block per SM and the staged operands fit shared memory; false when even one mode per block does not fit.
 bool mix_tile_cfg(const Shape& s, bool backward, MixTileParams& p, size_t& smem_bytes, int& grid) {
-  const char* e = getenv("DENO_MIX_TILE");
-  if (e != nullptr && e[0] == '0') return false;
+  const Options opt = options();
+  if (opt.mix_tile == 0) return false;
   p.md = make_decode(s);
   p.B = s.B; p.CI = s.CI; p.CO = s.CO;
   int TM = 4;
   while (TM > 1 && (s.M + TM - 1) / TM < 140) TM /= 2;
-  if (const char* t = getenv("DENO_MIX_TM")) { const int v = atoi(t); if (v == 1 || v == 2 || v == 4) TM = v; }   // experiments
+  if (opt.mix_tm != 0) TM = opt.mix_tm;   // experiments
   while (TM > 1 && (size_t)mix_tile_smem(s.B, s.CI, s.CO, TM, backward).total * 8 > (size_t)kMaxSmemBytes - 2048) TM /= 2;
   if ((size_t)mix_tile_smem(s.B, s.CI, s.CO, TM, backward).total * 8 > (size_t)kMaxSmemBytes - 2048) return false;
   p.TM = TM;
@@ -608,8 +636,7 @@ int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, con
   }
   // The forward product alone is too little work per block for the tiled kernel (18.7 us vs 13.3 us for the
   // thread-per-output kernel at the Darcy shape, which fills every SM with warps); DENO_MIX_TILE=2 forces it.
-  const char* tile_env = getenv("DENO_MIX_TILE");
-  if (!backward && tile_env != nullptr && tile_env[0] == '2') {
+  if (!backward && options().mix_tile == 2) {
     MixTileParams t;
     memset(&t, 0, sizeof(t));
     size_t tsm = 0;
@@ -858,8 +885,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
 
 int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, float* urow,
                             cudaStream_t st) {
-  const char* e = getenv("DENO_SYNTH_WS");
-  if (e != nullptr && e[0] == '1') return try_launch_synthesis_ws(s, p, tw, act, label, st);
+  if (options().synth_ws) return try_launch_synthesis_ws(s, p, tw, act, label, st);
   return try_launch_synthesis_bulk(s, p, tw, act, label, urow, st);
 }
 #endif
@@ -1096,7 +1122,10 @@ int proj_bwd_ws(const FnoShape& f, ProjBwdWs& w) {
   w.nsmall = f.Hd + f.O * f.Hd + f.O;
   size_t off = 0;
   w.gt = off;    off += align_up((size_t)f.B * f.Hd * ((f.g.nppts + 127) / 128 * 128) * 4);   // plain or 128-point blocks
-  w.small = off; off += align_up((size_t)w.nblk * w.nsmall * 4);
+  // one partial row per CTA of whichever backward kernel runs: the SIMT kernel launches nblk CTAs, the persistent
+  // tensor-core kernel min(tiles, kProjTcCtas) - size for the larger count so neither can run into `wpart`
+  const int nsmall_rows = w.nblk > kProjTcCtas ? w.nblk : kProjTcCtas;
+  w.small = off; off += align_up((size_t)nsmall_rows * w.nsmall * 4);
   const size_t nparts = (size_t)(wc.ncta > kWgradTcMaxCtas ? wc.ncta : kWgradTcMaxCtas);
   w.wpart = off; off += align_up(nparts * ((size_t)f.Hd * f.C + f.Hd) * 4);
   w.total = off;
@@ -1150,7 +1179,6 @@ int try_launch_proj_fwd_tc(const FnoShape& f, tc::ProjTcParams p, cudaStream_t s
   return -1;
 }
 
-constexpr int kProjTcCtas = 148;
 // The tensor-core backward writes gt in blocks of 128 points (strided 512-byte runs cost 2.4x in the store path,
 // profiles/r2m_phase_probe.txt), which only the tensor-core bypass_wgrad kernel reads: both or neither.
 bool proj_bwd_tc_eligible(const FnoShape& f) {
@@ -1192,6 +1220,13 @@ extern "C" {
 
 int deno_spectral_abi_version(void) { return DENO_SPECTRAL_ABI_VERSION; }
 
+int deno_reload_env(void) {
+  std::lock_guard<std::mutex> lock(g_opt_mutex);
+  g_options = read_options();
+  g_options_read = true;
+  return DENO_OK;
+}
+
 const char* deno_last_error(void) { return g_error.c_str(); }
 
 int deno_spectral_last_launch_count(void) { return g_launches; }
@@ -1213,7 +1248,7 @@ int deno_adam_step(float* p, const float* g, float* m, float* v, size_t n, float
 }
 
 int deno_debug_read(long long* host, int count, int clear) {
-#ifndef DENO_EMULATE
+#if !defined(DENO_EMULATE) && defined(DENO_PHASE_PROBE)
   if (host == nullptr || count < 0 || count > 64) return fail(DENO_E_INVALID, "deno_debug_read: bad arguments");
   cudaError_t e = cudaMemcpyFromSymbol(host, tc::g_dbg, sizeof(long long) * count);
   if (e != cudaSuccess) return fail(DENO_E_CUDA, cudaGetErrorString(e));
@@ -1223,7 +1258,8 @@ int deno_debug_read(long long* host, int count, int clear) {
     if (e != cudaSuccess) return fail(DENO_E_CUDA, cudaGetErrorString(e));
   }
 #else
-  for (int i = 0; i < count; ++i) host[i] = 0;
+  if (host == nullptr || count < 0 || count > 64) return fail(DENO_E_INVALID, "deno_debug_read: bad arguments");
+  for (int i = 0; i < count; ++i) host[i] = 0;   // product build: no phase probe compiled in
   (void)clear;
 #endif
   return DENO_OK;

@@ -222,11 +222,11 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
       }
     }
     for (int k = 0; k < nmine; ++k) {
-      const long long t0 = clock64();
+      const long long t0 = DENO_CLK();
       mbar_wait(&mbar_d1, phase);
       fence_after_sync();
       phase ^= 1;
-      const long long t1 = clock64();
+      const long long t1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(16, t1 - t0);          // slot 16: wait for GEMM 1
       const bool v_k = valid_cur;
       const int b_k = b_cur, pc_k = pc_cur;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
           it.next();
         }
       }
-      const long long t2 = clock64();
+      const long long t2 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(17, t2 - t1);          // slot 17: A1 image of the next tile + prefetch issue
       float yo[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t td = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)((k & 1) * HD + wg * (HD / 4));
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
         }
       }
       fence_before_sync();                               // D1 reads ordered before the next hand-off
-      const long long t3 = clock64();
+      const long long t3 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(18, t3 - t2);          // slot 18: epilogue math
       float* ysk = ys + (k & 1) * (4 * 128 * 4);
       *reinterpret_cast<float4*>(ysk + (wg * 128 + xrow) * 4) = make_float4(yo[0], yo[1], yo[2], yo[3]);
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kPjFwdThreads, 1) fno_proj_fwd_tc_kernel(ProjT
         for (int o = 0; o < 4; ++o)
           if (o < p.O) dst[o] = r[o] + b2s[o];
       }
-      if (warp == 1) { DENO_DBG_ADD(19, clock64() - t3); DENO_DBG_ADD(20, 1); }   // slots 19/20: exchange + store, tiles
+      if (warp == 1) { DENO_DBG_ADD(19, DENO_CLK() - t3); DENO_DBG_ADD(20, 1); }   // slots 19/20: exchange + store, tiles
     }
   }
   fence_before_sync();
@@ -416,11 +416,11 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
     }
     const int row_off = (xrow & 7) * 16 + (xrow >> 3) * 128;
     for (int k = 0; k < nmine; ++k) {
-      const long long t0 = clock64();
+      const long long t0 = DENO_CLK();
       mbar_wait(&mbar_d1, phase);
       fence_after_sync();
       phase ^= 1;
-      const long long t1 = clock64();
+      const long long t1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(21, t1 - t0);          // slot 21: wait for GEMM 1
       long long t_slot = 0;
       // gt in blocks of 128 points: [tile][HD][128], every tile one contiguous 64 KB run (bypass_wgrad_tc's gz_tps mode)
@@ -450,10 +450,10 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
           gt_dst[(c * 16 + jj + 1) * 128] = gt.y;
         }
         if (c >= 2) {                                    // the slot's previous chunk has been consumed by the tensor core
-          const long long ts = clock64();
+          const long long ts = DENO_CLK();
           mbar_wait(&mbar_slot[slot], slot_phase[slot]);
           slot_phase[slot] ^= 1;
-          t_slot += clock64() - ts;
+          t_slot += DENO_CLK() - ts;
         }
         unsigned char* ring_hi = smem + S::off_ring + slot * 2 * S::ring_one + (wg * 4) * S::a_lbo + row_off;
 #pragma unroll
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
         fence_before_sync();                             // D1 reads ordered before the hand-off
         nbar_arrive(kPjBarChunk0 + slot, kPjThreads);
       }
-      const long long t2 = clock64();
+      const long long t2 = DENO_CLK();
       if (warp == 1) { DENO_DBG_ADD(22, t2 - t1 - t_slot); DENO_DBG_ADD(23, t_slot); }   // slots 22/23: chunk math + stores, ring waits
       const bool inside_k = inside_cur;
       const int b_k = b_cur, pp_k = pp_cur;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
           gy_next = valid ? __ldg(p.gy + (long long)b * p.g.npts + pc) : 0.f;
         }
       }
-      const long long t3 = clock64();
+      const long long t3 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(24, t3 - t2);          // slot 24: A1 image of the next tile + prefetch issue
       // the last two chunks' commits: all of GEMM 2 (k) has completed after the second wait
       mbar_wait(&mbar_slot[NCH & 1], slot_phase[NCH & 1]);
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
       mbar_wait(&mbar_slot[(NCH + 1) & 1], slot_phase[(NCH + 1) & 1]);
       slot_phase[(NCH + 1) & 1] ^= 1;
       fence_after_sync();
-      const long long t4 = clock64();
+      const long long t4 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(25, t4 - t3);          // slot 25: wait for the rest of GEMM 2
       float* gh_dst = p.gh + ((long long)b_k * C + wg * (C / 2)) * p.g.nppts + pp_k;
 #pragma unroll
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kPjThreads, 1) fno_proj_bwd_tc_kernel(ProjTcPa
         }
       }
       fence_before_sync();                               // D2 reads ordered before the next tile's first hand-off
-      if (warp == 1) { DENO_DBG_ADD(26, clock64() - t4); DENO_DBG_ADD(27, 1); }   // slots 26/27: gh epilogue, tiles
+      if (warp == 1) { DENO_DBG_ADD(26, DENO_CLK() - t4); DENO_DBG_ADD(27, 1); }   // slots 26/27: gh epilogue, tiles
     }
     // end of kernel: sum the per-thread accumulators over the 128 lanes of each column half (fixed order)
     float* red = reinterpret_cast<float*>(smem + S::off_red);      // [4 (wq)][2 * HD + 4]

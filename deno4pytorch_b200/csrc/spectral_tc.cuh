@@ -18,10 +18,18 @@
 namespace deno {
 namespace tc {
 
-// Phase-timing scratch (measurement aid): block 0 of the warp-specialised kernels accumulates clock64()
-// deltas per role and phase here; read back with deno_debug_read().  Slots are documented at the writers.
+// Phase-timing scratch (measurement aid, compiled only with -DDENO_PHASE_PROBE: tools/phase_probe.py builds that
+// variant into tools/_build): block 0 of the warp-specialised kernels accumulates clock64() deltas per role and
+// phase here; read back with deno_debug_read().  Slots are documented at the writers.  The product build has
+// neither the global, nor the clock reads, nor the atomics.
+#ifdef DENO_PHASE_PROBE
 __device__ long long g_dbg[64];
+#define DENO_CLK() clock64()
 #define DENO_DBG_ADD(slot, dt) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_dbg[slot]), (unsigned long long)(dt)); } while (0)
+#else
+#define DENO_CLK() 0LL
+#define DENO_DBG_ADD(slot, dt) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   const int y0 = chunk * 128;
   const int ny = min(128, W - y0);
 
-  const long long tb0 = clock64();
+  const long long tb0 = DENO_CLK();
   if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)q.tmem_cols);
   if (tid == 32) {
     mbar_init(&mbar[0], 1);
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   };
   if (!is_mma) prefetch(0);
 
-  const long long tb1 = clock64();
+  const long long tb1 = DENO_CLK();
   if (warp == 1) DENO_DBG_ADD(48, tb1 - tb0);          // slot 48: TMEM alloc, weight / twiddle images, first prefetch issue
   // ---- stage A: U[r][o][l] = f_l * sum_k spec[o][k][l] e^{+i phi(k, x0 + r)}, written as B operand images ----
   // Normally precomputed (q.urow, bulk copy issued above); the in-kernel version below is kept for callers without
@@ -421,10 +429,10 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       const int rr = idx / KH, k = idx - rr * KH;
       twr[idx] = p.twH[(x0 + rr) * KH4 + k];
     }
-    if (warp == 1) DENO_DBG_ADD(57, clock64() - tb1);   // slot 57: zero fill + row twiddles
+    if (warp == 1) DENO_DBG_ADD(57, DENO_CLK() - tb1);   // slot 57: zero fill + row twiddles
     for (int o0 = 0; o0 < CO; o0 += OC) {
       const int oc = min(OC, CO - o0);
-      const long long tc0 = clock64();
+      const long long tc0 = DENO_CLK();
       __syncthreads();   // previous chunk consumed (first pass: zero fill / twiddles ordered before use)
       const float2* src = p.spec + ((long long)bp * CO + o0) * Q;
       for (int idx0 = 0; idx0 < oc * Q; idx0 += 8 * 256) {     // eight independent loads in flight per thread
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
         }
       }
       __syncthreads();
-      const long long tc1 = clock64();
+      const long long tc1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(58, tc1 - tc0);       // slot 58: spectrum chunk load (incl. barriers)
       // task = (row half, output channel, mode): two threads share an (o, l) pair, four rows each
       for (int task = wt; task < 2 * oc * MW; task += 256) {
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
           }
         }
       }
-      if (warp == 1) { DENO_DBG_ADD(59, clock64() - tc1); DENO_DBG_ADD(60, 1); }   // slots 59/60: chunk compute, chunks
+      if (warp == 1) { DENO_DBG_ADD(59, DENO_CLK() - tc1); DENO_DBG_ADD(60, 1); }   // slots 59/60: chunk compute, chunks
     }
     __syncthreads();     // the A_X area is about to be overwritten by the first row tile
   }
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   __syncthreads();
   fence_after_sync();
   mbar_wait(&mbar_u, 0);                               // twiddle (and U) images have landed (barrier initialised before the sync above)
-  const long long tb2 = clock64();
+  const long long tb2 = DENO_CLK();
   if (warp == 1) DENO_DBG_ADD(49, tb2 - tb1);          // slot 49: stage A
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = make_idesc_tf32(128, CO);
@@ -551,7 +559,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
     for (int rr = 0; rr < trows; ++rr) {
       nbar_sync(kSynBarAx, kSynThreads);
       fence_after_sync();
-      const long long tr3 = clock64();
+      const long long tr3 = DENO_CLK();
       // Back-to-back MMAs into ONE accumulator serialise on the tensor pipe's latency (measured ~120 cycles each at
       // N = 32), so the three split passes (hi*hi, lo*hi, hi*lo) accumulate into three separate TMEM tiles and are
       // issued round-robin; the epilogue adds the tiles.  Descriptors are built once and advanced by a constant.
@@ -581,14 +589,14 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       }
       if (leader) mma_commit(&mbar[rr & 1]);
       __syncwarp();
-      if (leader) DENO_DBG_ADD(53, clock64() - tr3);   // slot 53: MMA issue
+      if (leader) DENO_DBG_ADD(53, DENO_CLK() - tr3);   // slot 53: MMA issue
     }
   } else {
     // ---- workers: A_X images of row rr, then (while the tensor core works on it) the epilogue of row rr - 1 ----
     for (int rr = 0; rr < trows; ++rr) {
-      const long long tr0 = clock64();
+      const long long tr0 = DENO_CLK();
       if (rr > 0) mbar_wait(&mbar[(rr - 1) & 1], ((rr - 1) >> 1) & 1);   // MMA(rr-1) done: A_X free, D(rr-1) ready
-      const long long tr1 = clock64();
+      const long long tr1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(50, tr1 - tr0);        // slot 50: wait for the previous row's MMAs
       // registers -> A_X images (hi / lo)
 #pragma unroll
@@ -607,15 +615,15 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       fence_proxy_async();
       fence_before_sync();                               // also orders the D reads of epilogue(rr - 2) before the hand-off
       nbar_arrive(kSynBarAx, kSynThreads);
-      const long long tr4 = clock64();
+      const long long tr4 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(51, tr4 - tr1);        // slot 51: split + store + hand-off
       if (rr + 1 < trows) prefetch(rr + 1);
-      const long long tr5 = clock64();
+      const long long tr5 = DENO_CLK();
       if (rr > 0) {
         fence_after_sync();
         epilogue(rr - 1);
       }
-      if (warp == 1) { DENO_DBG_ADD(54, tr5 - tr4); DENO_DBG_ADD(55, clock64() - tr5); DENO_DBG_ADD(56, 1); }  // prefetch issue, epilogue, rows
+      if (warp == 1) { DENO_DBG_ADD(54, tr5 - tr4); DENO_DBG_ADD(55, DENO_CLK() - tr5); DENO_DBG_ADD(56, 1); }  // prefetch issue, epilogue, rows
     }
   }
   if (!is_mma) {
@@ -722,7 +730,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
     const int y0 = chunk * 128;
     const int ny = min(128, W - y0);
 
-    const long long t_unit0 = clock64();
+    const long long t_unit0 = DENO_CLK();
     // ---- per-unit setup by all warps: twiddle images (if the column chunk changed) and stage A ----
     if (chunk != cur_chunk) {
       const float4* src = reinterpret_cast<const float4*>(q.ae + (long long)chunk * 2 * KE * 128);
@@ -801,8 +809,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       fence_proxy_async();
       __syncthreads();     // operand images complete; the A_X stages are free for the loaders
     }
-    if (warp == 0) DENO_DBG_ADD(0, clock64() - t_unit0);                 // slot 0: unit setup (stage A)
-    const long long t_roles0 = clock64();
+    if (warp == 0) DENO_DBG_ADD(0, DENO_CLK() - t_unit0);                 // slot 0: unit setup (stage A)
+    const long long t_roles0 = DENO_CLK();
 
     if (warp < kWsEpiWarps) {
       // ===== epilogue warps: lane quadrant wq of TMEM, column slice wg =====
@@ -812,10 +820,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
       for (int rr = 0; rr < trows; ++rr) {
         const int i = it0 + rr, st = i & 1;
-        const long long te0 = clock64();
+        const long long te0 = DENO_CLK();
         mbar_wait(&bar_d_full[st], (uint32_t)((i >> 1) & 1));
         fence_after_sync();
-        const long long te1 = clock64();
+        const long long te1 = DENO_CLK();
         if (warp == 0) DENO_DBG_ADD(1, te1 - te0);                       // slot 1: epilogue waits for D
         const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(st * 3 * CO + wg * ncol_per);
         const long long pbase = obase_b + (long long)(x0 + rr) * W + y0 + yl;
@@ -847,7 +855,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
             }
           }
         }
-        if (warp == 0) DENO_DBG_ADD(2, clock64() - te1);                 // slot 2: epilogue work per row
+        if (warp == 0) DENO_DBG_ADD(2, DENO_CLK() - te1);                 // slot 2: epilogue work per row
       }
     } else if (warp < kWsEpiWarps + kWsLoadWarps) {
       // ===== loader warps: one thread = one point of the row and half of the channel quads; two rows of
@@ -871,9 +879,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       };
       auto publish = [&](int rr, float (&xr)[NQ][4]) {
         const int i = it0 + rr, st = i & 1;
-        const long long tl0 = clock64();
+        const long long tl0 = DENO_CLK();
         mbar_wait(&bar_ax_empty[st], (uint32_t)(((i >> 1) & 1) ^ 1));
-        const long long tl1 = clock64();
+        const long long tl1 = DENO_CLK();
         if (warp == kWsEpiWarps) DENO_DBG_ADD(3, tl1 - tl0);             // slot 3: loader waits for a free stage
         unsigned char* axh = smem + so.ax + st * 2 * so.ax_one;
 #pragma unroll
@@ -891,7 +899,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
         }
         fence_proxy_async();
         mbar_arrive(&bar_ax_full[st]);
-        if (warp == kWsEpiWarps) DENO_DBG_ADD(4, clock64() - tl1);       // slot 4: loader split + store (incl. wait for LDG data)
+        if (warp == kWsEpiWarps) DENO_DBG_ADD(4, DENO_CLK() - tl1);       // slot 4: loader split + store (incl. wait for LDG data)
       };
       prefetch(0, xa);
       if (trows > 1) prefetch(1, xb);
@@ -910,12 +918,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
       for (int rr = 0; rr < trows; ++rr) {
         const int i = it0 + rr, st = i & 1;
         const uint32_t par = (uint32_t)((i >> 1) & 1);
-        const long long tm0 = clock64();
+        const long long tm0 = DENO_CLK();
         mbar_wait(&bar_ax_full[st], par);
-        const long long tm1 = clock64();
+        const long long tm1 = DENO_CLK();
         mbar_wait(&bar_d_empty[st], par ^ 1);
         fence_after_sync();
-        const long long tm2 = clock64();
+        const long long tm2 = DENO_CLK();
         DENO_DBG_ADD(5, tm1 - tm0);                                      // slot 5: MMA warp waits for A_X
         DENO_DBG_ADD(6, tm2 - tm1);                                      // slot 6: MMA warp waits for a free accumulator
         const uint32_t d = tmem + (uint32_t)(st * 3 * CO);
@@ -948,10 +956,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
           mma_commit(&bar_d_full[st]);       // ... and the accumulators are ready for the epilogue warps
         }
         __syncwarp();
-        DENO_DBG_ADD(7, clock64() - tm2);                                // slot 7: MMA issue
+        DENO_DBG_ADD(7, DENO_CLK() - tm2);                                // slot 7: MMA issue
       }
     }
-    if (warp == 0) { DENO_DBG_ADD(8, clock64() - t_roles0); DENO_DBG_ADD(9, trows); }   // slots 8/9: role-phase cycles, rows
+    if (warp == 0) { DENO_DBG_ADD(8, DENO_CLK() - t_roles0); DENO_DBG_ADD(9, trows); }   // slots 8/9: role-phase cycles, rows
     it0 += trows;
     fence_before_sync();
     __syncthreads();      // unit drained: every role is done with the images, the A_X stages and TMEM
@@ -1102,10 +1110,10 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       uint64_t ah = make_desc(sbase + so.a, lbo_a, 128), al = make_desc(sbase + so.a + so.a_one, lbo_a, 128);
       uint64_t be = make_desc(sbase + so.e1, lbo_e1, 128);
       const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
-      const long long t0 = clock64();
+      const long long t0 = DENO_CLK();
       nbar_sync(kAnBarA, kAnThreads);
       fence_after_sync();
-      idle += clock64() - t0;
+      idle += DENO_CLK() - t0;
       prefetch_plane(j + 1);                           // every worker is past the staging buffer
       l2_prefetch(j + 2);
       for (int s2 = 0; s2 < Wp / 8; ++s2) {
@@ -1123,10 +1131,10 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     prefetch_plane(0);
     stage1(0);
     for (int j = 0; j < nmine; ++j) {
-      const long long t0 = clock64();
+      const long long t0 = DENO_CLK();
       nbar_sync(kAnBarB2, kAnThreads);                 // B2(j) stored; D1 and D2 of the previous plane drained
       fence_after_sync();
-      idle += clock64() - t0;
+      idle += DENO_CLK() - t0;
       uint64_t a2h = make_desc(sbase + so.a2, lbo_a2, 128), a2l = make_desc(sbase + so.a2 + so.a2_one, lbo_a2, 128);
       uint64_t b2 = make_desc(sbase + so.b2, lbo_b2, 128);
       const uint64_t inc_a2 = (uint64_t)((2 * lbo_a2) >> 4), inc_b2 = (uint64_t)((2 * lbo_b2) >> 4);
@@ -1156,7 +1164,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     };
     auto transform = [&](int j) {                      // staged plane j -> (gz) -> A images (hi / lo)
       const int q = blockIdx.x + j * gridDim.x;
-      const long long tq0 = clock64();
+      const long long tq0 = DENO_CLK();
       float4 zr[kAnZRegs];                             // act'(z) of this thread's first elements: in flight during the wait
       if (FUSE_GZ && bulk) {
         const float4* z4 = reinterpret_cast<const float4*>(p.z + plane_base(p.g, q / p.g.C, q % p.g.C));
@@ -1173,7 +1181,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         cp_async_wait_all();
         nbar_sync(kAnBarWorkers, kAnWorkers);
       }
-      const long long tq1 = clock64();
+      const long long tq1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);      // slot 32: wait for the staged plane
       if (FUSE_GZ) {                                   // gz = gy * act'(z): coalesced store, kept in staging
         const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
@@ -1206,7 +1214,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         }
         nbar_sync(kAnBarWorkers, kAnWorkers);
       }
-      const long long tq2 = clock64();
+      const long long tq2 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(40, tq2 - tq1);      // slot 40: gz pass
       {
         const int r0 = warp * 4 + (lane >> 3), r1 = r0 + (kAnWorkers / 32) * 4;     // Hp <= 128: at most two rows per thread
@@ -1250,17 +1258,17 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         nbar_sync(kAnBarWorkers, kAnWorkers);          // every worker is past the staging buffer
         issue_plane_cp_async(j + 1);
       }
-      if (warp == 1) { DENO_DBG_ADD(33, clock64() - tq1); DENO_DBG_ADD(41, clock64() - tq2); }   // slots 33/41: (gz +) transform, chunk loop
+      if (warp == 1) { DENO_DBG_ADD(33, DENO_CLK() - tq1); DENO_DBG_ADD(41, DENO_CLK() - tq2); }   // slots 33/41: (gz +) transform, chunk loop
     };
 
     if (!bulk) issue_plane_cp_async(0);
     transform(0);
     for (int j = 0; j < nmine; ++j) {
       const int q = blockIdx.x + j * gridDim.x;
-      const long long tq3 = clock64();
+      const long long tq3 = DENO_CLK();
       mbar_wait(&mbar[0], phase);
       fence_after_sync();
-      const long long tq4 = clock64();
+      const long long tq4 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(35, tq4 - tq3);      // slot 35: wait for the stage-1 MMAs
       // D1 -> B2 image [n][x]: hi rows n, lo rows N1 + n
       {
@@ -1291,13 +1299,13 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       fence_proxy_async();
       fence_before_sync();
       nbar_arrive(kAnBarB2, kAnThreads);
-      const long long tq5 = clock64();
+      const long long tq5 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(36, tq5 - tq4);      // slot 36: D1 -> B2 conversion
       if (j + 1 < nmine) transform(j + 1);
-      const long long tq6 = clock64();
+      const long long tq6 = DENO_CLK();
       mbar_wait(&mbar[1], phase);
       fence_after_sync();
-      const long long tq7 = clock64();
+      const long long tq7 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(37, tq7 - tq6);      // slot 37: wait for the stage-2 MMAs
       // epilogue: rows k (cos) and KS0 + k (sin) of D2 are combined through shared memory; warp group wg takes
       // the column passes c0 = 16 wg, 16 wg + 64, ...
@@ -1328,7 +1336,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         }
       }
       fence_before_sync();                             // D2 reads ordered before this thread's next hand-off
-      if (warp == 1) { DENO_DBG_ADD(38, clock64() - tq7); DENO_DBG_ADD(39, 1); }   // slots 38/39: epilogue, planes
+      if (warp == 1) { DENO_DBG_ADD(38, DENO_CLK() - tq7); DENO_DBG_ADD(39, 1); }   // slots 38/39: epilogue, planes
       phase ^= 1;
     }
   }
@@ -1494,9 +1502,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
     };
     auto publish = [&](int n, float4 (&regs)[NIT]) {
       const int st = n & 1;
-      const long long tp0 = clock64();
+      const long long tp0 = DENO_CLK();
       mbar_wait(&bar_empty[st], (uint32_t)(((n >> 1) & 1) ^ 1));      // MMAs of tile n-2 are done with this stage
-      const long long tp1 = clock64();
+      const long long tp1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(10, tp1 - tp0);                      // slot 10: loaders waiting for a free stage
       unsigned char* base = smem + so.stage[st];
 #pragma unroll
@@ -1516,20 +1524,20 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
       }
       fence_proxy_async();
       mbar_arrive(&bar_full[st]);
-      if (warp == 1) { DENO_DBG_ADD(11, clock64() - tp1); DENO_DBG_ADD(15, 1); }   // slots 11/15: wait for the data + split + stores, tiles
+      if (warp == 1) { DENO_DBG_ADD(11, DENO_CLK() - tp1); DENO_DBG_ADD(15, 1); }   // slots 11/15: wait for the data + split + stores, tiles
     };
     if (ntile_cta > 0) prefetch(0, ra);
     if (ntile_cta > 1) prefetch(1, rb);
     for (int n = 0; n < ntile_cta; n += 2) {   // (a third register buffer issued ahead of publish() spilled and was slower)
       publish(n, ra);
-      long long tf0 = clock64();
+      long long tf0 = DENO_CLK();
       if (n + 2 < ntile_cta) prefetch(n + 2, ra);
-      if (warp == 1) DENO_DBG_ADD(12, clock64() - tf0);                // slot 12: address arithmetic + load issue
+      if (warp == 1) DENO_DBG_ADD(12, DENO_CLK() - tf0);                // slot 12: address arithmetic + load issue
       if (n + 1 < ntile_cta) {
         publish(n + 1, rb);
-        tf0 = clock64();
+        tf0 = DENO_CLK();
         if (n + 3 < ntile_cta) prefetch(n + 3, rb);
-        if (warp == 1) DENO_DBG_ADD(12, clock64() - tf0);
+        if (warp == 1) DENO_DBG_ADD(12, DENO_CLK() - tf0);
       }
     }
   } else {
@@ -1540,10 +1548,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
     const uint64_t inc_g = (uint64_t)((2 * so.g_lbo) >> 4), inc_x = (uint64_t)((2 * so.x_lbo) >> 4);
     for (int n = 0; n < ntile_cta; ++n) {
       const int st = n & 1;
-      const long long tm0 = clock64();
+      const long long tm0 = DENO_CLK();
       mbar_wait(&bar_full[st], (uint32_t)((n >> 1) & 1));
       fence_after_sync();
-      const long long tm1 = clock64();
+      const long long tm1 = DENO_CLK();
       const uint32_t b0 = sbase + so.stage[st];
       uint64_t gh = make_desc(b0, so.g_lbo, 128), gl = make_desc(b0 + so.g_lo, so.g_lbo, 128);
       uint64_t xh = make_desc(b0 + so.x_hi, so.x_lbo, 128), xl = make_desc(b0 + so.x_lo, so.x_lbo, 128);
@@ -1559,7 +1567,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) bypass_wgrad_tc_kernel(Wgrad
       }
       if (leader) mma_commit(&bar_empty[st]);
       __syncwarp();
-      if (leader) { DENO_DBG_ADD(13, tm1 - tm0); DENO_DBG_ADD(14, clock64() - tm1); }   // slots 13/14: MMA warp waiting / issuing
+      if (leader) { DENO_DBG_ADD(13, tm1 - tm0); DENO_DBG_ADD(14, DENO_CLK() - tm1); }   // slots 13/14: MMA warp waiting / issuing
     }
     if (leader) mma_commit(&bar_done);
     __syncwarp();

@@ -16,8 +16,39 @@ import torch
 from . import _capi
 from ._lib import lib
 
+import os
+
 _TWIDDLES: Dict[tuple, torch.Tensor] = {}
 _LAUNCHES = {"count": 0}
+_POISON = {"on": os.environ.get("DENO_POISON", "0") == "1"}
+
+
+def set_poison(on: bool):
+    """Debug switch (also ``DENO_POISON=1``): every buffer this module hands to the library as an OUTPUT or as
+    scratch - workspace, ``y``, saved ``act'(z)`` and spectrum, ``gx``, parameter-gradient outputs that are not
+    registered sinks - is filled with a NaN bit pattern before the call.  A kernel that reads something it (or an
+    earlier kernel of the same call) did not write then produces NaNs instead of silently using whatever the caching
+    allocator left there.  Costs one fill kernel per buffer; off by default."""
+    _POISON["on"] = bool(on)
+
+
+def _poison(*tensors):
+    if not _POISON["on"]:
+        return
+    for t in tensors:
+        if t is None:
+            continue
+        if t.dtype == torch.uint8:
+            t.fill_(0xFF)                      # 0xFFFFFFFF is a quiet NaN as fp32
+        elif t.is_complex():
+            torch.view_as_real(t).fill_(float("nan"))
+        else:
+            t.fill_(float("nan"))
+
+
+def reload_env():
+    """Make the library read its ``DENO_*`` switches from the environment again (it reads them once)."""
+    lib().deno_reload_env()
 
 
 def launch_count() -> int:
@@ -87,9 +118,43 @@ def grad_sink(param, like: Optional[torch.Tensor] = None):
     return s
 
 
+def _claim_sink(param, like: Optional[torch.Tensor] = None):
+    """``grad_sink`` for ONE pending backward: a direct write overwrites, so a parameter that is used a second time
+    before the first use's backward has run (roll-out / BPTT, a loss that calls the model twice, micro-batch
+    accumulation with retained graphs) must not take the sink again - that use returns its gradient to autograd,
+    which accumulates it.  The first use's direct write then ZEROES nothing: to stay exact the first claim is
+    revoked as well (``_deno_sink_shared``), i.e. once a parameter is seen in two live graphs every use accumulates
+    through autograd until the sink is registered afresh (``FlatGradients.direct_writes``)."""
+    if param is None:
+        return None
+    s = grad_sink(param, like)
+    if s is None:
+        return None
+    if getattr(param, "_deno_sink_shared", False):
+        return None
+    if getattr(param, "_deno_sink_pending", 0) > 0:
+        param._deno_sink_shared = True       # a second live use: the sink cannot be used for either of them
+        return None
+    param._deno_sink_pending = 1
+    return s
+
+
+def _resolve_sink(param, sink):
+    """Backward-time view of a sink claimed in forward: None once the parameter has been seen in a second live graph
+    (the other use accumulates through autograd into the same ``.grad`` memory, which a direct write would clobber)."""
+    if sink is None or param is None or getattr(param, "_deno_sink_shared", False):
+        return None
+    return sink
+
+
+def _release_sink(param):
+    if param is not None and getattr(param, "_deno_sink_pending", 0) > 0:
+        param._deno_sink_pending = 0
+
+
 class _SpectralConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, lin_w, lin_b, modes, act, *weights):
+    def forward(ctx, x, lin_w, lin_b, modes, act, save, *weights):
         L = lib()
         _check_input(x, "input")
         ndim = x.dim() - 2
@@ -106,7 +171,9 @@ class _SpectralConvFn(torch.autograd.Function):
             _check_weight(w, cin, cout, modes, j)
         d = _capi.make_desc(B, cin, cout, spatial, modes, act)
 
-        needs_grad = any(ctx.needs_input_grad)
+        # ``save`` = grad mode of the CALLER (inside Function.forward it is always off): under torch.no_grad()
+        # (validation, roll-out inference) nothing is saved, so act'(z) and the spectrum are neither allocated nor written
+        needs_grad = bool(save) and any(ctx.needs_input_grad)
         xc = x.contiguous()
         wc = [w.contiguous() for w in weights]
         lw = lin_w.contiguous()
@@ -120,6 +187,7 @@ class _SpectralConvFn(torch.autograd.Function):
             xhat = torch.empty((B, cin, nmodes), dtype=torch.complex64, device=dev) if needs_grad else None
             nws = L.deno_spectral_workspace_bytes(C.byref(d), 0)
             ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+            _poison(ws, y, z, xhat)
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = L.deno_spectral_fwd(C.byref(d), xc.data_ptr(), _capi.pointer_array([w.data_ptr() for w in wc]),
                                      lw.data_ptr(), None if lb is None else lb.data_ptr(), tw.data_ptr(),
@@ -129,8 +197,9 @@ class _SpectralConvFn(torch.autograd.Function):
             _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
         if needs_grad:
             ctx.save_for_backward(xc, z, xhat, lw, *wc)
-            ctx.sinks = (grad_sink(lin_w, lw), None if lin_b is None else grad_sink(lin_b, lb),
-                         [grad_sink(w, c) for w, c in zip(weights, wc)])
+            ctx.sinks = (_claim_sink(lin_w, lw), None if lin_b is None else _claim_sink(lin_b, lb),
+                         [_claim_sink(w, c) for w, c in zip(weights, wc)])
+            ctx.sink_owners = [lin_w, lin_b] + list(weights)
             ctx.desc = d
             ctx.has_bias = lin_b is not None
             ctx.weight_meta = [(w.dtype, tuple(w.shape)) for w in weights]
@@ -151,6 +220,9 @@ class _SpectralConvFn(torch.autograd.Function):
             tw = _twiddles(d, dev)
             gx = torch.empty_like(xc) if need_x else None
             s_lw, s_lb, s_w = ctx.sinks
+            owners = ctx.sink_owners
+            s_lw, s_lb = _resolve_sink(owners[0], s_lw), _resolve_sink(owners[1], s_lb)
+            s_w = [_resolve_sink(o, sk) for o, sk in zip(owners[2:], s_w)]
             gws = [sk if sk is not None else torch.empty(shape, dtype=dtype, device=dev)
                    for sk, (dtype, shape) in zip(s_w, ctx.weight_meta)] if need_w else None
             glw = (s_lw if s_lw is not None else torch.empty_like(lw)) if need_lw else None
@@ -158,6 +230,8 @@ class _SpectralConvFn(torch.autograd.Function):
                 if (need_lb and ctx.has_bias) else None
             nws = L.deno_spectral_workspace_bytes(C.byref(d), 1)
             ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+            _poison(ws, gx, glw if s_lw is None else None, glb if s_lb is None else None,
+                    *([g for g, sk in zip(gws, s_w) if sk is None] if gws is not None else []))
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = L.deno_spectral_bwd(C.byref(d), gy.data_ptr(), xc.data_ptr(), z.data_ptr(), xhat.data_ptr(),
                                      _capi.pointer_array([w.data_ptr() for w in wc]), lw.data_ptr(), tw.data_ptr(),
@@ -167,9 +241,11 @@ class _SpectralConvFn(torch.autograd.Function):
                                      ws.data_ptr(), nws, stream)
             _capi.check(L, rc, "deno_spectral_bwd")
             _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
+        for owner in ctx.sink_owners:
+            _release_sink(owner)
         # gradients written straight into a registered sink are not handed to autograd (nothing left to accumulate)
         grads_w = tuple(None if sk is not None else g for sk, g in zip(s_w, gws)) if gws is not None else (None,) * len(wc)
-        return (gx, None if s_lw is not None else glw, None if s_lb is not None else glb, None, None) + grads_w
+        return (gx, None if s_lw is not None else glw, None if s_lb is not None else glb, None, None, None) + grads_w
 
 
 def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor], lin_w: torch.Tensor,
@@ -183,4 +259,4 @@ def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor], lin_w: torch
     modes = _normalize_modes(modes, x.dim() - 2)
     if activation not in _capi.ACTIVATION_IDS:
         raise ValueError(f"unknown activation {activation!r}")
-    return _SpectralConvFn.apply(x, lin_w, lin_b, modes, activation, *weights)
+    return _SpectralConvFn.apply(x, lin_w, lin_b, modes, activation, torch.is_grad_enabled(), *weights)

@@ -88,6 +88,14 @@ class FlatGradients:
         calls the model several times before ``backward``): a direct write overwrites, it does not accumulate."""
         for p in self.params:
             p._deno_grad_sink = p.grad if enable else None
+        self.reset_pending()
+
+    def reset_pending(self):
+        """Forget claims left behind by a forward whose backward never ran (an evaluation with grad mode on) and the
+        "used in two live graphs" marks; called when sinks are (de)registered and at the start of every eager step."""
+        for p in self.params:
+            p._deno_sink_pending = 0
+            p._deno_sink_shared = False
 
     def zero(self):
         self.flat.zero_()

@@ -47,7 +47,11 @@ class TrainStep:
                  overlap_allreduce: Optional[bool] = None):
         """``x``/``grid``/``target`` are example device tensors fixing the shapes; later calls copy new
         data into static buffers.  ``forward_fn(model, x, grid, target) -> loss`` overrides the default
-        single model call (e.g. the 10-step autoregressive rollout of Demo/Turbulence_2d+t)."""
+        single model call (e.g. the 10-step autoregressive rollout of Demo/Turbulence_2d+t).
+
+        Construction runs ``warmup`` throw-away iterations on the example batch (lazy initialisation, then graph
+        capture) and then RESTORES the parameters and zeroes the optimiser state: the model leaves the constructor
+        with the weights it came in with, and the first ``step()`` is Adam's step 1."""
         self.model = model
         self.loss_fn = loss_fn
         self.forward_fn = forward_fn
@@ -88,6 +92,7 @@ class TrainStep:
             if covered != self.grads.flat.numel():
                 raise RuntimeError("stage buckets do not cover the flat gradient buffer")
             model._stage_done = self._reduce_stage
+        self._fused_dp = False            # set by _setup_fused_dp() below when the multicast path is available
         self.loss = torch.zeros((), device=x.device)
         self._copy_stream = None          # input pipeline (prefetch): created on first use
         self._staged = None
@@ -111,6 +116,7 @@ class TrainStep:
         self._reduce_bucket(self._stage_grads[i])
 
     def _forward_backward(self):
+        self.grads.reset_pending()       # claims left by a forward whose backward never ran (functional._claim_sink)
         if not self._skip_zero:
             self.grads.zero()
         if self.forward_fn is not None:
@@ -125,7 +131,35 @@ class TrainStep:
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.AVG, group=self.group)
         self.loss.copy_(loss.detach())
 
+    def _snapshot(self):
+        """Parameters before the warm-up iterations (the optimiser TrainStep creates starts from zero moments)."""
+        with torch.no_grad():
+            if self.flat_params is not None:
+                return self.flat_params.flat.clone()
+            return [p.detach().clone() for p in self.model.parameters()]
+
+    def _restore(self, snap):
+        """Undo the warm-up: parameters back to the snapshot, Adam moments and step count back to zero - IN PLACE, the
+        captured graph keeps pointing at these tensors.  After construction the model and the optimiser are exactly
+        as the caller handed them over; the first ``step()`` is the first update (bias-correction step 1)."""
+        with torch.no_grad():
+            if self.flat_params is not None:
+                self.flat_params.flat.copy_(snap)
+                self.opt.exp_avg.zero_()
+                self.opt.exp_avg_sq.zero_()
+                self.opt.step_t.zero_()
+            else:
+                for p, q in zip(self.model.parameters(), snap):
+                    p.copy_(q)
+                for st in self.opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            self.grads.zero()
+            self.loss.zero_()
+
     def _capture(self, warmup: int):
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -134,6 +168,7 @@ class TrainStep:
                 if not (self._overlap or self._ingraph):
                     self.grads.all_reduce_mean(self.group)
                 self.opt.step()
+            self._restore(snap)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._g_bwd = torch.cuda.CUDAGraph()
@@ -149,12 +184,34 @@ class TrainStep:
         with torch.cuda.graph(self._g_opt):
             self.opt.step()
 
+    def allreduce_description(self) -> str:
+        """How this step combines gradients across ranks (bench.py's ``config.allreduce``)."""
+        if self.world == 1:
+            return "none"
+        if self._fused_dp:
+            return ("fused all-reduce + Adam kernel over NVLink multicast (multimem.ld_reduce of the flat gradient, "
+                    "update, multimem.st of the new parameters) inside the step graph")
+        if self._overlap:
+            return "per stage, overlapped with the backward, inside the graph"
+        if self._ingraph:
+            return "one flat averaged NCCL all-reduce inside the step graph"
+        return "one flat NCCL all-reduce between the backward and the optimiser graph"
+
     def close(self):
         """Drop the captured graphs.  Needed before ``dist.destroy_process_group()`` when the all-reduce was captured
         (a live graph keeps NCCL kernels referenced and communicator teardown waits for them forever)."""
         torch.cuda.synchronize()
         self._g_bwd = self._g_opt = None
         self.use_graph = False
+        # the parameters keep their ``.grad`` views but no longer advertise them as direct-write targets: any other
+        # backward on this model (gradient accumulation, a second loss) goes through autograd's accumulation again
+        self.grads.direct_writes(False)
+
+    def __del__(self):
+        try:
+            self.grads.direct_writes(False)
+        except Exception:      # interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------------------------
     def load(self, x=None, grid=None, target=None, non_blocking: bool = True):

@@ -70,6 +70,11 @@ typedef struct deno_spectral_desc {
 int deno_spectral_abi_version(void);
 const char* deno_last_error(void);
 
+/* The DENO_* switches (DENO_SPECTRAL_PATH = auto | simt | tc, and the experiment switches listed in csrc/capi.cu)
+ * are read from the environment once, at the first call that needs them.  deno_reload_env() reads them again
+ * (tests that flip DENO_SPECTRAL_PATH between cases call it; a product process never needs to). */
+int deno_reload_env(void);
+
 /* Number of retained complex modes M (1-D m; 2-D 2*m1*m2; 3-D 4*m1*m2*m3); 0 on a bad descriptor. */
 size_t deno_spectral_num_modes(const deno_spectral_desc* desc);
 
@@ -142,7 +147,8 @@ int deno_profile_end(deno_profile_record* records, int capacity);
 
 /* Phase-timing scratch of the warp-specialised kernels (64 x int64 clock64() sums written by CTA 0;
  * slots documented in spectral_tc.cuh).  Copies it to `host`, optionally clears it.  Synchronises the
- * device: measurement aid only. */
+ * device: measurement aid only.  The probe is compiled only into the -DDENO_PHASE_PROBE variant of the library
+ * (tools/phase_probe.py); the product build returns zeros. */
 int deno_debug_read(long long* host, int count, int clear);
 
 #ifdef __cplusplus

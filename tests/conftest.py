@@ -24,3 +24,22 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def set_deno_env(monkeypatch, name, value):
+    """Set a DENO_* switch for this test and make the library read it (it reads the environment once)."""
+    monkeypatch.setenv(name, value)
+    from deno4pytorch_b200.functional import reload_env
+    reload_env()
+
+
+@pytest.fixture(autouse=True)
+def _deno_env_is_fresh(request):
+    """Every GPU test starts with the library's switches re-read from the (restored) environment, so a switch set by
+    the previous test cannot leak.  DENO_POISON=1 in the environment poisons every output / scratch buffer."""
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            from deno4pytorch_b200.functional import reload_env
+            reload_env()
+    yield

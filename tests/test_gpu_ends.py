@@ -74,7 +74,8 @@ def test_lift_matches_float64_torch_ops(case):
 @pytest.mark.parametrize("case", CASES, ids=[str(c[5]) for c in CASES])
 def test_projection_matches_float64_torch_ops(case, path, monkeypatch):
     from deno4pytorch_b200.FNOs import _ProjFn
-    monkeypatch.setenv("DENO_SPECTRAL_PATH", path)      # the fc1 weight gradient reuses the bypass_wgrad kernels
+    from conftest import set_deno_env
+    set_deno_env(monkeypatch, "DENO_SPECTRAL_PATH", path)      # the fc1 weight gradient reuses the bypass_wgrad kernels
     B, Cw, Hd, Kx, O, spatial, pad = case
     nd = len(spatial)
     t, g = _make(case, 4)

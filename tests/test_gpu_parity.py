@@ -14,8 +14,9 @@ TOL = 1e-5
 @pytest.fixture(params=["simt", "auto"], autouse=True)
 def spectral_path(request, monkeypatch):
     """Every parity test runs twice: SIMT kernels only, and the default dispatch (tcgen05 kernels
-    wherever they cover the shape).  The library reads DENO_SPECTRAL_PATH on every call."""
-    monkeypatch.setenv("DENO_SPECTRAL_PATH", request.param)
+    wherever they cover the shape).  The library reads DENO_SPECTRAL_PATH once: set_deno_env() makes it re-read."""
+    from conftest import set_deno_env
+    set_deno_env(monkeypatch, "DENO_SPECTRAL_PATH", request.param)
     return request.param
 
 
@@ -70,9 +71,9 @@ def test_model_matches_reference_fixture_and_state_dict_roundtrip(name):
     y = model(x, g["inputs"]["grid"].to(_dev()))
     assert rel_l2(y.cpu(), g["out"]) < TOL
     (y * g["cot"].to(_dev())).sum().backward()
-    assert rel_l2(x.grad.cpu(), g["grad_inputs"]["x"]) < 2e-5
+    assert rel_l2(x.grad.cpu(), g["grad_inputs"]["x"]) < TOL
     for k, p in model.named_parameters():
-        assert rel_l2(p.grad.cpu(), g["grads"][k]) < 2e-5, k
+        assert rel_l2(p.grad.cpu(), g["grads"][k]) < TOL, k
     back = {k: v.cpu() for k, v in model.state_dict().items()}
     assert set(back) == set(g["params"])
     for k in back:
@@ -273,10 +274,11 @@ def test_trainstep_fused_adam_and_graph_match_oracle(use_graph):
     grid = fno_port.make_grid(4, (13, 13))
     port = fno_port.PortTrainer(params, ndim=2, modes=(4, 4), depth=2, padding=3)
     model = model.to(_dev())
-    step = TrainStep(model, xs[0].to(_dev()), grid.to(_dev()), ts[0].to(_dev()), use_graph=use_graph, warmup=1)
-    # TrainStep's warm-up / capture ran optimiser steps on the example batch: restart both sides from the same state
-    model.load_state_dict({k: v.to(_dev()) for k, v in params.items()})
-    step.opt.exp_avg.zero_(); step.opt.exp_avg_sq.zero_(); step.opt.step_t.zero_()
+    step = TrainStep(model, xs[0].to(_dev()), grid.to(_dev()), ts[0].to(_dev()), use_graph=use_graph, warmup=2)
+    # TrainStep's warm-up iterations are undone by the constructor: parameters and optimiser state are untouched
+    for k, v in model.state_dict().items():
+        assert torch.equal(v.cpu(), params[k]), k
+    assert float(step.opt.step_t) == 0.0 and float(step.opt.exp_avg.abs().max()) == 0.0
     for x, t in zip(xs, ts):
         ref_loss = port.step(x, grid, t)
         loss = float(step(x.to(_dev()), grid.to(_dev()), t.to(_dev())))

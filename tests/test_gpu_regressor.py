@@ -5,7 +5,8 @@ runs on the CUDA kernels unchanged.  Its use of the layers differs from the FNO 
 real-view (``use_complex=False``) weights - also in 2-D, the variant the reference's own layer crashes on -, the default
 ``norm='ortho'``, ``silu``, ``in_dim != out_dim``, the last layer's activation swapped for an ``Identity`` module, dropout.
 The test restates the regressor's forward (permute, layers, permute, two-layer MLP; lines 417-470) over this repo's layers
-on the GPU and over the CPU oracle with the same parameters.  Tolerance 1e-5 relative L2."""
+on the GPU and over the CPU oracle with the same parameters, and compares the output, the input gradient and EVERY
+parameter gradient.  Tolerance 1e-5 relative L2."""
 import pytest
 import torch
 import torch.nn as nn
@@ -49,21 +50,30 @@ class _Regressor(nn.Module):
         return self.regressor(x)
 
 
-def _oracle_forward(model, x, modes, activation, last_activation):
+def _leaf64(t):
+    return t.detach().cpu().double().requires_grad_(True)
+
+
+def _oracle_params(model):
+    """float64 leaf copies of every parameter the regressor owns, keyed like ``model.named_parameters()``."""
+    return {k: _leaf64(p) for k, p in model.named_parameters()}
+
+
+def _oracle_forward(model, p64, x, modes, activation, last_activation):
     from oracle import fno_port
     h = x.movedim(-1, 1)
     n = len(model.spectral_conv)
     for i, layer in enumerate(model.spectral_conv):
-        ws = [w.detach().cpu().double() for w in layer._weights()]
-        ws = [torch.view_as_complex(w.contiguous()) if not w.is_complex() else w for w in ws]
+        nblk = len(layer._weights())
+        ws = [torch.view_as_complex(p64[f"spectral_conv.{i}.weights{j + 1}"]) for j in range(nblk)]   # real-view leaves
         act = activation if (last_activation or i + 1 < n) else "identity"
-        h = fno_port.spectral_conv(h, ws, layer.linear.weight.detach().cpu().double(), layer.linear.bias.detach().cpu().double(),
+        h = fno_port.spectral_conv(h, ws, p64[f"spectral_conv.{i}.linear.weight"], p64[f"spectral_conv.{i}.linear.bias"],
                                    modes, activation=act, norm="ortho")
     h = h.movedim(1, -1)
-    lin1, actm, lin2 = model.regressor
-    h = torch.nn.functional.linear(h, lin1.weight.detach().cpu().double(), lin1.bias.detach().cpu().double())
+    _, actm, _ = model.regressor
+    h = torch.nn.functional.linear(h, p64["regressor.0.weight"], p64["regressor.0.bias"])
     h = actm(h)
-    return torch.nn.functional.linear(h, lin2.weight.detach().cpu().double(), lin2.bias.detach().cpu().double())
+    return torch.nn.functional.linear(h, p64["regressor.2.weight"], p64["regressor.2.bias"])
 
 
 CASES = [
@@ -95,11 +105,16 @@ def test_regressor_composition_matches_oracle(case):
     (y * cot.to(dev)).sum().backward()
     torch.cuda.synchronize()
     x64 = x.double().requires_grad_(True)
-    ref = _oracle_forward(model, x64, modes, activation, last_act)
+    p64 = _oracle_params(model)
+    ref = _oracle_forward(model, p64, x64, modes, activation, last_act)
     (ref * cot.double()).sum().backward()
     assert y.shape == ref.shape
     assert rel_l2(y.detach().cpu(), ref.detach()) < TOL
     assert rel_l2(xg.grad.cpu(), x64.grad) < TOL
+    # every parameter gradient: the real-view spectral weights, the bypass convs, the regressor MLP
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert rel_l2(p.grad.cpu(), p64[k].grad) < TOL, k
     # training mode with dropout p > 0 runs (the 2-D layer drops the spectral branch's input, spectral_layers.py:189-191)
     model.train()
     out = model(xg.detach())

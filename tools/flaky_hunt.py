@@ -32,7 +32,7 @@ bad = 0
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 25
 for rep in range(reps):
     for path in ("simt", "auto"):
-        os.environ["DENO_SPECTRAL_PATH"] = path
+        os.environ["DENO_SPECTRAL_PATH"] = path; __import__("deno4pytorch_b200.functional", fromlist=["reload_env"]).reload_env()
         for ci, (shape, x, ws, lw, lb, cot, ref, gref) in enumerate(cases):
             xg = x.to(dev).requires_grad_(True)
             wg = [w.to(dev).requires_grad_(True) for w in ws]

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from deno4pytorch_b200.functional import spectral_conv
-os.environ["DENO_SPECTRAL_PATH"] = sys.argv[1] if len(sys.argv) > 1 else "simt"
+os.environ["DENO_SPECTRAL_PATH"] = sys.argv[1] if len(sys.argv) > 1 else "simt"; __import__("deno4pytorch_b200.functional", fromlist=["reload_env"]).reload_env()
 B, cin, cout, spatial, modes, act = (2, 6, 6, (128, 40), (64, 16), "tanh")
 gen = torch.Generator().manual_seed(11)
 dev = torch.device("cuda", 0)

@@ -21,7 +21,7 @@ r64 = fno_port.spectral_conv(x64, w64, lw.double(), lb.double(), modes, activati
 print("fp32 oracle vs fp64 oracle: y %.2e gx %.2e" % (rel_l2(ref, r64), rel_l2(xr.grad, x64.grad)))
 dev = torch.device("cuda", 0)
 for path in ["simt", "auto", "simt", "auto"]:
-    os.environ["DENO_SPECTRAL_PATH"] = path
+    os.environ["DENO_SPECTRAL_PATH"] = path; __import__("deno4pytorch_b200.functional", fromlist=["reload_env"]).reload_env()
     xg = x.to(dev).requires_grad_(True); wg = [w.to(dev).requires_grad_(True) for w in ws]
     lwg = lw.to(dev).requires_grad_(True); lbg = lb.to(dev).requires_grad_(True)
     y = spectral_conv(xg, wg, lwg, lbg, modes, act); (y * cot.to(dev)).sum().backward(); torch.cuda.synchronize()
@@ -30,7 +30,7 @@ for path in ["simt", "auto", "simt", "auto"]:
         rel_l2(y.cpu(), r64), rel_l2(xg.grad.cpu(), x64.grad)))
 
 # nondeterminism hunt: the GPU path repeated (bitwise) and the fp32 CPU oracle repeated
-os.environ["DENO_SPECTRAL_PATH"] = "simt"
+os.environ["DENO_SPECTRAL_PATH"] = "simt"; __import__("deno4pytorch_b200.functional", fromlist=["reload_env"]).reload_env()
 first = None
 ndiff = 0
 worst = 0.0
