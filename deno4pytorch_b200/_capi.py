@@ -90,6 +90,9 @@ _PROTOTYPES = {
     "deno_debug_read": (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.c_int]),
     "deno_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "deno_dp_fused_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p]),
     "deno_spectral_num_modes": (C.c_size_t, [_DESC_P]),
     "deno_spectral_twiddle_bytes": (C.c_size_t, [_DESC_P]),
     "deno_spectral_twiddle_fill": (C.c_int, [_DESC_P, C.c_void_p, C.c_size_t]),

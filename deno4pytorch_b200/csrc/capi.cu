@@ -6,6 +6,7 @@
 // synchronisation, no global mutable state (except the opt-in profiling list).
 #include "../../include/deno_spectral.h"
 #include "../../include/deno_fno.h"
+#include "../../include/deno_dp.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -18,8 +19,10 @@
 
 #include "spectral_simt.cuh"
 #include "fno_pointwise.cuh"
+#include "dp_fused.cuh"
 #ifndef DENO_EMULATE
 #include "spectral_tc.cuh"
+#include "spectral_tma.cuh"
 #include "fno_proj_tc.cuh"
 #endif
 
@@ -982,6 +985,79 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
 #endif
 
 #ifndef DENO_EMULATE
+// ------------------------------------------------------------------------------------------
+// Tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// fp32 matrix [outer][inner] with `row_bytes` between rows, boxes of [box_outer][32 floats], SWIZZLE_128B, zero OOB fill
+bool make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long outer,
+                  unsigned long long row_bytes, unsigned box_outer) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_bytes & 15) != 0 || box_outer == 0 || box_outer > 256) return false;
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstr[1] = {row_bytes};
+  const cuuint32_t box[2] = {32, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// TMA + SWIZZLE_128B bypass weight gradient (spectral_tma.cuh); returns the number of partials written (one per CTA),
+// -1 if the shape / alignment is outside the kernel, -2 on a CUDA error.
+int try_launch_bypass_wgrad_tma(const Shape& s, const float* gz, const float* x, float* partial, cudaStream_t st, int gz_tps = 0) {
+  if (!options().wgrad_tma) return -1;
+  const int COs = round_up(s.CO, 8), CIs = round_up(s.CI, 8);
+  if (COs > 128 || CIs > 128) return -1;
+  int NS = 4;
+  while (NS > 1 && (NS * COs > 128 || NS * CIs > 128)) NS /= 2;
+  if ((NS * CIs) % 16 != 0) return -1;
+  if ((s.S % 4) != 0) return -1;                          // rows of the [B*C][S] matrices must start 16-byte aligned
+  const int nbatch = s.B;                                  // S spans the whole (X, H, W) volume of a batch entry
+  CUtensorMap tm_a, tm_b;
+  if (gz_tps > 0) {
+    if (!make_tmap_2d(&tm_a, gz, 128, (unsigned long long)nbatch * gz_tps * s.CO, 512, (unsigned)COs)) return -1;
+  } else {
+    if (!make_tmap_2d(&tm_a, gz, (unsigned long long)s.S, (unsigned long long)nbatch * s.CO, (unsigned long long)s.S * 4, (unsigned)COs)) return -1;
+  }
+  if (!make_tmap_2d(&tm_b, x, (unsigned long long)s.S, (unsigned long long)nbatch * s.CI, (unsigned long long)s.S * 4, (unsigned)CIs)) return -1;
+  tc::WgradTmaParams p;
+  p.partial = partial;
+  p.CO = s.CO; p.CI = s.CI; p.COs = COs; p.CIs = CIs; p.NS = NS;
+  p.nchunks = (int)((s.S + 31) / 32);
+  p.ngroups = (nbatch + NS - 1) / NS;
+  p.ntiles = p.ngroups * p.nchunks;
+  p.a_rows_per_batch = s.CO; p.b_rows_per_batch = s.CI;
+  p.a_tps = gz_tps;
+  const int stage_bytes = tc::wgrad_tma_stage_bytes(NS * CIs);
+  int nst = (kMaxSmemBytes - 2048) / stage_bytes;
+  if (nst > 4) nst = 4;
+  if (nst < 2) return -1;
+  if ((size_t)NS * s.CO * s.CI * 4 > (size_t)nst * stage_bytes) return -1;   // epilogue staging lives in the stages
+  p.nstages = nst;
+  const size_t smem = (size_t)nst * stage_bytes + 1024;
+  int grid = 148;
+  if (grid > p.ntiles) grid = p.ntiles;
+  if (allow_smem(tc::bypass_wgrad_tma_kernel, smem, "bypass_wgrad_tma") != DENO_OK) return -2;
+  prof_before("bypass_wgrad_tma", st);
+  DENO_LAUNCH((tc::bypass_wgrad_tma_kernel), dim3(grid), dim3(tc::kWtThreads), smem, st, tm_a, tm_b, p);
+  if (check_launch("bypass_wgrad_tma", st) != DENO_OK) return -2;
+  return grid;
+}
+
 bool wgrad_tc_eligible(const Shape& s) {
   if (path_pref() == PathPref::Simt) return false;
   const int COs = round_up(s.CO, 8), CIs = round_up(s.CI, 8);
@@ -1004,7 +1080,8 @@ int launch_bypass_wgrad(const Shape& s, const float* gz, const float* x, const f
   if (rc != DENO_OK) return rc;
 #ifndef DENO_EMULATE
   if (path_pref() != PathPref::Simt) {
-    const int nparts = try_launch_bypass_wgrad_tc(s, gz, x, partial, st);
+    int nparts = try_launch_bypass_wgrad_tma(s, gz, x, partial, st);
+    if (nparts == -1) nparts = try_launch_bypass_wgrad_tc(s, gz, x, partial, st);
     if (nparts == -2) return DENO_E_CUDA;
     if (nparts > 0) {
       WgradReduceParams r;
@@ -1245,6 +1322,39 @@ int deno_adam_step(float* p, const float* g, float* m, float* v, size_t n, float
   prof_before("adam_flat", st);
   DENO_LAUNCH(adam_flat_kernel, dim3((unsigned)blocks), dim3(256), 0, st, a);
   return check_launch("adam_flat", st);
+}
+
+int deno_dp_fused_adam(float* p_local, float* p_mc, float* g_mc, float* m, float* v, size_t n, int rank, int world,
+                       void* signal_pads, int write_back_grads, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, const float* step, void* stream) {
+  g_launches = 0;
+  if (!p_local || !p_mc || !g_mc || !m || !v || !signal_pads || !step)
+    return fail(DENO_E_INVALID, "deno_dp_fused_adam: null pointer argument");
+  if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(DENO_E_INVALID, "deno_dp_fused_adam: bad rank / world");
+  if ((n % 4) != 0) return fail(DENO_E_INVALID, "deno_dp_fused_adam: n must be a multiple of 4 floats");
+  if (((reinterpret_cast<uintptr_t>(p_local) | reinterpret_cast<uintptr_t>(p_mc) | reinterpret_cast<uintptr_t>(g_mc) |
+        reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) != 0)
+    return fail(DENO_E_INVALID, "deno_dp_fused_adam: buffers must be 16-byte aligned");
+  if (n == 0) return DENO_OK;
+#ifndef DENO_EMULATE
+  DpFusedParams a;
+  a.p_local = p_local; a.p_mc = p_mc; a.g_mc = g_mc; a.m = m; a.v = v; a.n = (long long)n;
+  a.rank = rank; a.world = world; a.signal_pads = static_cast<uint32_t**>(signal_pads);
+  a.write_back_grads = write_back_grads;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long per4 = ((long long)n / 4 + world - 1) / world;          // float4 of one rank's slice
+  long long blocks = (per4 + 2LL * kDpThreads - 1) / (2LL * kDpThreads);
+  if (blocks > kDpMaxBlocks) blocks = kDpMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  prof_before("dp_allreduce_adam", st);
+  // the blocks of all ranks wait for each other: never more blocks than can be resident (32 << 148 SMs)
+  dp_allreduce_adam_kernel<<<dim3((unsigned)blocks), dim3(kDpThreads), 0, st>>>(a);
+  return check_launch("dp_allreduce_adam", st);
+#else
+  (void)lr; (void)beta1; (void)beta2; (void)eps; (void)weight_decay; (void)write_back_grads; (void)stream;
+  return fail(DENO_E_UNSUPPORTED, "deno_dp_fused_adam: not available in the CPU emulation build");
+#endif
 }
 
 int deno_debug_read(long long* host, int count, int clear) {
@@ -1608,7 +1718,8 @@ int deno_fno_proj_bwd(const deno_fno_desc* desc, const float* gy, const float* h
   float* wpart = reinterpret_cast<float*>(ws + w.wpart);
 #ifndef DENO_EMULATE
   if (done) {                                          // gt is blocked: tensor-core weight gradient only
-    const int np = try_launch_bypass_wgrad_tc(s, p.gt, h, wpart, st, (f.g.nppts + 127) / 128);
+    int np = try_launch_bypass_wgrad_tma(s, p.gt, h, wpart, st, (f.g.nppts + 127) / 128);
+    if (np == -1) np = try_launch_bypass_wgrad_tc(s, p.gt, h, wpart, st, (f.g.nppts + 127) / 128);
     if (np <= 0) return np == -2 ? DENO_E_CUDA : fail(DENO_E_UNSUPPORTED, "bypass_wgrad_tc refused the projection shape");
     return launch_reduce(wpart, np, f.Hd * f.C, f.Hd * f.C, f.Hd * f.C, gw1, nullptr, "bypass_wgrad_reduce", st);
   }

@@ -53,7 +53,9 @@ def setup_ddp(backend: Optional[str] = None, verbose: bool = False):
 class FlatGradients:
     """Owns one flat fp32 buffer and makes every parameter's ``.grad`` a view into it."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], alloc=None):
+        """``alloc(numel, device) -> flat fp32 tensor`` overrides where the flat buffer lives (symmetric memory for the
+        fused multicast exchange); default is an ordinary device tensor."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -64,7 +66,11 @@ class FlatGradients:
                 raise TypeError(f"unsupported parameter dtype {p.dtype}")
             n = p.numel() * (2 if p.is_complex() else 1)
             sizes.append((n + 3) // 4 * 4)  # keep every view 16-byte aligned
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        if alloc is not None:
+            self.flat = alloc(sum(sizes), device)
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
         self.spans = {}            # id(param) -> (offset, padded length) inside ``flat``
         off = 0
         for p, n in zip(self.params, sizes):
@@ -124,10 +130,14 @@ class FlatParameters:
     dtypes - hence the state dict - are unchanged) and pairs it with a ``FlatGradients`` buffer of the same
     layout, so the optimiser can be a single fused kernel over flat arrays."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
-        self.grads = FlatGradients(params)
+    def __init__(self, params: Iterable[torch.nn.Parameter], alloc=None):
+        self.grads = FlatGradients(params, alloc=alloc)
         self.params = self.grads.params
-        self.flat = torch.zeros_like(self.grads.flat)
+        if alloc is not None:
+            self.flat = alloc(self.grads.flat.numel(), self.grads.flat.device)
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros_like(self.grads.flat)
         off = 0
         with torch.no_grad():
             for p in self.params:
@@ -165,6 +175,82 @@ class FlatAdam:
                                   self.eps, self.weight_decay, self.step_t.data_ptr(),
                                   torch.cuda.current_stream(f.flat.device).cuda_stream)
         _capi.check(L, rc, "deno_adam_step")
+        from .functional import _LAUNCHES
+        _LAUNCHES["count"] += 1
+
+
+class SymmetricFlatBuffers:
+    """Allocator + rendezvous of the flat buffers in SYMMETRIC memory (same size and offset on every rank, one
+    multicast mapping each) for the fused all-reduce + Adam kernel (include/deno_dp.h).  PyTorch's symmetric-memory
+    module is the plumbing: allocation, handle exchange, multicast binding, the signal pads."""
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm_mem = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.tensors: List[torch.Tensor] = []
+        self.handles = []
+
+    def alloc(self, numel: int, device) -> torch.Tensor:
+        t = self._symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.tensors.append(t)
+        return t
+
+    def rendezvous(self):
+        """Collective.  Returns False (on every rank, after agreeing) when any rank lacks multicast support."""
+        ok = 1
+        try:
+            self.handles = [self._symm_mem.rendezvous(t, self.group) for t in self.tensors]
+            for h in self.handles:
+                if not h.has_multicast_support or int(h.multicast_ptr) == 0:
+                    ok = 0
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.tensors[0].device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(flag.item())
+
+
+class FusedDPAdam:
+    """``FlatAdam`` for data-parallel training with the collective INSIDE the optimiser kernel: all-reduce(mean) of the
+    flat gradient through NVLink multicast, Adam on this rank's slice, multicast store of the new parameters
+    (``deno_dp_fused_adam``, csrc/dp_fused.cuh).  Replaces ``ncclAllReduce`` + ``adam_flat``.  The Adam moments are
+    sharded: ``exp_avg`` / ``exp_avg_sq`` hold valid values for this rank's slice only."""
+
+    def __init__(self, flat: FlatParameters, buffers: SymmetricFlatBuffers, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0, write_back_grads=False):
+        self.flat = flat
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(flat.flat)
+        self.exp_avg_sq = torch.zeros_like(flat.flat)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=flat.flat.device)
+        g_hdl, p_hdl = buffers.handles[0], buffers.handles[1]
+        assert buffers.tensors[0].data_ptr() == flat.grads.flat.data_ptr() and buffers.tensors[1].data_ptr() == flat.flat.data_ptr()
+        self._g_hdl, self._p_hdl = g_hdl, p_hdl          # keep the mappings alive
+        self.rank, self.world = g_hdl.rank, g_hdl.world_size
+        self.g_mc = int(g_hdl.multicast_ptr) + int(getattr(g_hdl, "offset", 0) or 0)
+        self.p_mc = int(p_hdl.multicast_ptr) + int(getattr(p_hdl, "offset", 0) or 0)
+        self.signal_pads = int(g_hdl.signal_pad_ptrs_dev)
+        if g_hdl.signal_pad_size < 4 * 32 * self.world:
+            raise RuntimeError("signal pad too small for the fused exchange")
+        self.write_back_grads = bool(write_back_grads)
+
+    def zero_grad(self):
+        self.flat.grads.zero()
+
+    def step(self):
+        from . import _capi
+        from ._lib import lib
+        L = lib()
+        f = self.flat
+        self.step_t.add_(1.0)
+        with torch.cuda.device(f.flat.device):
+            rc = L.deno_dp_fused_adam(f.flat.data_ptr(), self.p_mc, self.g_mc, self.exp_avg.data_ptr(),
+                                      self.exp_avg_sq.data_ptr(), f.flat.numel(), self.rank, self.world,
+                                      self.signal_pads, int(self.write_back_grads), self.lr, self.betas[0],
+                                      self.betas[1], self.eps, self.weight_decay, self.step_t.data_ptr(),
+                                      torch.cuda.current_stream(f.flat.device).cuda_stream)
+        _capi.check(L, rc, "deno_dp_fused_adam")
         from .functional import _LAUNCHES
         _LAUNCHES["count"] += 1
 

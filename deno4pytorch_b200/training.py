@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
-from .parallel import FlatAdam, FlatGradients, FlatParameters
+from .parallel import FlatAdam, FlatGradients, FlatParameters, FusedDPAdam, SymmetricFlatBuffers
 
 
 def _all_gradients_direct(model, x, grid) -> bool:
@@ -58,12 +58,39 @@ class TrainStep:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.sx, self.sg, self.st = x.clone(), grid.clone(), target.clone()
+        self._fused_dp = False
+        self.flat_params = None
         if fused_adam and x.is_cuda:
-            self.flat_params = FlatParameters(model.parameters())
+            # Data parallel on an NVSwitch box: gradients and parameters live in symmetric memory and ONE kernel does
+            # all-reduce + Adam + parameter broadcast over NVLink multicast (DENO_DP_FUSED=0: NCCL all-reduce + adam_flat)
+            want_fused = (self.world > 1 and dist.get_backend(group) == "nccl" and not overlap_allreduce
+                          and os.environ.get("DENO_DP_FUSED", "1") == "1" and os.environ.get("DENO_DP_OVERLAP", "0") != "1")
+            buffers = None
+            if want_fused:
+                try:
+                    buffers = SymmetricFlatBuffers(group)
+                    self.flat_params = FlatParameters(model.parameters(), alloc=buffers.alloc)
+                except Exception:
+                    buffers = None
+                flag = torch.tensor([1 if buffers is not None else 0], dtype=torch.int32, device=x.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # every rank or none
+                if flag.item() == 0:
+                    if buffers is not None:                                    # move the parameters back to plain memory
+                        self.flat_params = FlatParameters(model.parameters())
+                    buffers = None
+                elif not buffers.rendezvous():
+                    self.flat_params = FlatParameters(model.parameters())
+                    buffers = None
+            if self.flat_params is None:
+                self.flat_params = FlatParameters(model.parameters())
             self.grads = self.flat_params.grads
-            self.opt = FlatAdam(self.flat_params, lr=lr, betas=betas, weight_decay=weight_decay)
+            if buffers is not None:
+                self.opt = FusedDPAdam(self.flat_params, buffers, lr=lr, betas=betas, weight_decay=weight_decay,
+                                       write_back_grads=os.environ.get("DENO_DP_FUSED_WRITE_GRADS", "0") == "1")
+                self._fused_dp = True
+            else:
+                self.opt = FlatAdam(self.flat_params, lr=lr, betas=betas, weight_decay=weight_decay)
         else:
-            self.flat_params = None
             self.grads = FlatGradients(model.parameters())
             self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, weight_decay=weight_decay,
                                         capturable=use_graph, foreach=True)
@@ -76,12 +103,12 @@ class TrainStep:
         # backward() returns), so it overlaps the rest of the backward, and the whole step is ONE captured graph.
         if overlap_allreduce is None:     # opt-in (DENO_DP_OVERLAP=1) until it has been proven under graph capture on NCCL
             overlap_allreduce = os.environ.get("DENO_DP_OVERLAP", "0") == "1"
-        self._overlap = bool(overlap_allreduce and self.world > 1 and x.is_cuda and forward_fn is None
+        self._overlap = bool(overlap_allreduce and not self._fused_dp and self.world > 1 and x.is_cuda and forward_fn is None
                              and dist.get_backend(group) == "nccl" and _all_gradients_direct(model, x, grid))
         self._ar_stream = torch.cuda.Stream() if self._overlap else None
         # NCCL without the per-stage overlap: ONE averaged all-reduce of the flat buffer, captured in the same graph as
         # the backward and the optimiser (DENO_DP_INGRAPH=0 keeps it between two graphs, as gloo / eager runs do)
-        self._ingraph = bool(not self._overlap and self.world > 1 and x.is_cuda and use_graph
+        self._ingraph = bool(not self._overlap and not self._fused_dp and self.world > 1 and x.is_cuda and use_graph
                              and dist.get_backend(group) == "nccl" and os.environ.get("DENO_DP_INGRAPH", "1") == "1")
         if self._overlap:
             stages = [list(layer.parameters()) for layer in model.convs]
@@ -92,7 +119,6 @@ class TrainStep:
             if covered != self.grads.flat.numel():
                 raise RuntimeError("stage buckets do not cover the flat gradient buffer")
             model._stage_done = self._reduce_stage
-        self._fused_dp = False            # set by _setup_fused_dp() below when the multicast path is available
         self.loss = torch.zeros((), device=x.device)
         self._copy_stream = None          # input pipeline (prefetch): created on first use
         self._staged = None
@@ -165,14 +191,14 @@ class TrainStep:
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):   # also fills the twiddle cache and cuBLAS workspaces
                 self._forward_backward()
-                if not (self._overlap or self._ingraph):
+                if not (self._overlap or self._ingraph or self._fused_dp):
                     self.grads.all_reduce_mean(self.group)
                 self.opt.step()
             self._restore(snap)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._g_bwd = torch.cuda.CUDAGraph()
-        if self.world == 1 or self._overlap or self._ingraph:
+        if self.world == 1 or self._overlap or self._ingraph or self._fused_dp:
             # no separate collective between backward and optimiser: the whole step is one graph launch
             with torch.cuda.graph(self._g_bwd):
                 self._forward_backward()
@@ -279,7 +305,7 @@ class TrainStep:
                 self._g_opt.replay()
         else:
             self._forward_backward()
-            if not (self._overlap or self._ingraph):
+            if not (self._overlap or self._ingraph or self._fused_dp):
                 self.grads.all_reduce_mean(self.group)
             self.opt.step()
         if self._loss_slots is not None:
