@@ -134,10 +134,30 @@ ModeDecode make_decode(const Shape& s) {
 // Twiddle tables (host, fp64 -> fp32)
 // ------------------------------------------------------------------------------------------
 struct TwLayout {
-  size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, total;  // float offsets
+  size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, at_e1, at_a2, total;  // float offsets
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
   int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [2*N1 rows: hi, lo][Wp], A2 [hi|lo][KRp*Hp]
 };
+
+// Shape-only geometry of the TMA analysis kernel (independent of the planes-per-tile choice).
+struct AtGeom { bool ok; int g, HG, HGp, N1, KHp, nchunks, K2p; };
+AtGeom at_geom(const Shape& s) {
+  AtGeom a;
+  memset(&a, 0, sizeof(a));
+  if (s.ndim < 2) return a;
+  const int r = s.W % 4;
+  a.g = r == 0 ? 1 : (r == 2 ? 2 : 4);
+  if (s.H % a.g != 0) return a;
+  a.HG = s.H / a.g;
+  a.HGp = round_up(a.HG, 16);
+  a.N1 = round_up(2 * s.MW, 8);
+  a.KHp = round_up(s.KH, 8);
+  a.nchunks = (s.W + 31) / 32;
+  a.K2p = round_up(a.g * a.HGp, 32);
+  if (a.N1 > 32 || 4 * a.KHp > 128 || a.HG > 256 || a.g * a.HGp > 256) return a;
+  a.ok = true;
+  return a;
+}
 
 TwLayout tw_layout(const Shape& s) {
   TwLayout t;
@@ -157,6 +177,12 @@ TwLayout tw_layout(const Shape& s) {
   const bool an = (s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128);   // shapes the tensor-core analysis kernel can take
   t.an_e1 = off; off += an ? (size_t)2 * t.N1 * t.Wp : 0;
   t.an_a2 = off; off += an ? (size_t)2 * t.KRp * t.Hp : 0;
+  // TMA analysis kernel (spectral_tma.cuh): E image nchunks x [2 N1 rows][32], A2 image (K2p / 32) x [4 KHp rows][32],
+  // both already in their SWIZZLE_128B shared-memory layout
+  const AtGeom ag = at_geom(s);
+  off = (off + 63) / 64 * 64;                      // 256-byte aligned: the images are bulk-copied
+  t.at_e1 = off; off += ag.ok ? (size_t)ag.nchunks * 2 * ag.N1 * 32 : 0;
+  t.at_a2 = off; off += ag.ok ? (size_t)(ag.K2p / 32) * 4 * ag.KHp * 32 : 0;
   t.total = off;
   return t;
 }
@@ -411,6 +437,40 @@ int allow_smem(K kernel, size_t bytes, const char* what) {
   return DENO_OK;
 }
 
+#ifndef DENO_EMULATE
+// ------------------------------------------------------------------------------------------
+// Tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// fp32 matrix [outer][inner] with `row_bytes` between rows, boxes of [box_outer][32 floats], SWIZZLE_128B, zero OOB fill
+bool make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long outer,
+                  unsigned long long row_bytes, unsigned box_outer) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_bytes & 15) != 0 || box_outer == 0 || box_outer > 256) return false;
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstr[1] = {row_bytes};
+  const cuuint32_t box[2] = {32, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+#endif
+
 // Analysis operand images (see plane_analysis_tc_kernel): E1[n][y] (n = 2l: cos, 2l+1: -sin of 2 pi l y / W)
 // as ONE B operand image with 2 N1 rows (tf32 hi parts, then lo parts), and A2[r][x] (rows r < KH: cos, rows
 // KS0 + k: sin of 2 pi f_k x / H) as hi / lo A operand images.
@@ -449,8 +509,55 @@ void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
     }
 }
 
+// byte offset of element (row, k) of a K-major SWIZZLE_128B image made of [rows][32 fp32] chunks
+inline size_t sw128_off(int row, int k, int rows) {
+  return (size_t)(k >> 5) * rows * 128 + (size_t)row * 128 + (size_t)((((k & 31) >> 2) ^ (row & 7)) << 4) + (size_t)(k & 3) * 4;
+}
+
+// Operand images of plane_analysis_tma_kernel.  E rows n < N1: tf32 hi of (n = 2l: cos, 2l+1: -sin)(2 pi l w / W), rows
+// N1 + n: the lo parts; A2 rows grp * KHp + k (grp 0 cos hi, 1 sin hi, 2 cos lo, 3 sin lo of 2 pi f_k h / H) over the
+// permuted row index K' = j * HGp + hh with h = g * hh + j.
+void fill_analysis_tma_images(float* base, const Shape& s, const TwLayout& t) {
+  const AtGeom a = at_geom(s);
+  if (!a.ok) return;
+  const double two_pi = 6.283185307179586476925286766559;
+  float* e1 = base + t.at_e1;
+  const int ER = 2 * a.N1;
+  for (int n = 0; n < a.N1; ++n)
+    for (int w = 0; w < a.nchunks * 32; ++w) {
+      const int l = n / 2;
+      double v = 0.0;
+      if (l < s.MW && w < s.W) {
+        const double ang = two_pi * (double)(((long long)l * w) % s.W) / (double)s.W;
+        v = (n & 1) ? -sin(ang) : cos(ang);
+      }
+      const float h = tf32_mask((float)v);
+      e1[sw128_off(n, w, ER) / 4] = h;
+      e1[sw128_off(a.N1 + n, w, ER) / 4] = (float)(v - (double)h);
+    }
+  float* a2 = base + t.at_a2;
+  const int AR = 4 * a.KHp;
+  for (int k = 0; k < a.KHp; ++k)
+    for (int kp = 0; kp < a.K2p; ++kp) {
+      const int j = kp / a.HGp, hh = kp - j * a.HGp;
+      double c = 0.0, sn = 0.0;
+      if (k < s.KH && j < a.g && hh < a.HG) {
+        const long long hrow = (long long)a.g * hh + j;
+        const long long f = (k < s.mH) ? k : (long long)s.H - 2 * s.mH + k;
+        const double ang = two_pi * (double)((f * hrow) % s.H) / (double)s.H;
+        c = cos(ang);
+        sn = sin(ang);
+      }
+      const float ch = tf32_mask((float)c), sh = tf32_mask((float)sn);
+      a2[sw128_off(0 * a.KHp + k, kp, AR) / 4] = ch;
+      a2[sw128_off(1 * a.KHp + k, kp, AR) / 4] = sh;
+      a2[sw128_off(2 * a.KHp + k, kp, AR) / 4] = (float)(c - (double)ch);
+      a2[sw128_off(3 * a.KHp + k, kp, AR) / 4] = (float)(sn - (double)sh);
+    }
+}
+
 struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; const float* synth_ae;
-                const float* an_e1; const float* an_a2; };
+                const float* an_e1; const float* an_a2; const float* at_e1; const float* at_a2; };
 
 TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   const float* base = static_cast<const float*>(twiddles);
@@ -463,6 +570,8 @@ TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   p.synth_ae = base + t.synth_ae;
   p.an_e1 = base + t.an_e1;
   p.an_a2 = base + t.an_a2;
+  p.at_e1 = base + t.at_e1;
+  p.at_a2 = base + t.at_a2;
   return p;
 }
 
@@ -504,6 +613,73 @@ Options options() {
 PathPref path_pref() { return options().path; }
 
 #ifndef DENO_EMULATE
+// TMA + SWIZZLE_128B analysis (spectral_tma.cuh); -1 when the shape / alignment is outside the kernel's coverage.
+int try_launch_analysis_tma(const Shape& s, int channels, const float* u, const float* z, float* gz_out, float2* out,
+                            const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
+  if (!options().an_tma) return -1;
+  const AtGeom a = at_geom(s);
+  if (!a.ok) return -1;
+  const bool gz = (z != nullptr);
+  if ((reinterpret_cast<uintptr_t>(u) & 15) != 0) return -1;
+  if (gz && (((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gz_out)) & 15) != 0)) return -1;
+  tc::AnalysisTmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.H = s.H; p.W = s.W; p.g = a.g; p.HG = a.HG; p.HGp = a.HGp;
+  p.KH = s.KH; p.KHp = a.KHp; p.MW = s.MW; p.N1 = a.N1;
+  p.C = channels; p.X = s.X;
+  const long long NP = (long long)s.B * channels * s.X;
+  if (NP * a.HG >= (1LL << 31)) return -1;
+  p.NP = (int)NP;
+  p.nchunks = a.nchunks; p.K2p = a.K2p;
+  // planes per tile: two when that fits (stage-1 MMAs cost max(~75, N / 2) cycles whatever N is), one for the gz variant
+  // (three activation streams per plane: bandwidth-bound long before the tensor pipe) and when two do not fit
+  int bestP = 0, best_nsh = 0, best_nsl = 0;
+  for (int P = gz ? 1 : 2; P >= 1 && bestP == 0; --P) {
+    p.P = P; p.N = a.g * P * a.HGp; p.N2 = 2 * P * a.N1;
+    if (p.N > 256 || (p.N % 16) != 0 || 2 * p.N + p.N2 > 512) continue;
+    for (int nsh = 4; nsh >= 2 && bestP == 0; --nsh) {
+      p.nsh = nsh; p.nsl = 2;
+      if (tc::analysis_tma_smem(p, gz).total + 1024 <= kMaxSmemBytes) { bestP = P; best_nsh = nsh; best_nsl = 2; }
+    }
+  }
+  if (bestP == 0) return -1;
+  p.P = bestP; p.N = a.g * bestP * a.HGp; p.N2 = 2 * bestP * a.N1; p.nsh = best_nsh; p.nsl = best_nsl;
+  p.ntiles = (int)((NP + bestP - 1) / bestP);
+  p.e1 = tw.at_e1; p.a2 = tw.at_a2; p.cl = tw.cl; p.scale = scale; p.herm = herm; p.out = out;
+  p.u_base = u; p.z_base = z;
+  p.l2_prefetch = ((long long)s.H * s.W) % 4 == 0 ? 1 : 0;
+  tc::AnalysisTmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int j = 0; j < a.g; ++j) {
+    const long long off_bytes = (long long)j * s.W * 4;
+    const long long base_off = off_bytes & ~15LL;
+    p.shift[j] = (int)((off_bytes - base_off) / 4);
+    const unsigned long long inner = (unsigned long long)s.W + p.shift[j];
+    const unsigned long long outer = (unsigned long long)NP * a.HG;
+    const unsigned long long row_bytes = (unsigned long long)a.g * s.W * 4;
+    if (!make_tmap_2d(&maps.u[j], reinterpret_cast<const char*>(u) + base_off, inner, outer, row_bytes, (unsigned)a.HG)) return -1;
+    if (gz) {
+      if (!make_tmap_2d(&maps.z[j], reinterpret_cast<const char*>(z) + base_off, inner, outer, row_bytes, (unsigned)a.HG)) return -1;
+      if (!make_tmap_2d(&maps.gz[j], reinterpret_cast<const char*>(gz_out) + base_off, inner, outer, row_bytes, (unsigned)a.HG)) return -1;
+    }
+  }
+  const size_t smem = (size_t)tc::analysis_tma_smem(p, gz).total + 1024;
+  const int grid = p.ntiles < 148 ? p.ntiles : 148;
+  int rc;
+  if (gz) {
+    rc = allow_smem(tc::plane_analysis_tma_kernel<true>, smem, "plane_analysis_tma");
+    if (rc != DENO_OK) return rc;
+    prof_before("plane_analysis_gz_tma", st);
+    DENO_LAUNCH((tc::plane_analysis_tma_kernel<true>), dim3(grid), dim3(tc::kAtThreads), smem, st, maps, p);
+  } else {
+    rc = allow_smem(tc::plane_analysis_tma_kernel<false>, smem, "plane_analysis_tma");
+    if (rc != DENO_OK) return rc;
+    prof_before("plane_analysis_tma", st);
+    DENO_LAUNCH((tc::plane_analysis_tma_kernel<false>), dim3(grid), dim3(tc::kAtThreads), smem, st, maps, p);
+  }
+  return check_launch("plane_analysis_tma", st);
+}
+
 // Tensor-core analysis; -1 when the shape is outside the kernel's coverage.
 int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const float* z, float* gz_out, float2* out,
                            const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
@@ -544,7 +720,9 @@ int launch_analysis(const Shape& s, int channels, const float* u, const float* z
   {
     const PathPref pref = path_pref();
     if (pref != PathPref::Simt) {
-      const int trc = try_launch_analysis_tc(s, channels, u, z, gz_out, out, tw, scale, herm, st);
+      int trc = try_launch_analysis_tma(s, channels, u, z, gz_out, out, tw, scale, herm, st);
+      if (trc >= 0) return trc;
+      trc = try_launch_analysis_tc(s, channels, u, z, gz_out, out, tw, scale, herm, st);
       if (trc >= 0) return trc;
     }
   }
@@ -985,37 +1163,6 @@ int try_launch_bypass_wgrad_tc(const Shape& s, const float* gz, const float* x, 
 #endif
 
 #ifndef DENO_EMULATE
-// ------------------------------------------------------------------------------------------
-// Tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency)
-// ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-// fp32 matrix [outer][inner] with `row_bytes` between rows, boxes of [box_outer][32 floats], SWIZZLE_128B, zero OOB fill
-bool make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long outer,
-                  unsigned long long row_bytes, unsigned box_outer) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return false;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_bytes & 15) != 0 || box_outer == 0 || box_outer > 256) return false;
-  const cuuint64_t gdim[2] = {inner, outer};
-  const cuuint64_t gstr[1] = {row_bytes};
-  const cuuint32_t box[2] = {32, box_outer};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // TMA + SWIZZLE_128B bypass weight gradient (spectral_tma.cuh); returns the number of partials written (one per CTA),
 // -1 if the shape / alignment is outside the kernel, -2 on a CUDA error.
 int try_launch_bypass_wgrad_tma(const Shape& s, const float* gz, const float* x, float* partial, cudaStream_t st, int gz_tps = 0) {
@@ -1432,6 +1579,8 @@ int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, s
   if (s.ndim == 3) fill_axis(base + t.outer, s.X, s.KX, s.KX4, s.mX, false);
   fill_synth_ae(base + t.synth_ae, s, t);
   fill_analysis_images(base, s, t);
+  memset(base + t.at_e1, 0, (t.total - t.at_e1) * sizeof(float));
+  fill_analysis_tma_images(base, s, t);
   for (int l = 0; l < s.MWp; ++l) {
     float c = 0.f;
     if (l < s.MW) {

@@ -226,3 +226,370 @@ bypass_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 
 }  // namespace tc
 }  // namespace deno
+
+namespace deno {
+namespace tc {
+
+// ----------------------------------------------------------------------------------------------
+// plane_analysis_tma: same contract as plane_analysis_tc_kernel - truncated forward rDFT of every (b, c) plane, and
+// (FUSE_GZ) gz = gy * act'(z) written once on the way - with the planes brought in by tensor-map TMA.
+//
+// Rows of a plane are W floats apart, which is a multiple of 16 bytes only every g = 4 / gcd(W, 4) rows, so the
+// flat [rows][W] matrix is described by g tensor maps, one per row class j = row mod g (row stride g*W*4 bytes, base
+// rounded down to 16 bytes, the residue `shift_j` floats added to the inner coordinate).  A box [H/g rows][32 floats]
+// of class j of plane pp lands as rows ((j*P + pp)*HGp + hh) of a K-major SWIZZLE_128B tile: the B operand of
+//   stage 1 (transposed)   D1[n, r] = sum_w E[n, w] * x[r, w]      A = E image: rows n < N1 tf32 hi, rows N1 + n lo
+//                          two MMAs per K = 8 step: B = tf32(x) (masked in place) and B = x - tf32(x), one accumulator
+//                          -> T[n, r] = D1[n, r] + D1[N1 + n, r]       (n = 2l: Re, 2l+1: Im of sum_w x e^{-i psi_l w})
+//   conversion             T -> tf32 hi / lo rows of the stage-2 B image  Timg[(part, pp, n), K' = j*HGp + hh]
+//   stage 2                D2[(grp, k), (part, pp, n)] = sum_K' A2[(grp, k), K'] * Timg[(part, pp, n), K']
+//                          A2 rows: grp 0 cos hi, 1 sin hi, 2 cos lo, 3 sin lo of phi_k h (h = g*hh + j); ONE MMA per step
+//   epilogue               C = D2[cos hi][hi] + D2[cos hi][lo] + D2[cos lo][hi],  S likewise with the sin rows
+//                          X^[k, l] = (C[2l] + S[2l+1]) + i (C[2l+1] - S[2l]),  scaled, -> global
+// Warp roles: 0-3 conversion + epilogue (TMEM lane quadrants), 4 TMA producer, 5 MMA issuer, 6-13 builders (tf32
+// split of the landed tiles; FUSE_GZ: the multiply and the TMA store of gz).  Everything is handed over through
+// mbarriers; the tensor pipe order is S1(t), S2(t-1), S1(t+1), ... so the conversion of tile t runs under S1(t+1).
+// ----------------------------------------------------------------------------------------------
+struct AnalysisTmaParams {
+  int H, W, g, HG, HGp, P;       // rows, cols, row classes, rows per class (H / g), padded to 16, planes per tile
+  int KH, KHp, MW, N1;           // packed modes along H (padded to 8), modes along W, E rows per part (2 MW padded to 8)
+  int C, X, NP, ntiles;          // channels, outer extent (3-D), planes in memory order, tiles
+  int nchunks;                   // ceil(W / 32)
+  int N, K2p, N2;                // stage-1 N (g*P*HGp), stage-2 K (padded to 32), stage-2 N (2*P*N1)
+  int shift[4];                  // inner-coordinate shift of row class j (floats)
+  int nsh, nsl;                  // stages of the landed-tile ring / the lo-tile ring
+  const float* e1;               // E image, final shared-memory layout: nchunks x [2 N1 rows][32] SWIZZLE_128B
+  const float* a2;               // A2 image: (K2p / 32) x [4 KHp rows][32] SWIZZLE_128B
+  const float* cl;
+  float scale;
+  int herm;
+  float2* out;                   // [B * X][C][KH][MW]
+  const float* u_base;           // x / gy (L2 prefetch only)
+  const float* z_base;
+  int l2_prefetch;               // plane bytes are 16-byte multiples: bulk L2 prefetch of upcoming tiles
+};
+
+struct AnalysisTmaMaps { CUtensorMap u[4], z[4], gz[4]; };
+
+constexpr int kAtEpiWarps = 4, kAtBuildWarps = 8;
+constexpr int kAtThreads = (kAtEpiWarps + 2 + kAtBuildWarps) * 32;
+constexpr int kAtBarConv = 4, kAtBarEpi = 5, kAtBarBuild = 6;
+
+struct AnalysisTmaSmem { int e1, a2, timg, hi, lo, stg, xch, total; int hi_stage, lo_stage, e1_bytes, a2_bytes, t_bytes, xch_pitch; };
+
+__host__ __device__ inline AnalysisTmaSmem analysis_tma_smem(const AnalysisTmaParams& p, bool fuse_gz) {
+  AnalysisTmaSmem m;
+  m.e1_bytes = p.nchunks * 2 * p.N1 * 128;
+  m.a2_bytes = (p.K2p / 32) * 4 * p.KHp * 128;
+  m.t_bytes = (p.K2p / 32) * p.N2 * 128;
+  m.hi_stage = p.N * 128 * (fuse_gz ? 2 : 1);
+  m.lo_stage = p.N * 128;
+  m.xch_pitch = p.P * p.N1 + 1;
+  int off = 0;
+  m.e1 = off;   off += (m.e1_bytes + 1023) / 1024 * 1024;
+  m.a2 = off;   off += (m.a2_bytes + 1023) / 1024 * 1024;
+  m.timg = off; off += (m.t_bytes + 1023) / 1024 * 1024;
+  m.hi = off;   off += p.nsh * m.hi_stage;
+  m.lo = off;   off += p.nsl * m.lo_stage;
+  m.stg = off;  off += 2 * p.N1 * 16 * 4;
+  m.xch = off;  off += (2 * p.KHp * m.xch_pitch * 4 + 15) / 16 * 16;
+  m.total = off;
+  return m;
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(src_smem)) : "memory");
+}
+
+template <bool FUSE_GZ>
+__global__ void __launch_bounds__(kAtThreads, 1)
+plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, AnalysisTmaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar_hi_full[4], bar_hi_empty[4], bar_lo_full[4], bar_lo_empty[4];
+  __shared__ __align__(8) uint64_t bar_d1_full[2], bar_d1_empty[2], bar_t_full, bar_t_empty, bar_d2_full, bar_d2_empty, bar_const;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const AnalysisTmaSmem so = analysis_tma_smem(p, FUSE_GZ);
+  const int N = p.N, N1 = p.N1, N2 = p.N2, P = p.P, g = p.g, HG = p.HG, HGp = p.HGp;
+  const int NSH = p.nsh, NSL = p.nsl;
+  const int nk2 = p.K2p / 32;
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * N + N2) ncols *= 2;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  if (tid == 32) {
+    for (int s = 0; s < NSH; ++s) { mbar_init(&bar_hi_full[s], 1); mbar_init(&bar_hi_empty[s], FUSE_GZ ? 2 : 1); }
+    for (int s = 0; s < NSL; ++s) { mbar_init(&bar_lo_full[s], kAtBuildWarps); mbar_init(&bar_lo_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_d1_full[b], 1); mbar_init(&bar_d1_empty[b], 2); }
+    mbar_init(&bar_t_full, 2); mbar_init(&bar_t_empty, 1);
+    mbar_init(&bar_d2_full, 1); mbar_init(&bar_d2_empty, kAtEpiWarps);
+    mbar_init(&bar_const, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar_const, (uint32_t)(so.e1_bytes + so.a2_bytes));
+    bulk_g2s(smem + so.e1, p.e1, (uint32_t)so.e1_bytes, &bar_const);
+    bulk_g2s(smem + so.a2, p.a2, (uint32_t)so.a2_bytes, &bar_const);
+  }
+  // Tile rows no box ever writes (the pad rows hh >= HG of every 16-row-padded block, the K' pad of the stage-2 image)
+  // are read by the MMAs and multiplied by zero twiddles: they must be finite, so everything starts as zeros.
+  for (int i = tid; i < (so.total - so.timg) / 16; i += kAtThreads)
+    reinterpret_cast<float4*>(smem + so.timg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  DENO_PDL_SYNC();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_d2 = tmem + (uint32_t)(2 * N);
+  const int ntile_cta = (p.ntiles > (int)blockIdx.x) ? (p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nch = p.nchunks;
+
+  if (warp == 4) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      const uint32_t tx = (uint32_t)(g * P * HG * 128 * (FUSE_GZ ? 2 : 1));
+      const long long plane_bytes = (long long)p.H * p.W * 4;
+      auto l2_prefetch = [&](int n) {
+        if (!p.l2_prefetch || n >= ntile_cta) return;
+        const long long m0 = ((long long)blockIdx.x + (long long)n * gridDim.x) * P;
+        const int np = (int)min((long long)P, (long long)p.NP - m0);
+        if (np <= 0) return;
+        const uint32_t bytes = (uint32_t)(np * plane_bytes);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.u_base + m0 * p.H * p.W), "r"(bytes) : "memory");
+        if (FUSE_GZ) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.z_base + m0 * p.H * p.W), "r"(bytes) : "memory");
+      };
+      l2_prefetch(0); l2_prefetch(1); l2_prefetch(2);
+      int ci = 0;
+      for (int n = 0; n < ntile_cta; ++n) {
+        l2_prefetch(n + 3);
+        const int m0 = ((int)blockIdx.x + n * (int)gridDim.x) * P;
+        for (int c = 0; c < nch; ++c, ++ci) {
+          const int st = ci % NSH, use = ci / NSH;
+          mbar_wait(&bar_hi_empty[st], (uint32_t)((use & 1) ^ 1));
+          unsigned char* dst = smem + so.hi + st * so.hi_stage;
+          mbar_expect_tx(&bar_hi_full[st], tx);
+          for (int j = 0; j < g; ++j)
+            for (int pp = 0; pp < P; ++pp) {
+              const int row0 = (j * P + pp) * HGp;
+              tma_load_2d(dst + row0 * 128, &maps.u[j], p.shift[j] + 32 * c, (m0 + pp) * HG, &bar_hi_full[st]);
+              if (FUSE_GZ) tma_load_2d(dst + N * 128 + row0 * 128, &maps.z[j], p.shift[j] + 32 * c, (m0 + pp) * HG, &bar_hi_full[st]);
+            }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================================================== MMA issuer
+    const bool leader = elect_one();
+    const uint32_t idesc1 = make_idesc_tf32(128, N), idesc2 = make_idesc_tf32(128, N2);
+    const uint32_t sbase = smem_u32(smem);
+    mbar_wait(&bar_const, 0);
+    auto stage2 = [&](int n) {                         // S2 of this CTA's n-th tile
+      mbar_wait(&bar_t_full, (uint32_t)(n & 1));
+      mbar_wait(&bar_d2_empty, (uint32_t)((n & 1) ^ 1));
+      fence_after_sync();
+      for (int c = 0; c < nk2; ++c) {
+        uint64_t a = make_desc_sw128(sbase + so.a2 + c * (4 * p.KHp * 128));
+        uint64_t b = make_desc_sw128(sbase + so.timg + c * (N2 * 128));
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          if (leader) mma_tf32(tmem_d2, a, b, idesc2, (c | s2) ? 1u : 0u);
+          a += 2; b += 2;
+        }
+      }
+      if (leader) { mma_commit(&bar_t_empty); mma_commit(&bar_d2_full); }
+      __syncwarp();
+    };
+    int ci = 0;
+    for (int n = 0; n < ntile_cta; ++n) {
+      const int b = n & 1;
+      mbar_wait(&bar_d1_empty[b], (uint32_t)(((n >> 1) & 1) ^ 1));
+      fence_after_sync();
+      const uint32_t d1 = tmem + (uint32_t)(b * N);
+      for (int c = 0; c < nch; ++c, ++ci) {
+        const int sl = ci % NSL, sh = ci % NSH;
+        mbar_wait(&bar_lo_full[sl], (uint32_t)((ci / NSL) & 1));      // implies the landed tile is complete (and masked)
+        fence_after_sync();
+        uint64_t e = make_desc_sw128(sbase + so.e1 + c * (2 * N1 * 128));
+        uint64_t xh = make_desc_sw128(sbase + so.hi + sh * so.hi_stage);
+        uint64_t xl = make_desc_sw128(sbase + so.lo + sl * so.lo_stage);
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          if (leader) {
+            mma_tf32(d1, e, xh, idesc1, (c | s2) ? 1u : 0u);
+            mma_tf32(d1, e, xl, idesc1, 1u);
+          }
+          e += 2; xh += 2; xl += 2;
+        }
+        if (leader) { mma_commit(&bar_hi_empty[sh]); mma_commit(&bar_lo_empty[sl]); }
+        __syncwarp();
+      }
+      if (leader) mma_commit(&bar_d1_full[b]);
+      __syncwarp();
+      if (n > 0) stage2(n - 1);
+    }
+    if (ntile_cta > 0) stage2(ntile_cta - 1);
+  } else if (warp >= 6) {
+    // ===================================================================== builders
+    const int bt = tid - 6 * 32, nb = kAtBuildWarps * 32;
+    const int nvec = N * 8;                                    // float4 per tile
+    int ci = 0;
+    for (int n = 0; n < ntile_cta; ++n) {
+      const int m0 = ((int)blockIdx.x + n * (int)gridDim.x) * P;
+      for (int c = 0; c < nch; ++c, ++ci) {
+        const int sh = ci % NSH, sl = ci % NSL;
+        mbar_wait(&bar_hi_full[sh], (uint32_t)((ci / NSH) & 1));
+        mbar_wait(&bar_lo_empty[sl], (uint32_t)(((ci / NSL) & 1) ^ 1));
+        float4* hi = reinterpret_cast<float4*>(smem + so.hi + sh * so.hi_stage);
+        float4* zt = hi + nvec;
+        float4* lo = reinterpret_cast<float4*>(smem + so.lo + sl * so.lo_stage);
+        for (int i = bt; i < nvec; i += nb) {
+          float4 v = hi[i];
+          if (FUSE_GZ) {
+            const float4 z = zt[i];
+            v = make_float4(v.x * z.x, v.y * z.y, v.z * z.z, v.w * z.w);
+            zt[i] = v;                                           // gz itself: stored to global from here by TMA
+          }
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+          hi[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();
+        if (FUSE_GZ) {
+          nbar_sync(kAtBarBuild, nb);                            // the whole gz tile is in shared memory
+          if (bt == 0) {
+            for (int j = 0; j < g; ++j)
+              for (int pp = 0; pp < P; ++pp)
+                if (m0 + pp < p.NP)
+                  tma_store_2d(&maps.gz[j], reinterpret_cast<unsigned char*>(zt) + (j * P + pp) * HGp * 128,
+                               p.shift[j] + 32 * c, (m0 + pp) * HG);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_lo_full[sl]);
+        if (FUSE_GZ && bt == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has read the tile: stage reusable
+          mbar_arrive(&bar_hi_empty[sh]);
+        }
+      }
+    }
+    if (FUSE_GZ && bt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // gz fully written before exit
+  } else {
+    // ===================================================================== conversion + epilogue (warps 0-3)
+    const int L = warp * 32 + lane;                    // TMEM lane
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    float* stg = reinterpret_cast<float*>(smem + so.stg);       // [2][N1][16]
+    float* xch = reinterpret_cast<float*>(smem + so.xch);       // [2][KHp][xch_pitch]
+    const int XP = so.xch_pitch;
+    const int PN = P * N1;
+    mbar_wait(&bar_const, 0);
+    auto conversion = [&](int n) {
+      if (warp >= 2) return;
+      const int b = n & 1;
+      mbar_wait(&bar_d1_full[b], (uint32_t)((n >> 1) & 1));
+      mbar_wait(&bar_t_empty, (uint32_t)((n & 1) ^ 1));
+      fence_after_sync();
+      const uint32_t d1 = tmem + (uint32_t)(b * N) + lane_addr;
+      const bool is_lo = L >= N1 && L < 2 * N1, is_hi = L < N1;
+      const int nn = is_lo ? L - N1 : L;
+      int sb = 0;
+      for (int j = 0; j < g; ++j)
+        for (int pp = 0; pp < P; ++pp)
+          for (int u = 0; u < HGp / 16; ++u) {
+            float v[16];
+            tmem_ld16(d1 + (uint32_t)((j * P + pp) * HGp + 16 * u), v);
+            float4* sg = reinterpret_cast<float4*>(stg + (sb * N1 + nn) * 16);
+            if (is_lo) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sg[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            nbar_sync(kAtBarConv, 64);
+            if (is_hi) {
+              const int kp = j * HGp + 16 * u;                   // K' of the first of the 16 values
+              const int chunk = kp >> 5, c16 = (kp & 31) >> 2;
+              const int row_hi = pp * N1 + nn, row_lo = PN + row_hi;
+              unsigned char* base = smem + so.timg + chunk * (N2 * 128);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 s4 = sg[q];
+                float4 h, l;
+                split_tf32(v[4 * q] + s4.x, h.x, l.x);
+                split_tf32(v[4 * q + 1] + s4.y, h.y, l.y);
+                split_tf32(v[4 * q + 2] + s4.z, h.z, l.z);
+                split_tf32(v[4 * q + 3] + s4.w, h.w, l.w);
+                *reinterpret_cast<float4*>(base + row_hi * 128 + (((c16 + q) ^ (row_hi & 7)) << 4)) = h;
+                *reinterpret_cast<float4*>(base + row_lo * 128 + (((c16 + q) ^ (row_lo & 7)) << 4)) = l;
+              }
+            }
+            sb ^= 1;
+          }
+      fence_before_sync();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bar_d1_empty[b]); mbar_arrive(&bar_t_full); }
+    };
+    auto epilogue = [&](int n) {
+      const int m0 = ((int)blockIdx.x + n * (int)gridDim.x) * P;
+      mbar_wait(&bar_d2_full, (uint32_t)(n & 1));
+      fence_after_sync();
+      const int grp = L / p.KHp, k = L - grp * p.KHp;
+      const bool row_ok = grp < 4 && k < p.KH;
+      const uint32_t d2 = tmem_d2 + lane_addr;
+      // phase 1: the tf32-hi twiddle rows (cos: grp 0, sin: grp 1) write  D2[.., hi part] + D2[.., lo part]
+      // phase 2: the lo twiddle rows (grp 2, 3) add  D2[.., hi part]
+      for (int ph = 0; ph < 2; ++ph) {
+        const bool mine = row_ok && ((ph == 0) ? grp < 2 : grp >= 2);
+        if (warp * 32 < 4 * p.KHp) {                   // warp holds twiddle rows at all (tcgen05.ld is warp-collective)
+          for (int c0 = 0; c0 < PN; c0 += 16) {
+            if ((ph == 0 && warp * 32 >= 2 * p.KHp) || (ph == 1 && warp * 32 + 32 <= 2 * p.KHp)) continue;
+            float a[16], bb[16];
+            tmem_ld16(d2 + (uint32_t)c0, a);
+            if (ph == 0) tmem_ld16(d2 + (uint32_t)(PN + c0), bb);
+            if (mine) {
+              float* dst = xch + ((grp & 1) * p.KHp + k) * XP + c0;
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (c0 + q < PN) dst[q] = (ph == 0) ? a[q] + bb[q] : dst[q] + a[q];
+            }
+          }
+        }
+        if (ph == 1) {
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_d2_empty);
+        }
+        nbar_sync(kAtBarEpi, kAtEpiWarps * 32);
+      }
+      // combine: one thread per (plane, k, l)
+      const int nitem = P * p.KH * p.MW;
+      for (int it = L; it < nitem; it += kAtEpiWarps * 32) {
+        const int l = it % p.MW, t2 = it / p.MW;
+        const int k2 = t2 % p.KH, pp = t2 / p.KH;
+        const int m = m0 + pp;
+        if (m < p.NP) {
+          const int CX = p.C * p.X;
+          const int bo = m / CX, r = m - bo * CX, c = r / p.X, xi = r - c * p.X;
+          const long long q_out = ((long long)bo * p.X + xi) * p.C + c;
+          const float* cr = xch + k2 * XP + pp * N1 + 2 * l;
+          const float* sr = xch + (p.KHp + k2) * XP + pp * N1 + 2 * l;
+          const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+          p.out[q_out * p.KH * p.MW + (long long)k2 * p.MW + l] = make_float2((cr[0] + sr[1]) * f, (cr[1] - sr[0]) * f);
+        }
+      }
+      nbar_sync(kAtBarEpi, kAtEpiWarps * 32);          // xch is rewritten by the next tile's phase 1
+    };
+    for (int n = 0; n < ntile_cta; ++n) {
+      conversion(n);
+      if (n > 0) epilogue(n - 1);
+    }
+    if (ntile_cta > 0) epilogue(ntile_cta - 1);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace tc
+}  // namespace deno

@@ -96,9 +96,9 @@ def test_rollout_training_gradients_match_port(path, monkeypatch):
     T, B = 10, 4
     model = d4.FNO2d(**cfg)
     with torch.no_grad():                     # reference init makes the spectral branch ~1e-4 of the bypass: lift it
-        for k, p in model.named_parameters():
-            if ".weights" in k:
-                p.mul_(cfg["width"] ** 2 / 4)
+        for k, p in model.named_parameters():   # (x256; x1024 makes the untrained ten-step roll-out grow 10x per step,
+            if ".weights" in k:                 # an ill-conditioned comparison in any precision)
+                p.mul_(cfg["width"] ** 2 / 16)
     params = {k: v.detach().clone() for k, v in model.state_dict().items()}
     gen = torch.Generator().manual_seed(13)
     x = torch.randn(B, 64, 64, 10, generator=gen)
