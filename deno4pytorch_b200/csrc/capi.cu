@@ -586,8 +586,9 @@ struct Options {
   int mix_tile = 1;      // 0 / 1 (default) / 2
   int mix_tm = 0;        // 0 = heuristic
   bool synth_ws = false;
-  bool wgrad_tma = true; // DENO_WGRAD_TMA=0: the register-staged bypass_wgrad_tc kernel instead of the TMA one
-  bool an_tma = true;    // DENO_ANALYSIS_TMA=0: the bulk-copy + SIMT-transform analysis kernel instead of the TMA one
+  bool wgrad_tma = false; // DENO_WGRAD_TMA=1: the TMA bypass weight-gradient kernel instead of the register-staged one (wrong for small row counts on hardware: profiles/r2c_wgrad_diag.txt)
+  int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
+  bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
 Options read_options() {
   Options o;
@@ -598,8 +599,9 @@ Options read_options() {
   if (const char* e = getenv("DENO_MIX_TILE")) { if (e[0] == '0') o.mix_tile = 0; else if (e[0] == '2') o.mix_tile = 2; }
   if (const char* e = getenv("DENO_MIX_TM")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) o.mix_tm = v; }
   if (const char* e = getenv("DENO_SYNTH_WS")) o.synth_ws = e[0] == '1';
-  if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] != '0';
-  if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] != '0';
+  if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] == '1';
+  if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] == '1';
+  if (const char* e = getenv("DENO_AT_DBG")) o.at_dbg = atoi(e);
   return o;
 }
 std::mutex g_opt_mutex;
@@ -648,6 +650,8 @@ int try_launch_analysis_tma(const Shape& s, int channels, const float* u, const 
   p.e1 = tw.at_e1; p.a2 = tw.at_a2; p.cl = tw.cl; p.scale = scale; p.herm = herm; p.out = out;
   p.u_base = u; p.z_base = z;
   p.l2_prefetch = ((long long)s.H * s.W) % 4 == 0 ? 1 : 0;
+  p.dbg = options().at_dbg;
+  if (p.dbg & 1) p.l2_prefetch = 0;
   tc::AnalysisTmaMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int j = 0; j < a.g; ++j) {
@@ -1173,6 +1177,7 @@ int try_launch_bypass_wgrad_tma(const Shape& s, const float* gz, const float* x,
   while (NS > 1 && (NS * COs > 128 || NS * CIs > 128)) NS /= 2;
   if ((NS * CIs) % 16 != 0) return -1;
   if ((s.S % 4) != 0) return -1;                          // rows of the [B*C][S] matrices must start 16-byte aligned
+  if (COs != s.CO || CIs != s.CI) return -1;              // boxes never straddle the end of the tensor along its rows
   const int nbatch = s.B;                                  // S spans the whole (X, H, W) volume of a batch entry
   CUtensorMap tm_a, tm_b;
   if (gz_tps > 0) {
@@ -1189,6 +1194,7 @@ int try_launch_bypass_wgrad_tma(const Shape& s, const float* gz, const float* x,
   p.ntiles = p.ngroups * p.nchunks;
   p.a_rows_per_batch = s.CO; p.b_rows_per_batch = s.CI;
   p.a_tps = gz_tps;
+  p.nbatch = nbatch;
   const int stage_bytes = tc::wgrad_tma_stage_bytes(NS * CIs);
   int nst = (kMaxSmemBytes - 2048) / stage_bytes;
   if (nst > 4) nst = 4;

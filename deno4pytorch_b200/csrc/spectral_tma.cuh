@@ -58,6 +58,7 @@ struct WgradTmaParams {
   int b_rows_per_batch;  // ... in the x tensor map (CI)
   int a_tps;             // > 0: gz is stored in blocks of 128 points [batch][a_tps][CO][128] (fno_proj_bwd_tc)
   int nstages;
+  int nbatch;            // batch entries; slots of the last group beyond it are never loaded (builders write zeros)
 };
 
 constexpr int kWtBuilders = 256;                       // 8 builder / epilogue warps
@@ -106,7 +107,6 @@ bypass_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      const uint32_t tx = (uint32_t)(NS * COs * 128 + NS * CIs * 128);
       for (int n = 0; n < ntile_cta; ++n) {
         const int st = n % NST, use = n / NST;
         mbar_wait(&bar_empty[st], (uint32_t)((use & 1) ^ 1));     // MMAs of the previous use of this stage have retired
@@ -115,9 +115,12 @@ bypass_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
         const int p0 = chunk * 32;
         unsigned char* sa = smem + st * stage_bytes;
         unsigned char* sb = sa + 2 * a_bytes;
-        mbar_expect_tx(&bar_tma[st], tx);
-        for (int j = 0; j < NS; ++j) {
-          const int b = grp * NS + j;                              // beyond the batch: the box is out of bounds -> zeros
+        // Slots beyond the batch are NOT loaded: a box that lies entirely outside the tensor was measured to corrupt
+        // other slots of the tile (profiles/r2c_wgrad_diag.txt); the builders write zeros there instead.
+        const int nvalid = min(NS, p.nbatch - grp * NS);
+        mbar_expect_tx(&bar_tma[st], (uint32_t)(nvalid * (COs + CIs) * 128));
+        for (int j = 0; j < nvalid; ++j) {
+          const int b = grp * NS + j;
           if (p.a_tps > 0) tma_load_2d(sa + j * COs * 128, &tm_a, p0 & 127, (b * p.a_tps + (p0 >> 7)) * p.a_rows_per_batch, &bar_tma[st]);
           else tma_load_2d(sa + j * COs * 128, &tm_a, p0, b * p.a_rows_per_batch, &bar_tma[st]);
           tma_load_2d(sb + j * CIs * 128, &tm_b, p0, b * p.b_rows_per_batch, &bar_tma[st]);
@@ -162,17 +165,25 @@ bypass_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       float4* al = ah + a_bytes / 16;
       float4* bh = al + a_bytes / 16;
       float4* bl = bh + b_bytes / 16;
+      const int t = (int)blockIdx.x + n * (int)gridDim.x;
+      const int nvalid = min(NS, p.nbatch - (t / p.nchunks) * NS);
+      const int validA = nvalid * COs * 8, validB = nvalid * CIs * 8;   // float4 of the slots that were loaded
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int i = bt; i < nvecA; i += kWtBuilders) {
-        const float4 v = ah[i];
-        float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        float4 h = zero4, l = zero4;
+        if (i < validA) {
+          const float4 v = ah[i];
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        }
         ah[i] = h;
         al[i] = l;
       }
       for (int i = bt; i < nvecB; i += kWtBuilders) {
-        const float4 v = bh[i];
-        float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        float4 h = zero4, l = zero4;
+        if (i < validB) {
+          const float4 v = bh[i];
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        }
         bh[i] = h;
         bl[i] = l;
       }
@@ -190,8 +201,9 @@ bypass_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     if (ntile_cta > 0) {
       mbar_wait(&bar_done, 0);
       fence_after_sync();
-      const int ew = warp - 2;                                     // 0..7
-      const int wq = ew & 3, wh = ew >> 2;                         // TMEM lane quadrant, column half
+      // tcgen05.ld reaches only the TMEM lane quadrant (warp index % 4) of the issuing warp, whatever the address says:
+      // warps 2..9 -> quadrants 2, 3, 0, 1, 2, 3, 0, 1; the first four take the low column half, the last four the high
+      const int wq = warp & 3, wh = (warp - 2) >> 2;
       const int row = wq * 32 + lane;
       const int j = row / COs, o = row - j * COs;
       const bool valid = j < NS && o < CO;
@@ -267,6 +279,7 @@ struct AnalysisTmaParams {
   const float* u_base;           // x / gy (L2 prefetch only)
   const float* z_base;
   int l2_prefetch;               // plane bytes are 16-byte multiples: bulk L2 prefetch of upcoming tiles
+  int dbg;                       // bring-up switches (DENO_AT_DBG): 2 no MMA issue, 4 no TMA loads, 8 no TMEM loads
 };
 
 struct AnalysisTmaMaps { CUtensorMap u[4], z[4], gz[4]; };
@@ -368,6 +381,7 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
           const int st = ci % NSH, use = ci / NSH;
           mbar_wait(&bar_hi_empty[st], (uint32_t)((use & 1) ^ 1));
           unsigned char* dst = smem + so.hi + st * so.hi_stage;
+          if (p.dbg & 4) { mbar_arrive(&bar_hi_full[st]); continue; }
           mbar_expect_tx(&bar_hi_full[st], tx);
           for (int j = 0; j < g; ++j)
             for (int pp = 0; pp < P; ++pp) {
@@ -381,6 +395,7 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
   } else if (warp == 5) {
     // ===================================================================== MMA issuer
     const bool leader = elect_one();
+    const bool issue = leader && !(p.dbg & 2);
     const uint32_t idesc1 = make_idesc_tf32(128, N), idesc2 = make_idesc_tf32(128, N2);
     const uint32_t sbase = smem_u32(smem);
     mbar_wait(&bar_const, 0);
@@ -393,7 +408,7 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
         uint64_t b = make_desc_sw128(sbase + so.timg + c * (N2 * 128));
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
-          if (leader) mma_tf32(tmem_d2, a, b, idesc2, (c | s2) ? 1u : 0u);
+          if (issue) mma_tf32(tmem_d2, a, b, idesc2, (c | s2) ? 1u : 0u);
           a += 2; b += 2;
         }
       }
@@ -415,7 +430,7 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
         uint64_t xl = make_desc_sw128(sbase + so.lo + sl * so.lo_stage);
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
-          if (leader) {
+          if (issue) {
             mma_tf32(d1, e, xh, idesc1, (c | s2) ? 1u : 0u);
             mma_tf32(d1, e, xl, idesc1, 1u);
           }
@@ -499,7 +514,8 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
         for (int pp = 0; pp < P; ++pp)
           for (int u = 0; u < HGp / 16; ++u) {
             float v[16];
-            tmem_ld16(d1 + (uint32_t)((j * P + pp) * HGp + 16 * u), v);
+            if (p.dbg & 8) { for (int q = 0; q < 16; ++q) v[q] = 0.f; }
+            else tmem_ld16(d1 + (uint32_t)((j * P + pp) * HGp + 16 * u), v);
             float4* sg = reinterpret_cast<float4*>(stg + (sb * N1 + nn) * 16);
             if (is_lo) {
 #pragma unroll
@@ -545,8 +561,11 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
           for (int c0 = 0; c0 < PN; c0 += 16) {
             if ((ph == 0 && warp * 32 >= 2 * p.KHp) || (ph == 1 && warp * 32 + 32 <= 2 * p.KHp)) continue;
             float a[16], bb[16];
-            tmem_ld16(d2 + (uint32_t)c0, a);
-            if (ph == 0) tmem_ld16(d2 + (uint32_t)(PN + c0), bb);
+            if (p.dbg & 8) { for (int q = 0; q < 16; ++q) { a[q] = 0.f; bb[q] = 0.f; } }
+            else {
+              tmem_ld16(d2 + (uint32_t)c0, a);
+              if (ph == 0) tmem_ld16(d2 + (uint32_t)(PN + c0), bb);
+            }
             if (mine) {
               float* dst = xch + ((grp & 1) * p.KHp + k) * XP + c0;
 #pragma unroll
