@@ -588,7 +588,7 @@ def run_own(args):
     torch_gpu = None
     if world == 1:
         # bounded CPU sample on rank 0: a few full steps of the same workload (about 10-30 s of CPU work)
-        n_cpu = args.cpu_steps
+        n_cpu = max(1, args.cpu_steps)
         rate, ms, cores, b = cpu_reference_rate(args.workload, n_cpu, 1)
         cpu = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full train steps at batch {b} after 1 warm-up ({ms:.0f} ms/step), "

@@ -140,7 +140,12 @@ struct TwLayout {
 };
 
 // Shape-only geometry of the TMA analysis kernel (independent of the planes-per-tile choice).
-struct AtGeom { bool ok; int g, HG, HGp, N1, KHp, nchunks, K2p; };
+// Row class j = row mod g starts j * W floats into the plane; a TMA box must start on a 16-byte boundary in global
+// memory (an inner coordinate that is not a multiple of 4 floats is an illegal instruction on hardware:
+// profiles/r2g_tma_box_probe.txt), so class j is described from the 16-byte boundary below its first row and the
+// `shift[j]` leading floats of every landed row (the tail of the previous row) meet zero columns of that class's
+// twiddle image.
+struct AtGeom { bool ok; int g, HG, HGp, N1, KHp, nchunks, K2p; int shift[4]; };
 AtGeom at_geom(const Shape& s) {
   AtGeom a;
   memset(&a, 0, sizeof(a));
@@ -152,7 +157,12 @@ AtGeom at_geom(const Shape& s) {
   a.HGp = round_up(a.HG, 16);
   a.N1 = round_up(2 * s.MW, 8);
   a.KHp = round_up(s.KH, 8);
-  a.nchunks = (s.W + 31) / 32;
+  int max_shift = 0;
+  for (int j = 0; j < a.g; ++j) {
+    a.shift[j] = (int)(((long long)j * s.W) % 4);
+    if (a.shift[j] > max_shift) max_shift = a.shift[j];
+  }
+  a.nchunks = (s.W + max_shift + 31) / 32;
   a.K2p = round_up(a.g * a.HGp, 32);
   if (a.N1 > 32 || 4 * a.KHp > 128 || a.HG > 256 || a.g * a.HGp > 256) return a;
   a.ok = true;
@@ -181,7 +191,7 @@ TwLayout tw_layout(const Shape& s) {
   // both already in their SWIZZLE_128B shared-memory layout
   const AtGeom ag = at_geom(s);
   off = (off + 63) / 64 * 64;                      // 256-byte aligned: the images are bulk-copied
-  t.at_e1 = off; off += ag.ok ? (size_t)ag.nchunks * 2 * ag.N1 * 32 : 0;
+  t.at_e1 = off; off += ag.ok ? (size_t)ag.g * ag.nchunks * 2 * ag.N1 * 32 : 0;
   t.at_a2 = off; off += ag.ok ? (size_t)(ag.K2p / 32) * 4 * ag.KHp * 32 : 0;
   t.total = off;
   return t;
@@ -521,20 +531,22 @@ void fill_analysis_tma_images(float* base, const Shape& s, const TwLayout& t) {
   const AtGeom a = at_geom(s);
   if (!a.ok) return;
   const double two_pi = 6.283185307179586476925286766559;
-  float* e1 = base + t.at_e1;
   const int ER = 2 * a.N1;
-  for (int n = 0; n < a.N1; ++n)
-    for (int w = 0; w < a.nchunks * 32; ++w) {
-      const int l = n / 2;
-      double v = 0.0;
-      if (l < s.MW && w < s.W) {
-        const double ang = two_pi * (double)(((long long)l * w) % s.W) / (double)s.W;
-        v = (n & 1) ? -sin(ang) : cos(ang);
+  for (int j = 0; j < a.g; ++j) {                 // one image per row class: column kc of the landed tile is w = kc - shift[j]
+    float* e1 = base + t.at_e1 + (size_t)j * a.nchunks * ER * 32;
+    for (int n = 0; n < a.N1; ++n)
+      for (int kc = 0; kc < a.nchunks * 32; ++kc) {
+        const int l = n / 2, w = kc - a.shift[j];
+        double v = 0.0;
+        if (l < s.MW && w >= 0 && w < s.W) {
+          const double ang = two_pi * (double)(((long long)l * w) % s.W) / (double)s.W;
+          v = (n & 1) ? -sin(ang) : cos(ang);
+        }
+        const float h = tf32_mask((float)v);
+        e1[sw128_off(n, kc, ER) / 4] = h;
+        e1[sw128_off(a.N1 + n, kc, ER) / 4] = (float)(v - (double)h);
       }
-      const float h = tf32_mask((float)v);
-      e1[sw128_off(n, w, ER) / 4] = h;
-      e1[sw128_off(a.N1 + n, w, ER) / 4] = (float)(v - (double)h);
-    }
+  }
   float* a2 = base + t.at_a2;
   const int AR = 4 * a.KHp;
   for (int k = 0; k < a.KHp; ++k)
@@ -586,7 +598,7 @@ struct Options {
   int mix_tile = 1;      // 0 / 1 (default) / 2
   int mix_tm = 0;        // 0 = heuristic
   bool synth_ws = false;
-  bool wgrad_tma = false; // DENO_WGRAD_TMA=1: the TMA bypass weight-gradient kernel instead of the register-staged one (wrong for small row counts on hardware: profiles/r2c_wgrad_diag.txt)
+  bool wgrad_tma = true; // DENO_WGRAD_TMA=0: the register-staged bypass_wgrad_tc kernel instead of the TMA one
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
@@ -599,7 +611,7 @@ Options read_options() {
   if (const char* e = getenv("DENO_MIX_TILE")) { if (e[0] == '0') o.mix_tile = 0; else if (e[0] == '2') o.mix_tile = 2; }
   if (const char* e = getenv("DENO_MIX_TM")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) o.mix_tm = v; }
   if (const char* e = getenv("DENO_SYNTH_WS")) o.synth_ws = e[0] == '1';
-  if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] == '1';
+  if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] != '0';
   if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] == '1';
   if (const char* e = getenv("DENO_AT_DBG")) o.at_dbg = atoi(e);
   return o;
@@ -638,7 +650,7 @@ int try_launch_analysis_tma(const Shape& s, int channels, const float* u, const 
   int bestP = 0, best_nsh = 0, best_nsl = 0;
   for (int P = gz ? 1 : 2; P >= 1 && bestP == 0; --P) {
     p.P = P; p.N = a.g * P * a.HGp; p.N2 = 2 * P * a.N1;
-    if (p.N > 256 || (p.N % 16) != 0 || 2 * p.N + p.N2 > 512) continue;
+    if (P * a.HGp > 256 || 2 * p.N + p.N2 > 512) continue;   // per-class stage-1 N = P * HGp
     for (int nsh = 4; nsh >= 2 && bestP == 0; --nsh) {
       p.nsh = nsh; p.nsl = 2;
       if (tc::analysis_tma_smem(p, gz).total + 1024 <= kMaxSmemBytes) { bestP = P; best_nsh = nsh; best_nsl = 2; }
@@ -658,6 +670,7 @@ int try_launch_analysis_tma(const Shape& s, int channels, const float* u, const 
     const long long off_bytes = (long long)j * s.W * 4;
     const long long base_off = off_bytes & ~15LL;
     p.shift[j] = (int)((off_bytes - base_off) / 4);
+    if (p.shift[j] != a.shift[j]) return -1;
     const unsigned long long inner = (unsigned long long)s.W + p.shift[j];
     const unsigned long long outer = (unsigned long long)NP * a.HG;
     const unsigned long long row_bytes = (unsigned long long)a.g * s.W * 4;
@@ -943,6 +956,7 @@ int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int
   q.KE = tl.KE;
   q.nchunks = tl.nchunks;
   q.tmem_cols = cols;
+  q.COT = CO; q.nco = 1; q.npass = 1;
   const size_t smem = (size_t)tc::synth_ws_smem(CIP, CO, tl.KE, bestR).total;
   const long long nunits = (long long)s.B * s.X * p.tiles * tl.nchunks;
   const int grid = (int)(nunits < 148 ? nunits : 148);
@@ -980,22 +994,31 @@ int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int
 // DENO_SYNTH_WS=1 selects the warp-specialised kernel.
 int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, float* urow, cudaStream_t st) {
   const int CI = p.g.C, CO = p.CO;
-  if (CI > 64 || CO > 128 || (CO % 32) != 0) return -1;
+  if (CI > 256 || CO > 256 || (CO % 32) != 0) return -1;
+  // Wide layers (Airfoil / Pipe, width 128): the output channels are cut into tiles of 64 (one CTA each: 6 * COT TMEM
+  // columns for the double-buffered split-pass accumulators) and the input channels go through the A_X buffer in K
+  // passes of 64.  Up to 64 channels nothing changes (one tile, one pass).
+  const int COT = (6 * CO <= 512) ? CO : 64;
+  if (CO % COT != 0) return -1;
+  const int nco = CO / COT;
   const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
+  const int npass = (CI + CIP - 1) / CIP;
   const TwLayout tl = tw_layout(s);
+  const bool tiled = nco > 1 || npass > 1;
+  if (tiled && (urow == nullptr || p.g.H <= 1)) return -1;   // the in-kernel row-axis stage knows one tile / one pass only
   // stage A stages the packed spectrum through the A_X area: at least one output channel must fit
-  if (2 * CIP * 128 * 4 - round_up(kSynthMaxRows * p.g.KH, 2) * 8 < p.g.KH * p.g.MW * 8) return -1;
+  if (!tiled && 2 * CIP * 128 * 4 - round_up(kSynthMaxRows * p.g.KH, 2) * 8 < p.g.KH * p.g.MW * 8) return -1;
   int bestR = 0;
   double best_eff = -1.0;
   const int maxR = p.g.H > 1 ? (p.g.H < kSynthMaxRows ? p.g.H : kSynthMaxRows) : 1;
   for (int R = maxR; R >= 1; --R) {
-    const size_t bytes = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, R).total;
+    const size_t bytes = (size_t)tc::synth_tc_smem(CIP, COT, tl.KE, R, npass).total;
     if (bytes > (size_t)kMaxSmemBytes) continue;
     int per_sm = (int)((228 * 1024) / (bytes + 2048));
     if (per_sm > 4) per_sm = 4;
-    if (per_sm * 6 * CO > 512) per_sm = 512 / (6 * CO) > 0 ? 512 / (6 * CO) : 1;   // TMEM columns per SM
+    if (per_sm * 6 * COT > 512) per_sm = 512 / (6 * COT) > 0 ? 512 / (6 * COT) : 1;   // TMEM columns per SM
     if (per_sm < 1) per_sm = 1;
-    const long long ctas = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks;
+    const long long ctas = (long long)p.g.NBO * p.g.NBI * ((p.g.H + R - 1) / R) * tl.nchunks * nco;
     const long long slots = 148LL * per_sm;
     const long long waves = (ctas + slots - 1) / slots;
     double eff = (double)ctas / (double)(waves * slots);
@@ -1017,7 +1040,9 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
     r.Qp = tc::row_synth_pitch(r.KH, r.MW, r.KE);
     r.tiles = (r.H + tc::kRowSynthRows - 1) / tc::kRowSynthRows;
     r.ocb = CO;   // whole spectrum per block (8-channel blocks with staged 128-byte stores measured slower: 22 vs 16 us)
+    while (r.ocb > 8 && tc::row_synth_smem_bytes(r.ocb, r.KH, r.MW, r.KE) > (size_t)kMaxSmemBytes) r.ocb = (r.ocb + 1) / 2;   // width 128: two halves
     r.ogroups = (CO + r.ocb - 1) / r.ocb;
+    r.COT = COT; r.nco = nco;
     const size_t rs_smem = tc::row_synth_smem_bytes(r.ocb, r.KH, r.MW, r.KE);
     if (rs_smem <= (size_t)kMaxSmemBytes) {
       int rrc = allow_smem(tc::row_synthesis_kernel, rs_smem, "row_synthesis");
@@ -1031,14 +1056,16 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
       q.urow = urow;
     }
   }
+  if (tiled && q.urow == nullptr) return -1;
   q.KE = tl.KE;
   q.nchunks = tl.nchunks;
+  q.COT = COT; q.nco = nco; q.npass = npass;
   int cols = 32;
-  while (cols < 6 * CO) cols *= 2;
+  while (cols < 6 * COT) cols *= 2;
   if (cols > 512) return -1;
   q.tmem_cols = cols;
-  const size_t smem = (size_t)tc::synth_tc_smem(CIP, CO, tl.KE, bestR).total;
-  const int grid = s.B * s.X * p.tiles * tl.nchunks;
+  const size_t smem = (size_t)tc::synth_tc_smem(CIP, COT, tl.KE, bestR, npass).total;
+  const int grid = s.B * s.X * p.tiles * tl.nchunks * nco;
   int rc = DENO_OK;
 #define DENO_TC_CASE2(ACT, CIPV)                                                                    \
   {                                                                                                 \

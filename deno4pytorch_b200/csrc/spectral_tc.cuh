@@ -168,8 +168,10 @@ struct SynthTcParams {
   const float* ae;        // pre-split twiddle images [chunk][hi|lo][KE * 128] floats
   int KE;                 // 2 * MWp rounded up to a multiple of 8
   int nchunks;            // column chunks of 128 per row
-  int tmem_cols;          // power of two >= 6 * CO (two row buffers x three split-pass tiles)
-  const float* urow;      // row-axis synthesis U, pre-split B operand images [NB'][H][hi|lo][KE * CO] (row_synthesis_kernel)
+  int tmem_cols;          // power of two >= 6 * COT (two row buffers x three split-pass tiles)
+  const float* urow;      // row-axis synthesis U, pre-split B operand images [NB'][H][cot][hi|lo][KE * COT] (row_synthesis_kernel)
+  int COT, nco;           // output channels per CTA (the GEMM N), CO / COT channel tiles (width 128: two tiles of 64)
+  int npass;              // K passes of CIP input channels each through the one A_X buffer (width 128: two passes of 64)
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -193,6 +195,7 @@ struct RowSynthParams {
   int Qp;                // padded per-channel pitch of the staged spectrum (bank-conflict-free (o, l) lanes)
   int tiles;             // ceil(H / kRowSynthRows)
   int ocb, ogroups;      // output channels per block, ceil(CO / ocb); gridDim.x = NB' * tiles * ogroups
+  int COT, nco;          // channel tiling of the images: [NB'][H][nco][hi|lo][KE * COT]
 };
 
 __host__ __device__ inline int row_synth_pitch(int KH, int MW, int KE) {
@@ -254,7 +257,8 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
   }
   __syncthreads();
   const int LH = p.KE / 2;                                          // (cos, sin) column pairs incl. zero padding
-  const size_t img = (size_t)p.KE * p.CO;                           // floats per hi (or lo) image
+  const size_t img = (size_t)p.KE * p.COT;                          // floats per hi (or lo) image of one channel tile
+  const size_t rowpitch = (size_t)p.nco * 2 * img;                  // floats between consecutive rows
   // (8-channel blocks that stage their results in shared memory and store full 128-byte lines were tried and measured
   // slower - 22 vs 16 us - as were lane pairs splitting the k range)
   for (int task = tid; task < noc * LH; task += nthr) {
@@ -281,16 +285,17 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
       }
       f = p.scale * (p.herm ? p.cl[l] : 1.0f);
     }
-    const int off = kmajor_off(o, 2 * l, p.CO) / 4;                 // floats; columns 2l and 2l + 1 are adjacent
-    float* dst = p.u + ((size_t)bp * p.H + x0) * 2 * img + off;
+    const int ot = o / p.COT, oi = o - ot * p.COT;
+    const int off = kmajor_off(oi, 2 * l, p.COT) / 4;               // floats; columns 2l and 2l + 1 are adjacent
+    float* dst = p.u + ((size_t)bp * p.H + x0) * rowpitch + (size_t)ot * 2 * img + off;
 #pragma unroll
     for (int rr = 0; rr < kRowSynthRows; ++rr) {
       if (rr < trows) {
         float h0, l0, h1, l1;
         split_tf32(ar[rr] * f, h0, l0);
         split_tf32(-ai[rr] * f, h1, l1);
-        *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img) = make_float2(h0, h1);
-        *reinterpret_cast<float2*>(dst + (size_t)rr * 2 * img + img) = make_float2(l0, l1);
+        *reinterpret_cast<float2*>(dst + (size_t)rr * rowpitch) = make_float2(h0, h1);
+        *reinterpret_cast<float2*>(dst + (size_t)rr * rowpitch + img) = make_float2(l0, l1);
       }
     }
   }
@@ -301,11 +306,14 @@ struct SynthTcSmem {
   int bu_one;                                                     // bytes of one (hi or lo) U image
 };
 
-__host__ __device__ inline SynthTcSmem synth_tc_smem(int CIP, int CO, int KE, int R) {
+// CO = output channels of ONE CTA (the channel tile); npass weight images [pass][hi|lo] when the input channels go
+// through the A_X buffer in several K passes (bw_lo = offset of pass 0's lo image, pass stride 2 * CIP * CO * 4)
+__host__ __device__ inline SynthTcSmem synth_tc_smem(int CIP, int CO, int KE, int R, int npass = 1) {
   SynthTcSmem m;
   int off = 0;
   m.bw_hi = off; off += CIP * CO * 4;
   m.bw_lo = off; off += CIP * CO * 4;
+  off += (npass - 1) * 2 * CIP * CO * 4;
   m.ae_hi = off; off += KE * 128 * 4;
   m.ae_lo = off; off += KE * 128 * 4;
   m.bu_one = KE * CO * 4;
@@ -329,15 +337,20 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_mma = warp == 8;             // ninth warp: issues the MMAs, takes no part in the SIMT work
   const int wt = is_mma ? (1 << 28) : tid;     // loop start of the 256 worker threads (beyond every bound for the MMA warp)
-  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = p.CO;
+  // CO below is the channel tile of THIS CTA (the GEMM N); the layer's output channels are p.CO = q.nco * q.COT
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = q.COT;
   const int KH4 = round_up(KH, 4);
   const int KE = q.KE, R = p.R;
-  const SynthTcSmem so = synth_tc_smem(CIP, CO, KE, R);
+  const int npass = q.npass;
+  const SynthTcSmem so = synth_tc_smem(CIP, CO, KE, R, npass);
+  const int bw_pass = 2 * CIP * CO * 4;            // bytes between the weight images of consecutive K passes
   constexpr int NIT = CIP / 8;            // (point, channel-quad) items per thread: 128 * CIP/4 / 256
 
   // CTA coordinates
   int bid = blockIdx.x;
   const int chunk = bid % q.nchunks; bid /= q.nchunks;
+  const int cot = bid % q.nco; bid /= q.nco;      // channel tiles of the same rows on neighbouring CTAs (x re-read from L2)
+  const int co0 = cot * CO;
   const int tile = bid % p.tiles;
   const int bp = bid / p.tiles;
   const int x0 = tile * R;
@@ -355,47 +368,53 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
     // constant twiddle images (final layout in global memory) and, when row_synthesis_kernel ran (q.urow), this
     // tile's U images: bulk async copies, so the prologue costs one memory round trip instead of one per loop trip
     const uint32_t ae_bytes = (uint32_t)(2 * KE * 128 * 4);
-    const uint32_t u_bytes = q.urow != nullptr ? (uint32_t)(trows * 2 * so.bu_one) : 0u;
+    const uint32_t u_bytes = q.urow != nullptr ? (uint32_t)(trows * 2 * so.bu_one) : 0u;   // one bulk copy per row
     mbar_expect_tx(&mbar_u, ae_bytes + u_bytes);
     bulk_g2s(smem + so.ae_hi, q.ae + (long long)chunk * 2 * KE * 128, ae_bytes, &mbar_u);
   }
 
   // ---- constant operands -------------------------------------------------------------------
   // bypass weight image B_W[n = o][k = i], split on the fly; four loads in flight per thread
-  for (int idx0 = wt; idx0 < CO * CIP; idx0 += 4 * 256) {
-    float wv[4];
+  for (int ps = 0; ps < npass; ++ps)
+    for (int idx0 = wt; idx0 < CO * CIP; idx0 += 4 * 256) {
+      float wv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = min(idx0 + u * 256, CO * CIP - 1);
-      const int o = idx / CIP, i = idx - o * CIP;
-      wv[u] = (i < CI) ? ldg_ordered(p.lw + (long long)o * p.lw_so + (long long)i * p.lw_si) : 0.f;
-    }
+      for (int u = 0; u < 4; ++u) {
+        const int idx = min(idx0 + u * 256, CO * CIP - 1);
+        const int o = idx / CIP, i = ps * CIP + (idx - o * CIP);
+        wv[u] = (i < CI) ? ldg_ordered(p.lw + (long long)(co0 + o) * p.lw_so + (long long)i * p.lw_si) : 0.f;
+      }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = idx0 + u * 256;
-      if (idx < CO * CIP) {
-        const int o = idx / CIP, i = idx - o * CIP;
-        float hi, lo;
-        split_tf32(wv[u], hi, lo);
-        const int off = kmajor_off(o, i, CO);
-        *reinterpret_cast<float*>(smem + so.bw_hi + off) = hi;
-        *reinterpret_cast<float*>(smem + so.bw_lo + off) = lo;
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * 256;
+        if (idx < CO * CIP) {
+          const int o = idx / CIP, i = idx - o * CIP;
+          float hi, lo;
+          split_tf32(wv[u], hi, lo);
+          const int off = ps * bw_pass + kmajor_off(o, i, CO);
+          *reinterpret_cast<float*>(smem + so.bw_hi + off) = hi;
+          *reinterpret_cast<float*>(smem + so.bw_lo + off) = lo;
+        }
       }
     }
-  }
   float* bias_s = reinterpret_cast<float*>(smem + so.bias);
-  for (int o = wt; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[o] : 0.f;
+  for (int o = wt; o < CO; o += 256) bias_s[o] = (p.bias != nullptr) ? p.bias[co0 + o] : 0.f;
 
   // Everything above depends on constants and weights only.  The U images come from the immediate predecessor
   // (row_synthesis_kernel) and x / gz from earlier kernels: from here on the predecessor must have completed.
   DENO_PDL_SYNC();
-  if (tid == 32 && q.urow != nullptr)
-    bulk_g2s(smem + so.bu, q.urow + ((size_t)bp * H + x0) * 2 * (size_t)(so.bu_one / 4), (uint32_t)(trows * 2 * so.bu_one), &mbar_u);
+  if (tid == 32 && q.urow != nullptr) {
+    const size_t img2 = 2 * (size_t)(so.bu_one / 4);                 // floats of one row's hi + lo images of one channel tile
+    for (int rr = 0; rr < trows; ++rr)
+      bulk_g2s(smem + so.bu + rr * 2 * so.bu_one, q.urow + (((size_t)bp * H + x0 + rr) * q.nco + cot) * img2,
+               (uint32_t)(2 * so.bu_one), &mbar_u);
+  }
 
   // ---- x row prefetch (registers) ------------------------------------------------------------
   float xr[NIT][4];
   const long long ubase = plane_base(p.g, bp, 0);
-  auto prefetch = [&](int rr) {
+  auto prefetch = [&](int step) {                    // step = row * npass + K pass
+    const int rr = step / npass, ps = step - rr * npass;
     const long long rowoff = ubase + (long long)(x0 + rr) * W + y0;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -403,7 +422,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       const int pt = item & 127, cq = item >> 7;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int ch = cq * 4 + j;
+        const int ch = ps * CIP + cq * 4 + j;
         xr[it][j] = (pt < ny && ch < CI) ? p.u[rowoff + (long long)ch * p.g.sc + pt] : 0.f;
       }
     }
@@ -504,7 +523,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   const int wq = warp & 3, wg = warp >> 2;          // TMEM lane quadrant / column half
   const int ncol_half = CO / 2;
   const int yl = wq * 32 + lane;                    // this thread's point inside the chunk
-  const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi;
+  const long long obase_b = (long long)(bp / p.g.NBI) * p.sbo_out + (long long)(bp % p.g.NBI) * p.g.sbi + (long long)co0 * p.g.sc;
 
   auto epilogue = [&](int rr) {
     const uint32_t tb = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)((rr & 1) * 3 * CO + wg * ncol_half);
@@ -556,7 +575,8 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
     // ---- MMA warp: per row, wait until the 256 workers have stored the A_X images, issue, commit ----
     const bool leader = elect_one();   // warp-uniform loop (descriptors in uniform registers); one lane issues
     const uint64_t inc_m = (uint64_t)((2 * lbo_m) >> 4), inc_n = (uint64_t)((2 * lbo_n) >> 4);
-    for (int rr = 0; rr < trows; ++rr) {
+    for (int step = 0; step < trows * npass; ++step) {
+      const int rr = step / npass, ps = step - rr * npass;
       nbar_sync(kSynBarAx, kSynThreads);
       fence_after_sync();
       const long long tr3 = DENO_CLK();
@@ -565,10 +585,10 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       // issued round-robin; the epilogue adds the tiles.  Descriptors are built once and advanced by a constant.
       const uint32_t d = tmem + (uint32_t)((rr & 1) * 3 * CO);
       uint64_t axh = make_desc(sbase + so.ax_hi, lbo_m, 128), axl = make_desc(sbase + so.ax_lo, lbo_m, 128);
-      uint64_t bwh = make_desc(sbase + so.bw_hi, lbo_n, 128), bwl = make_desc(sbase + so.bw_lo, lbo_n, 128);
+      uint64_t bwh = make_desc(sbase + so.bw_hi + ps * bw_pass, lbo_n, 128), bwl = make_desc(sbase + so.bw_lo + ps * bw_pass, lbo_n, 128);
 #pragma unroll
       for (int s = 0; s < CIP / 8; ++s) {
-        const uint32_t acc = s > 0 ? 1u : 0u;
+        const uint32_t acc = (s > 0 || ps > 0) ? 1u : 0u;
         if (leader) {
           mma_tf32(d, axh, bwh, idesc, acc);            // hi * hi
           mma_tf32(d + CO, axl, bwh, idesc, acc);       // lo * hi
@@ -576,26 +596,29 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
         }
         axh += inc_m; axl += inc_m; bwh += inc_n; bwl += inc_n;
       }
-      uint64_t aeh = make_desc(sbase + so.ae_hi, lbo_m, 128), ael = make_desc(sbase + so.ae_lo, lbo_m, 128);
-      uint64_t buh = make_desc(sbase + so.bu + (2 * rr) * so.bu_one, lbo_n, 128);
-      uint64_t bul = make_desc(sbase + so.bu + (2 * rr + 1) * so.bu_one, lbo_n, 128);
-      for (int s = 0; s < KE / 8; ++s) {
-        if (leader) {
-          mma_tf32(d, aeh, buh, idesc, 1u);
-          mma_tf32(d + CO, ael, buh, idesc, 1u);
-          mma_tf32(d + 2 * CO, aeh, bul, idesc, 1u);
+      if (ps == npass - 1) {                            // last K pass of the row: the last-axis synthesis on top
+        uint64_t aeh = make_desc(sbase + so.ae_hi, lbo_m, 128), ael = make_desc(sbase + so.ae_lo, lbo_m, 128);
+        uint64_t buh = make_desc(sbase + so.bu + (2 * rr) * so.bu_one, lbo_n, 128);
+        uint64_t bul = make_desc(sbase + so.bu + (2 * rr + 1) * so.bu_one, lbo_n, 128);
+        for (int s = 0; s < KE / 8; ++s) {
+          if (leader) {
+            mma_tf32(d, aeh, buh, idesc, 1u);
+            mma_tf32(d + CO, ael, buh, idesc, 1u);
+            mma_tf32(d + 2 * CO, aeh, bul, idesc, 1u);
+          }
+          aeh += inc_m; ael += inc_m; buh += inc_n; bul += inc_n;
         }
-        aeh += inc_m; ael += inc_m; buh += inc_n; bul += inc_n;
       }
-      if (leader) mma_commit(&mbar[rr & 1]);
+      if (leader) mma_commit(&mbar[step & 1]);
       __syncwarp();
       if (leader) DENO_DBG_ADD(53, DENO_CLK() - tr3);   // slot 53: MMA issue
     }
   } else {
     // ---- workers: A_X images of row rr, then (while the tensor core works on it) the epilogue of row rr - 1 ----
-    for (int rr = 0; rr < trows; ++rr) {
+    for (int step = 0; step < trows * npass; ++step) {
+      const int rr = step / npass, ps = step - rr * npass;
       const long long tr0 = DENO_CLK();
-      if (rr > 0) mbar_wait(&mbar[(rr - 1) & 1], ((rr - 1) >> 1) & 1);   // MMA(rr-1) done: A_X free, D(rr-1) ready
+      if (step > 0) mbar_wait(&mbar[(step - 1) & 1], ((step - 1) >> 1) & 1);   // MMAs of the previous step done: A_X free (ps == 0: D(rr-1) ready)
       const long long tr1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(50, tr1 - tr0);        // slot 50: wait for the previous row's MMAs
       // registers -> A_X images (hi / lo)
@@ -617,9 +640,9 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       nbar_arrive(kSynBarAx, kSynThreads);
       const long long tr4 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(51, tr4 - tr1);        // slot 51: split + store + hand-off
-      if (rr + 1 < trows) prefetch(rr + 1);
+      if (step + 1 < trows * npass) prefetch(step + 1);
       const long long tr5 = DENO_CLK();
-      if (rr > 0) {
+      if (rr > 0 && ps == 0) {
         fence_after_sync();
         epilogue(rr - 1);
       }
@@ -627,7 +650,8 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
     }
   }
   if (!is_mma) {
-    mbar_wait(&mbar[(trows - 1) & 1], ((trows - 1) >> 1) & 1);
+    const int last = trows * npass - 1;
+    mbar_wait(&mbar[last & 1], (last >> 1) & 1);
     fence_after_sync();
     epilogue(trows - 1);
   }

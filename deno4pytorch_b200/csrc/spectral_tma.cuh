@@ -247,9 +247,12 @@ namespace tc {
 // (FUSE_GZ) gz = gy * act'(z) written once on the way - with the planes brought in by tensor-map TMA.
 //
 // Rows of a plane are W floats apart, which is a multiple of 16 bytes only every g = 4 / gcd(W, 4) rows, so the
-// flat [rows][W] matrix is described by g tensor maps, one per row class j = row mod g (row stride g*W*4 bytes, base
-// rounded down to 16 bytes, the residue `shift_j` floats added to the inner coordinate).  A box [H/g rows][32 floats]
-// of class j of plane pp lands as rows ((j*P + pp)*HGp + hh) of a K-major SWIZZLE_128B tile: the B operand of
+// flat [rows][W] matrix is described by g tensor maps, one per row class j = row mod g (row stride g*W*4 bytes).  A TMA
+// box must start on a 16-byte boundary in global memory (an inner coordinate of 2 floats is an illegal instruction on
+// hardware, profiles/r2g_tma_box_probe.txt), so class j starts at the 16-byte boundary BELOW its first row: every landed
+// row carries shift_j = (j*W) mod 4 leading floats of the previous row, and class j has its own twiddle image E_j whose
+// column kc stands for w = kc - shift_j (zero columns under the foreign floats).  A box [H/g rows][32 floats] of class j
+// of plane pp lands as rows ((j*P + pp)*HGp + hh) of a K-major SWIZZLE_128B tile: the B operand (per class) of
 //   stage 1 (transposed)   D1[n, r] = sum_w E[n, w] * x[r, w]      A = E image: rows n < N1 tf32 hi, rows N1 + n lo
 //                          two MMAs per K = 8 step: B = tf32(x) (masked in place) and B = x - tf32(x), one accumulator
 //                          -> T[n, r] = D1[n, r] + D1[N1 + n, r]       (n = 2l: Re, 2l+1: Im of sum_w x e^{-i psi_l w})
@@ -268,7 +271,7 @@ struct AnalysisTmaParams {
   int C, X, NP, ntiles;          // channels, outer extent (3-D), planes in memory order, tiles
   int nchunks;                   // ceil(W / 32)
   int N, K2p, N2;                // stage-1 N (g*P*HGp), stage-2 K (padded to 32), stage-2 N (2*P*N1)
-  int shift[4];                  // inner-coordinate shift of row class j (floats)
+  int shift[4];                  // leading foreign floats of every landed row of class j (host-side image construction)
   int nsh, nsl;                  // stages of the landed-tile ring / the lo-tile ring
   const float* e1;               // E image, final shared-memory layout: nchunks x [2 N1 rows][32] SWIZZLE_128B
   const float* a2;               // A2 image: (K2p / 32) x [4 KHp rows][32] SWIZZLE_128B
@@ -292,7 +295,7 @@ struct AnalysisTmaSmem { int e1, a2, timg, hi, lo, stg, xch, total; int hi_stage
 
 __host__ __device__ inline AnalysisTmaSmem analysis_tma_smem(const AnalysisTmaParams& p, bool fuse_gz) {
   AnalysisTmaSmem m;
-  m.e1_bytes = p.nchunks * 2 * p.N1 * 128;
+  m.e1_bytes = p.g * p.nchunks * 2 * p.N1 * 128;       // one twiddle image per row class (columns shifted by shift[j])
   m.a2_bytes = (p.K2p / 32) * 4 * p.KHp * 128;
   m.t_bytes = (p.K2p / 32) * p.N2 * 128;
   m.hi_stage = p.N * 128 * (fuse_gz ? 2 : 1);
@@ -386,8 +389,8 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
           for (int j = 0; j < g; ++j)
             for (int pp = 0; pp < P; ++pp) {
               const int row0 = (j * P + pp) * HGp;
-              tma_load_2d(dst + row0 * 128, &maps.u[j], p.shift[j] + 32 * c, (m0 + pp) * HG, &bar_hi_full[st]);
-              if (FUSE_GZ) tma_load_2d(dst + N * 128 + row0 * 128, &maps.z[j], p.shift[j] + 32 * c, (m0 + pp) * HG, &bar_hi_full[st]);
+              tma_load_2d(dst + row0 * 128, &maps.u[j], 32 * c, (m0 + pp) * HG, &bar_hi_full[st]);
+              if (FUSE_GZ) tma_load_2d(dst + N * 128 + row0 * 128, &maps.z[j], 32 * c, (m0 + pp) * HG, &bar_hi_full[st]);
             }
         }
       }
@@ -396,7 +399,8 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
     // ===================================================================== MMA issuer
     const bool leader = elect_one();
     const bool issue = leader && !(p.dbg & 2);
-    const uint32_t idesc1 = make_idesc_tf32(128, N), idesc2 = make_idesc_tf32(128, N2);
+    const int NC = P * HGp;                            // stage-1 N of one row class
+    const uint32_t idesc1 = make_idesc_tf32(128, NC), idesc2 = make_idesc_tf32(128, N2);
     const uint32_t sbase = smem_u32(smem);
     mbar_wait(&bar_const, 0);
     auto stage2 = [&](int n) {                         // S2 of this CTA's n-th tile
@@ -425,16 +429,19 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
         const int sl = ci % NSL, sh = ci % NSH;
         mbar_wait(&bar_lo_full[sl], (uint32_t)((ci / NSL) & 1));      // implies the landed tile is complete (and masked)
         fence_after_sync();
-        uint64_t e = make_desc_sw128(sbase + so.e1 + c * (2 * N1 * 128));
-        uint64_t xh = make_desc_sw128(sbase + so.hi + sh * so.hi_stage);
-        uint64_t xl = make_desc_sw128(sbase + so.lo + sl * so.lo_stage);
+        for (int j = 0; j < g; ++j) {                    // per row class: its own (shifted) twiddle image, its rows of the tile
+          uint64_t e = make_desc_sw128(sbase + so.e1 + (j * nch + c) * (2 * N1 * 128));
+          uint64_t xh = make_desc_sw128(sbase + so.hi + sh * so.hi_stage + j * NC * 128);
+          uint64_t xl = make_desc_sw128(sbase + so.lo + sl * so.lo_stage + j * NC * 128);
+          const uint32_t dj = d1 + (uint32_t)(j * NC);
 #pragma unroll
-        for (int s2 = 0; s2 < 4; ++s2) {
-          if (issue) {
-            mma_tf32(d1, e, xh, idesc1, (c | s2) ? 1u : 0u);
-            mma_tf32(d1, e, xl, idesc1, 1u);
+          for (int s2 = 0; s2 < 4; ++s2) {
+            if (issue) {
+              mma_tf32(dj, e, xh, idesc1, (c | s2) ? 1u : 0u);
+              mma_tf32(dj, e, xl, idesc1, 1u);
+            }
+            e += 2; xh += 2; xl += 2;
           }
-          e += 2; xh += 2; xl += 2;
         }
         if (leader) { mma_commit(&bar_hi_empty[sh]); mma_commit(&bar_lo_empty[sl]); }
         __syncwarp();
@@ -478,7 +485,7 @@ plane_analysis_tma_kernel(const __grid_constant__ AnalysisTmaMaps maps, Analysis
               for (int pp = 0; pp < P; ++pp)
                 if (m0 + pp < p.NP)
                   tma_store_2d(&maps.gz[j], reinterpret_cast<unsigned char*>(zt) + (j * P + pp) * HGp * 128,
-                               p.shift[j] + 32 * c, (m0 + pp) * HG);
+                               32 * c, (m0 + pp) * HG);   // the shift[j] leading floats are the previous row's tail: same values its own class writes
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }

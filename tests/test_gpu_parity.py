@@ -90,10 +90,14 @@ SHAPES = [
     (1, 32, 32, (70, 70, 46), (8, 8, 8), "gelu"),  # C5 layer
     (2, 5, 7, (33, 20), (16, 11), "silu"),        # ragged channels, max modes
     (2, 6, 6, (128, 40), (64, 16), "tanh"),       # the (64, 16) modes of the Airfoil/Pipe demos
+    # wide layers on the tensor-core synthesis: output-channel tiles of 64, input channels in K passes of 64
+    (2, 96, 128, (40, 36), (6, 5), "gelu"),       # second K pass half empty, two channel tiles
+    (2, 128, 64, (37, 30), (5, 6), "silu"),       # two K passes, one tile (backward: one pass, two tiles)
+    (1, 72, 192, (24, 44), (4, 7), "relu"),       # three channel tiles
 ]
 
 
-@pytest.mark.parametrize("shape", SHAPES, ids=[str(s[3]) for s in SHAPES])
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"{s[1]}x{s[2]}-{s[3]}" for s in SHAPES])
 def test_layer_matches_cpu_oracle_at_config_shapes(shape):
     """Isolated-branch-safe check: weights rescaled so the spectral branch is O(1) of the bypass."""
     from oracle import fno_port
