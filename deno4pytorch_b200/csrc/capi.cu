@@ -23,6 +23,7 @@
 #ifndef DENO_EMULATE
 #include "spectral_tc.cuh"
 #include "spectral_tma.cuh"
+#include "spectral_mix_tc.cuh"
 #include "fno_proj_tc.cuh"
 #endif
 
@@ -599,6 +600,7 @@ struct Options {
   int mix_tm = 0;        // 0 = heuristic
   bool synth_ws = false;
   bool wgrad_tma = true; // DENO_WGRAD_TMA=0: the register-staged bypass_wgrad_tc kernel instead of the TMA one
+  bool mix_tc = true;    // DENO_MIX_TC=0: the SIMT mode-mix kernels also for width >= 64
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
@@ -614,6 +616,7 @@ Options read_options() {
   if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] != '0';
   if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] == '1';
   if (const char* e = getenv("DENO_AT_DBG")) o.at_dbg = atoi(e);
+  if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
 std::mutex g_opt_mutex;
@@ -671,7 +674,10 @@ int try_launch_analysis_tma(const Shape& s, int channels, const float* u, const 
     const long long base_off = off_bytes & ~15LL;
     p.shift[j] = (int)((off_bytes - base_off) / 4);
     if (p.shift[j] != a.shift[j]) return -1;
-    const unsigned long long inner = (unsigned long long)s.W + p.shift[j];
+    // extent rounded up to 16 bytes: a TMA STORE clips in 16-byte units (an extent of 94 floats let the class-0 store
+    // zero the first two floats of the next row, gpurun r2i); the extra floats are the next row's head - loaded,
+    // multiplied and stored back with the very values that row's own class writes
+    const unsigned long long inner = (unsigned long long)round_up(s.W + p.shift[j], 4);
     const unsigned long long outer = (unsigned long long)NP * a.HG;
     const unsigned long long row_bytes = (unsigned long long)a.g * s.W * 4;
     if (!make_tmap_2d(&maps.u[j], reinterpret_cast<const char*>(u) + base_off, inner, outer, row_bytes, (unsigned)a.HG)) return -1;
@@ -815,8 +821,88 @@ bool mix_tile_cfg(const Shape& s, bool backward, MixTileParams& p, size_t& smem_
   return true;
 }
 
+#ifndef DENO_EMULATE
+// Tensor-core channel mix (spectral_mix_tc.cuh): width >= 64 on both sides (where the per-mode product is a real dense
+// GEMM, north_star item 2), channels in tiles of 64, at most 64 batch entries (the GEMM N), enough modes to fill the
+// machine.  Narrower layers keep the SIMT kernels.
+bool mix_tc_eligible(const Shape& s) {
+  if (path_pref() == PathPref::Simt || !options().mix_tc) return false;
+  if (s.CI < 64 || s.CO < 64 || (s.CI % 64) != 0 || (s.CO % 64) != 0) return false;
+  if (s.B > 64 || s.M < 64) return false;
+  return true;
+}
+int mix_tc_modes_per_cta(const Shape& s, int ckp, int bp) {   // 2 when pairs of adjacent modes share 16-byte loads and fit
+  const int mlast = s.ndim == 1 ? s.mW : s.MW;
+  if ((mlast % 2) != 0 || (s.M % 2) != 0) return 1;
+  return tc::mix_tc_smem(2, ckp, bp).total <= kMaxSmemBytes ? 2 : 1;
+}
+
+int launch_mix_tc(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks, cudaStream_t st) {
+  tc::MixTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = in; p.out = out;
+  p.md = make_decode(s);
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < 4; ++j) p.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
+  p.B = s.B;
+  if (!backward) {
+    p.CK = s.CI; p.CR = s.CO;
+    p.w_sck = (long long)s.CO * p.md.Mblk; p.w_scr = p.md.Mblk;
+    p.conj_w = 0;
+  } else {
+    p.CK = s.CO; p.CR = s.CI;
+    p.w_sck = p.md.Mblk; p.w_scr = (long long)s.CO * p.md.Mblk;
+    p.conj_w = 1;
+  }
+  p.Bp = round_up(s.B, 8); p.CKp = round_up(p.CK, 8);
+  p.TM = mix_tc_modes_per_cta(s, p.CKp, p.Bp);
+  p.ntile = (p.CR + tc::kMixTcTile - 1) / tc::kMixTcTile;
+  const size_t smem = (size_t)tc::mix_tc_smem(p.TM, p.CKp, p.Bp).total;
+  if (smem > (size_t)kMaxSmemBytes) return -1;
+  int rc = allow_smem(tc::mode_mix_tc_kernel, smem, "mode_mix_tc");
+  if (rc != DENO_OK) return rc;
+  const int grid = (s.M / p.TM) * p.ntile;
+  prof_before(backward ? "mode_mix_bwd_tc" : "mode_mix_tc", st);
+  DENO_LAUNCH((tc::mode_mix_tc_kernel), dim3(grid), dim3(tc::kMixTcThreads), smem, st, p);
+  return check_launch("mode_mix_tc", st);
+}
+
+int launch_mix_wgrad_tc(const Shape& s, const float2* xhat, const float2* ghat, void* const* gw_blocks, float* glb_from_dc,
+                        cudaStream_t st) {
+  tc::MixWgradTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.xhat = xhat; p.ghat = ghat;
+  p.glb = glb_from_dc; p.s_total = (float)s.S;
+  p.md = make_decode(s);
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < 4; ++j) p.gw[j] = static_cast<float2*>(gw_blocks[j < nblk ? j : 0]);
+  p.B = s.B; p.CI = s.CI; p.CO = s.CO;
+  p.Kp = round_up(s.B, 8);
+  const int mlast = s.ndim == 1 ? s.mW : s.MW;
+  p.TM = ((mlast % 2) == 0 && (s.M % 2) == 0 && tc::mix_wgrad_tc_smem(2, p.Kp).total <= kMaxSmemBytes) ? 2 : 1;
+  p.nti = (s.CI + tc::kMixTcTile - 1) / tc::kMixTcTile;
+  p.nto = (s.CO + tc::kMixTcTile - 1) / tc::kMixTcTile;
+  const size_t smem = (size_t)tc::mix_wgrad_tc_smem(p.TM, p.Kp).total;
+  if (smem > (size_t)kMaxSmemBytes) return -1;
+  int rc = allow_smem(tc::mode_mix_wgrad_tc_kernel, smem, "mode_mix_wgrad_tc");
+  if (rc != DENO_OK) return rc;
+  const int grid = (s.M / p.TM) * p.nti * p.nto;
+  prof_before("mode_mix_wgrad_tc", st);
+  DENO_LAUNCH((tc::mode_mix_wgrad_tc_kernel), dim3(grid), dim3(tc::kMixTcThreads), smem, st, p);
+  return check_launch("mode_mix_wgrad_tc", st);
+}
+#else
+bool mix_tc_eligible(const Shape&) { return false; }
+#endif
+
 int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks,
                cudaStream_t st) {
+#ifndef DENO_EMULATE
+  if (mix_tc_eligible(s)) {
+    const int trc = launch_mix_tc(s, backward, in, out, w_blocks, st);
+    if (trc >= 0) return trc;
+  }
+#endif
   MixParams p;
   p.in = in; p.out = out;
   p.md = make_decode(s);
@@ -874,6 +960,32 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
 int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat, float2* gxhat, const void* const* w_blocks,
                          void* const* gw_blocks, float* glb_from_dc, cudaStream_t st) {
   const int nblk = 1 << (s.ndim - 1);
+#ifndef DENO_EMULATE
+  if (mix_tc_eligible(s)) {   // width >= 64: two tensor-core launches (+ the DC-mode bias gradient) instead of the fused SIMT one
+    int rc = DENO_OK;
+    if (gxhat != nullptr && w_blocks != nullptr) {
+      rc = launch_mix_tc(s, true, ghat, gxhat, w_blocks, st);
+      if (rc > 0) return rc;
+    }
+    bool bias_done = false;
+    if (rc == DENO_OK && gw_blocks != nullptr) {
+      rc = launch_mix_wgrad_tc(s, xhat, ghat, gw_blocks, glb_from_dc, st);
+      if (rc > 0) return rc;
+      bias_done = rc == DENO_OK;
+    }
+    if (rc == DENO_OK) {
+      if (glb_from_dc != nullptr && !bias_done) {
+        tc::BiasDcParams bp;
+        bp.ghat = ghat; bp.glb = glb_from_dc; bp.B = s.B; bp.CO = s.CO; bp.M = s.M; bp.s_total = (float)s.S;
+        prof_before("bias_from_dc", st);
+        DENO_LAUNCH((tc::bias_from_dc_kernel), dim3((s.CO + 127) / 128), dim3(128), 0, st, bp);
+        return check_launch("bias_from_dc", st);
+      }
+      return DENO_OK;
+    }
+    // rc < 0: a kernel declined before launching anything that cannot be redone below
+  }
+#endif
   {
     MixTileParams t;
     memset(&t, 0, sizeof(t));

@@ -19,10 +19,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 MODES = {
-    "ingraph": dict(DENO_DP_OVERLAP="0", DENO_DP_INGRAPH="1", DENO_DP_FUSED="0"),
-    "overlap": dict(DENO_DP_OVERLAP="1", DENO_DP_INGRAPH="1", DENO_DP_FUSED="0"),
-    "two_graphs": dict(DENO_DP_OVERLAP="0", DENO_DP_INGRAPH="0", DENO_DP_FUSED="0"),
-    "fused": dict(DENO_DP_OVERLAP="0", DENO_DP_INGRAPH="1", DENO_DP_FUSED="1"),
+    "ingraph": dict(DENO_DP_OVERLAP="0", DENO_DP_INGRAPH="1", DENO_DP_FUSED="0", DENO_DP_FUSED_WRITE_GRADS="0"),
+    "overlap": dict(DENO_DP_OVERLAP="1", DENO_DP_INGRAPH="1", DENO_DP_FUSED="0", DENO_DP_FUSED_WRITE_GRADS="0"),
+    "two_graphs": dict(DENO_DP_OVERLAP="0", DENO_DP_INGRAPH="0", DENO_DP_FUSED="0", DENO_DP_FUSED_WRITE_GRADS="0"),
+    # the fused kernel consumes the reduced gradient in registers; the test asks it to store the average back as well
+    "fused": dict(DENO_DP_OVERLAP="0", DENO_DP_INGRAPH="1", DENO_DP_FUSED="1", DENO_DP_FUSED_WRITE_GRADS="1"),
 }
 
 

@@ -94,6 +94,10 @@ SHAPES = [
     (2, 96, 128, (40, 36), (6, 5), "gelu"),       # second K pass half empty, two channel tiles
     (2, 128, 64, (37, 30), (5, 6), "silu"),       # two K passes, one tile (backward: one pass, two tiles)
     (1, 72, 192, (24, 44), (4, 7), "relu"),       # three channel tiles
+    # tensor-core channel mix (width >= 64, multiples of 64): single-mode CTAs (odd last-axis mode count), two channel
+    # tiles on one side, and a batch beyond one 32-entry epilogue pass
+    (3, 64, 128, (40, 36), (6, 7), "gelu"),
+    (40, 64, 64, (20, 24), (6, 6), "tanh"),
 ]
 
 
