@@ -252,6 +252,8 @@ def kernel_algorithmic_bytes(A, spec_small, Wb):
         "bypass_wgrad_partial": 2 * A, "bypass_wgrad_tc": 2 * A, "bypass_wgrad_tma": 2 * A,         # read gz, x
         "mode_mix_bwd_fused": 3 * spec_small + 3 * Wb,      # read G^, X^, W; write G^x, gW
         "mode_mix": 2 * spec_small + Wb, "mode_mix_bwd": 2 * spec_small + Wb, "mode_mix_wgrad": 2 * spec_small + Wb,
+        "mode_mix_tc": 2 * spec_small + Wb, "mode_mix_bwd_tc": 2 * spec_small + Wb, "mode_mix_wgrad_tc": 2 * spec_small + Wb,
+        "line_analysis": A + spec_small, "line_analysis_gz": 3 * A + spec_small,
         "row_synthesis": spec_small + A // 2,
     }
 

@@ -229,6 +229,8 @@ class _FNONd(nn.Module):
         desc = self._ends_desc(x, grid)
         if desc is not None:
             h = _LiftFn.apply(x, grid, self.fc0.weight, self.fc0.bias, desc, torch.is_grad_enabled())
+        elif x.is_cuda and _fused_ends_enabled():
+            h = self._lift_channels_first(x, grid)
         else:
             h = _tall_linear(torch.cat((x, grid), dim=-1), self.fc0)
             h = h.movedim(-1, 1)
@@ -247,10 +249,41 @@ class _FNONd(nn.Module):
         if desc is not None:
             return _ProjFn.apply(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, desc,
                                  torch.is_grad_enabled())
+        if h.is_cuda and _fused_ends_enabled():
+            return self._proj_channels_first(h)
         if self.padding != 0:
             h = h[(Ellipsis,) + (slice(None, -self.padding),) * nd]
         h = h.movedim(1, -1)
         return _tall_linear(F.gelu(_tall_linear(h, self.fc1)), self.fc2)
+
+    # Widths outside the fused point-wise kernels (include/deno_fno.h: > 64, e.g. the width-128 Airfoil / Pipe stacks):
+    # library GEMMs, but arranged channels-first so that no activation-sized permute / pad / crop copy is made around
+    # them (the op-by-op order of FNOs.py:136-151 costs ~10 such passes per step at width 128).
+    def _lift_channels_first(self, x, grid):
+        """``pad(permute(fc0(cat(x, grid))))`` as ONE batched GEMM that writes the padded channels-first tensor: the few
+        input features are permuted and zero-padded first (tiny), with a constant-one feature carrying the bias so that
+        the padding stays exactly zero."""
+        nd = self.ndim
+        feats = torch.cat((x, grid, torch.ones_like(x[..., :1])), dim=-1).movedim(-1, 1)     # (B, K + 1, *spatial)
+        if self.padding != 0:
+            feats = F.pad(feats, [0, self.padding] * nd)
+        w = torch.cat((self.fc0.weight, self.fc0.bias[:, None]), dim=1)                         # (C, K + 1)
+        h = torch.matmul(w, feats.reshape(feats.shape[0], feats.shape[1], -1))                  # (B, C, S)
+        return h.view((h.shape[0], h.shape[1]) + tuple(feats.shape[2:]))
+
+    def _proj_channels_first(self, h):
+        """``fc2(gelu(fc1(permute(crop(h)))))`` on the padded channels-first tensor as it is (1x1 convs = batched GEMMs over
+        the point axis); only the ``out_dim``-channel result is cropped and permuted."""
+        nd = self.ndim
+        B, C = h.shape[:2]
+        psp = tuple(h.shape[2:])
+        t = torch.baddbmm(self.fc1.bias.view(1, -1, 1), self.fc1.weight.unsqueeze(0).expand(B, -1, -1), h.reshape(B, C, -1))
+        t = F.gelu(t)
+        y = torch.baddbmm(self.fc2.bias.view(1, -1, 1), self.fc2.weight.unsqueeze(0).expand(B, -1, -1), t)
+        y = y.view((B, y.shape[1]) + psp)
+        if self.padding != 0:
+            y = y[(Ellipsis,) + (slice(None, -self.padding),) * nd]
+        return y.movedim(1, -1).contiguous()
 
     def _ends_desc(self, x, grid):
         """Descriptor of the fused lift / projection kernels, or None when this call stays on torch ops

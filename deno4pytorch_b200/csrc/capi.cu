@@ -750,6 +750,31 @@ int launch_analysis(const Shape& s, int channels, const float* u, const float* z
     }
   }
 #endif
+  if (s.ndim == 1 && s.MWp <= kLineThreads) {            // 1-D layers: lines, not planes (line_analysis_kernel)
+    LineAnalysisParams lp;
+    lp.g = make_geom(s, channels);
+    lp.u = u; lp.z = z; lp.gz_out = gz_out; lp.out = out;
+    lp.twW = tw.last; lp.cl = tw.cl; lp.scale = scale; lp.herm = herm;
+    lp.nlines = s.B * s.X * channels;
+    lp.MWp = s.MWp; lp.NS = kLineThreads / s.MWp;
+    const size_t lsm = line_analysis_smem(s.W, lp.MWp, lp.NS);
+    if (lsm <= (size_t)kMaxSmemBytes) {
+      const int lgrid = (lp.nlines + kLineRows - 1) / kLineRows;
+      int lrc;
+      if (z != nullptr) {
+        lrc = allow_smem(line_analysis_kernel<true>, lsm, "line_analysis");
+        if (lrc != DENO_OK) return lrc;
+        prof_before("line_analysis_gz", st);
+        DENO_LAUNCH(line_analysis_kernel<true>, dim3(lgrid), dim3(kLineThreads), lsm, st, lp);
+      } else {
+        lrc = allow_smem(line_analysis_kernel<false>, lsm, "line_analysis");
+        if (lrc != DENO_OK) return lrc;
+        prof_before("line_analysis", st);
+        DENO_LAUNCH(line_analysis_kernel<false>, dim3(lgrid), dim3(kLineThreads), lsm, st, lp);
+      }
+      return check_launch("line_analysis", st);
+    }
+  }
   AnalysisParams p;
   p.g = make_geom(s, channels);
   AnalysisCfg c;
@@ -1636,8 +1661,9 @@ int deno_dp_fused_adam(float* p_local, float* p_mc, float* g_mc, float* m, float
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long per4 = ((long long)n / 4 + world - 1) / world;          // float4 of one rank's slice
-  long long blocks = (per4 + 2LL * kDpThreads - 1) / (2LL * kDpThreads);
+  long long blocks = (per4 + (long long)kDpInFlight * kDpThreads - 1) / ((long long)kDpInFlight * kDpThreads);
   if (blocks > kDpMaxBlocks) blocks = kDpMaxBlocks;
+  if (blocks * world > 512) blocks = 512 / world;                          // slots of a 2 KB signal pad
   if (blocks < 1) blocks = 1;
   prof_before("dp_allreduce_adam", st);
   // the blocks of all ranks wait for each other: never more blocks than can be resident (32 << 148 SMs)

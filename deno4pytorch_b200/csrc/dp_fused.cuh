@@ -36,7 +36,8 @@ struct DpFusedParams {
 };
 
 constexpr int kDpThreads = 512;
-constexpr int kDpMaxBlocks = 32;            // 32 blocks x 8 ranks = 256 of the 512 slots of a 2 KB signal pad
+constexpr int kDpMaxBlocks = 64;            // 64 blocks x 8 ranks = the 512 slots of a 2 KB signal pad (the host clamps to the pad size)
+constexpr int kDpInFlight = 4;              // independent multimem reductions per thread: the exchange is bound by NVLink round trips, not bandwidth
 constexpr long long kDpSpinLimit = 4000000000LL;   // ~2 s of SM clocks
 
 #ifndef DENO_EMULATE
@@ -100,16 +101,19 @@ __global__ void __launch_bounds__(kDpThreads) dp_allreduce_adam_kernel(DpFusedPa
   const long long lo = per * a.rank, hi = (lo + per < n4) ? lo + per : n4;
 
   dp_sync_blocks(a);                                   // every rank's gradients are complete
-  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += 2LL * gridDim.x * blockDim.x) {
-    const long long i1 = i0 + (long long)gridDim.x * blockDim.x;     // two independent reductions in flight per thread
-    const bool two = i1 < hi;
-    float4 g0 = multimem_ld_reduce_add(a.g_mc + 4 * i0);
-    float4 g1 = two ? multimem_ld_reduce_add(a.g_mc + 4 * i1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += kDpInFlight * stride) {
+    float4 gq[kDpInFlight];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !two) break;
-      const long long i = u == 0 ? i0 : i1;
-      float4 g = u == 0 ? g0 : g1;
+    for (int u = 0; u < kDpInFlight; ++u) {              // all reductions of this trip in flight before the first is used
+      const long long i = i0 + u * stride;
+      gq[u] = i < hi ? multimem_ld_reduce_add(a.g_mc + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kDpInFlight; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= hi) break;
+      float4 g = gq[u];
       g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
       float4 pv = reinterpret_cast<const float4*>(a.p_local)[i];
       float4 mv = reinterpret_cast<const float4*>(a.m)[i];

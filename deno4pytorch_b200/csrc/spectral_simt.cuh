@@ -198,6 +198,123 @@ __global__ void plane_analysis_kernel(AnalysisParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// line_analysis: the 1-D layers' truncated forward rDFT (and, FUSE_GZ, gz = gy * act'(z) on the way), one (b, c) line
+// of W points per "plane".  plane_analysis_kernel is built around planes with many rows; for single-row planes it left
+// a CTA with 8 rows x 4 mode quads of parallelism walking ~1 000 columns (41 / 45 us at the Burgers shape, 5 MB of
+// input).  Here a CTA stages kLineRows lines in shared memory and EVERY thread owns one retained mode l and one of NS
+// interleaved column slices for all staged lines: the twiddle (one coalesced global load per column, L2-resident
+// table) is reused across the lines, the line values are shared-memory broadcasts, and the slices are summed in a
+// fixed order at the end (bitwise reproducible).
+// ----------------------------------------------------------------------------------------------
+constexpr int kLineRows = 8;
+constexpr int kLineThreads = 256;
+
+struct LineAnalysisParams {
+  PlaneGeom g;           // H == 1
+  const float* u;        // x, or gy when FUSE_GZ
+  const float* z;
+  float* gz_out;
+  float2* out;           // [nlines][MW]
+  const float2* twW;     // [W][MWp] (cos, sin)
+  const float* cl;
+  float scale;
+  int herm;
+  int nlines;            // NBO * NBI * C
+  int MWp;               // retained modes rounded up to 4 (twiddle pitch); MWp <= kLineThreads
+  int NS;                // column slices = kLineThreads / MWp
+};
+
+__host__ __device__ inline size_t line_analysis_smem(int W, int MWp, int NS) {
+  return ((size_t)kLineRows * (W + 1) + (size_t)NS * kLineRows * MWp * 2) * sizeof(float);
+}
+
+template <bool FUSE_GZ>
+__global__ void __launch_bounds__(kLineThreads) line_analysis_kernel(LineAnalysisParams p) {
+  DENO_PDL_SYNC();
+  DENO_DYN_SMEM(smem_raw);
+  float* xs = reinterpret_cast<float*>(smem_raw);                         // [kLineRows][W + 1]
+  const int W = p.g.W, MW = p.g.MW, MWp = p.MWp, NS = p.NS, Wp = W + 1;
+  float2* red = reinterpret_cast<float2*>(xs + kLineRows * Wp);           // [NS][kLineRows][MWp]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kLineThreads / 32;
+  const int q0 = blockIdx.x * kLineRows;
+  const int nl = min(kLineRows, p.nlines - q0);
+
+  for (int rr = warp; rr < kLineRows; rr += nwarps) {                      // one warp per line: coalesced
+    float* dst = xs + rr * Wp;
+    if (rr < nl) {
+      const int q = q0 + rr;
+      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+      // eight independent loads (sixteen with act'(z)) in flight per lane: a loop of dependent load -> store pairs cost
+      // one memory round trip per 32 columns (35 us for the gz variant at the Burgers shape)
+      for (int j0 = 0; j0 < W; j0 += 8 * 32) {
+        float v[8], zz[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int j = min(j0 + t * 32 + lane, W - 1);
+          v[t] = ldg_ordered(p.u + base + j);
+          if (FUSE_GZ) zz[t] = ldg_ordered(p.z + base + j);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int j = j0 + t * 32 + lane;
+          if (j < W) {
+            float val = v[t];
+            if (FUSE_GZ) {
+              val *= zz[t];
+              p.gz_out[base + j] = val;
+            }
+            dst[j] = val;
+          }
+        }
+      }
+    } else {
+      for (int j = lane; j < W; j += 32) dst[j] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int l = tid % MWp, sl = tid / MWp;
+  if (sl < NS) {
+    float re[kLineRows], im[kLineRows];
+#pragma unroll
+    for (int r = 0; r < kLineRows; ++r) re[r] = im[r] = 0.f;
+    const float2* tw = p.twW + l;
+    for (int y0 = sl; y0 < W; y0 += 4 * NS) {                              // four twiddle loads in flight
+      float2 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int y = y0 + u * NS;
+        t[u] = y < W ? tw[(long long)y * MWp] : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int y = min(y0 + u * NS, W - 1);                             // t[u] = 0 beyond the line
+#pragma unroll
+        for (int r = 0; r < kLineRows; ++r) {
+          const float xv = xs[r * Wp + y];
+          re[r] = fmaf(xv, t[u].x, re[r]);
+          im[r] = fmaf(-xv, t[u].y, im[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kLineRows; ++r) red[(sl * kLineRows + r) * MWp + l] = make_float2(re[r], im[r]);
+  }
+  __syncthreads();
+  for (int o = tid; o < nl * MW; o += kLineThreads) {
+    const int r = o / MW, lo = o - r * MW;
+    float sr = 0.f, si = 0.f;
+    for (int s2 = 0; s2 < NS; ++s2) {
+      const float2 v = red[(s2 * kLineRows + r) * MWp + lo];
+      sr += v.x;
+      si += v.y;
+    }
+    const float f = p.scale * (p.herm ? p.cl[lo] : 1.0f);
+    p.out[(long long)(q0 + r) * MW + lo] = make_float2(sr * f, si * f);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // outer axis (3-D): in/out are complex arrays indexed [b][x or k][c][Q] / [b][c][k][Q]
 // ----------------------------------------------------------------------------------------------
 struct OuterParams {

@@ -231,7 +231,7 @@ class FusedDPAdam:
         self.g_mc = int(g_hdl.multicast_ptr) + int(getattr(g_hdl, "offset", 0) or 0)
         self.p_mc = int(p_hdl.multicast_ptr) + int(getattr(p_hdl, "offset", 0) or 0)
         self.signal_pads = int(g_hdl.signal_pad_ptrs_dev)
-        if g_hdl.signal_pad_size < 4 * 32 * self.world:
+        if g_hdl.signal_pad_size < 2048:             # 512 slots: up to 64 blocks x 8 ranks (include/deno_dp.h)
             raise RuntimeError("signal pad too small for the fused exchange")
         self.write_back_grads = bool(write_back_grads)
 

@@ -26,7 +26,7 @@ extern "C" {
  *   p_local     this rank's replica of the flat fp32 parameter buffer (n floats, n % 4 == 0, 16-byte aligned)
  *   p_mc, g_mc  multicast addresses of the parameter / gradient buffers of all `world` ranks
  *   m, v        Adam moments, n floats each, local; only this rank's slice [rank * ceil(n/4/world) * 4, ...) is used
- *   signal_pads DEVICE array of `world` pointers: the 32-bit signal pad of every rank (>= 32 * world slots, zero
+ *   signal_pads DEVICE array of `world` pointers: the 32-bit signal pad of every rank (2 KB = 512 slots, zero
  *               before the first call; the kernel leaves them zero)
  *   step        device scalar: Adam's step count t for this update (float, already incremented)
  *   write_back_grads  non-zero: the averaged gradient is also stored into every rank's gradient buffer (tests, logging)

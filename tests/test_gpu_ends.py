@@ -134,3 +134,47 @@ def test_model_fused_ends_match_op_by_op_ends(cfg, monkeypatch):
         a = torch.view_as_real(g) if g.is_complex() else g
         b = torch.view_as_real(gref) if gref.is_complex() else gref
         assert rel_l2(a.cpu(), b.cpu()) < 2 * TOL, k
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_wide_model_channels_first_ends_match_port(nd):
+    """Width 128 (Airfoil / Pipe stacks, BASELINE configs[3]) is outside the fused point-wise kernels: lift and projection
+    run as channels-first batched GEMMs (FNOs._lift_channels_first / _proj_channels_first) around the tensor-core
+    layers.  Output and every parameter gradient against the float64 port (reference order of operations:
+    /root/reference/Models/fno/FNOs.py:136-151) evaluated on the GPU."""
+    import deno4pytorch_b200 as d4
+    from golden_util import rel_l2
+    from oracle import fno_port
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(21)
+    if nd == 2:
+        cfg = dict(in_dim=2, out_dim=1, modes=(6, 6), width=128, depth=2, hidden=128, steps=1, padding=5)
+        sp, cls = (27, 31), d4.FNO2d
+    else:
+        cfg = dict(in_dim=1, out_dim=2, modes=(3, 4, 4), width=128, depth=2, hidden=64, steps=1, padding=2, use_complex=False)
+        sp, cls = (10, 12, 14), d4.FNO3d
+    model = cls(**cfg)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if ".weights" in k:
+                p.mul_(cfg["width"] ** 2 / 8)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    gen = torch.Generator().manual_seed(22)
+    B = 3
+    x = torch.randn((B,) + sp + (cfg["in_dim"],), generator=gen)
+    grid = fno_port.make_grid(B, sp)
+    tgt = torch.randn((B,) + sp + (cfg["out_dim"],), generator=gen)
+    model = model.to(dev)
+    assert model._ends_desc(x.to(dev), grid.to(dev)) is None          # really the channels-first GEMM path
+    y = model(x.to(dev), grid.to(dev))
+    loss = torch.nn.functional.mse_loss(y, tgt.to(dev))
+    loss.backward()
+    p64 = {k: (v.to(dev).to(torch.complex128) if v.is_complex() else v.to(dev).double()).requires_grad_(True)
+           for k, v in params.items()}
+    ref = fno_port.fno_forward(p64, x.to(dev).double(), grid.to(dev).double(), ndim=nd, modes=cfg["modes"],
+                               depth=cfg["depth"], padding=cfg["padding"])
+    rl = torch.nn.functional.mse_loss(ref, tgt.to(dev).double())
+    rl.backward()
+    assert rel_l2(y.detach().cpu(), ref.detach().cpu()) < 1e-5
+    for k, p in model.named_parameters():
+        assert rel_l2(p.grad.cpu(), p64[k].grad.cpu()) < 1e-5, k
