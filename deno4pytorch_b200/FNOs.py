@@ -268,8 +268,11 @@ class _FNONd(nn.Module):
         if self.padding != 0:
             feats = F.pad(feats, [0, self.padding] * nd)
         w = torch.cat((self.fc0.weight, self.fc0.bias[:, None]), dim=1)                         # (C, K + 1)
-        h = torch.matmul(w, feats.reshape(feats.shape[0], feats.shape[1], -1))                  # (B, C, S)
-        return h.view((h.shape[0], h.shape[1]) + tuple(feats.shape[2:]))
+        B = feats.shape[0]
+        # bmm with the (stride-0) expanded weight: torch.matmul(2-D, 3-D) folds the batch into a transposed mm and pays an
+        # activation-sized clone in forward and backward (tools/copy_hunt.py)
+        h = torch.bmm(w.unsqueeze(0).expand(B, -1, -1), feats.reshape(B, feats.shape[1], -1))   # (B, C, S)
+        return h.view((B, h.shape[1]) + tuple(feats.shape[2:]))
 
     def _proj_channels_first(self, h):
         """``fc2(gelu(fc1(permute(crop(h)))))`` on the padded channels-first tensor as it is (1x1 convs = batched GEMMs over
