@@ -137,8 +137,18 @@ ModeDecode make_decode(const Shape& s) {
 struct TwLayout {
   size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, at_e1, at_a2, total;  // float offsets
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
-  int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [2*N1 rows: hi, lo][Wp], A2 [hi|lo][KRp*Hp]
+  int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [2*N1 rows: hi, lo][Wp], A2 [slab][hi|lo][KRp*Hp]
+  int an_nsub, an_HS;                            // row slabs of the tensor-core analysis (0: shape not covered); Hp = an_HS
 };
+
+// Shared-memory bytes of plane_analysis_tc_kernel for slabs of HS rows (mirrors tc::analysis_tc_smem, which the launcher
+// checks against; kept here because the twiddle layout is also needed by the CPU emulation build).
+inline long long an_tc_smem_total(int HS, int W, int KH, int N1, int Wp, int KRp, int nsub) {
+  const long long e1 = 2LL * N1 * Wp * 4, a2_one = (long long)KRp * HS * 4;
+  const long long a_one = (long long)(Wp / 4) * (16 * HS + 16), b2 = (long long)(HS / 4) * (16 * 2 * N1 + 16);
+  const long long xch = round_up(KH * (N1 + 1) * 4, 16), stage = (long long)round_up(HS * W, 4) * 4;
+  return e1 + nsub * 2 * a2_one + 2 * a_one + b2 + xch + stage + 4096;
+}
 
 // Shape-only geometry of the TMA analysis kernel (independent of the planes-per-tile choice).
 // Row class j = row mod g starts j * W floats into the plane; a TMA box must start on a 16-byte boundary in global
@@ -185,9 +195,20 @@ TwLayout tw_layout(const Shape& s) {
   t.Hp = round_up(s.H, 8);
   t.KS0 = s.KH;                                  // sin rows of the stage-2 operand follow the cos rows
   t.KRp = round_up(t.KS0 + s.KH, 8);
-  const bool an = (s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128);   // shapes the tensor-core analysis kernel can take
+  // shapes the tensor-core analysis kernel can take: planes of up to 128 rows as they are, taller ones (Airfoil 229,
+  // Pipe 137) as the fewest row slabs of a multiple of 8 rows that fit shared memory
+  t.an_nsub = 0; t.an_HS = 0;
+  if (s.ndim >= 2 && t.KS0 + s.KH <= 128 && 6 * t.N1 <= 512) {
+    for (int n = (s.H + 127) / 128; n <= 4 && t.an_nsub == 0; ++n) {
+      const int HS = round_up((s.H + n - 1) / n, 8);
+      if (HS > 128 || (n - 1) * HS >= s.H) continue;
+      if (an_tc_smem_total(HS, s.W, s.KH, t.N1, t.Wp, t.KRp, n) <= kMaxSmemBytes - 1024) { t.an_nsub = n; t.an_HS = HS; }
+    }
+  }
+  const bool an = t.an_nsub > 0;
+  if (an) t.Hp = t.an_HS;
   t.an_e1 = off; off += an ? (size_t)2 * t.N1 * t.Wp : 0;
-  t.an_a2 = off; off += an ? (size_t)2 * t.KRp * t.Hp : 0;
+  t.an_a2 = off; off += an ? (size_t)t.an_nsub * 2 * t.KRp * t.Hp : 0;
   // TMA analysis kernel (spectral_tma.cuh): E image nchunks x [2 N1 rows][32], A2 image (K2p / 32) x [4 KHp rows][32],
   // both already in their SWIZZLE_128B shared-memory layout
   const AtGeom ag = at_geom(s);
@@ -487,7 +508,7 @@ bool make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long inner, un
 // KS0 + k: sin of 2 pi f_k x / H) as hi / lo A operand images.
 void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
   const double two_pi = 6.283185307179586476925286766559;
-  if (!(s.ndim >= 2 && s.H <= 128 && t.KS0 + s.KH <= 128)) return;
+  if (t.an_nsub == 0) return;
   float* e1 = base + t.an_e1;                    // one B image: rows n (hi) and N1 + n (lo)
   for (int n = 0; n < t.N1; ++n)
     for (int y = 0; y < t.Wp; ++y) {
@@ -501,23 +522,26 @@ void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
       e1[kmajor_off(n, y, 2 * t.N1) / 4] = h;
       e1[kmajor_off(t.N1 + n, y, 2 * t.N1) / 4] = (float)(v - (double)h);
     }
-  float* a2hi = base + t.an_a2;
-  float* a2lo = a2hi + (size_t)t.KRp * t.Hp;
-  for (int r = 0; r < t.KRp; ++r)
-    for (int x = 0; x < t.Hp; ++x) {
-      const bool is_cos = r < s.KH, is_sin = r >= t.KS0 && r < t.KS0 + s.KH;
-      const int k = is_cos ? r : r - t.KS0;
-      double v = 0.0;
-      if ((is_cos || is_sin) && x < s.H) {
-        const long long f = (k < s.mH) ? k : (long long)s.H - 2 * s.mH + k;
-        const double ang = two_pi * (double)((f * x) % s.H) / (double)s.H;
-        v = is_cos ? cos(ang) : sin(ang);
+  for (int sub = 0; sub < t.an_nsub; ++sub) {      // one [hi | lo] image pair per row slab: local row xl is plane row sub * HS + xl
+    float* a2hi = base + t.an_a2 + (size_t)sub * 2 * t.KRp * t.Hp;
+    float* a2lo = a2hi + (size_t)t.KRp * t.Hp;
+    for (int r = 0; r < t.KRp; ++r)
+      for (int xl = 0; xl < t.Hp; ++xl) {
+        const bool is_cos = r < s.KH, is_sin = r >= t.KS0 && r < t.KS0 + s.KH;
+        const int k = is_cos ? r : r - t.KS0;
+        const long long x = (long long)sub * t.an_HS + xl;
+        double v = 0.0;
+        if ((is_cos || is_sin) && x < s.H) {
+          const long long f = (k < s.mH) ? k : (long long)s.H - 2 * s.mH + k;
+          const double ang = two_pi * (double)((f * x) % s.H) / (double)s.H;
+          v = is_cos ? cos(ang) : sin(ang);
+        }
+        const float h = tf32_mask((float)v);
+        const int off = kmajor_off(r, xl, t.KRp) / 4;
+        a2hi[off] = h;
+        a2lo[off] = (float)(v - (double)h);
       }
-      const float h = tf32_mask((float)v);
-      const int off = kmajor_off(r, x, t.KRp) / 4;
-      a2hi[off] = h;
-      a2lo[off] = (float)(v - (double)h);
-    }
+  }
 }
 
 // byte offset of element (row, k) of a K-major SWIZZLE_128B image made of [rows][32 fp32] chunks
@@ -706,12 +730,13 @@ int try_launch_analysis_tma(const Shape& s, int channels, const float* u, const 
 // Tensor-core analysis; -1 when the shape is outside the kernel's coverage.
 int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const float* z, float* gz_out, float2* out,
                            const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
-  if (s.ndim < 2 || s.H > 128) return -1;
+  if (s.ndim < 2) return -1;
   const TwLayout tl = tw_layout(s);
-  if (6 * tl.N1 > 512 || tl.KS0 + s.KH > 128) return -1;
+  if (tl.an_nsub == 0) return -1;
   const bool gz = (z != nullptr);
-  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(s.H, s.W, s.KH, tl.N1, tl.Wp, tl.Hp, tl.KRp);
-  if (sm.total > kMaxSmemBytes - 1024) return -1;
+  const tc::AnalysisTcSmem sm = tc::analysis_tc_smem(tl.an_HS, s.W, s.KH, tl.N1, tl.Wp, tl.Hp, tl.KRp, tl.an_nsub);
+  if (sm.total > kMaxSmemBytes - 1024 || (long long)sm.total != an_tc_smem_total(tl.an_HS, s.W, s.KH, tl.N1, tl.Wp, tl.KRp, tl.an_nsub))
+    return -1;
   tc::AnalysisTcParams p;
   p.g = make_geom(s, channels);
   p.u = u; p.z = z; p.gz_out = gz_out; p.out = out;
@@ -719,6 +744,7 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   p.scale = scale; p.herm = herm; p.act = s.act;
   p.nplanes = s.B * s.X * channels;
   p.N1 = tl.N1; p.Wp = tl.Wp; p.Hp = tl.Hp; p.KS0 = tl.KS0; p.KRp = tl.KRp;
+  p.nsub = tl.an_nsub; p.HS = tl.an_HS;
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
   if (gz) {

@@ -1028,6 +1028,7 @@ struct AnalysisTcParams {
   int act;
   int nplanes;
   int N1, Wp, Hp, KS0, KRp;
+  int nsub, HS;          // planes taller than 128 rows: nsub row slabs of HS rows (Hp = HS padded to 8), stage 2 accumulates over them
 };
 
 struct AnalysisTcSmem {
@@ -1039,7 +1040,7 @@ constexpr int kAnWorkers = 512;               // 16 worker warps: every SIMT pha
 constexpr int kAnThreads = kAnWorkers + 32;   // + the MMA-issuing warp
 constexpr int kAnZRegs = 5;                   // float4 of act'(z) per worker loaded ahead of the staged plane
 
-__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int KH, int N1, int Wp, int Hp, int KRp) {
+__host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int KH, int N1, int Wp, int Hp, int KRp, int nsub = 1) {
   AnalysisTcSmem m;
   m.e1_bytes = 2 * N1 * Wp * 4;
   m.a2_one = KRp * Hp * 4;
@@ -1049,7 +1050,7 @@ __host__ __device__ inline AnalysisTcSmem analysis_tc_smem(int H, int W, int KH,
   m.b2_bytes = (Hp / 4) * m.b2_lbo;
   int off = 0;
   m.e1 = off; off += m.e1_bytes;
-  m.a2 = off; off += 2 * m.a2_one;
+  m.a2 = off; off += nsub * 2 * m.a2_one;   // [slab][hi | lo]
   m.a = off; off += 2 * m.a_one;
   m.b2 = off; off += m.b2_bytes;
   m.xch = off; off += round_up(KH * (N1 + 1) * 4, 16);
@@ -1077,10 +1078,17 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t mbar[2], bar_stage, bar_const;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
+  // A plane of up to 128 rows is one item.  Taller planes (the 229- and 137-row Airfoil / Pipe grids) are cut into
+  // nsub row slabs of HS rows: every slab goes through the staging buffer, the transform and stage 1 like a plane of
+  // its own, and stage 2 - the contraction over the rows - accumulates the slabs in TMEM with the slab's own row
+  // twiddle image; the epilogue runs after the last slab.  Below, H is the slab height (HS) and `hrows` the rows of the
+  // current slab (the last one may be shorter).
+  const int Hfull = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
+  const int nsub = p.nsub, H = p.HS;
   const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
-  const AnalysisTcSmem so = analysis_tc_smem(H, W, KH, N1, Wp, Hp, KRp);
-  const int HW = H * W;
+  const AnalysisTcSmem so = analysis_tc_smem(H, W, KH, N1, Wp, Hp, KRp, nsub);
+  const int HW = H * W;                                  // elements of a full slab
+  const int hlast = Hfull - (nsub - 1) * H;              // rows of the last slab
   float* stage = reinterpret_cast<float*>(smem + so.stage);
 
   const uint32_t tmem_cols = 6 * N1 <= 64 ? 64u : (6 * N1 <= 128 ? 128u : (6 * N1 <= 256 ? 256u : 512u));
@@ -1092,9 +1100,9 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     mbar_init(&bar_const, 1);
     mbar_fence_init();
     // constant operand images (final layout in global memory): two bulk async copies
-    mbar_expect_tx(&bar_const, (uint32_t)(so.e1_bytes + 2 * so.a2_one));
+    mbar_expect_tx(&bar_const, (uint32_t)(so.e1_bytes + nsub * 2 * so.a2_one));
     bulk_g2s(smem + so.e1, p.e1, (uint32_t)so.e1_bytes, &bar_const);
-    bulk_g2s(smem + so.a2, p.a2, (uint32_t)(2 * so.a2_one), &bar_const);
+    bulk_g2s(smem + so.a2, p.a2, (uint32_t)(nsub * 2 * so.a2_one), &bar_const);
   }
   fence_before_sync();
   __syncthreads();                                     // barriers initialised, TMEM allocated
@@ -1108,27 +1116,31 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 32 * N1, lbo_a2 = 16 * KRp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int nyq = Wp / 4;                 // column quads of a row
   const int nchunk = (nyq + 7) / 8;       // a warp covers 8 quads (32 columns) x 4 rows per step
-  const int nmine = (p.nplanes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // planes of this CTA
-  // Planes whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
+  const int nplanes_mine = (p.nplanes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // planes of this CTA
+  const int nmine = nplanes_mine * nsub;                 // items (slabs) of this CTA: item j = slab j % nsub of its plane j / nsub
+  // Slabs whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
   // completion on an mbarrier) issued by the MMA warp; others fall back to per-thread 4-byte cp.async by the workers.
-  const bool bulk = (HW % 4) == 0;
+  const bool bulk = ((Hfull * W) % 4) == 0 && (HW % 4) == 0 && ((hlast * W) % 4) == 0;
+  auto item_rows = [&](int j) { return (j % nsub == nsub - 1) ? hlast : H; };
+  auto item_base = [&](int j) {                          // element offset of slab j of this CTA
+    const int q = blockIdx.x + (j / nsub) * gridDim.x;
+    return plane_base(p.g, q / p.g.C, q % p.g.C) + (long long)(j % nsub) * HW;
+  };
 
   if (warp == kAnWorkers / 32) {
     // ------------------------------------------------------------------ MMA warp
     const bool leader = elect_one();
-    auto l2_prefetch = [&](int j) {                    // pull plane j (and its act'(z)) into L2 ahead of its bulk copy
+    auto l2_prefetch = [&](int j) {                    // pull slab j (and its act'(z)) into L2 ahead of its bulk copy
       if (!bulk || j >= nmine || !leader) return;
-      const int q = blockIdx.x + j * gridDim.x;
-      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-      const uint32_t bytes = (uint32_t)HW * 4u;
+      const long long base = item_base(j);
+      const uint32_t bytes = (uint32_t)(item_rows(j) * W) * 4u;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.u + base), "r"(bytes) : "memory");
       if (FUSE_GZ) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.z + base), "r"(bytes) : "memory");
     };
-    auto prefetch_plane = [&](int j) {                 // bulk copy of this CTA's j-th plane into the staging buffer
+    auto prefetch_plane = [&](int j) {                 // bulk copy of this CTA's j-th slab into the staging buffer
       if (!bulk || j >= nmine || !leader) return;
-      const int q = blockIdx.x + j * gridDim.x;
-      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-      const uint32_t bytes = (uint32_t)HW * 4u;
+      const long long base = item_base(j);
+      const uint32_t bytes = (uint32_t)(item_rows(j) * W) * 4u;
       const uint32_t bar = smem_u32(&bar_stage);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1164,11 +1176,13 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       nbar_sync(kAnBarB2, kAnThreads);                 // B2(j) stored; D1 and D2 of the previous plane drained
       fence_after_sync();
       idle += DENO_CLK() - t0;
-      uint64_t a2h = make_desc(sbase + so.a2, lbo_a2, 128), a2l = make_desc(sbase + so.a2 + so.a2_one, lbo_a2, 128);
+      const int sub = j % nsub;                        // slab: its row-twiddle image; slabs after the first accumulate
+      const uint32_t a2base = sbase + so.a2 + sub * 2 * so.a2_one;
+      uint64_t a2h = make_desc(a2base, lbo_a2, 128), a2l = make_desc(a2base + so.a2_one, lbo_a2, 128);
       uint64_t b2 = make_desc(sbase + so.b2, lbo_b2, 128);
       const uint64_t inc_a2 = (uint64_t)((2 * lbo_a2) >> 4), inc_b2 = (uint64_t)((2 * lbo_b2) >> 4);
       for (int s2 = 0; s2 < Hp / 8; ++s2) {
-        const uint32_t acc = s2 > 0 ? 1u : 0u;
+        const uint32_t acc = (s2 > 0 || sub > 0) ? 1u : 0u;
         if (leader) {
           mma_tf32(tmem_d2, a2h, b2, idesc_n2, acc);
           mma_tf32(tmem_d2 + 2 * N1, a2l, b2, idesc_n1, acc);
@@ -1186,21 +1200,22 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / row r of D2)
     uint32_t phase = 0, stage_phase = 0;
     auto issue_plane_cp_async = [&](int j) {           // non-bulk fallback
-      const int q = blockIdx.x + j * gridDim.x;
-      const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
-      for (int i = tid; i < HW; i += kAnWorkers) cp_async4(stage + i, p.u + base + i);
+      const long long base = item_base(j);
+      const int n = item_rows(j) * W;
+      for (int i = tid; i < n; i += kAnWorkers) cp_async4(stage + i, p.u + base + i);
       cp_async_commit();
     };
-    auto transform = [&](int j) {                      // staged plane j -> (gz) -> A images (hi / lo)
-      const int q = blockIdx.x + j * gridDim.x;
+    auto transform = [&](int j) {                      // staged slab j -> (gz) -> A images (hi / lo)
+      const int hrows = item_rows(j);
+      const int nel = hrows * W;
       const long long tq0 = DENO_CLK();
       float4 zr[kAnZRegs];                             // act'(z) of this thread's first elements: in flight during the wait
       if (FUSE_GZ && bulk) {
-        const float4* z4 = reinterpret_cast<const float4*>(p.z + plane_base(p.g, q / p.g.C, q % p.g.C));
+        const float4* z4 = reinterpret_cast<const float4*>(p.z + item_base(j));
 #pragma unroll
         for (int r = 0; r < kAnZRegs; ++r) {
           const int i = tid + r * kAnWorkers;
-          zr[r] = i < HW / 4 ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          zr[r] = i < nel / 4 ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       if (bulk) {
@@ -1213,14 +1228,14 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       const long long tq1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);      // slot 32: wait for the staged plane
       if (FUSE_GZ) {                                   // gz = gy * act'(z): coalesced store, kept in staging
-        const long long base = plane_base(p.g, q / p.g.C, q % p.g.C);
+        const long long base = item_base(j);
         if (bulk) {
           float4* s4 = reinterpret_cast<float4*>(stage);
           float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
 #pragma unroll
           for (int r = 0; r < kAnZRegs; ++r) {
             const int i = tid + r * kAnWorkers;
-            if (i < HW / 4) {
+            if (i < nel / 4) {
               const float4 a = s4[i], b = zr[r];
               const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
               s4[i] = v;
@@ -1228,17 +1243,26 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
             }
           }
           const float4* z4 = reinterpret_cast<const float4*>(p.z + base);
-          for (int i = tid + kAnZRegs * kAnWorkers; i < HW / 4; i += kAnWorkers) {   // planes beyond the register window
+          for (int i = tid + kAnZRegs * kAnWorkers; i < nel / 4; i += kAnWorkers) {   // planes beyond the register window
             const float4 a = s4[i], b = __ldg(z4 + i);
             const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
             s4[i] = v;
             g4[i] = v;
           }
         } else {
-          for (int i = tid; i < HW; i += kAnWorkers) {
-            const float v = stage[i] * __ldg(p.z + base + i);
-            stage[i] = v;
-            p.gz_out[base + i] = v;
+          for (int i0 = tid; i0 < nel; i0 += 8 * kAnWorkers) {      // eight act'(z) loads in flight per thread
+            float zz[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) zz[u] = ldg_ordered(p.z + base + min(i0 + u * kAnWorkers, nel - 1));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = i0 + u * kAnWorkers;
+              if (i < nel) {
+                const float v = stage[i] * zz[u];
+                stage[i] = v;
+                p.gz_out[base + i] = v;
+              }
+            }
           }
         }
         nbar_sync(kAnBarWorkers, kAnWorkers);
@@ -1256,8 +1280,8 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int y = yq * 4 + jj;
-              v0[jj] = (r0 < H && y < W) ? s0[y] : 0.f;
-              v1[jj] = (r1 < H && y < W) ? s1[y] : 0.f;
+              v0[jj] = (r0 < hrows && y < W) ? s0[y] : 0.f;
+              v1[jj] = (r1 < hrows && y < W) ? s1[y] : 0.f;
             }
             float4 hi, lo;
             if (r0 < Hp) {
@@ -1293,7 +1317,9 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     if (!bulk) issue_plane_cp_async(0);
     transform(0);
     for (int j = 0; j < nmine; ++j) {
-      const int q = blockIdx.x + j * gridDim.x;
+      const int q = blockIdx.x + (j / nsub) * gridDim.x;
+      const int hrows = item_rows(j);
+      const bool last_slab = (j % nsub) == nsub - 1;
       const long long tq3 = DENO_CLK();
       mbar_wait(&mbar[0], phase);
       fence_after_sync();
@@ -1315,7 +1341,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
               const int n = wg * ncol_q + c0 + jj;
-              const float t = xrow < H ? v[jj] + (v1[jj] + v2[jj]) : 0.f;
+              const float t = xrow < hrows ? v[jj] + (v1[jj] + v2[jj]) : 0.f;
               float th, tl;
               split_tf32(t, th, tl);
               const int r0 = (n & 7) * 16 + (n >> 3) * 128;
@@ -1336,9 +1362,9 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       fence_after_sync();
       const long long tq7 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(37, tq7 - tq6);      // slot 37: wait for the stage-2 MMAs
-      // epilogue: rows k (cos) and KS0 + k (sin) of D2 are combined through shared memory; warp group wg takes
-      // the column passes c0 = 16 wg, 16 wg + 64, ...
-      {
+      // epilogue (after the plane's last slab): rows k (cos) and KS0 + k (sin) of D2 are combined through shared
+      // memory; warp group wg takes the column passes c0 = 16 wg, 16 wg + 64, ...
+      if (last_slab) {
         float* xch = reinterpret_cast<float*>(smem + so.xch);     // [KH][N1 + 1] sin-row values (odd pitch: conflict-free)
         const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
         const bool warp_used = (wq * 32 < KH) || (wq * 32 + 32 > KS0 && wq * 32 < KS0 + KH);   // any cos / sin row in this quadrant

@@ -98,6 +98,10 @@ SHAPES = [
     # tiles on one side, and a batch beyond one 32-entry epilogue pass
     (3, 64, 128, (40, 36), (6, 7), "gelu"),
     (40, 64, 64, (20, 24), (6, 6), "tanh"),
+    # planes taller than 128 rows on the tensor-core analysis: row slabs accumulated in stage 2 (the C4 shapes above take
+    # the 4-byte cp.async staging because their planes are not 16-byte multiples; these take the bulk-copy staging)
+    (2, 8, 8, (136, 24), (5, 5), "gelu"),
+    (1, 8, 12, (5, 200, 16), (2, 7, 4), "silu"),
 ]
 
 
