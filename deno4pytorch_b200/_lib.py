@@ -8,7 +8,8 @@ import os
 from . import _capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdeno_spectral.so")
+# DENO_LIB_PATH: A/B timing of an older build of the same ABI (tools/ab_layer.py); never a different implementation
+LIB_PATH = os.environ.get("DENO_LIB_PATH") or os.path.join(_HERE, "csrc", "libdeno_spectral.so")
 _lib = None
 
 

@@ -747,17 +747,19 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   p.nsub = tl.an_nsub; p.HS = tl.an_HS;
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
-  if (gz) {
-    rc = allow_smem(tc::plane_analysis_tc_kernel<true>, (size_t)sm.total, "plane_analysis_tc");
-    if (rc != DENO_OK) return rc;
-    prof_before("plane_analysis_gz_tc", st);
-    DENO_LAUNCH((tc::plane_analysis_tc_kernel<true>), dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st, p);
-  } else {
-    rc = allow_smem(tc::plane_analysis_tc_kernel<false>, (size_t)sm.total, "plane_analysis_tc");
-    if (rc != DENO_OK) return rc;
-    prof_before("plane_analysis_tc", st);
-    DENO_LAUNCH((tc::plane_analysis_tc_kernel<false>), dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st, p);
+#define DENO_AN_CASE(GZ, SLABS, LABEL)                                                                         \
+  {                                                                                                            \
+    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS>, (size_t)sm.total, "plane_analysis_tc");           \
+    if (rc != DENO_OK) return rc;                                                                              \
+    prof_before(LABEL, st);                                                                                    \
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS>), dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st, p); \
   }
+  const bool slabs = p.nsub > 1;
+  if (gz && slabs) DENO_AN_CASE(true, true, "plane_analysis_gz_tc")
+  else if (gz) DENO_AN_CASE(true, false, "plane_analysis_gz_tc")
+  else if (slabs) DENO_AN_CASE(false, true, "plane_analysis_tc")
+  else DENO_AN_CASE(false, false, "plane_analysis_tc")
+#undef DENO_AN_CASE
   return check_launch("plane_analysis_tc", st);
 }
 #endif
@@ -1164,10 +1166,10 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   const int COT = (6 * CO <= 512) ? CO : 64;
   if (CO % COT != 0) return -1;
   const int nco = CO / COT;
-  const int CIP = CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64));
+  const bool tiled = nco > 1 || CI > 64;                    // tiled instances are built for K passes of 64 channels only
+  const int CIP = tiled ? 64 : (CI <= 8 ? 8 : (CI <= 16 ? 16 : (CI <= 32 ? 32 : 64)));
   const int npass = (CI + CIP - 1) / CIP;
   const TwLayout tl = tw_layout(s);
-  const bool tiled = nco > 1 || npass > 1;
   if (tiled && (urow == nullptr || p.g.H <= 1)) return -1;   // the in-kernel row-axis stage knows one tile / one pass only
   // stage A stages the packed spectrum through the A_X area: at least one output channel must fit
   if (!tiled && 2 * CIP * 128 * 4 - round_up(kSynthMaxRows * p.g.KH, 2) * 8 < p.g.KH * p.g.MW * 8) return -1;
@@ -1230,19 +1232,20 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   const size_t smem = (size_t)tc::synth_tc_smem(CIP, COT, tl.KE, bestR, npass).total;
   const int grid = s.B * s.X * p.tiles * tl.nchunks * nco;
   int rc = DENO_OK;
-#define DENO_TC_CASE2(ACT, CIPV)                                                                    \
+#define DENO_TC_CASE3(ACT, CIPV, TILEDV)                                                            \
   {                                                                                                 \
-    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV>, smem, "plane_synthesis_tc");          \
+    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV>, smem, "plane_synthesis_tc");  \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);               \
+    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);       \
   }
 #define DENO_TC_CASE(ACT)                                                                           \
   case ACT:                                                                                         \
-    if (CIP == 8) DENO_TC_CASE2(ACT, 8)                                                             \
-    else if (CIP == 16) DENO_TC_CASE2(ACT, 16)                                                      \
-    else if (CIP == 32) DENO_TC_CASE2(ACT, 32)                                                      \
-    else DENO_TC_CASE2(ACT, 64)                                                                     \
+    if (tiled) DENO_TC_CASE3(ACT, 64, true)                                                         \
+    else if (CIP == 8) DENO_TC_CASE3(ACT, 8, false)                                                 \
+    else if (CIP == 16) DENO_TC_CASE3(ACT, 16, false)                                               \
+    else if (CIP == 32) DENO_TC_CASE3(ACT, 32, false)                                               \
+    else DENO_TC_CASE3(ACT, 64, false)                                                              \
     break;
   switch (act) {
     DENO_TC_CASE(ACT_IDENTITY)
@@ -1254,7 +1257,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
     default: return fail(DENO_E_INVALID, "unknown activation id");
   }
 #undef DENO_TC_CASE
-#undef DENO_TC_CASE2
+#undef DENO_TC_CASE3
   return check_launch("plane_synthesis_tc", st);
 }
 

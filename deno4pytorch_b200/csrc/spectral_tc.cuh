@@ -328,8 +328,11 @@ __host__ __device__ inline SynthTcSmem synth_tc_smem(int CIP, int CO, int KE, in
 constexpr int kSynThreads = 256 + 32;   // 8 worker warps + the MMA-issuing warp
 constexpr int kSynBarAx = 2;            // A_X images of a row stored (workers arrive, MMA warp syncs)
 
-template <int ACT, int CIP>
-__global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(SynthTcParams q) {
+// Two CTAs per SM up to 32 input channels (96 registers); from 64 channels on the operand images leave room for one CTA
+// only, so the register cap is lifted there (at 96 registers the 64-channel instances spilled in the row loop).
+// TILED = false (every layer up to 64 channels): one channel tile, one K pass, known at compile time.
+template <int ACT, int CIP, bool TILED>
+__global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthesis_tc_kernel(SynthTcParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(8) uint64_t mbar[2], mbar_u;
@@ -341,7 +344,8 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = q.COT;
   const int KH4 = round_up(KH, 4);
   const int KE = q.KE, R = p.R;
-  const int npass = q.npass;
+  const int npass = TILED ? q.npass : 1;
+  const int nco = TILED ? q.nco : 1;
   const SynthTcSmem so = synth_tc_smem(CIP, CO, KE, R, npass);
   const int bw_pass = 2 * CIP * CO * 4;            // bytes between the weight images of consecutive K passes
   constexpr int NIT = CIP / 8;            // (point, channel-quad) items per thread: 128 * CIP/4 / 256
@@ -349,7 +353,8 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   // CTA coordinates
   int bid = blockIdx.x;
   const int chunk = bid % q.nchunks; bid /= q.nchunks;
-  const int cot = bid % q.nco; bid /= q.nco;      // channel tiles of the same rows on neighbouring CTAs (x re-read from L2)
+  int cot = 0;
+  if (TILED) { cot = bid % nco; bid /= nco; }     // channel tiles of the same rows on neighbouring CTAs (x re-read from L2)
   const int co0 = cot * CO;
   const int tile = bid % p.tiles;
   const int bp = bid / p.tiles;
@@ -375,25 +380,22 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
 
   // ---- constant operands -------------------------------------------------------------------
   // bypass weight image B_W[n = o][k = i], split on the fly; four loads in flight per thread
-  // consecutive threads walk the CONTIGUOUS index of lw: the input channel in the forward call (lw_si == 1), the output
-  // channel in the backward call (transposed use, lw_so == 1; there the other order made every load its own 32-byte
-  // sector: 80 vs 62 us for the backward launch at width 64, 771 vs 596 us at width 128)
-  const bool o_fast = p.lw_so < p.lw_si;
+  // (walking the contiguous index of lw in the transposed backward call as well was measured: no change - the 25 %
+  // the backward launch loses to the forward one at width >= 64 is not in this prologue)
   for (int ps = 0; ps < npass; ++ps)
     for (int idx0 = wt; idx0 < CO * CIP; idx0 += 4 * 256) {
       float wv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int idx = min(idx0 + u * 256, CO * CIP - 1);
-        const int o = o_fast ? idx % CO : idx / CIP;
-        const int i = ps * CIP + (o_fast ? idx / CO : idx % CIP);
+        const int o = idx / CIP, i = ps * CIP + (idx - o * CIP);
         wv[u] = (i < CI) ? ldg_ordered(p.lw + (long long)(co0 + o) * p.lw_so + (long long)i * p.lw_si) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int idx = idx0 + u * 256;
         if (idx < CO * CIP) {
-          const int o = o_fast ? idx % CO : idx / CIP, i = o_fast ? idx / CO : idx % CIP;
+          const int o = idx / CIP, i = idx - o * CIP;
           float hi, lo;
           split_tf32(wv[u], hi, lo);
           const int off = ps * bw_pass + kmajor_off(o, i, CO);
@@ -411,15 +413,14 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
   if (tid == 32 && q.urow != nullptr) {
     const size_t img2 = 2 * (size_t)(so.bu_one / 4);                 // floats of one row's hi + lo images of one channel tile
     for (int rr = 0; rr < trows; ++rr)
-      bulk_g2s(smem + so.bu + rr * 2 * so.bu_one, q.urow + (((size_t)bp * H + x0 + rr) * q.nco + cot) * img2,
+      bulk_g2s(smem + so.bu + rr * 2 * so.bu_one, q.urow + (((size_t)bp * H + x0 + rr) * nco + cot) * img2,
                (uint32_t)(2 * so.bu_one), &mbar_u);
   }
 
   // ---- x row prefetch (registers) ------------------------------------------------------------
   float xr[NIT][4];
   const long long ubase = plane_base(p.g, bp, 0);
-  auto prefetch = [&](int step) {                    // step = row * npass + K pass
-    const int rr = step / npass, ps = step - rr * npass;
+  auto prefetch = [&](int rr, int ps) {              // row of the tile, K pass
     const long long rowoff = ubase + (long long)(x0 + rr) * W + y0;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       }
     }
   };
-  if (!is_mma) prefetch(0);
+  if (!is_mma) prefetch(0, 0);
 
   const long long tb1 = DENO_CLK();
   if (warp == 1) DENO_DBG_ADD(48, tb1 - tb0);          // slot 48: TMEM alloc, weight / twiddle images, first prefetch issue
@@ -580,8 +581,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
     // ---- MMA warp: per row, wait until the 256 workers have stored the A_X images, issue, commit ----
     const bool leader = elect_one();   // warp-uniform loop (descriptors in uniform registers); one lane issues
     const uint64_t inc_m = (uint64_t)((2 * lbo_m) >> 4), inc_n = (uint64_t)((2 * lbo_n) >> 4);
-    for (int step = 0; step < trows * npass; ++step) {
-      const int rr = step / npass, ps = step - rr * npass;
+    for (int step = 0, rr = 0, ps = 0; rr < trows; ++step, ps = (ps + 1 == npass) ? 0 : ps + 1, rr += (ps == 0)) {
       nbar_sync(kSynBarAx, kSynThreads);
       fence_after_sync();
       const long long tr3 = DENO_CLK();
@@ -620,8 +620,7 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
     }
   } else {
     // ---- workers: A_X images of row rr, then (while the tensor core works on it) the epilogue of row rr - 1 ----
-    for (int step = 0; step < trows * npass; ++step) {
-      const int rr = step / npass, ps = step - rr * npass;
+    for (int step = 0, rr = 0, ps = 0; rr < trows; ++step, ps = (ps + 1 == npass) ? 0 : ps + 1, rr += (ps == 0)) {
       const long long tr0 = DENO_CLK();
       if (step > 0) mbar_wait(&mbar[(step - 1) & 1], ((step - 1) >> 1) & 1);   // MMAs of the previous step done: A_X free (ps == 0: D(rr-1) ready)
       const long long tr1 = DENO_CLK();
@@ -645,7 +644,10 @@ __global__ void __launch_bounds__(kSynThreads, 2) plane_synthesis_tc_kernel(Synt
       nbar_arrive(kSynBarAx, kSynThreads);
       const long long tr4 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(51, tr4 - tr1);        // slot 51: split + store + hand-off
-      if (step + 1 < trows * npass) prefetch(step + 1);
+      {
+        const int nps = (ps + 1 == npass) ? 0 : ps + 1, nrr = rr + (nps == 0);
+        if (nrr < trows) prefetch(nrr, nps);
+      }
       const long long tr5 = DENO_CLK();
       if (rr > 0 && ps == 0) {
         fence_after_sync();
@@ -1072,7 +1074,7 @@ constexpr int kAnBarEpi0 = 8;      // 8..11: sin rows exchanged, one barrier per
 constexpr int kAnBarWorkers = 12;  // workers only
 constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp syncs)
 
-template <bool FUSE_GZ>
+template <bool FUSE_GZ, bool SLABS>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
@@ -1084,7 +1086,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   // twiddle image; the epilogue runs after the last slab.  Below, H is the slab height (HS) and `hrows` the rows of the
   // current slab (the last one may be shorter).
   const int Hfull = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
-  const int nsub = p.nsub, H = p.HS;
+  const int nsub = SLABS ? p.nsub : 1, H = p.HS;      // SLABS = false: the one-slab code is the compile-time special case
   const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
   const AnalysisTcSmem so = analysis_tc_smem(H, W, KH, N1, Wp, Hp, KRp, nsub);
   const int HW = H * W;                                  // elements of a full slab
@@ -1121,10 +1123,15 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   // Slabs whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
   // completion on an mbarrier) issued by the MMA warp; others fall back to per-thread 4-byte cp.async by the workers.
   const bool bulk = ((Hfull * W) % 4) == 0 && (HW % 4) == 0 && ((hlast * W) % 4) == 0;
-  auto item_rows = [&](int j) { return (j % nsub == nsub - 1) ? hlast : H; };
+  // (the one-slab case takes no integer division here: these run on the MMA warp's issuing lane, the critical path -
+  // ten divisions per item cost 18 % at the 3-D turbulence shape with its 151 small planes per CTA)
+  constexpr bool one_slab = !SLABS;
+  auto item_sub = [&](int j) { return one_slab ? 0 : j % nsub; };
+  auto item_plane = [&](int j) { return (int)blockIdx.x + (one_slab ? j : j / nsub) * (int)gridDim.x; };
+  auto item_rows = [&](int j) { return (one_slab || item_sub(j) == nsub - 1) ? hlast : H; };
   auto item_base = [&](int j) {                          // element offset of slab j of this CTA
-    const int q = blockIdx.x + (j / nsub) * gridDim.x;
-    return plane_base(p.g, q / p.g.C, q % p.g.C) + (long long)(j % nsub) * HW;
+    const int q = item_plane(j);
+    return plane_base(p.g, q / p.g.C, q % p.g.C) + (long long)item_sub(j) * HW;
   };
 
   if (warp == kAnWorkers / 32) {
@@ -1176,7 +1183,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       nbar_sync(kAnBarB2, kAnThreads);                 // B2(j) stored; D1 and D2 of the previous plane drained
       fence_after_sync();
       idle += DENO_CLK() - t0;
-      const int sub = j % nsub;                        // slab: its row-twiddle image; slabs after the first accumulate
+      const int sub = item_sub(j);                     // slab: its row-twiddle image; slabs after the first accumulate
       const uint32_t a2base = sbase + so.a2 + sub * 2 * so.a2_one;
       uint64_t a2h = make_desc(a2base, lbo_a2, 128), a2l = make_desc(a2base + so.a2_one, lbo_a2, 128);
       uint64_t b2 = make_desc(sbase + so.b2, lbo_b2, 128);
@@ -1317,9 +1324,9 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     if (!bulk) issue_plane_cp_async(0);
     transform(0);
     for (int j = 0; j < nmine; ++j) {
-      const int q = blockIdx.x + (j / nsub) * gridDim.x;
+      const int q = item_plane(j);
       const int hrows = item_rows(j);
-      const bool last_slab = (j % nsub) == nsub - 1;
+      const bool last_slab = one_slab || item_sub(j) == nsub - 1;
       const long long tq3 = DENO_CLK();
       mbar_wait(&mbar[0], phase);
       fence_after_sync();
