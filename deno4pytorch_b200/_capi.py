@@ -70,6 +70,11 @@ def make_fno_desc(batch, width, hidden, in_feats, grid_feats, out_dim, spatial, 
     return d
 
 
+class Overlap(C.Structure):
+    """struct deno_overlap: side stream + fork / join events of deno_spectral_bwd_overlap"""
+    _fields_ = [("side_stream", C.c_void_p), ("ev_fork", C.c_void_p), ("ev_join", C.c_void_p)]
+
+
 class ProfileRecord(C.Structure):
     """struct deno_profile_record"""
     _fields_ = [("name", C.c_char * 32), ("ms", C.c_float)]
@@ -103,6 +108,11 @@ _PROTOTYPES = {
     "deno_spectral_bwd": (C.c_int, [_DESC_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
                                     C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),
+    "deno_overlap_create": (C.c_int, [C.POINTER(Overlap)]),
+    "deno_overlap_destroy": (C.c_int, [C.POINTER(Overlap)]),
+    "deno_spectral_bwd_overlap": (C.c_int, [_DESC_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p, C.POINTER(Overlap)]),
     "deno_fno_supported": (C.c_int, [_FNO_P]),
     "deno_fno_workspace_bytes": (C.c_size_t, [_FNO_P, C.c_int]),
     "deno_fno_lift_fwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V]),

@@ -1011,7 +1011,8 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
 
 // Fused launch of the backward consumers of G^ (see mode_mix_bwd_fused_kernel).  Any role may be disabled.
 int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat, float2* gxhat, const void* const* w_blocks,
-                         void* const* gw_blocks, float* glb_from_dc, cudaStream_t st) {
+                         void* const* gw_blocks, float* glb_from_dc, cudaStream_t st,
+                         const char* label = "mode_mix_bwd_fused") {
   const int nblk = 1 << (s.ndim - 1);
 #ifndef DENO_EMULATE
   if (mix_tc_eligible(s)) {   // width >= 64: two tensor-core launches (+ the DC-mode bias gradient) instead of the fused SIMT one
@@ -1053,7 +1054,7 @@ int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat,
       t.glb = glb_from_dc; t.s_total = (float)s.S;
       int rc = allow_smem(mode_mix_bwd_tile_kernel, tsm, "mode_mix_bwd_tile");
       if (rc != DENO_OK) return rc;
-      prof_before("mode_mix_bwd_fused", st);
+      prof_before(label, st);
       DENO_LAUNCH(mode_mix_bwd_tile_kernel, dim3(tgrid), dim3(kMixTileThreads), tsm, st, t);
       return check_launch("mode_mix_bwd_tile", st);
     }
@@ -1079,7 +1080,7 @@ int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat,
   f.ghat = ghat; f.glb = glb_from_dc; f.B = s.B; f.CO = s.CO; f.M = s.M; f.s_total = (float)s.S;
   const int total = f.ax * f.ay * f.az + f.bx * f.by * f.bz + (glb_from_dc != nullptr ? 1 : 0);
   if (total == 0) return DENO_OK;
-  prof_before("mode_mix_bwd_fused", st);
+  prof_before(label, st);
   DENO_LAUNCH(mode_mix_bwd_fused_kernel, dim3(total), dim3(32, 8), 0, st, f);
   return check_launch("mode_mix_bwd_fused", st);
 }
@@ -1844,11 +1845,16 @@ int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void
                           s.act, reinterpret_cast<float*>(wsb + ws.urow), st);
 }
 
-int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const float* x,
-                      const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
-                      const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
-                      float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
-                      void* stream) {
+// Shared body of deno_spectral_bwd / deno_spectral_bwd_overlap.  With `ov` the kernels that only PRODUCE parameter
+// gradients (gW of the mode mix, the bypass weight / bias gradient and its reduction) go to ov->side_stream right after
+// gz and G^ exist, and the input-gradient chain (G^x -> row synthesis -> plane synthesis) continues on `stream`; the
+// two meet again before the call returns.  Both sides only read gz / G^ / X^ / x and write disjoint outputs and
+// disjoint workspace regions (BwdWs: gxhat, v, urow on the chain; partial on the side).
+static int spectral_bwd_impl(const deno_spectral_desc* desc, const float* gy, const float* x,
+                             const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                             const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                             float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                             void* stream, const deno_overlap* ov) {
   g_launches = 0;
   Shape s;
   int rc = parse_desc(desc, s);
@@ -1880,11 +1886,31 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
   } else {
     if ((rc = launch_analysis(s, s.CO, gy, z_saved, gz, ghat, tw, inv_s, 1, st))) return rc;
   }
-  // one launch: G^x = conj(W) G^ (if gx is wanted), gW (if wanted) and, on the tensor-core wgrad path, the bias gradient
   const bool bias_from_dc = (glin_b != nullptr) && wgrad_tc_eligible(s);
-  if ((rc = launch_mix_bwd_fused(s, xhat, ghat, gx != nullptr ? gxhat : nullptr, w_blocks, gw_blocks,
-                                 bias_from_dc ? glin_b : nullptr, st)))
-    return rc;
+  const bool want_side = gw_blocks != nullptr || glin_w != nullptr || glin_b != nullptr;
+  cudaStream_t sd = st;
+#ifndef DENO_EMULATE
+  // per-launch event bracketing (deno_profile_begin) keeps everything on one stream: same launches, serial
+  const bool fork = ov != nullptr && ov->side_stream != nullptr && gx != nullptr && want_side && !g_profiling;
+  if (fork) {
+    sd = static_cast<cudaStream_t>(ov->side_stream);
+    if (cudaEventRecord(static_cast<cudaEvent_t>(ov->ev_fork), st) != cudaSuccess ||
+        cudaStreamWaitEvent(sd, static_cast<cudaEvent_t>(ov->ev_fork), 0) != cudaSuccess)
+      return fail(DENO_E_CUDA, std::string("bwd overlap fork: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+#else
+  const bool fork = false;
+  (void)ov;
+#endif
+  const bool split = ov != nullptr && gx != nullptr && want_side;   // two role launches instead of the fused one
+  if (!split) {
+    // one launch: G^x = conj(W) G^ (if gx is wanted), gW (if wanted) and, on the tensor-core wgrad path, the bias gradient
+    if ((rc = launch_mix_bwd_fused(s, xhat, ghat, gx != nullptr ? gxhat : nullptr, w_blocks, gw_blocks,
+                                   bias_from_dc ? glin_b : nullptr, st)))
+      return rc;
+  } else {
+    if ((rc = launch_mix_bwd_fused(s, xhat, ghat, gxhat, w_blocks, nullptr, nullptr, st, "mode_mix_bwd_gx"))) return rc;
+  }
   if (gx != nullptr) {
     const float2* spec = gxhat;
     if (s.ndim == 3) {
@@ -1897,10 +1923,71 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
                                DENO_ACT_IDENTITY, reinterpret_cast<float*>(wsb + ws.urow), st)))
       return rc;
   }
+  if (split && (gw_blocks != nullptr || bias_from_dc)) {
+    if ((rc = launch_mix_bwd_fused(s, xhat, ghat, nullptr, nullptr, gw_blocks, bias_from_dc ? glin_b : nullptr, sd,
+                                   "mode_mix_bwd_gw")))
+      return rc;
+  }
   if (glin_w != nullptr || glin_b != nullptr) {
     float* partial = reinterpret_cast<float*>(wsb + ws.partial);
-    if ((rc = launch_bypass_wgrad(s, gz, x, ghat, partial, glin_w, glin_b, bias_from_dc, st))) return rc;
+    if ((rc = launch_bypass_wgrad(s, gz, x, ghat, partial, glin_w, glin_b, bias_from_dc, sd))) return rc;
   }
+#ifndef DENO_EMULATE
+  if (fork) {
+    if (cudaEventRecord(static_cast<cudaEvent_t>(ov->ev_join), sd) != cudaSuccess ||
+        cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(ov->ev_join), 0) != cudaSuccess)
+      return fail(DENO_E_CUDA, std::string("bwd overlap join: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+#endif
+  return DENO_OK;
+}
+
+int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const float* x,
+                      const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                      const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                      float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  return spectral_bwd_impl(desc, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
+                           workspace, workspace_bytes, stream, nullptr);
+}
+
+int deno_spectral_bwd_overlap(const deno_spectral_desc* desc, const float* gy, const float* x,
+                              const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                              const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                              float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                              void* stream, const deno_overlap* ov) {
+  return spectral_bwd_impl(desc, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
+                           workspace, workspace_bytes, stream, ov);
+}
+
+int deno_overlap_create(deno_overlap* out) {
+  if (out == nullptr) return fail(DENO_E_INVALID, "null deno_overlap");
+  memset(out, 0, sizeof(*out));
+#ifndef DENO_EMULATE
+  cudaStream_t sd = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess) {
+    const std::string msg = std::string("deno_overlap_create: ") + cudaGetErrorString(cudaGetLastError());
+    if (e1) cudaEventDestroy(e1);
+    if (e0) cudaEventDestroy(e0);
+    if (sd) cudaStreamDestroy(sd);
+    return fail(DENO_E_CUDA, msg);
+  }
+  out->side_stream = sd; out->ev_fork = e0; out->ev_join = e1;
+#endif
+  return DENO_OK;
+}
+
+int deno_overlap_destroy(deno_overlap* ov) {
+  if (ov == nullptr) return DENO_OK;
+#ifndef DENO_EMULATE
+  if (ov->ev_join) cudaEventDestroy(static_cast<cudaEvent_t>(ov->ev_join));
+  if (ov->ev_fork) cudaEventDestroy(static_cast<cudaEvent_t>(ov->ev_fork));
+  if (ov->side_stream) cudaStreamDestroy(static_cast<cudaStream_t>(ov->side_stream));
+#endif
+  memset(ov, 0, sizeof(*ov));
   return DENO_OK;
 }
 

@@ -21,6 +21,30 @@ import os
 _TWIDDLES: Dict[tuple, torch.Tensor] = {}
 _LAUNCHES = {"count": 0}
 _POISON = {"on": os.environ.get("DENO_POISON", "0") == "1"}
+# DENO_BWD_OVERLAP=0: parameter-gradient kernels stay on the caller's stream (deno_spectral_bwd instead of _overlap)
+_OVERLAP = {"on": os.environ.get("DENO_BWD_OVERLAP", "1") != "0"}
+_OVERLAP_HANDLES: Dict[int, "_capi.Overlap"] = {}
+
+
+def set_bwd_overlap(on: bool):
+    """Run the parameter-gradient kernels of every layer's backward on a side stream next to the input-gradient
+    chain (``deno_spectral_bwd_overlap``, include/deno_spectral.h).  On by default; ``DENO_BWD_OVERLAP=0`` turns it off."""
+    _OVERLAP["on"] = bool(on)
+
+
+def _overlap_handle(dev: torch.device):
+    """Side stream + fork / join events of this device (created once by the library, owned here for the process's life)."""
+    if not _OVERLAP["on"]:
+        return None
+    h = _OVERLAP_HANDLES.get(dev.index)
+    if h is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                       # never create streams / events inside a capture; the warm-up steps do it
+        L = lib()
+        h = _capi.Overlap()
+        _capi.check(L, L.deno_overlap_create(C.byref(h)), "deno_overlap_create")
+        _OVERLAP_HANDLES[dev.index] = h
+    return h
 
 
 def set_poison(on: bool):
@@ -233,13 +257,15 @@ class _SpectralConvFn(torch.autograd.Function):
             _poison(ws, gx, glw if s_lw is None else None, glb if s_lb is None else None,
                     *([g for g, sk in zip(gws, s_w) if sk is None] if gws is not None else []))
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = L.deno_spectral_bwd(C.byref(d), gy.data_ptr(), xc.data_ptr(), z.data_ptr(), xhat.data_ptr(),
-                                     _capi.pointer_array([w.data_ptr() for w in wc]), lw.data_ptr(), tw.data_ptr(),
-                                     None if gx is None else gx.data_ptr(),
-                                     None if gws is None else _capi.pointer_array([g.data_ptr() for g in gws]),
-                                     None if glw is None else glw.data_ptr(), None if glb is None else glb.data_ptr(),
-                                     ws.data_ptr(), nws, stream)
-            _capi.check(L, rc, "deno_spectral_bwd")
+            ov = _overlap_handle(dev)
+            rc = L.deno_spectral_bwd_overlap(
+                C.byref(d), gy.data_ptr(), xc.data_ptr(), z.data_ptr(), xhat.data_ptr(),
+                _capi.pointer_array([w.data_ptr() for w in wc]), lw.data_ptr(), tw.data_ptr(),
+                None if gx is None else gx.data_ptr(),
+                None if gws is None else _capi.pointer_array([g.data_ptr() for g in gws]),
+                None if glw is None else glw.data_ptr(), None if glb is None else glb.data_ptr(),
+                ws.data_ptr(), nws, stream, None if ov is None else C.byref(ov))
+            _capi.check(L, rc, "deno_spectral_bwd_overlap")
             _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
         for owner in ctx.sink_owners:
             _release_sink(owner)

@@ -118,6 +118,30 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
                       void* stream);
 
 /*
+ * deno_spectral_bwd with its parameter-gradient kernels on a second stream.  After gz = gy * act'(z) and its spectrum
+ * exist, the backward splits into two independent parts: the input-gradient chain (G^x -> row synthesis -> plane
+ * synthesis, which the NEXT layer's backward waits for) and the kernels that only produce gW / glin_w / glin_b.  With a
+ * `deno_overlap` the second part is enqueued on `ov->side_stream` (fork and join through the two events, both recorded
+ * inside this call: when it returns, `stream` is ordered after everything).  Replaces the serial order in which
+ * PyTorch's autograd engine runs the same nodes.  Capturable in a CUDA graph (the side stream
+ * joins the capture through ev_fork and leaves it through ev_join).  `ov == NULL` is deno_spectral_bwd.
+ * The stream and events are created by deno_overlap_create on the CURRENT device and owned by the caller.
+ */
+typedef struct deno_overlap {
+  void* side_stream; /* cudaStream_t, non-blocking        */
+  void* ev_fork;     /* cudaEvent_t, timing disabled      */
+  void* ev_join;     /* cudaEvent_t, timing disabled      */
+} deno_overlap;
+
+int deno_overlap_create(deno_overlap* out);
+int deno_overlap_destroy(deno_overlap* ov);
+int deno_spectral_bwd_overlap(const deno_spectral_desc* desc, const float* gy, const float* x,
+                              const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                              const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                              float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                              void* stream, const deno_overlap* ov);
+
+/*
  * One fused Adam step over flat fp32 buffers (all device pointers, `n` elements each), replacing the per-tensor
  * foreach Adam of the reference demos (`torch.optim.Adam(..., betas=(0.7, 0.9), weight_decay=1e-4)`,
  * /root/reference/Demo/Darcy_2d/run_FNO&UNet.py:209).  Same update rule as torch.optim.Adam (no amsgrad); complex

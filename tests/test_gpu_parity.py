@@ -345,6 +345,69 @@ def test_bitwise_repeatability(shape):
                                torch.view_as_real(b) if b.is_complex() else b)
 
 
+@pytest.mark.parametrize("shape", [
+    (20, 32, 32, (94, 94), (12, 12)),      # Darcy layer at the bench batch
+    (4, 64, 64, (72, 72), (12, 12)),       # width 64: tensor-core mix kernels, separate weight-gradient launch
+    (3, 16, 16, (1026,), (16,)),           # 1-D
+    (2, 8, 8, (20, 22, 18), (4, 5, 6)),    # 3-D
+], ids=["darcy", "w64", "1d", "3d"])
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_backward_overlap_is_bitwise_the_serial_backward(shape, graph):
+    """deno_spectral_bwd_overlap runs the parameter-gradient kernels on a side stream next to the input-gradient
+    chain.  Same kernels, same summation order: every gradient must be bit-identical to the one-stream backward,
+    eagerly and under CUDA-graph capture (the side stream joins and leaves the capture), 6 repetitions each."""
+    from deno4pytorch_b200 import functional
+    from deno4pytorch_b200.functional import spectral_conv
+    B, cin, cout, spatial, modes = shape
+    nd = len(spatial)
+    dev = _dev()
+    gen = torch.Generator().manual_seed(33)
+    x = torch.randn((B, cin) + spatial, generator=gen).to(dev).requires_grad_(True)
+    ws = [torch.view_as_complex(torch.randn((cin, cout) + modes + (2,), generator=gen) / cin).to(dev).requires_grad_(True)
+          for _ in range(2 ** (nd - 1))]
+    lw = (torch.randn((cout, cin) + (1,) * nd, generator=gen) / cin ** 0.5).to(dev).requires_grad_(True)
+    lb = torch.randn(cout, generator=gen).to(dev).requires_grad_(True)
+    cot = torch.randn((B, cout) + spatial, generator=gen).to(dev)
+    leaves = [x, lw, lb] + ws
+
+    def one():
+        for t in leaves:
+            t.grad = None
+        spectral_conv(x, ws, lw, lb, modes, "gelu").backward(cot)
+
+    def grads():
+        torch.cuda.synchronize()
+        return [(torch.view_as_real(t.grad) if t.grad.is_complex() else t.grad).clone() for t in leaves]
+
+    try:
+        functional.set_bwd_overlap(False)
+        one()
+        serial = grads()
+        functional.set_bwd_overlap(True)
+        one()                                   # creates the side stream / events outside any capture
+        runner = one
+        if graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                one()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one()
+            runner = g.replay
+        for _ in range(6):
+            for t in leaves:
+                if t.grad is not None:
+                    (torch.view_as_real(t.grad) if t.grad.is_complex() else t.grad).fill_(float("nan"))
+            runner()
+            for a, b in zip(serial, grads()):
+                assert torch.equal(a, b)
+    finally:
+        functional.set_bwd_overlap(True)
+
+
 def test_direct_gradient_writes_match_autograd_accumulation():
     """parallel.FlatGradients.direct_writes(): the backward kernels write parameter gradients straight into the flat
     buffer and return None to autograd.  Same numbers as the accumulate path, and no gradient is left unwritten."""
