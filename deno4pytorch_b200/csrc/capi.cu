@@ -626,6 +626,7 @@ struct Options {
   bool wgrad_tma = true; // DENO_WGRAD_TMA=0: the register-staged bypass_wgrad_tc kernel instead of the TMA one
   bool mix_tc = true;    // DENO_MIX_TC=0: the SIMT mode-mix kernels also for width >= 64
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
+  int an_ring = 1;       // DENO_AN_RING: 0 = one staging buffer (round-1 layout), 1 = ring + staged act'(z) where it fits, 2 = ring, z by registers
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
 Options read_options() {
@@ -640,6 +641,7 @@ Options read_options() {
   if (const char* e = getenv("DENO_WGRAD_TMA")) o.wgrad_tma = e[0] != '0';
   if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] == '1';
   if (const char* e = getenv("DENO_AT_DBG")) o.at_dbg = atoi(e);
+  if (const char* e = getenv("DENO_AN_RING")) o.an_ring = atoi(e);
   if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
@@ -745,14 +747,45 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   p.nplanes = s.B * s.X * channels;
   p.N1 = tl.N1; p.Wp = tl.Wp; p.Hp = tl.Hp; p.KS0 = tl.KS0; p.KRp = tl.KRp;
   p.nsub = tl.an_nsub; p.HS = tl.an_HS;
+  // Staging ring: what fits next to the operand images.  Wanted: two slots (slab j + 1 lands while slab j is transformed;
+  // with one slot its copy only starts when slab j has been consumed and ~0.9 k cycles of it are exposed per plane) and,
+  // in the gz variant, act'(z) staged next to gy (the per-thread global loads of z were another ~1.5 k exposed cycles).
+  // Tight fits (the 94 x 94 Darcy plane) put the epilogue's exchange buffer inside the B2 image and drop the
+  // descriptor over-read pad, which the ring itself then covers.
+  const int HWs = tl.an_HS * s.W, hlast = s.H - (tl.an_nsub - 1) * tl.an_HS;
+  const bool bulk = ((long long)s.H * s.W) % 4 == 0 && (HWs % 4) == 0 && (hlast * s.W) % 4 == 0;
+  const int stage_bytes = round_up(HWs, 4) * 4;
+  const int limit = kMaxSmemBytes - 256;       // static shared memory (barriers, TMEM slot) + the array's 128-byte alignment
+  int smem_total = sm.total;
+  p.nslots = 1; p.zstage = 0; p.stage_off = sm.stage; p.xch_off = sm.xch; p.xch_alias = 0;
+  if (bulk && options().an_ring) {
+    const int zs = (gz && options().an_ring != 2) ? 1 : 0;
+    const int want[3][2] = {{2, zs}, {zs ? 1 : 2, zs}, {1, 0}};   // (slots, z staged), best first
+    for (int c = 0; c < 3; ++c) {
+      const int bufs = want[c][0] * (1 + want[c][1]);
+      if (bufs == 1) break;
+      const int plain = sm.total + (bufs - 1) * stage_bytes;
+      const int xch_bytes = sm.stage - sm.xch;
+      const int tight = sm.total - 4096 - xch_bytes + (bufs - 1) * stage_bytes;
+      if (plain <= limit) {
+        p.nslots = want[c][0]; p.zstage = want[c][1]; smem_total = plain;
+        break;
+      }
+      if (tight <= limit && (bufs - 1) * stage_bytes >= 4096 && xch_bytes <= sm.b2_bytes) {
+        p.nslots = want[c][0]; p.zstage = want[c][1]; smem_total = tight;
+        p.xch_alias = 1; p.xch_off = sm.b2; p.stage_off = sm.xch;
+        break;
+      }
+    }
+  }
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
 #define DENO_AN_CASE(GZ, SLABS, LABEL)                                                                         \
   {                                                                                                            \
-    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS>, (size_t)sm.total, "plane_analysis_tc");           \
+    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS>, (size_t)smem_total, "plane_analysis_tc");         \
     if (rc != DENO_OK) return rc;                                                                              \
     prof_before(LABEL, st);                                                                                    \
-    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS>), dim3(grid), dim3(tc::kAnThreads), (size_t)sm.total, st, p); \
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
   }
   const bool slabs = p.nsub > 1;
   if (gz && slabs) DENO_AN_CASE(true, true, "plane_analysis_gz_tc")

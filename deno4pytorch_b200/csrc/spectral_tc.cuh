@@ -1031,6 +1031,12 @@ struct AnalysisTcParams {
   int nplanes;
   int N1, Wp, Hp, KS0, KRp;
   int nsub, HS;          // planes taller than 128 rows: nsub row slabs of HS rows (Hp = HS padded to 8), stage 2 accumulates over them
+  // Staging ring (chosen by the launcher from what fits next to the operand images): `nslots` slots of one slab each,
+  // filled by bulk copies issued nslots items ahead; with `zstage` a slot also holds the slab's act'(z) (FUSE_GZ), so the
+  // gz pass reads both factors from shared memory instead of waiting for per-thread global loads.
+  int nslots, zstage;
+  int stage_off, xch_off;   // byte offsets of the ring and of the epilogue exchange buffer
+  int xch_alias;            // the exchange buffer lives inside the B2 image (tight fits): one more worker barrier per plane
 };
 
 struct AnalysisTcSmem {
@@ -1076,9 +1082,11 @@ constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp 
 
 template <bool FUSE_GZ, bool SLABS>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+  // no-swizzle descriptors need 16-byte alignment only; a 1024-byte aligned array would cost the tight fits 1 KB
+  extern __shared__ __align__(128) unsigned char an_smem[];
+  unsigned char* const smem = an_smem;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar[2], bar_stage, bar_const;
+  __shared__ __align__(8) uint64_t mbar[2], bar_stage[2], bar_const;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // A plane of up to 128 rows is one item.  Taller planes (the 229- and 137-row Airfoil / Pipe grids) are cut into
   // nsub row slabs of HS rows: every slab goes through the staging buffer, the transform and stage 1 like a plane of
@@ -1091,14 +1099,20 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const AnalysisTcSmem so = analysis_tc_smem(H, W, KH, N1, Wp, Hp, KRp, nsub);
   const int HW = H * W;                                  // elements of a full slab
   const int hlast = Hfull - (nsub - 1) * H;              // rows of the last slab
-  float* stage = reinterpret_cast<float*>(smem + so.stage);
+  float* const stage_ring = reinterpret_cast<float*>(smem + p.stage_off);
+  const int stage_floats = round_up(HW, 4);                  // one staged slab (u, or act'(z))
+  const int slot_floats = stage_floats * (1 + p.zstage);
+  const bool two_slots = p.nslots == 2;
+  const bool zstage = FUSE_GZ && p.zstage != 0;
+  auto slot_of = [&](int j) { return two_slots ? (j & 1) : 0; };
 
   const uint32_t tmem_cols = 6 * N1 <= 64 ? 64u : (6 * N1 <= 128 ? 128u : (6 * N1 <= 256 ? 256u : 512u));
   if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
   if (tid == 32) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
-    mbar_init(&bar_stage, 1);
+    mbar_init(&bar_stage[0], 1);
+    mbar_init(&bar_stage[1], 1);
     mbar_init(&bar_const, 1);
     mbar_fence_init();
     // constant operand images (final layout in global memory): two bulk async copies
@@ -1144,14 +1158,19 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.u + base), "r"(bytes) : "memory");
       if (FUSE_GZ) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.z + base), "r"(bytes) : "memory");
     };
-    auto prefetch_plane = [&](int j) {                 // bulk copy of this CTA's j-th slab into the staging buffer
+    auto prefetch_plane = [&](int j) {                 // bulk copy of this CTA's j-th slab (and its act'(z)) into ring slot j % nslots
       if (!bulk || j >= nmine || !leader) return;
       const long long base = item_base(j);
       const uint32_t bytes = (uint32_t)(item_rows(j) * W) * 4u;
-      const uint32_t bar = smem_u32(&bar_stage);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      const int slot = slot_of(j);
+      const uint32_t bar = smem_u32(&bar_stage[slot]);
+      float* dst = stage_ring + slot * slot_floats;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(zstage ? 2u * bytes : bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_u32(stage)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
+                   ::"r"(smem_u32(dst)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
+      if (zstage)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst + stage_floats)), "l"(p.z + base), "r"(bytes), "r"(bar) : "memory");
     };
     long long idle = 0;
     auto stage1 = [&](int j) {                         // stage-1 MMAs of plane j once its A images are stored
@@ -1162,8 +1181,10 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       nbar_sync(kAnBarA, kAnThreads);
       fence_after_sync();
       idle += DENO_CLK() - t0;
-      prefetch_plane(j + 1);                           // every worker is past the staging buffer
-      l2_prefetch(j + 2);
+      // With a two-slot ring the MMAs go first: the workers wait for them next, while the copy below is for the item
+      // after next and its address arithmetic (integer divisions in item_base) is ~0.5 k cycles of this single issuing
+      // lane.  With one slot the copy is what the next transform waits for, so it keeps its place in front.
+      if (!two_slots) { prefetch_plane(j + 1); l2_prefetch(j + 2); }
       for (int s2 = 0; s2 < Wp / 8; ++s2) {
         const uint32_t acc = s2 > 0 ? 1u : 0u;
         if (leader) {
@@ -1173,10 +1194,12 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         ah += inc_a; al += inc_a; be += inc_b;
       }
       if (leader) mma_commit(&mbar[0]);
+      if (two_slots) { prefetch_plane(j + 2); l2_prefetch(j + 3); }   // every worker is past item j's ring slot
       __syncwarp();
     };
-    l2_prefetch(1);
     prefetch_plane(0);
+    if (two_slots) prefetch_plane(1);
+    l2_prefetch(p.nslots);
     stage1(0);
     for (int j = 0; j < nmine; ++j) {
       const long long t0 = DENO_CLK();
@@ -1205,7 +1228,8 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
     // ------------------------------------------------------------------ workers
     const int wq = warp & 3, wg = warp >> 2;
     const int xrow = wq * 32 + lane;        // TMEM lane owned by this thread (row x of D1 / row r of D2)
-    uint32_t phase = 0, stage_phase = 0;
+    uint32_t phase = 0;
+    float* const stage = stage_ring;                   // non-bulk fallback: one slot
     auto issue_plane_cp_async = [&](int j) {           // non-bulk fallback
       const long long base = item_base(j);
       const int n = item_rows(j) * W;
@@ -1216,8 +1240,9 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       const int hrows = item_rows(j);
       const int nel = hrows * W;
       const long long tq0 = DENO_CLK();
+      float* const stage = stage_ring + slot_of(j) * slot_floats;
       float4 zr[kAnZRegs];                             // act'(z) of this thread's first elements: in flight during the wait
-      if (FUSE_GZ && bulk) {
+      if (FUSE_GZ && bulk && !zstage) {
         const float4* z4 = reinterpret_cast<const float4*>(p.z + item_base(j));
 #pragma unroll
         for (int r = 0; r < kAnZRegs; ++r) {
@@ -1226,8 +1251,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         }
       }
       if (bulk) {
-        mbar_wait(&bar_stage, stage_phase);
-        stage_phase ^= 1;
+        mbar_wait(&bar_stage[slot_of(j)], (uint32_t)((two_slots ? (j >> 1) : j) & 1));
       } else {
         cp_async_wait_all();
         nbar_sync(kAnBarWorkers, kAnWorkers);
@@ -1236,7 +1260,17 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);      // slot 32: wait for the staged plane
       if (FUSE_GZ) {                                   // gz = gy * act'(z): coalesced store, kept in staging
         const long long base = item_base(j);
-        if (bulk) {
+        if (zstage) {                                  // both factors staged: shared memory -> shared memory + global
+          float4* s4 = reinterpret_cast<float4*>(stage);
+          const float4* zs4 = reinterpret_cast<const float4*>(stage + stage_floats);
+          float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
+          for (int i = tid; i < nel / 4; i += kAnWorkers) {
+            const float4 a = s4[i], b = zs4[i];
+            const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            s4[i] = v;
+            g4[i] = v;
+          }
+        } else if (bulk) {
           float4* s4 = reinterpret_cast<float4*>(stage);
           float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
 #pragma unroll
@@ -1372,7 +1406,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       // epilogue (after the plane's last slab): rows k (cos) and KS0 + k (sin) of D2 are combined through shared
       // memory; warp group wg takes the column passes c0 = 16 wg, 16 wg + 64, ...
       if (last_slab) {
-        float* xch = reinterpret_cast<float*>(smem + so.xch);     // [KH][N1 + 1] sin-row values (odd pitch: conflict-free)
+        float* xch = reinterpret_cast<float*>(smem + p.xch_off);  // [KH][N1 + 1] sin-row values (odd pitch: conflict-free)
         const bool is_cos = xrow < KH, is_sin = xrow >= KS0 && xrow < KS0 + KH;
         const bool warp_used = (wq * 32 < KH) || (wq * 32 + 32 > KS0 && wq * 32 < KS0 + KH);   // any cos / sin row in this quadrant
         for (int c0 = wg * 16; c0 < N1; c0 += 64) {
@@ -1398,6 +1432,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         }
       }
       fence_before_sync();                             // D2 reads ordered before this thread's next hand-off
+      if (p.xch_alias) nbar_sync(kAnBarWorkers, kAnWorkers);   // exchange buffer inside B2: no worker may store B2(j+1) before all have read it
       if (warp == 1) { DENO_DBG_ADD(38, DENO_CLK() - tq7); DENO_DBG_ADD(39, 1); }   // slots 38/39: epilogue, planes
       phase ^= 1;
     }
