@@ -139,6 +139,8 @@ struct TwLayout {
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
   int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [2*N1 rows: hi, lo][Wp], A2 [slab][hi|lo][KRp*Hp]
   int an_nsub, an_HS;                            // row slabs of the tensor-core analysis (0: shape not covered); Hp = an_HS
+  size_t rs_a;                                   // row_synthesis_tc A images [rs_ntm][hi|lo][rs_KP * 128] (float offset)
+  int rs_KP, rs_ntm;                             // 2 * round_up(KH, 4) columns; 128-row tiles (0: no row axis / too tall)
 };
 
 // Shared-memory bytes of plane_analysis_tc_kernel for slabs of HS rows (mirrors tc::analysis_tc_smem, which the launcher
@@ -215,6 +217,11 @@ TwLayout tw_layout(const Shape& s) {
   off = (off + 63) / 64 * 64;                      // 256-byte aligned: the images are bulk-copied
   t.at_e1 = off; off += ag.ok ? (size_t)ag.g * ag.nchunks * 2 * ag.N1 * 32 : 0;
   t.at_a2 = off; off += ag.ok ? (size_t)(ag.K2p / 32) * 4 * ag.KHp * 32 : 0;
+  // row_synthesis_tc: cos / sin of the row axis as tcgen05 A operand images (K-major, 128 rows per tile)
+  t.rs_KP = 2 * s.KH4;
+  t.rs_ntm = (s.ndim >= 2 && s.H <= 256) ? (s.H + 127) / 128 : 0;
+  off = (off + 63) / 64 * 64;
+  t.rs_a = off; off += (size_t)t.rs_ntm * 2 * t.rs_KP * 128;
   t.total = off;
   return t;
 }
@@ -544,6 +551,32 @@ void fill_analysis_images(float* base, const Shape& s, const TwLayout& t) {
   }
 }
 
+// row_synthesis_tc A operand: A[x, k] = cos(2 pi f_k x / H), A[x, KP/2 + k] = sin(...), tf32 hi / lo from fp64, zero
+// outside the grid rows and the retained modes.
+void fill_row_synth_images(float* base, const Shape& s, const TwLayout& t) {
+  const double two_pi = 6.283185307179586476925286766559;
+  const int KH2 = t.rs_KP / 2;
+  for (int tm = 0; tm < t.rs_ntm; ++tm) {
+    float* hi = base + t.rs_a + (size_t)tm * 2 * t.rs_KP * 128;
+    float* lo = hi + (size_t)t.rs_KP * 128;
+    for (int r = 0; r < 128; ++r)
+      for (int kp = 0; kp < t.rs_KP; ++kp) {
+        const int k = kp < KH2 ? kp : kp - KH2;
+        const long long x = (long long)tm * 128 + r;
+        double v = 0.0;
+        if (k < s.KH && x < s.H) {
+          const long long f = (k < s.mH) ? k : (long long)s.H - 2 * s.mH + k;
+          const double ang = two_pi * (double)((f * x) % s.H) / (double)s.H;
+          v = kp < KH2 ? cos(ang) : sin(ang);
+        }
+        const float h = tf32_mask((float)v);
+        const int off = kmajor_off(r, kp, 128) / 4;
+        hi[off] = h;
+        lo[off] = (float)(v - (double)h);
+      }
+  }
+}
+
 // byte offset of element (row, k) of a K-major SWIZZLE_128B image made of [rows][32 fp32] chunks
 inline size_t sw128_off(int row, int k, int rows) {
   return (size_t)(k >> 5) * rows * 128 + (size_t)row * 128 + (size_t)((((k & 31) >> 2) ^ (row & 7)) << 4) + (size_t)(k & 3) * 4;
@@ -594,7 +627,7 @@ void fill_analysis_tma_images(float* base, const Shape& s, const TwLayout& t) {
 }
 
 struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; const float* synth_ae;
-                const float* an_e1; const float* an_a2; const float* at_e1; const float* at_a2; };
+                const float* an_e1; const float* an_a2; const float* at_e1; const float* at_a2; const float* rs_a; };
 
 TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   const float* base = static_cast<const float*>(twiddles);
@@ -609,6 +642,7 @@ TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   p.an_a2 = base + t.an_a2;
   p.at_e1 = base + t.at_e1;
   p.at_a2 = base + t.at_a2;
+  p.rs_a = base + t.rs_a;
   return p;
 }
 
@@ -627,6 +661,7 @@ struct Options {
   bool mix_tc = true;    // DENO_MIX_TC=0: the SIMT mode-mix kernels also for width >= 64
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   int an_ring = 1;       // DENO_AN_RING: 0 = one staging buffer (round-1 layout), 1 = ring + staged act'(z) where it fits, 2 = ring, z by registers
+  bool rowsynth_tc = true;  // DENO_ROWSYNTH_TC=0: the SIMT row_synthesis kernel instead of the tensor-core one
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
 Options read_options() {
@@ -642,6 +677,7 @@ Options read_options() {
   if (const char* e = getenv("DENO_ANALYSIS_TMA")) o.an_tma = e[0] == '1';
   if (const char* e = getenv("DENO_AT_DBG")) o.at_dbg = atoi(e);
   if (const char* e = getenv("DENO_AN_RING")) o.an_ring = atoi(e);
+  if (const char* e = getenv("DENO_ROWSYNTH_TC")) o.rowsynth_tc = e[0] != '0';
   if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
@@ -1243,7 +1279,38 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
     r.ogroups = (CO + r.ocb - 1) / r.ocb;
     r.COT = COT; r.nco = nco;
     const size_t rs_smem = tc::row_synth_smem_bytes(r.ocb, r.KH, r.MW, r.KE);
-    if (rs_smem <= (size_t)kMaxSmemBytes) {
+    // tensor-core version: one GEMM per (batch entry, channel tile, G image column quads)
+    bool rs_done = false;
+    if (options().rowsynth_tc && tl.rs_ntm > 0 && (COT % 8) == 0 && (tl.KE % 4) == 0) {
+      tc::RowSynthTcParams rt;
+      rt.spec = p.spec; rt.ta = tw.rs_a; rt.cl = p.cl; rt.u = urow; rt.scale = p.scale; rt.herm = p.herm;
+      rt.H = p.g.H; rt.KH = p.g.KH; rt.MW = p.g.MW; rt.CO = CO; rt.KE = tl.KE; rt.KP = tl.rs_KP;
+      rt.COT = COT; rt.nco = nco; rt.ntm = tl.rs_ntm;
+      const int nkq = tl.KE / 4;
+      const long long units = (long long)p.g.NBO * p.g.NBI * nco;
+      int G = 0, Gmin = 0;
+      for (int g = nkq; g >= 1; --g) {                 // largest column group that still gives every SM a CTA
+        if (nkq % g != 0 || g * 4 * COT > 256) continue;
+        if (tl.rs_ntm * g * 4 * COT > 512) continue;   // TMEM columns
+        if ((size_t)tc::row_synth_tc_smem(rt.KP, g * 4 * COT, rt.ntm).total > (size_t)kMaxSmemBytes - 256) continue;
+        Gmin = g;
+        if (G == 0 && units * (nkq / g) >= 148) G = g;
+      }
+      if (G == 0) G = Gmin;                            // small problems: as many CTAs as the shape allows
+      if (G > 0) {
+        rt.G = G; rt.ngrp = nkq / G;
+        const size_t tsm = (size_t)tc::row_synth_tc_smem(rt.KP, G * 4 * COT, rt.ntm).total;
+        int rrc = allow_smem(tc::row_synthesis_tc_kernel, tsm, "row_synthesis_tc");
+        if (rrc != DENO_OK) return rrc;
+        prof_before("row_synthesis_tc", st);
+        DENO_LAUNCH((tc::row_synthesis_tc_kernel), dim3((unsigned)(units * rt.ngrp)), dim3(tc::kRsTcThreads), tsm, st, rt);
+        rrc = check_launch("row_synthesis_tc", st);
+        if (rrc != DENO_OK) return rrc;
+        q.urow = urow;
+        rs_done = true;
+      }
+    }
+    if (!rs_done && rs_smem <= (size_t)kMaxSmemBytes) {
       int rrc = allow_smem(tc::row_synthesis_kernel, rs_smem, "row_synthesis");
       if (rrc != DENO_OK) return rrc;
       int threads = round_up(r.ocb * (tl.KE / 2), 32);
@@ -1815,6 +1882,7 @@ int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, s
   fill_analysis_images(base, s, t);
   memset(base + t.at_e1, 0, (t.total - t.at_e1) * sizeof(float));
   fill_analysis_tma_images(base, s, t);
+  fill_row_synth_images(base, s, t);
   for (int l = 0; l < s.MWp; ++l) {
     float c = 0.f;
     if (l < s.MW) {

@@ -301,6 +301,212 @@ __global__ void __launch_bounds__(384) row_synthesis_kernel(RowSynthParams p) {
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// row_synthesis_tc: the same U images as row_synthesis_kernel, as ONE real GEMM per (batch entry, channel tile,
+// column group) on the tensor cores.  With A[x, k] = cos phi(k, x), A[x, KH2 + k] = sin phi(k, x) (constant, host-built
+// hi / lo images) and, per image column n = (o, 2l + r),
+//     S[n(o,l,0), k] =  f_l Re Y^[o,k,l]    S[n(o,l,0), KH2 + k] = -f_l Im Y^[o,k,l]        ->  D[x, n] =  Re U
+//     S[n(o,l,1), k] = -f_l Im Y^[o,k,l]    S[n(o,l,1), KH2 + k] = -f_l Re Y^[o,k,l]        ->  D[x, n] = -Im U
+// D[x, n] = sum_k' A[x, k'] S[n, k'] is exactly the pair (Re, -Im) the synthesis kernel's B operand wants, and when the
+// N index walks the image in memory order - n = kq * 4 COT + o * 4 + kr for image column 4 kq + kr - the thread that
+// owns accumulator row x streams its columns straight into row x's image.  3xTF32 into one accumulator
+// (hi*hi + lo*hi + hi*lo).  The SIMT kernel spent 14 us per launch at the Darcy shape on 69 M fp32 FMAs at ~10 % of the
+// FMA pipe; here the arithmetic is 18-36 instructions per CTA.
+// CTA = (batch entry, channel tile, G column quads); rows in tiles of 128 (ntm <= 2).
+// ----------------------------------------------------------------------------------------------
+struct RowSynthTcParams {
+  const float2* spec;    // [NB'][CO][KH][MW]
+  const float* ta;       // row-twiddle A images [ntm][hi|lo][KP * 128] (final tcgen05 layout, from the twiddle table)
+  const float* cl;
+  float* u;              // [NB'][H][nco][hi|lo][KE * COT]
+  float scale;
+  int herm;
+  int H, KH, MW, CO, KE;
+  int KP;                // 2 * round_up(KH, 4): cos columns [0, KP/2), sin columns [KP/2, KP)
+  int COT, nco;
+  int G, ngrp;           // image column quads per CTA, CTAs per channel tile (G * ngrp = KE / 4)
+  int ntm;               // 128-row tiles
+};
+constexpr int kRsTcThreads = 256;
+
+struct RowSynthTcSmem { int a_one, b_lbo, b_one, a, b, total; };
+__host__ __device__ inline RowSynthTcSmem row_synth_tc_smem(int KP, int NT, int ntm) {
+  RowSynthTcSmem m;
+  m.a_one = 128 * KP * 4;
+  m.b_lbo = 16 * NT + 16;                  // padded K-direction stride: lanes walking along k store conflict-free
+  m.b_one = (KP / 4) * m.b_lbo;
+  m.a = 0;
+  m.b = ntm * 2 * m.a_one;
+  m.total = m.b + 2 * m.b_one + 2048;      // the M = 128 / N descriptors read whole 8-row groups: keep the tail inside
+  const int tiles = (kRsTcThreads / 32) * 32 * (64 + 4) * 4;   // the epilogue's per-warp transpose tiles reuse the operand area
+  if (m.total < tiles) m.total = tiles;
+  return m;
+}
+
+__global__ void __launch_bounds__(kRsTcThreads, 2) row_synthesis_tc_kernel(RowSynthTcParams p) {
+  extern __shared__ __align__(128) unsigned char rst_smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar_a, bar_mma;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int COT = p.COT, KP = p.KP, KH2 = KP / 2, ntm = p.ntm;
+  const int NT = p.G * 4 * COT;
+  const RowSynthTcSmem so = row_synth_tc_smem(KP, NT, ntm);
+  unsigned char* sa = rst_smem + so.a;
+  unsigned char* sb = rst_smem + so.b;
+  int bid = blockIdx.x;
+  const int grp = bid % p.ngrp; bid /= p.ngrp;
+  const int cot = bid % p.nco;
+  const int bp = bid / p.nco;
+  const int kq0 = grp * p.G;
+  uint32_t ncols = 32;
+  while ((int)ncols < ntm * NT) ncols *= 2;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  if (tid == 32) {
+    mbar_init(&bar_a, 1);
+    mbar_init(&bar_mma, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar_a, (uint32_t)(ntm * 2 * so.a_one));
+    for (int i = 0; i < ntm * 2; ++i)                  // constant images: one bulk copy each
+      bulk_g2s(sa + i * so.a_one, p.ta + (size_t)i * (so.a_one / 4), (uint32_t)so.a_one, &bar_a);
+  }
+  DENO_PDL_SYNC();                                     // the packed spectrum comes from the predecessor (mode mix / outer synthesis)
+
+  // ---- B images: S[n][k'] from the packed spectrum, split hi / lo; lanes walk along k ----
+  {
+    const int LS = 2 * p.G;                            // last-axis modes of this CTA: l = 2 kq0 + ls
+    const int ntask = COT * LS * KH2;
+    const float2* src = p.spec + ((long long)bp * p.CO + (long long)cot * COT) * p.KH * p.MW;
+    constexpr int NL = 8;                              // loads in flight per thread: the whole slice in one round trip at the usual shapes
+    for (int t0 = tid; t0 < ntask; t0 += NL * kRsTcThreads) {
+      float2 v[NL];
+      int kk[NL], nl[NL];
+#pragma unroll
+      for (int uu = 0; uu < NL; ++uu) {
+        const int t = t0 + uu * kRsTcThreads;
+        const int k = t % KH2, q = t / KH2;
+        const int ls = q % LS, oi = q / LS;
+        const int l = 2 * kq0 + ls;
+        kk[uu] = k;
+        nl[uu] = (ls >> 1) * 4 * COT + oi * 4 + (ls & 1) * 2;
+        v[uu] = make_float2(0.f, 0.f);
+        if (t < ntask && k < p.KH && l < p.MW) {
+          const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
+          const float2 y = ldg_ordered(src + ((long long)oi * p.KH + k) * p.MW + l);
+          v[uu] = make_float2(y.x * f, y.y * f);
+        }
+      }
+#pragma unroll
+      for (int uu = 0; uu < NL; ++uu) {
+        if (t0 + uu * kRsTcThreads < ntask) {
+          const int n0 = nl[uu], k = kk[uu];
+          const int r0 = (n0 & 7) * 16 + (n0 >> 3) * 128;            // row n0 (r = 0); row n0 + 1 is 16 bytes further
+          const int c0 = (k & 3) * 4 + (k >> 2) * so.b_lbo;          // cos column k
+          const int c1 = ((KH2 + k) & 3) * 4 + ((KH2 + k) >> 2) * so.b_lbo;   // sin column KH2 + k
+          float h, l2;
+          split_tf32(v[uu].x, h, l2);                                // +Re: (n0, k);  -Re: (n0 + 1, KH2 + k)
+          *reinterpret_cast<float*>(sb + r0 + c0) = h;
+          *reinterpret_cast<float*>(sb + so.b_one + r0 + c0) = l2;
+          *reinterpret_cast<float*>(sb + r0 + 16 + c1) = -h;
+          *reinterpret_cast<float*>(sb + so.b_one + r0 + 16 + c1) = -l2;
+          split_tf32(v[uu].y, h, l2);                                // -Im: (n0, KH2 + k) and (n0 + 1, k)
+          *reinterpret_cast<float*>(sb + r0 + c1) = -h;
+          *reinterpret_cast<float*>(sb + so.b_one + r0 + c1) = -l2;
+          *reinterpret_cast<float*>(sb + r0 + 16 + c0) = -h;
+          *reinterpret_cast<float*>(sb + so.b_one + r0 + 16 + c0) = -l2;
+        }
+      }
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    mbar_wait(&bar_a, 0);                              // constant images landed
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_tf32(128, NT);
+    const uint32_t sbase = smem_u32(rst_smem);
+    const uint32_t lbo_a = 16 * 128, lbo_b = (uint32_t)so.b_lbo;
+    const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_b) >> 4);
+    for (int tm = 0; tm < ntm; ++tm) {
+      uint64_t ah = make_desc(sbase + so.a + (2 * tm) * so.a_one, lbo_a, 128);
+      uint64_t al = make_desc(sbase + so.a + (2 * tm + 1) * so.a_one, lbo_a, 128);
+      uint64_t bh = make_desc(sbase + so.b, lbo_b, 128), bl = make_desc(sbase + so.b + so.b_one, lbo_b, 128);
+      const uint32_t d = tmem + (uint32_t)(tm * NT);
+      for (int s2 = 0; s2 < KP / 8; ++s2) {
+        if (leader) {
+          mma_tf32(d, ah, bh, idesc, s2 > 0 ? 1u : 0u);   // hi * hi
+          mma_tf32(d, al, bh, idesc, 1u);                 // lo * hi
+          mma_tf32(d, ah, bl, idesc, 1u);                 // hi * lo
+        }
+        ah += inc_a; al += inc_a; bh += inc_b; bl += inc_b;
+      }
+    }
+    if (leader) mma_commit(&bar_mma);
+    __syncwarp();
+  }
+  mbar_wait(&bar_mma, 0);
+  fence_after_sync();
+
+  // ---- epilogue: accumulator row x -> tf32 hi / lo -> row x's image (columns in memory order) ----
+  // A thread owns one row, so storing straight from registers would put every lane of a store on a different
+  // 128-byte line (measured: 31 sectors per request, ~8 k LSU cycles per CTA).  Each warp therefore transposes blocks
+  // of CB columns through a private tile in the (now idle) operand area and stores whole row segments.
+  {
+    const int wq = warp & 3, wh = warp >> 2;           // TMEM lane quadrant of this warp, column half
+    const int nhalf = NT / 2;
+    const int cbs = (nhalf % 64 == 0) ? 6 : ((nhalf % 32 == 0) ? 5 : 4);   // block width 64 / 32 / 16 columns (nhalf is a multiple of 16)
+    const int CB = 1 << cbs;
+    const int pitch = CB + 4;                          // floats; 16-byte rows, conflict-free for both access patterns
+    float* tile = reinterpret_cast<float*>(rst_smem) + (size_t)warp * 32 * (64 + 4);
+    const int q4s = cbs - 2;                           // log2 of the float4 per row of the block
+    const int sr = lane >> q4s, sc4 = lane & ((1 << q4s) - 1), srstep = 32 >> q4s;   // this lane's first row / float4 column / row step
+    const size_t img = (size_t)p.KE * COT;
+    for (int tm = 0; tm < ntm; ++tm) {
+      const int xw = tm * 128 + wq * 32;               // first row of this warp
+      const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(tm * NT + wh * nhalf);
+      float* base = p.u + (((size_t)bp * p.H) * p.nco + cot) * 2 * img + (size_t)kq0 * 4 * COT + (size_t)wh * nhalf;
+      const size_t rowpitch = (size_t)p.nco * 2 * img;
+      for (int cb = 0; cb < nhalf; cb += CB) {
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {         // hi image, then lo image, through the same tile
+          for (int c0 = 0; c0 < CB; c0 += 16) {
+            float v[16];
+            tmem_ld16(ta + (uint32_t)(cb + c0), v);
+            float4* dst = reinterpret_cast<float4*>(tile + lane * pitch + c0);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 h, l2;
+              split_tf32(v[j], h.x, l2.x);
+              split_tf32(v[j + 1], h.y, l2.y);
+              split_tf32(v[j + 2], h.z, l2.z);
+              split_tf32(v[j + 3], h.w, l2.w);
+              dst[j >> 2] = part == 0 ? h : l2;
+            }
+          }
+          __syncwarp();
+          {
+            const float* src = tile + sr * pitch + sc4 * 4;
+            float* dstg = base + (size_t)(xw + sr) * rowpitch + (size_t)part * img + cb + sc4 * 4;
+            for (int r = sr; r < 32 && xw + r < p.H; r += srstep) {
+              *reinterpret_cast<float4*>(dstg) = *reinterpret_cast<const float4*>(src);
+              src += srstep * pitch;
+              dstg += (size_t)srstep * rowpitch;
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, ncols);
+}
+
 struct SynthTcSmem {
   int bw_hi, bw_lo, ae_hi, ae_lo, bu, ax_hi, ax_lo, bias, total;  // byte offsets
   int bu_one;                                                     // bytes of one (hi or lo) U image
