@@ -253,6 +253,8 @@ def kernel_algorithmic_bytes(A, spec_small, Wb):
         "mode_mix_bwd_fused": 3 * spec_small + 3 * Wb,      # read G^, X^, W; write G^x, gW
         "mode_mix": 2 * spec_small + Wb, "mode_mix_bwd": 2 * spec_small + Wb, "mode_mix_wgrad": 2 * spec_small + Wb,
         "mode_mix_tc": 2 * spec_small + Wb, "mode_mix_bwd_tc": 2 * spec_small + Wb, "mode_mix_wgrad_tc": 2 * spec_small + Wb,
+        "mode_mix_lane": 2 * spec_small + Wb, "mode_mix_bwd_lane": 2 * spec_small + Wb,
+        "mode_mix_bwd_gx": 2 * spec_small + Wb, "mode_mix_bwd_gw": 2 * spec_small + Wb,   # the fused backward mix split by role (side stream)
         "line_analysis": A + spec_small, "line_analysis_gz": 3 * A + spec_small,
         "row_synthesis": spec_small + A // 2, "row_synthesis_tc": spec_small + A // 2,
     }

@@ -661,6 +661,7 @@ struct Options {
   bool mix_tc = true;    // DENO_MIX_TC=0: the SIMT mode-mix kernels also for width >= 64
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   int an_ring = 1;       // DENO_AN_RING: 0 = one staging buffer (round-1 layout), 1 = ring + staged act'(z) where it fits, 2 = ring, z by registers
+  int mix_lane = 1;      // DENO_MIX_LANE: 0 = never, 1 (default) = mode_mix_lane (lane = mode, batch-tiled, staged spectrum) instead of the tensor-core mix for width >= 128, 2 = for every width
   bool rowsynth_tc = true;  // DENO_ROWSYNTH_TC=0: the SIMT row_synthesis kernel instead of the tensor-core one
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
@@ -678,6 +679,7 @@ Options read_options() {
   if (const char* e = getenv("DENO_AT_DBG")) o.at_dbg = atoi(e);
   if (const char* e = getenv("DENO_AN_RING")) o.an_ring = atoi(e);
   if (const char* e = getenv("DENO_ROWSYNTH_TC")) o.rowsynth_tc = e[0] != '0';
+  if (const char* e = getenv("DENO_MIX_LANE")) o.mix_lane = atoi(e);
   if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
@@ -1017,8 +1019,44 @@ int launch_mix_wgrad_tc(const Shape& s, const float2* xhat, const float2* ghat, 
 bool mix_tc_eligible(const Shape&) { return false; }
 #endif
 
+// lane = mode, batch-tiled product with the contracted spectrum staged in shared memory (mode_mix_lane_kernel)
+int launch_mix_lane(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks, cudaStream_t st) {
+  MixParams p;
+  p.in = in; p.out = out;
+  p.md = make_decode(s);
+  const int nblk = 1 << (s.ndim - 1);
+  for (int j = 0; j < 4; ++j) p.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
+  p.B = s.B;
+  if (!backward) {
+    p.CI = s.CI; p.CO = s.CO;
+    p.w_sci = (long long)s.CO * p.md.Mblk; p.w_sco = p.md.Mblk;
+    p.conj_w = 0;
+  } else {
+    p.CI = s.CO; p.CO = s.CI;
+    p.w_sci = p.md.Mblk; p.w_sco = (long long)s.CO * p.md.Mblk;
+    p.conj_w = 1;
+  }
+  const size_t smem = mix_lane_smem_bytes(p.CI);
+  int rc = allow_smem(mode_mix_lane_kernel, smem, "mode_mix_lane");
+  if (rc != DENO_OK) return rc;
+  dim3 block(32, 8);
+  dim3 grid((s.M + 31) / 32, (p.CO + 7) / 8, (s.B + kMixLaneB - 1) / kMixLaneB);
+  prof_before(backward ? "mode_mix_bwd_lane" : "mode_mix_lane", st);
+  DENO_LAUNCH(mode_mix_lane_kernel, grid, block, smem, st, p);
+  return check_launch("mode_mix_lane", st);
+}
+
+bool mix_lane_wanted(const Shape& s) {
+  const int ml = options().mix_lane;
+  if (ml == 2) return true;
+  // measured (gpurun r3p / r3q): width 128 (C4b) layer 1865 -> 1822 us with the lane kernel, width 64 (C3) 283 -> 280
+  // (a wash: the tensor-core mix stays there), width 32 (C2) 148 -> 154 (worse: the thread-per-output kernel has more warps)
+  return ml == 1 && s.CI >= 128 && s.CO >= 128;
+}
+
 int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, const void* const* w_blocks,
                cudaStream_t st) {
+  if (mix_lane_wanted(s)) return launch_mix_lane(s, backward, in, out, w_blocks, st);
 #ifndef DENO_EMULATE
   if (mix_tc_eligible(s)) {
     const int trc = launch_mix_tc(s, backward, in, out, w_blocks, st);
@@ -1083,6 +1121,12 @@ int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat,
                          void* const* gw_blocks, float* glb_from_dc, cudaStream_t st,
                          const char* label = "mode_mix_bwd_fused") {
   const int nblk = 1 << (s.ndim - 1);
+  if (mix_lane_wanted(s) && gxhat != nullptr && w_blocks != nullptr) {   // G^x by the lane kernel, the other roles below
+    const int lrc = launch_mix_lane(s, true, ghat, gxhat, w_blocks, st);
+    if (lrc != DENO_OK) return lrc;
+    gxhat = nullptr;
+    if (gw_blocks == nullptr && glb_from_dc == nullptr) return DENO_OK;
+  }
 #ifndef DENO_EMULATE
   if (mix_tc_eligible(s)) {   // width >= 64: two tensor-core launches (+ the DC-mode bias gradient) instead of the fused SIMT one
     int rc = DENO_OK;

@@ -457,6 +457,100 @@ __global__ void mode_mix_kernel(MixParams p) {
   mode_mix_body(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
+// ----------------------------------------------------------------------------------------------
+// mode_mix_lane: the same product as mode_mix (out[b,co,p] = sum_ci in[b,ci,p] * (conj?) W[ci,co,p]) for layers
+// where the contracted width makes the weight stream the cost (width >= 64: 9.4 - 37.7 MB of weights per layer).
+// Lane = packed mode, exactly like mode_mix (every global access is a coalesced 256-byte row of the mode-innermost
+// layouts), but a thread owns kMixLaneB batch entries of one produced channel: the weight element it loads is used
+// kMixLaneB times, and the contracted-channel spectrum of those batch entries is staged in shared memory once per
+// block instead of being re-read from L2 by every produced channel.  Weights cross L2 -> SM  B / kMixLaneB  times
+// instead of B times; no operand images, no tensor cores: the arithmetic is 0.2 GFLOP.
+// blockDim = (32 modes, 8 produced channels); grid = (ceil(M / 32), ceil(CO / 8), ceil(B / kMixLaneB)).
+// ----------------------------------------------------------------------------------------------
+constexpr int kMixLaneB = 5;        // batch entries per thread
+constexpr int kMixLaneChunk = 64;   // contracted channels staged per pass
+constexpr int kMixLaneUnroll = 8;   // weight loads in flight per thread (16 measured slower: C3 layer 280 -> 288 us, C4b 1822 -> 1848)
+
+__host__ __device__ inline size_t mix_lane_smem_bytes(int CI) {
+  const int cc = CI < kMixLaneChunk ? CI : kMixLaneChunk;
+  return (size_t)kMixLaneB * cc * 32 * sizeof(float2);
+}
+
+__global__ void __launch_bounds__(256) mode_mix_lane_kernel(MixParams p) {
+  DENO_PDL_SYNC();
+  DENO_DYN_SMEM(ml_smem);
+  float2* xs = reinterpret_cast<float2*>(ml_smem);              // [kMixLaneB][chunk][32]
+  const int M = p.md.M;
+  const int lane = threadIdx.x, cy = threadIdx.y;
+  const int tid = cy * 32 + lane;
+  const int pm = blockIdx.x * 32 + lane;
+  const int pmc = min(pm, M - 1);
+  const int co = blockIdx.y * 8 + cy;
+  const int b0 = blockIdx.z * kMixLaneB;
+  const int nb = min(kMixLaneB, p.B - b0);
+  const int cc = p.CI < kMixLaneChunk ? p.CI : kMixLaneChunk;
+  int blk, off;
+  decode_mode(p.md, pmc, blk, off);
+  const float2* wb = blk == 0 ? p.w[0] : (blk == 1 ? p.w[1] : (blk == 2 ? p.w[2] : p.w[3]));
+  const float2* w = wb + (long long)min(co, p.CO - 1) * p.w_sco + off;
+  const float sgn = p.conj_w ? -1.0f : 1.0f;
+  float ar[kMixLaneB], ai[kMixLaneB];
+#pragma unroll
+  for (int j = 0; j < kMixLaneB; ++j) ar[j] = ai[j] = 0.f;
+
+  for (int c0 = 0; c0 < p.CI; c0 += cc) {
+    const int ncc = min(cc, p.CI - c0);
+    if (c0 > 0) __syncthreads();                                  // previous chunk consumed
+    // stage in[b0 .. b0 + nb)[c0 .. c0 + ncc)[32 modes]: rows of 256 bytes, eight loads in flight per thread
+    const int nrow = nb * ncc;
+    for (int r0 = cy; r0 < nrow; r0 += 8 * 8) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = min(r0 + u * 8, nrow - 1);
+        const int j = r / ncc, ci = r - j * ncc;
+        v[u] = ldg_ordered(p.in + ((long long)(b0 + j) * p.CI + c0 + ci) * M + pmc);
+      }
+      DENO_SCHED_FENCE();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u * 8;
+        if (r < nrow) {
+          const int j = r / ncc, ci = r - j * ncc;
+          xs[(j * cc + ci) * 32 + lane] = v[u];
+        }
+      }
+    }
+    __syncthreads();
+    const float2* wc = w + (long long)c0 * p.w_sci;
+    for (int ci0 = 0; ci0 < ncc; ci0 += kMixLaneUnroll) {
+      float2 wv[kMixLaneUnroll];
+#pragma unroll
+      for (int u = 0; u < kMixLaneUnroll; ++u) wv[u] = ldg_ordered(wc + (long long)min(ci0 + u, ncc - 1) * p.w_sci);
+      DENO_SCHED_FENCE();
+#pragma unroll
+      for (int u = 0; u < kMixLaneUnroll; ++u) {
+        const bool live = ci0 + u < ncc;
+        const float wr = live ? wv[u].x : 0.f;
+        const float wi = live ? wv[u].y * sgn : 0.f;
+        const float2* xp = xs + min(ci0 + u, ncc - 1) * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < kMixLaneB; ++j) {
+          const float2 x = xp[j * cc * 32];                      // rows of batch entries >= nb hold stale data: never stored
+          ar[j] = fmaf(x.x, wr, fmaf(-x.y, wi, ar[j]));
+          ai[j] = fmaf(x.x, wi, fmaf(x.y, wr, ai[j]));
+        }
+      }
+    }
+  }
+  (void)tid;
+  if (pm < M && co < p.CO) {
+#pragma unroll
+    for (int j = 0; j < kMixLaneB; ++j)
+      if (j < nb) p.out[((long long)(b0 + j) * p.CO + co) * M + pm] = make_float2(ar[j], ai[j]);
+  }
+}
+
 // gW[i,o,p] = sum_b conj(xhat[b,i,p]) * ghat[b,o,p]
 struct MixWgradParams {
   const float2* xhat;

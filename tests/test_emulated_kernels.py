@@ -134,3 +134,17 @@ def test_descriptor_validation_errors():
     w2 = [np.zeros((2, 2, 5, 2), dtype=np.complex64)] * 2
     with pytest.raises(_capi.DenoError, match="overlapping"):
         emu_harness.EmuLayer(rng.standard_normal((1, 2, 8, 8)), w2, lin_w2, None, (5, 2), "gelu")
+
+
+@pytest.mark.parametrize("idx", [2, 5, 8, 12])
+def test_emulated_lane_mix_kernel(idx, monkeypatch):
+    """mode_mix_lane_kernel (lane = mode, five batch entries per thread, spectrum staged in shared memory) forced for
+    every width: same truth, ragged batch / channel tails included."""
+    monkeypatch.setenv("DENO_MIX_LANE", "2")
+    lib = emu_harness.load()
+    lib.deno_reload_env()
+    try:
+        test_emulated_layer_random_shapes(idx)
+    finally:
+        monkeypatch.delenv("DENO_MIX_LANE")
+        lib.deno_reload_env()
