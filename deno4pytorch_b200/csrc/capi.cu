@@ -2172,8 +2172,17 @@ int deno_fno_lift_fwd(const deno_fno_desc* desc, const float* x, const float* gr
   p.x = x; p.grid = grid; p.w0 = w0; p.b0 = b0; p.h = h;
   p.chunks = (f.g.nppts + kLiftThreads - 1) / kLiftThreads;
   const size_t smem = (size_t)f.C * (f.Kx + f.ND + 1) * sizeof(float);
+  const int K = f.Kx + f.ND;
   prof_before("fno_lift", st);
-  DENO_LAUNCH(fno_lift_kernel, dim3((unsigned)(f.B * p.chunks)), dim3(kLiftThreads), smem, st, p);
+#define DENO_LIFT_CASE(KT) DENO_LAUNCH(fno_lift_kernel<KT>, dim3((unsigned)(f.B * p.chunks)), dim3(kLiftThreads), smem, st, p)
+  if (K <= 2) DENO_LIFT_CASE(2);
+  else if (K <= 3) DENO_LIFT_CASE(3);
+  else if (K <= 4) DENO_LIFT_CASE(4);
+  else if (K <= 8) DENO_LIFT_CASE(8);
+  else if (K <= 12) DENO_LIFT_CASE(12);
+  else if (K <= 13) DENO_LIFT_CASE(13);
+  else DENO_LIFT_CASE(16);
+#undef DENO_LIFT_CASE
   return check_launch("fno_lift", st);
 }
 

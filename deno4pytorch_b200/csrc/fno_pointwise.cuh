@@ -54,6 +54,10 @@ struct LiftParams {
   int chunks;            // ceil(nppts / kLiftThreads); gridDim.x = B * chunks
 };
 
+// KT = compile-time bound on the feature count K (2 .. 16): the per-channel dot product is KT FMAs with the features in
+// registers.  With the bound fixed at 16 for every model the Darcy lift (K = 3) executed 72 warp instructions per
+// 128-byte store (ncu: 12.9 M instructions, 19 us for a 22.6 MB write).
+template <int KT>
 __global__ void __launch_bounds__(kLiftThreads) fno_lift_kernel(LiftParams p) {
   DENO_PDL_SYNC();   // first kernel after the optimiser step: even the weights need the predecessor
   DENO_DYN_SMEM(smem_raw);
@@ -68,23 +72,25 @@ __global__ void __launch_bounds__(kLiftThreads) fno_lift_kernel(LiftParams p) {
   if (pp >= p.g.nppts) return;
   int pc;
   const bool valid = padded_to_cropped(p.g, pp, pc);
-  float v[kLiftMaxK];
+  float v[KT];
 #pragma unroll
-  for (int k = 0; k < kLiftMaxK; ++k) {
+  for (int k = 0; k < KT; ++k) {
     float t = 0.f;
     if (valid && k < p.Kx) t = p.x[((long long)b * p.g.npts + pc) * p.Kx + k];
     else if (valid && k < K) t = p.grid[((long long)b * p.g.npts + pc) * p.ND + (k - p.Kx)];
     v[k] = t;
   }
   float* out = p.h + (long long)b * p.C * p.g.nppts + pp;
-  for (int c = 0; c < p.C; ++c) {
-    float acc = 0.f;
-    if (valid) {
-      acc = b0s[c];
+  if (!valid) {                                        // padding: zeros
+    for (int c = 0; c < p.C; ++c) out[(long long)c * p.g.nppts] = 0.f;
+    return;
+  }
+  const float* wr = w0s;
+  for (int c = 0; c < p.C; ++c, wr += K) {
+    float acc = b0s[c];
 #pragma unroll
-      for (int k = 0; k < kLiftMaxK; ++k)
-        if (k < K) acc = fmaf(w0s[c * K + k], v[k], acc);
-    }
+    for (int k = 0; k < KT; ++k)
+      if (k < K) acc = fmaf(wr[k], v[k], acc);
     out[(long long)c * p.g.nppts] = acc;
   }
 }
