@@ -662,6 +662,10 @@ struct Options {
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   int an_ring = 1;       // DENO_AN_RING: 0 = one staging buffer (round-1 layout), 1 = ring + staged act'(z) where it fits, 2 = ring, z by registers
   int mix_lane = 1;      // DENO_MIX_LANE: 0 = never, 1 (default) = mode_mix_lane (lane = mode, batch-tiled, staged spectrum) instead of the tensor-core mix for width >= 128, 2 = for every width
+  int an_piece = 0;      // DENO_AN_PIECE: bytes per bulk copy of a staged slab (multiple of 16; 0 = one copy per slab)
+  int an_ablate = 0;     // DENO_AN_ABLATE: timing-only ablation bits of plane_analysis_tc (results wrong; see AnalysisTcParams::ablate)
+  bool an_chase = false; // DENO_AN_CHASE=1: stage-1 MMAs start on the first column groups while the rest of the plane is still being transformed
+                         // (measured slower - more barriers per plane: C5 layer 2024 -> 2080 us, C4b 1838 -> 1863, C3 282 -> 286, C2 146 -> 146)
   bool rowsynth_tc = true;  // DENO_ROWSYNTH_TC=0: the SIMT row_synthesis kernel instead of the tensor-core one
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
@@ -680,6 +684,9 @@ Options read_options() {
   if (const char* e = getenv("DENO_AN_RING")) o.an_ring = atoi(e);
   if (const char* e = getenv("DENO_ROWSYNTH_TC")) o.rowsynth_tc = e[0] != '0';
   if (const char* e = getenv("DENO_MIX_LANE")) o.mix_lane = atoi(e);
+  if (const char* e = getenv("DENO_AN_CHASE")) o.an_chase = e[0] == '1';
+  if (const char* e = getenv("DENO_AN_ABLATE")) o.an_ablate = atoi(e);
+  if (const char* e = getenv("DENO_AN_PIECE")) o.an_piece = atoi(e) & ~15;
   if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
@@ -792,30 +799,37 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   // descriptor over-read pad, which the ring itself then covers.
   const int HWs = tl.an_HS * s.W, hlast = s.H - (tl.an_nsub - 1) * tl.an_HS;
   const bool bulk = ((long long)s.H * s.W) % 4 == 0 && (HWs % 4) == 0 && (hlast * s.W) % 4 == 0;
-  const int stage_bytes = round_up(HWs, 4) * 4;
-  const int limit = kMaxSmemBytes - 256;       // static shared memory (barriers, TMEM slot) + the array's 128-byte alignment
+  const int stage_bytes = round_up((tl.an_nsub == 1 ? s.H : tl.an_HS) * s.W, 4) * 4;   // the rows that exist (HS is H rounded up to 8)
+  const int limit = kMaxSmemBytes - 64;        // the barrier words (appended below) are the only other shared memory of the kernel
   int smem_total = sm.total;
   p.nslots = 1; p.zstage = 0; p.stage_off = sm.stage; p.xch_off = sm.xch; p.xch_alias = 0;
+  p.chase = options().an_chase ? 1 : 0;
+  p.ablate = options().an_ablate;
+  p.piece_bytes = options().an_piece;
   if (bulk && options().an_ring) {
     const int zs = (gz && options().an_ring != 2) ? 1 : 0;
     const int want[3][2] = {{2, zs}, {zs ? 1 : 2, zs}, {1, 0}};   // (slots, z staged), best first
     for (int c = 0; c < 3; ++c) {
       const int bufs = want[c][0] * (1 + want[c][1]);
       if (bufs == 1) break;
-      const int plain = sm.total + (bufs - 1) * stage_bytes;
-      const int xch_bytes = sm.stage - sm.xch;
-      const int tight = sm.total - 4096 - xch_bytes + (bufs - 1) * stage_bytes;
+      const int plain = sm.stage + bufs * stage_bytes + 4096;
+      const int tight = sm.xch + bufs * stage_bytes;               // exchange buffer inside B2, no over-read pad (the ring covers it)
       if (plain <= limit) {
         p.nslots = want[c][0]; p.zstage = want[c][1]; smem_total = plain;
         break;
       }
-      if (tight <= limit && (bufs - 1) * stage_bytes >= 4096 && xch_bytes <= sm.b2_bytes) {
+      if (tight <= limit && bufs * stage_bytes >= 4096 && (sm.stage - sm.xch) <= sm.b2_bytes) {
         p.nslots = want[c][0]; p.zstage = want[c][1]; smem_total = tight;
         p.xch_alias = 1; p.xch_off = sm.b2; p.stage_off = sm.xch;
         break;
       }
     }
   }
+  p.sync_off = round_up(smem_total, 16);
+  smem_total = p.sync_off + 64;
+  if (getenv("DENO_AN_DEBUG") != nullptr)
+    fprintf(stderr, "[deno] analysis_tc H=%d W=%d gz=%d: base smem %d, stage %d, limit %d -> nslots %d zstage %d alias %d smem %d\n",
+            s.H, s.W, (int)gz, sm.total, stage_bytes, limit, p.nslots, p.zstage, p.xch_alias, smem_total);
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
 #define DENO_AN_CASE(GZ, SLABS, LABEL)                                                                         \

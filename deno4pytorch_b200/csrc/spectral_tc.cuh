@@ -1243,6 +1243,11 @@ struct AnalysisTcParams {
   int nslots, zstage;
   int stage_off, xch_off;   // byte offsets of the ring and of the epilogue exchange buffer
   int xch_alias;            // the exchange buffer lives inside the B2 image (tight fits): one more worker barrier per plane
+  int ablate;               // DENO_AN_ABLATE (measurement only, results WRONG): bit 0 no stage-1 MMAs, 1 no stage-2 MMAs, 2 no A-image stores,
+                            // 3 no B2 stores, 4 no spectrum stores, 5 no gz stores, 6 no staged-plane loads in the transform
+  int sync_off;             // byte offset of the barrier words (6 x 8 bytes) inside the dynamic allocation
+  int piece_bytes;          // bulk copies of a slab are issued in pieces of this many bytes (multiple of 16; 0: one copy)
+  int chase;                // stage-1 MMAs start on the first column groups while the rest of the plane is still being transformed
 };
 
 struct AnalysisTcSmem {
@@ -1281,7 +1286,7 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int kAnBarA = 2;         // A images stored (workers arrive, MMA warp syncs)
+constexpr int kAnBarA = 2;         // 2..5: A images stored, one per column group (workers arrive, MMA warp syncs)
 constexpr int kAnBarEpi0 = 8;      // 8..11: sin rows exchanged, one barrier per worker warp group
 constexpr int kAnBarWorkers = 12;  // workers only
 constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp syncs)
@@ -1291,8 +1296,13 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   // no-swizzle descriptors need 16-byte alignment only; a 1024-byte aligned array would cost the tight fits 1 KB
   extern __shared__ __align__(128) unsigned char an_smem[];
   unsigned char* const smem = an_smem;
-  __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t mbar[2], bar_stage[2], bar_const;
+  // The barriers and the TMEM slot live at the end of the DYNAMIC allocation: static shared memory of a kernel in this
+  // translation unit is padded to the 1024-byte alignment of the other kernels' arrays, which the tight fits cannot spare.
+  uint64_t* const sync_words = reinterpret_cast<uint64_t*>(an_smem + p.sync_off);
+  uint64_t* const mbar = sync_words;                   // [2]
+  uint64_t* const bar_stage = sync_words + 2;          // [2]
+  uint64_t& bar_const = sync_words[4];
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(sync_words + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // A plane of up to 128 rows is one item.  Taller planes (the 229- and 137-row Airfoil / Pipe grids) are cut into
   // nsub row slabs of HS rows: every slab goes through the staging buffer, the transform and stage 1 like a plane of
@@ -1306,7 +1316,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const int HW = H * W;                                  // elements of a full slab
   const int hlast = Hfull - (nsub - 1) * H;              // rows of the last slab
   float* const stage_ring = reinterpret_cast<float*>(smem + p.stage_off);
-  const int stage_floats = round_up(HW, 4);                  // one staged slab (u, or act'(z))
+  const int stage_floats = round_up((nsub == 1 ? Hfull : H) * W, 4);   // one staged slab (u, or act'(z)): the rows that exist
   const int slot_floats = stage_floats * (1 + p.zstage);
   const bool two_slots = p.nslots == 2;
   const bool zstage = FUSE_GZ && p.zstage != 0;
@@ -1338,6 +1348,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 32 * N1, lbo_a2 = 16 * KRp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int nyq = Wp / 4;                 // column quads of a row
   const int nchunk = (nyq + 7) / 8;       // a warp covers 8 quads (32 columns) x 4 rows per step
+  const int nsig = p.chase ? (nchunk < 4 ? nchunk : 4) : 1;   // hand-off points of the A images to the MMA warp (named barriers kAnBarA .. kAnBarA + 3)
   const int nplanes_mine = (p.nplanes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // planes of this CTA
   const int nmine = nplanes_mine * nsub;                 // items (slabs) of this CTA: item j = slab j % nsub of its plane j / nsub
   // Slabs whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
@@ -1372,32 +1383,47 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       const uint32_t bar = smem_u32(&bar_stage[slot]);
       float* dst = stage_ring + slot * slot_floats;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(zstage ? 2u * bytes : bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(smem_u32(dst)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
-      if (zstage)
+      // One slab goes out as several bulk copies of `piece` bytes: the copy engine works on them concurrently, where a
+      // single 35 KB copy streamed at a few bytes per cycle (the kernel with every arithmetic phase ablated still took
+      // 80 % of its time at the Darcy shape: profiles/round2_s3_analysis_ablation.txt).
+      const uint32_t piece = p.piece_bytes > 0 ? (uint32_t)p.piece_bytes : bytes;
+      for (uint32_t o = 0; o < bytes; o += piece) {
+        const uint32_t nb = min(piece, bytes - o);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst + stage_floats)), "l"(p.z + base), "r"(bytes), "r"(bar) : "memory");
+                     ::"r"(smem_u32(dst) + o), "l"(reinterpret_cast<const char*>(p.u + base) + o), "r"(nb), "r"(bar) : "memory");
+        if (zstage)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(dst + stage_floats) + o), "l"(reinterpret_cast<const char*>(p.z + base) + o), "r"(nb), "r"(bar) : "memory");
+      }
     };
     long long idle = 0;
     auto stage1 = [&](int j) {                         // stage-1 MMAs of plane j once its A images are stored
       uint64_t ah = make_desc(sbase + so.a, lbo_a, 128), al = make_desc(sbase + so.a + so.a_one, lbo_a, 128);
       uint64_t be = make_desc(sbase + so.e1, lbo_e1, 128);
       const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
-      const long long t0 = DENO_CLK();
-      nbar_sync(kAnBarA, kAnThreads);
-      fence_after_sync();
-      idle += DENO_CLK() - t0;
-      // With a two-slot ring the MMAs go first: the workers wait for them next, while the copy below is for the item
-      // after next and its address arithmetic (integer divisions in item_base) is ~0.5 k cycles of this single issuing
-      // lane.  With one slot the copy is what the next transform waits for, so it keeps its place in front.
-      if (!two_slots) { prefetch_plane(j + 1); l2_prefetch(j + 2); }
-      for (int s2 = 0; s2 < Wp / 8; ++s2) {
-        const uint32_t acc = s2 > 0 ? 1u : 0u;
-        if (leader) {
-          mma_tf32(tmem_d1, ah, be, idesc_n2, acc);              // hi * [hi | lo]
-          mma_tf32(tmem_d1 + 2 * N1, al, be, idesc_n1, acc);     // lo * hi
+      // The stage-1 K loop CHASES the transform: the workers hand the A images over in up to four column groups
+      // (32 columns = four K steps each, the last group takes the rest), so the tensor core works on the first columns
+      // while the later ones are still being split (it used to start after the whole transform: ~1.1 k cycles of
+      // MMAs exposed per plane).  One named barrier per group: a warp may run a group ahead of the others.
+      // With a two-slot ring the copies for the item after next wait until the MMAs are issued (their address
+      // arithmetic - integer divisions in item_base - is ~0.5 k cycles of this single issuing lane); with one slot the
+      // copy is what the next transform waits for, so it goes out as soon as the last group has left the staging buffer.
+      const int ksteps = Wp / 8;
+      for (int g = 0; g < nsig; ++g) {
+        const long long t0 = DENO_CLK();
+        nbar_sync(kAnBarA + g, kAnThreads);
+        fence_after_sync();
+        idle += DENO_CLK() - t0;
+        const int k1 = (g == nsig - 1) ? ksteps : min(4 * g + 4, ksteps);
+        if (g == nsig - 1 && !two_slots) { prefetch_plane(j + 1); l2_prefetch(j + 2); }
+        for (int s2 = 4 * g; s2 < k1; ++s2) {
+          const uint32_t acc = s2 > 0 ? 1u : 0u;
+          if (leader && !(p.ablate & 1)) {
+            mma_tf32(tmem_d1, ah, be, idesc_n2, acc);              // hi * [hi | lo]
+            mma_tf32(tmem_d1 + 2 * N1, al, be, idesc_n1, acc);     // lo * hi
+          }
+          ah += inc_a; al += inc_a; be += inc_b;
         }
-        ah += inc_a; al += inc_a; be += inc_b;
       }
       if (leader) mma_commit(&mbar[0]);
       if (two_slots) { prefetch_plane(j + 2); l2_prefetch(j + 3); }   // every worker is past item j's ring slot
@@ -1419,7 +1445,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       const uint64_t inc_a2 = (uint64_t)((2 * lbo_a2) >> 4), inc_b2 = (uint64_t)((2 * lbo_b2) >> 4);
       for (int s2 = 0; s2 < Hp / 8; ++s2) {
         const uint32_t acc = (s2 > 0 || sub > 0) ? 1u : 0u;
-        if (leader) {
+        if (leader && !(p.ablate & 2)) {
           mma_tf32(tmem_d2, a2h, b2, idesc_n2, acc);
           mma_tf32(tmem_d2 + 2 * N1, a2l, b2, idesc_n1, acc);
         }
@@ -1464,19 +1490,13 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       }
       const long long tq1 = DENO_CLK();
       if (warp == 1) DENO_DBG_ADD(32, tq1 - tq0);      // slot 32: wait for the staged plane
-      if (FUSE_GZ) {                                   // gz = gy * act'(z): coalesced store, kept in staging
+      // gz = gy * act'(z).  With act'(z) staged next to gy the product is formed INSIDE the transform loop below: the
+      // thread that splits a row quad also multiplies it and stores it to gz (a warp's store covers 4 row segments of
+      // 128 bytes), so there is no separate pass over the plane, no write-back into the staging buffer and no barrier
+      // between the two (that pass + barrier was 1.5 - 2.3 k cycles per plane, profiles/round2_s3_phase_probe.txt).
+      if (FUSE_GZ && !zstage) {                        // z by per-thread global loads: separate pass, gz kept in staging
         const long long base = item_base(j);
-        if (zstage) {                                  // both factors staged: shared memory -> shared memory + global
-          float4* s4 = reinterpret_cast<float4*>(stage);
-          const float4* zs4 = reinterpret_cast<const float4*>(stage + stage_floats);
-          float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
-          for (int i = tid; i < nel / 4; i += kAnWorkers) {
-            const float4 a = s4[i], b = zs4[i];
-            const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
-            s4[i] = v;
-            g4[i] = v;
-          }
-        } else if (bulk) {
+        if (bulk) {
           float4* s4 = reinterpret_cast<float4*>(stage);
           float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
 #pragma unroll
@@ -1520,18 +1540,56 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         const int r0 = warp * 4 + (lane >> 3), r1 = r0 + (kAnWorkers / 32) * 4;     // Hp <= 128: at most two rows per thread
         const float* s0 = stage + r0 * W;
         const float* s1 = stage + r1 * W;
+        const bool fuse = zstage;                      // multiply by the staged act'(z) and store gz here
+        const float* zs = stage + stage_floats;
+        float* gout = FUSE_GZ ? p.gz_out + item_base(j) : nullptr;
+        const bool even = (W & 1) == 0;                // rows start 8-byte aligned: 64-bit shared / global accesses
+        // one row quad (4 consecutive columns of row r): load, (multiply + store gz), zero outside the slab
+        auto load_quad = [&](const float* srow, int r, int y0, float (&v)[4]) {
+          const bool rok = r < hrows && !(p.ablate & 64);
+          if (even) {
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            if (rok && y0 < W) a = *reinterpret_cast<const float2*>(srow + y0);
+            if (rok && y0 + 2 < W) b = *reinterpret_cast<const float2*>(srow + y0 + 2);
+            if (fuse) {
+              const float* zrow = zs + (srow - stage);
+              float* grow = gout + (srow - stage);
+              if (rok && y0 < W) {
+                const float2 za = *reinterpret_cast<const float2*>(zrow + y0);
+                a.x *= za.x; a.y *= za.y;
+                if (!(p.ablate & 32)) *reinterpret_cast<float2*>(grow + y0) = a;
+              }
+              if (rok && y0 + 2 < W) {
+                const float2 zb = *reinterpret_cast<const float2*>(zrow + y0 + 2);
+                b.x *= zb.x; b.y *= zb.y;
+                if (!(p.ablate & 32)) *reinterpret_cast<float2*>(grow + y0 + 2) = b;
+              }
+            }
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int y = y0 + jj;
+              float t = 0.f;
+              if (rok && y < W) {
+                t = srow[y];
+                if (fuse) {
+                  t *= zs[(srow - stage) + y];
+                  gout[(srow - stage) + y] = t;
+                }
+              }
+              v[jj] = t;
+            }
+          }
+        };
         for (int c = 0; c < nchunk; ++c) {
           const int yq = c * 8 + (lane & 7);
           if (yq < nyq) {
             float v0[4], v1[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int y = yq * 4 + jj;
-              v0[jj] = (r0 < hrows && y < W) ? s0[y] : 0.f;
-              v1[jj] = (r1 < hrows && y < W) ? s1[y] : 0.f;
-            }
+            load_quad(s0, r0, yq * 4, v0);
+            load_quad(s1, r1, yq * 4, v1);
             float4 hi, lo;
-            if (r0 < Hp) {
+            if (r0 < Hp && !(p.ablate & 4)) {
               split_tf32(v0[0], hi.x, lo.x);
               split_tf32(v0[1], hi.y, lo.y);
               split_tf32(v0[2], hi.z, lo.z);
@@ -1540,7 +1598,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               *reinterpret_cast<float4*>(smem + so.a + off) = hi;
               *reinterpret_cast<float4*>(smem + so.a + so.a_one + off) = lo;
             }
-            if (r1 < Hp) {
+            if (r1 < Hp && !(p.ablate & 4)) {
               split_tf32(v1[0], hi.x, lo.x);
               split_tf32(v1[1], hi.y, lo.y);
               split_tf32(v1[2], hi.z, lo.z);
@@ -1550,10 +1608,14 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               *reinterpret_cast<float4*>(smem + so.a + so.a_one + off) = lo;
             }
           }
+          if (c < nsig - 1) {                          // column group c complete for this thread: hand it to the MMA warp
+            fence_proxy_async();
+            nbar_arrive(kAnBarA + c, kAnThreads);
+          }
         }
       }
       fence_proxy_async();
-      nbar_arrive(kAnBarA, kAnThreads);
+      nbar_arrive(kAnBarA + nsig - 1, kAnThreads);     // last group (all remaining columns)
       if (!bulk && j + 1 < nmine) {
         nbar_sync(kAnBarWorkers, kAnWorkers);          // every worker is past the staging buffer
         issue_plane_cp_async(j + 1);
@@ -1592,8 +1654,10 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               float th, tl;
               split_tf32(t, th, tl);
               const int r0 = (n & 7) * 16 + (n >> 3) * 128;
-              *reinterpret_cast<float*>(b2hi + r0 + kc) = th;
-              *reinterpret_cast<float*>(b2lo + r0 + kc) = tl;
+              if (!(p.ablate & 8)) {
+                *reinterpret_cast<float*>(b2hi + r0 + kc) = th;
+                *reinterpret_cast<float*>(b2lo + r0 + kc) = tl;
+              }
             }
           }
         }
@@ -1631,7 +1695,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               if (l < MW) {
                 const float sr = xch[xrow * (N1 + 1) + c0 + jj], si = xch[xrow * (N1 + 1) + c0 + jj + 1];
                 const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
-                dst[l] = make_float2((dsum[jj] + si) * f, (dsum[jj + 1] - sr) * f);
+                if (!(p.ablate & 16)) dst[l] = make_float2((dsum[jj] + si) * f, (dsum[jj + 1] - sr) * f);
               }
             }
           }
