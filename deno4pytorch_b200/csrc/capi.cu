@@ -662,10 +662,9 @@ struct Options {
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   int an_ring = 1;       // DENO_AN_RING: 0 = one staging buffer (round-1 layout), 1 = ring + staged act'(z) where it fits, 2 = ring, z by registers
   int mix_lane = 1;      // DENO_MIX_LANE: 0 = never, 1 (default) = mode_mix_lane (lane = mode, batch-tiled, staged spectrum) instead of the tensor-core mix for width >= 128, 2 = for every width
+  bool an_fuse_gz = true; // DENO_AN_FUSEGZ=0: gz product as a separate pass over the staged slab
   int an_piece = 0;      // DENO_AN_PIECE: bytes per bulk copy of a staged slab (multiple of 16; 0 = one copy per slab)
   int an_ablate = 0;     // DENO_AN_ABLATE: timing-only ablation bits of plane_analysis_tc (results wrong; see AnalysisTcParams::ablate)
-  bool an_chase = false; // DENO_AN_CHASE=1: stage-1 MMAs start on the first column groups while the rest of the plane is still being transformed
-                         // (measured slower - more barriers per plane: C5 layer 2024 -> 2080 us, C4b 1838 -> 1863, C3 282 -> 286, C2 146 -> 146)
   bool rowsynth_tc = true;  // DENO_ROWSYNTH_TC=0: the SIMT row_synthesis kernel instead of the tensor-core one
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
 };
@@ -684,9 +683,9 @@ Options read_options() {
   if (const char* e = getenv("DENO_AN_RING")) o.an_ring = atoi(e);
   if (const char* e = getenv("DENO_ROWSYNTH_TC")) o.rowsynth_tc = e[0] != '0';
   if (const char* e = getenv("DENO_MIX_LANE")) o.mix_lane = atoi(e);
-  if (const char* e = getenv("DENO_AN_CHASE")) o.an_chase = e[0] == '1';
   if (const char* e = getenv("DENO_AN_ABLATE")) o.an_ablate = atoi(e);
   if (const char* e = getenv("DENO_AN_PIECE")) o.an_piece = atoi(e) & ~15;
+  if (const char* e = getenv("DENO_AN_FUSEGZ")) o.an_fuse_gz = e[0] != '0';
   if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
@@ -803,9 +802,9 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   const int limit = kMaxSmemBytes - 64;        // the barrier words (appended below) are the only other shared memory of the kernel
   int smem_total = sm.total;
   p.nslots = 1; p.zstage = 0; p.stage_off = sm.stage; p.xch_off = sm.xch; p.xch_alias = 0;
-  p.chase = options().an_chase ? 1 : 0;
   p.ablate = options().an_ablate;
   p.piece_bytes = options().an_piece;
+  p.fuse_gz = options().an_fuse_gz ? 1 : 0;
   if (bulk && options().an_ring) {
     const int zs = (gz && options().an_ring != 2) ? 1 : 0;
     const int want[3][2] = {{2, zs}, {zs ? 1 : 2, zs}, {1, 0}};   // (slots, z staged), best first
@@ -832,18 +831,23 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
             s.H, s.W, (int)gz, sm.total, stage_bytes, limit, p.nslots, p.zstage, p.xch_alias, smem_total);
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
-#define DENO_AN_CASE(GZ, SLABS, LABEL)                                                                         \
+#define DENO_AN_CASE(GZ, SLABS, EVENW, LABEL)                                                                  \
   {                                                                                                            \
-    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS>, (size_t)smem_total, "plane_analysis_tc");         \
+    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW>, (size_t)smem_total, "plane_analysis_tc");  \
     if (rc != DENO_OK) return rc;                                                                              \
     prof_before(LABEL, st);                                                                                    \
-    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
   }
   const bool slabs = p.nsub > 1;
-  if (gz && slabs) DENO_AN_CASE(true, true, "plane_analysis_gz_tc")
-  else if (gz) DENO_AN_CASE(true, false, "plane_analysis_gz_tc")
-  else if (slabs) DENO_AN_CASE(false, true, "plane_analysis_tc")
-  else DENO_AN_CASE(false, false, "plane_analysis_tc")
+  const bool evenw = (s.W % 2) == 0;
+  if (gz && slabs && evenw) DENO_AN_CASE(true, true, true, "plane_analysis_gz_tc")
+  else if (gz && slabs) DENO_AN_CASE(true, true, false, "plane_analysis_gz_tc")
+  else if (gz && evenw) DENO_AN_CASE(true, false, true, "plane_analysis_gz_tc")
+  else if (gz) DENO_AN_CASE(true, false, false, "plane_analysis_gz_tc")
+  else if (slabs && evenw) DENO_AN_CASE(false, true, true, "plane_analysis_tc")
+  else if (slabs) DENO_AN_CASE(false, true, false, "plane_analysis_tc")
+  else if (evenw) DENO_AN_CASE(false, false, true, "plane_analysis_tc")
+  else DENO_AN_CASE(false, false, false, "plane_analysis_tc")
 #undef DENO_AN_CASE
   return check_launch("plane_analysis_tc", st);
 }

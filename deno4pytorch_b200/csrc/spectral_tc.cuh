@@ -1245,9 +1245,9 @@ struct AnalysisTcParams {
   int xch_alias;            // the exchange buffer lives inside the B2 image (tight fits): one more worker barrier per plane
   int ablate;               // DENO_AN_ABLATE (measurement only, results WRONG): bit 0 no stage-1 MMAs, 1 no stage-2 MMAs, 2 no A-image stores,
                             // 3 no B2 stores, 4 no spectrum stores, 5 no gz stores, 6 no staged-plane loads in the transform
+  int fuse_gz;              // gz = gy * act'(z) formed inside the transform loop (staged act'(z), even widths) instead of a separate pass
   int sync_off;             // byte offset of the barrier words (6 x 8 bytes) inside the dynamic allocation
   int piece_bytes;          // bulk copies of a slab are issued in pieces of this many bytes (multiple of 16; 0: one copy)
-  int chase;                // stage-1 MMAs start on the first column groups while the rest of the plane is still being transformed
 };
 
 struct AnalysisTcSmem {
@@ -1286,19 +1286,34 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int kAnBarA = 2;         // 2..5: A images stored, one per column group (workers arrive, MMA warp syncs)
+constexpr int kAnBarA = 2;         // A images stored (workers arrive, MMA warp syncs)
 constexpr int kAnBarEpi0 = 8;      // 8..11: sin rows exchanged, one barrier per worker warp group
 constexpr int kAnBarWorkers = 12;  // workers only
 constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp syncs)
 
-template <bool FUSE_GZ, bool SLABS>
+// Timing-only ablation bits (AnalysisTcParams::ablate) are compiled in only with -DDENO_AN_ABLATE_BUILD
+// (tools/an_ablate.py builds that variant): in the product kernel the tests cost registers and issue slots.
+#ifdef DENO_AN_ABLATE_BUILD
+#define DENO_AN_ABL(bit) (p.ablate & (bit))
+#else
+#define DENO_AN_ABL(bit) 0
+#endif
+// EVEN: the plane width is even, i.e. every row of the staged slab starts 8-byte aligned (64-bit accesses, gz fused into
+// the transform loop).  A template argument: as a run-time branch inside the transform loop it cost the odd-width Pipe
+// planes 2 % of the layer (two code paths live in the hot loop of a latency-bound kernel).
+template <bool FUSE_GZ, bool SLABS, bool EVEN>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   // no-swizzle descriptors need 16-byte alignment only; a 1024-byte aligned array would cost the tight fits 1 KB
   extern __shared__ __align__(128) unsigned char an_smem[];
   unsigned char* const smem = an_smem;
   // The barriers and the TMEM slot live at the end of the DYNAMIC allocation: static shared memory of a kernel in this
   // translation unit is padded to the 1024-byte alignment of the other kernels' arrays, which the tight fits cannot spare.
+#ifdef DENO_AN_STATICBAR
+  __shared__ __align__(8) uint64_t static_sync_words[6];
+  uint64_t* const sync_words = static_sync_words;
+#else
   uint64_t* const sync_words = reinterpret_cast<uint64_t*>(an_smem + p.sync_off);
+#endif
   uint64_t* const mbar = sync_words;                   // [2]
   uint64_t* const bar_stage = sync_words + 2;          // [2]
   uint64_t& bar_const = sync_words[4];
@@ -1348,7 +1363,8 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const uint32_t lbo_a = (uint32_t)so.a_lbo, lbo_e1 = 32 * N1, lbo_a2 = 16 * KRp, lbo_b2 = (uint32_t)so.b2_lbo;
   const int nyq = Wp / 4;                 // column quads of a row
   const int nchunk = (nyq + 7) / 8;       // a warp covers 8 quads (32 columns) x 4 rows per step
-  const int nsig = p.chase ? (nchunk < 4 ? nchunk : 4) : 1;   // hand-off points of the A images to the MMA warp (named barriers kAnBarA .. kAnBarA + 3)
+  // (handing the A images to the MMA warp in column groups, so that the stage-1 K loop chases the transform, was measured
+  // slower at every shape - one more fence + barrier per group: profiles/round2_ab_analysis_chase.txt)
   const int nplanes_mine = (p.nplanes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // planes of this CTA
   const int nmine = nplanes_mine * nsub;                 // items (slabs) of this CTA: item j = slab j % nsub of its plane j / nsub
   // Slabs whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
@@ -1401,29 +1417,21 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       uint64_t ah = make_desc(sbase + so.a, lbo_a, 128), al = make_desc(sbase + so.a + so.a_one, lbo_a, 128);
       uint64_t be = make_desc(sbase + so.e1, lbo_e1, 128);
       const uint64_t inc_a = (uint64_t)((2 * lbo_a) >> 4), inc_b = (uint64_t)((2 * lbo_e1) >> 4);
-      // The stage-1 K loop CHASES the transform: the workers hand the A images over in up to four column groups
-      // (32 columns = four K steps each, the last group takes the rest), so the tensor core works on the first columns
-      // while the later ones are still being split (it used to start after the whole transform: ~1.1 k cycles of
-      // MMAs exposed per plane).  One named barrier per group: a warp may run a group ahead of the others.
-      // With a two-slot ring the copies for the item after next wait until the MMAs are issued (their address
-      // arithmetic - integer divisions in item_base - is ~0.5 k cycles of this single issuing lane); with one slot the
-      // copy is what the next transform waits for, so it goes out as soon as the last group has left the staging buffer.
-      const int ksteps = Wp / 8;
-      for (int g = 0; g < nsig; ++g) {
-        const long long t0 = DENO_CLK();
-        nbar_sync(kAnBarA + g, kAnThreads);
-        fence_after_sync();
-        idle += DENO_CLK() - t0;
-        const int k1 = (g == nsig - 1) ? ksteps : min(4 * g + 4, ksteps);
-        if (g == nsig - 1 && !two_slots) { prefetch_plane(j + 1); l2_prefetch(j + 2); }
-        for (int s2 = 4 * g; s2 < k1; ++s2) {
-          const uint32_t acc = s2 > 0 ? 1u : 0u;
-          if (leader && !(p.ablate & 1)) {
-            mma_tf32(tmem_d1, ah, be, idesc_n2, acc);              // hi * [hi | lo]
-            mma_tf32(tmem_d1 + 2 * N1, al, be, idesc_n1, acc);     // lo * hi
-          }
-          ah += inc_a; al += inc_a; be += inc_b;
+      const long long t0 = DENO_CLK();
+      nbar_sync(kAnBarA, kAnThreads);
+      fence_after_sync();
+      idle += DENO_CLK() - t0;
+      // With a two-slot ring the MMAs go first: the workers wait for them next, while the copy below is for the item
+      // after next and its address arithmetic (integer divisions in item_base) is ~0.5 k cycles of this single issuing
+      // lane.  With one slot the copy is what the next transform waits for, so it keeps its place in front.
+      if (!two_slots) { prefetch_plane(j + 1); l2_prefetch(j + 2); }
+      for (int s2 = 0; s2 < Wp / 8; ++s2) {
+        const uint32_t acc = s2 > 0 ? 1u : 0u;
+        if (leader && !DENO_AN_ABL(1)) {
+          mma_tf32(tmem_d1, ah, be, idesc_n2, acc);              // hi * [hi | lo]
+          mma_tf32(tmem_d1 + 2 * N1, al, be, idesc_n1, acc);     // lo * hi
         }
+        ah += inc_a; al += inc_a; be += inc_b;
       }
       if (leader) mma_commit(&mbar[0]);
       if (two_slots) { prefetch_plane(j + 2); l2_prefetch(j + 3); }   // every worker is past item j's ring slot
@@ -1445,7 +1453,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       const uint64_t inc_a2 = (uint64_t)((2 * lbo_a2) >> 4), inc_b2 = (uint64_t)((2 * lbo_b2) >> 4);
       for (int s2 = 0; s2 < Hp / 8; ++s2) {
         const uint32_t acc = (s2 > 0 || sub > 0) ? 1u : 0u;
-        if (leader && !(p.ablate & 2)) {
+        if (leader && !DENO_AN_ABL(2)) {
           mma_tf32(tmem_d2, a2h, b2, idesc_n2, acc);
           mma_tf32(tmem_d2 + 2 * N1, a2l, b2, idesc_n1, acc);
         }
@@ -1494,9 +1502,20 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       // thread that splits a row quad also multiplies it and stores it to gz (a warp's store covers 4 row segments of
       // 128 bytes), so there is no separate pass over the plane, no write-back into the staging buffer and no barrier
       // between the two (that pass + barrier was 1.5 - 2.3 k cycles per plane, profiles/round2_s3_phase_probe.txt).
-      if (FUSE_GZ && !zstage) {                        // z by per-thread global loads: separate pass, gz kept in staging
+      const bool fuse_in_loop = EVEN && zstage && p.fuse_gz != 0;   // odd widths: rows are 4-byte aligned only, the float4 pass below is faster
+      if (FUSE_GZ && !fuse_in_loop) {                  // separate pass over the slab, gz kept in staging
         const long long base = item_base(j);
-        if (bulk) {
+        if (zstage) {                                  // both factors staged: shared memory -> shared memory + global
+          float4* s4 = reinterpret_cast<float4*>(stage);
+          const float4* zs4 = reinterpret_cast<const float4*>(stage + stage_floats);
+          float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
+          for (int i = tid; i < nel / 4; i += kAnWorkers) {
+            const float4 a = s4[i], b = zs4[i];
+            const float4 v = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+            s4[i] = v;
+            if (!DENO_AN_ABL(32)) g4[i] = v;
+          }
+        } else if (bulk) {
           float4* s4 = reinterpret_cast<float4*>(stage);
           float4* g4 = reinterpret_cast<float4*>(p.gz_out + base);
 #pragma unroll
@@ -1540,14 +1559,14 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         const int r0 = warp * 4 + (lane >> 3), r1 = r0 + (kAnWorkers / 32) * 4;     // Hp <= 128: at most two rows per thread
         const float* s0 = stage + r0 * W;
         const float* s1 = stage + r1 * W;
-        const bool fuse = zstage;                      // multiply by the staged act'(z) and store gz here
+        const bool fuse = fuse_in_loop;                // multiply by the staged act'(z) and store gz here
         const float* zs = stage + stage_floats;
-        float* gout = FUSE_GZ ? p.gz_out + item_base(j) : nullptr;
-        const bool even = (W & 1) == 0;                // rows start 8-byte aligned: 64-bit shared / global accesses
+        float* gout = (FUSE_GZ && EVEN) ? p.gz_out + item_base(j) : nullptr;
+        constexpr bool even = EVEN;                    // rows start 8-byte aligned: 64-bit shared / global accesses
         // one row quad (4 consecutive columns of row r): load, (multiply + store gz), zero outside the slab
         auto load_quad = [&](const float* srow, int r, int y0, float (&v)[4]) {
-          const bool rok = r < hrows && !(p.ablate & 64);
-          if (even) {
+          const bool rok = r < hrows && !DENO_AN_ABL(64);
+          {
             float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
             if (rok && y0 < W) a = *reinterpret_cast<const float2*>(srow + y0);
             if (rok && y0 + 2 < W) b = *reinterpret_cast<const float2*>(srow + y0 + 2);
@@ -1557,39 +1576,34 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               if (rok && y0 < W) {
                 const float2 za = *reinterpret_cast<const float2*>(zrow + y0);
                 a.x *= za.x; a.y *= za.y;
-                if (!(p.ablate & 32)) *reinterpret_cast<float2*>(grow + y0) = a;
+                if (!DENO_AN_ABL(32)) *reinterpret_cast<float2*>(grow + y0) = a;
               }
               if (rok && y0 + 2 < W) {
                 const float2 zb = *reinterpret_cast<const float2*>(zrow + y0 + 2);
                 b.x *= zb.x; b.y *= zb.y;
-                if (!(p.ablate & 32)) *reinterpret_cast<float2*>(grow + y0 + 2) = b;
+                if (!DENO_AN_ABL(32)) *reinterpret_cast<float2*>(grow + y0 + 2) = b;
               }
             }
             v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int y = y0 + jj;
-              float t = 0.f;
-              if (rok && y < W) {
-                t = srow[y];
-                if (fuse) {
-                  t *= zs[(srow - stage) + y];
-                  gout[(srow - stage) + y] = t;
-                }
-              }
-              v[jj] = t;
-            }
           }
         };
         for (int c = 0; c < nchunk; ++c) {
           const int yq = c * 8 + (lane & 7);
           if (yq < nyq) {
             float v0[4], v1[4];
-            load_quad(s0, r0, yq * 4, v0);
-            load_quad(s1, r1, yq * 4, v1);
+            if (even) {
+              load_quad(s0, r0, yq * 4, v0);
+              load_quad(s1, r1, yq * 4, v1);
+            } else {                                   // odd widths (137-wide Pipe planes): plain predicated 4-byte loads
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int y = yq * 4 + jj;
+                v0[jj] = (r0 < hrows && y < W) ? s0[y] : 0.f;
+                v1[jj] = (r1 < hrows && y < W) ? s1[y] : 0.f;
+              }
+            }
             float4 hi, lo;
-            if (r0 < Hp && !(p.ablate & 4)) {
+            if (r0 < Hp && !DENO_AN_ABL(4)) {
               split_tf32(v0[0], hi.x, lo.x);
               split_tf32(v0[1], hi.y, lo.y);
               split_tf32(v0[2], hi.z, lo.z);
@@ -1598,7 +1612,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               *reinterpret_cast<float4*>(smem + so.a + off) = hi;
               *reinterpret_cast<float4*>(smem + so.a + so.a_one + off) = lo;
             }
-            if (r1 < Hp && !(p.ablate & 4)) {
+            if (r1 < Hp && !DENO_AN_ABL(4)) {
               split_tf32(v1[0], hi.x, lo.x);
               split_tf32(v1[1], hi.y, lo.y);
               split_tf32(v1[2], hi.z, lo.z);
@@ -1608,14 +1622,10 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               *reinterpret_cast<float4*>(smem + so.a + so.a_one + off) = lo;
             }
           }
-          if (c < nsig - 1) {                          // column group c complete for this thread: hand it to the MMA warp
-            fence_proxy_async();
-            nbar_arrive(kAnBarA + c, kAnThreads);
-          }
         }
       }
       fence_proxy_async();
-      nbar_arrive(kAnBarA + nsig - 1, kAnThreads);     // last group (all remaining columns)
+      nbar_arrive(kAnBarA, kAnThreads);
       if (!bulk && j + 1 < nmine) {
         nbar_sync(kAnBarWorkers, kAnWorkers);          // every worker is past the staging buffer
         issue_plane_cp_async(j + 1);
@@ -1654,7 +1664,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               float th, tl;
               split_tf32(t, th, tl);
               const int r0 = (n & 7) * 16 + (n >> 3) * 128;
-              if (!(p.ablate & 8)) {
+              if (!DENO_AN_ABL(8)) {
                 *reinterpret_cast<float*>(b2hi + r0 + kc) = th;
                 *reinterpret_cast<float*>(b2lo + r0 + kc) = tl;
               }
@@ -1695,7 +1705,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
               if (l < MW) {
                 const float sr = xch[xrow * (N1 + 1) + c0 + jj], si = xch[xrow * (N1 + 1) + c0 + jj + 1];
                 const float f = p.scale * (p.herm ? p.cl[l] : 1.0f);
-                if (!(p.ablate & 16)) dst[l] = make_float2((dsum[jj] + si) * f, (dsum[jj + 1] - sr) * f);
+                if (!DENO_AN_ABL(16)) dst[l] = make_float2((dsum[jj] + si) * f, (dsum[jj + 1] - sr) * f);
               }
             }
           }

@@ -122,6 +122,9 @@ class TrainStep:
         self.loss = torch.zeros((), device=x.device)
         self._copy_stream = None          # input pipeline (prefetch): created on first use
         self._staged = None
+        self._sets = None                 # two static input sets + two graphs once prefetch() is used under graph replay
+        self._graphs = None
+        self._active = 0
         self._loss_slots = None           # pipelined loss read-back (enable_loss_readback)
         self._nsteps = 0
         self.use_graph = use_graph
@@ -228,6 +231,8 @@ class TrainStep:
         (a live graph keeps NCCL kernels referenced and communicator teardown waits for them forever)."""
         torch.cuda.synchronize()
         self._g_bwd = self._g_opt = None
+        self._graphs = None
+        self._sets = None
         self.use_graph = False
         # the parameters keep their ``.grad`` views but no longer advertise them as direct-write targets: any other
         # backward on this model (gradient accumulation, a second loss) goes through autograd's accumulation again
@@ -250,21 +255,59 @@ class TrainStep:
             self.st.copy_(target, non_blocking=non_blocking)
 
     def prefetch(self, x, grid, target):
-        """Input pipeline: start the host-to-device copy of the NEXT batch (pinned host tensors) on a copy stream
-        into staging buffers, so it overlaps the step that is running; the next ``step()`` without arguments
-        moves the staged batch into the graph's static buffers (device-to-device) and runs on it."""
+        """Input pipeline: start the host-to-device copy of the NEXT batch (pinned host tensors) on a copy stream so it
+        overlaps the step that is running; the next ``step()`` without arguments runs on it.
+
+        Under graph replay the batch lands DIRECTLY in static inputs: the step is captured a second time on a second
+        set of input buffers (same memory pool, the two graphs never run concurrently), ``prefetch`` fills the set the
+        running step is not using and ``step()`` replays the graph that reads it - no staging buffers, no
+        device-to-device copies.  Eager steps (``use_graph=False``) stage and copy."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
-            self._stage_bufs = (torch.empty_like(self.sx), torch.empty_like(self.sg), torch.empty_like(self.st))
             self._staged_ready = torch.cuda.Event()
-            self._stage_free = torch.cuda.Event()
-            self._stage_free.record()
+            if self.use_graph and self._g_opt is None and self._g_bwd is not None:
+                self._capture_second_set()
+            if self._sets is None:
+                self._stage_bufs = (torch.empty_like(self.sx), torch.empty_like(self.sg), torch.empty_like(self.st))
+                self._stage_free = torch.cuda.Event()
+                self._stage_free.record()
+        if self._sets is not None:
+            tgt = 1 - self._active                              # the set the running / last step does not read
+            self._copy_stream.wait_event(self._set_free[tgt])   # its previous step has finished with it
+            with torch.cuda.stream(self._copy_stream):
+                for dst, src in zip(self._sets[tgt], (x, grid, target)):
+                    dst.copy_(src, non_blocking=True)
+                self._staged_ready.record()
+            self._staged = tgt + 1                              # truthy: set index + 1
+            return
         self._copy_stream.wait_event(self._stage_free)      # the previous staged batch has been consumed
         with torch.cuda.stream(self._copy_stream):
             for dst, src in zip(self._stage_bufs, (x, grid, target)):
                 dst.copy_(src, non_blocking=True)
             self._staged_ready.record()
         self._staged = True
+
+    def _capture_second_set(self):
+        """Second capture of the whole step on a second set of static inputs (shares the first graph's memory pool)."""
+        first = (self.sx, self.sg, self.st)
+        second = tuple(torch.empty_like(t) for t in first)
+        for d, s_ in zip(second, first):
+            d.copy_(s_)
+        torch.cuda.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        self.sx, self.sg, self.st = second
+        try:
+            with torch.cuda.graph(g2, pool=self._g_bwd.pool()):
+                self._forward_backward()
+                self.opt.step()
+        finally:
+            self.sx, self.sg, self.st = first
+        self._sets = [first, second]
+        self._graphs = [self._g_bwd, g2]
+        self._set_free = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in self._set_free:
+            ev.record()
+        self._active = 0
 
     def enable_loss_readback(self):
         """Every step additionally copies its loss to pinned host memory (asynchronously, two slots);
@@ -294,20 +337,32 @@ class TrainStep:
     def __call__(self, x=None, grid=None, target=None) -> torch.Tensor:
         """Runs one optimiser step; returns the (device) loss of this rank's shard.  Without arguments it runs on
         the batch staged by ``prefetch`` (if any), else on the batch already in the static buffers."""
-        if x is None and grid is None and target is None and self._staged:
-            self._consume_staged()
+        if x is None and grid is None and target is None and self._staged and self._sets is not None:
+            # the staged batch already sits in the other graph's static inputs: switch graphs
+            self._active = self._staged - 1
+            self._staged = None
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged_ready)
+            self.sx, self.sg, self.st = self._sets[self._active]
+            self._graphs[self._active].replay()
+            self._set_free[self._active].record(cur)
         else:
-            self.load(x, grid, target)
-        if self.use_graph:
-            self._g_bwd.replay()
-            if self._g_opt is not None:
-                self.grads.all_reduce_mean(self.group)
-                self._g_opt.replay()
-        else:
-            self._forward_backward()
-            if not (self._overlap or self._ingraph or self._fused_dp):
-                self.grads.all_reduce_mean(self.group)
-            self.opt.step()
+            if x is None and grid is None and target is None and self._staged:
+                self._consume_staged()
+            else:
+                self.load(x, grid, target)
+            if self.use_graph:
+                (self._graphs[self._active] if self._graphs is not None else self._g_bwd).replay()
+                if self._sets is not None:
+                    self._set_free[self._active].record()
+                if self._g_opt is not None:
+                    self.grads.all_reduce_mean(self.group)
+                    self._g_opt.replay()
+            else:
+                self._forward_backward()
+                if not (self._overlap or self._ingraph or self._fused_dp):
+                    self.grads.all_reduce_mean(self.group)
+                self.opt.step()
         if self._loss_slots is not None:
             buf, ev = self._loss_slots[self._nsteps % 2]
             buf.copy_(self.loss, non_blocking=True)

@@ -1,5 +1,7 @@
 """Timing-only ablations of plane_analysis_tc (DENO_AN_ABLATE bits; results are wrong on purpose): which phase does the
-kernel's duration actually depend on?  python tools/an_ablate.py C2 C5   (each variant in its own child process)"""
+kernel's duration actually depend on?  The bits are compiled in only with -DDENO_AN_ABLATE_BUILD:
+    nvcc <flags of deno4pytorch_b200/build.py> -DDENO_AN_ABLATE_BUILD -o tools/_build/libdeno_ablate.so deno4pytorch_b200/csrc/capi.cu
+    DENO_LIB_PATH=tools/_build/libdeno_ablate.so python tools/an_ablate.py C2 C5   (each variant in its own child process)"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
