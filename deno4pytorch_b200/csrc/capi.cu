@@ -1395,16 +1395,21 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   const size_t smem = (size_t)tc::synth_tc_smem(CIP, COT, tl.KE, bestR, npass).total;
   const int grid = s.B * s.X * p.tiles * tl.nchunks * nco;
   int rc = DENO_OK;
-#define DENO_TC_CASE3(ACT, CIPV, TILEDV)                                                            \
+#define DENO_TC_CASE4(ACT, CIPV, TILEDV, STAGEA)                                                    \
   {                                                                                                 \
-    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV>, smem, "plane_synthesis_tc");  \
+    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV, STAGEA>, smem, "plane_synthesis_tc");  \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);       \
+    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV, STAGEA>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);       \
+  }
+#define DENO_TC_CASE3(ACT, CIPV, TILEDV)                                                            \
+  {                                                                                                 \
+    if (q.urow == nullptr) DENO_TC_CASE4(ACT, CIPV, false, true)                                    \
+    else DENO_TC_CASE4(ACT, CIPV, TILEDV, false)                                                    \
   }
 #define DENO_TC_CASE(ACT)                                                                           \
   case ACT:                                                                                         \
-    if (tiled) DENO_TC_CASE3(ACT, 64, true)                                                         \
+    if (tiled) DENO_TC_CASE4(ACT, 64, true, false)                                                  \
     else if (CIP == 8) DENO_TC_CASE3(ACT, 8, false)                                                 \
     else if (CIP == 16) DENO_TC_CASE3(ACT, 16, false)                                               \
     else if (CIP == 32) DENO_TC_CASE3(ACT, 32, false)                                               \
@@ -1420,6 +1425,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
     default: return fail(DENO_E_INVALID, "unknown activation id");
   }
 #undef DENO_TC_CASE
+#undef DENO_TC_CASE4
 #undef DENO_TC_CASE3
   return check_launch("plane_synthesis_tc", st);
 }

@@ -537,7 +537,9 @@ constexpr int kSynBarAx = 2;            // A_X images of a row stored (workers a
 // Two CTAs per SM up to 32 input channels (96 registers); from 64 channels on the operand images leave room for one CTA
 // only, so the register cap is lifted there (at 96 registers the 64-channel instances spilled in the row loop).
 // TILED = false (every layer up to 64 channels): one channel tile, one K pass, known at compile time.
-template <int ACT, int CIP, bool TILED>
+// STAGE_A: the row-axis synthesis runs inside this kernel (1-D layers, callers without the U workspace) instead of
+// arriving as precomputed images; a template argument so that the usual instances do not carry that code path.
+template <int ACT, int CIP, bool TILED, bool STAGE_A>
 __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthesis_tc_kernel(SynthTcParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthe
     // constant twiddle images (final layout in global memory) and, when row_synthesis_kernel ran (q.urow), this
     // tile's U images: bulk async copies, so the prologue costs one memory round trip instead of one per loop trip
     const uint32_t ae_bytes = (uint32_t)(2 * KE * 128 * 4);
-    const uint32_t u_bytes = q.urow != nullptr ? (uint32_t)(trows * 2 * so.bu_one) : 0u;   // one bulk copy per row
+    const uint32_t u_bytes = !STAGE_A ? (uint32_t)(trows * 2 * so.bu_one) : 0u;   // one bulk copy per row
     mbar_expect_tx(&mbar_u, ae_bytes + u_bytes);
     bulk_g2s(smem + so.ae_hi, q.ae + (long long)chunk * 2 * KE * 128, ae_bytes, &mbar_u);
   }
@@ -616,7 +618,7 @@ __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthe
   // Everything above depends on constants and weights only.  The U images come from the immediate predecessor
   // (row_synthesis_kernel) and x / gz from earlier kernels: from here on the predecessor must have completed.
   DENO_PDL_SYNC();
-  if (tid == 32 && q.urow != nullptr) {
+  if (!STAGE_A && tid == 32) {
     const size_t img2 = 2 * (size_t)(so.bu_one / 4);                 // floats of one row's hi + lo images of one channel tile
     for (int rr = 0; rr < trows; ++rr)
       bulk_g2s(smem + so.bu + rr * 2 * so.bu_one, q.urow + (((size_t)bp * H + x0 + rr) * nco + cot) * img2,
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthe
   // Normally precomputed (q.urow, bulk copy issued above); the in-kernel version below is kept for callers without
   // the workspace: the packed spectrum of this batch entry is staged through the (still unused) A_X area in chunks
   // of OC output channels with fully coalesced loads, so the k-loop runs out of shared memory.
-  if (q.urow == nullptr) {
+  if (STAGE_A) {
     unsigned char* bu = smem + so.bu;
     for (int idx = wt; idx < 2 * R * so.bu_one / 16; idx += 256) reinterpret_cast<float4*>(bu)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     float2* twr = reinterpret_cast<float2*>(smem + so.ax_hi);            // [trows][KH] row twiddles
