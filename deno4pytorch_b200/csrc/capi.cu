@@ -662,8 +662,6 @@ struct Options {
   int at_dbg = 0;        // DENO_AT_DBG: bring-up switches of the TMA analysis kernel (see AnalysisTmaParams::dbg)
   int an_ring = 1;       // DENO_AN_RING: 0 = one staging buffer (round-1 layout), 1 = ring + staged act'(z) where it fits, 2 = ring, z by registers
   int mix_lane = 1;      // DENO_MIX_LANE: 0 = never, 1 (default) = mode_mix_lane (lane = mode, batch-tiled, staged spectrum) instead of the tensor-core mix for width >= 128, 2 = for every width
-  bool an_fuse_gz = true; // DENO_AN_FUSEGZ=0: gz product as a separate pass over the staged slab
-  int an_piece = 0;      // DENO_AN_PIECE: bytes per bulk copy of a staged slab (multiple of 16; 0 = one copy per slab)
   int an_ablate = 0;     // DENO_AN_ABLATE: timing-only ablation bits of plane_analysis_tc (results wrong; see AnalysisTcParams::ablate)
   bool rowsynth_tc = true;  // DENO_ROWSYNTH_TC=0: the SIMT row_synthesis kernel instead of the tensor-core one
   bool an_tma = false;   // DENO_ANALYSIS_TMA=1: the TMA analysis kernel instead of the bulk-copy + SIMT-transform one (not yet green on hardware)
@@ -684,8 +682,6 @@ Options read_options() {
   if (const char* e = getenv("DENO_ROWSYNTH_TC")) o.rowsynth_tc = e[0] != '0';
   if (const char* e = getenv("DENO_MIX_LANE")) o.mix_lane = atoi(e);
   if (const char* e = getenv("DENO_AN_ABLATE")) o.an_ablate = atoi(e);
-  if (const char* e = getenv("DENO_AN_PIECE")) o.an_piece = atoi(e) & ~15;
-  if (const char* e = getenv("DENO_AN_FUSEGZ")) o.an_fuse_gz = e[0] != '0';
   if (const char* e = getenv("DENO_MIX_TC")) o.mix_tc = e[0] != '0';
   return o;
 }
@@ -803,8 +799,6 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   int smem_total = sm.total;
   p.nslots = 1; p.zstage = 0; p.stage_off = sm.stage; p.xch_off = sm.xch; p.xch_alias = 0;
   p.ablate = options().an_ablate;
-  p.piece_bytes = options().an_piece;
-  p.fuse_gz = options().an_fuse_gz ? 1 : 0;
   if (bulk && options().an_ring) {
     const int zs = (gz && options().an_ring != 2) ? 1 : 0;
     const int want[3][2] = {{2, zs}, {zs ? 1 : 2, zs}, {1, 0}};   // (slots, z staged), best first
@@ -831,23 +825,45 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
             s.H, s.W, (int)gz, sm.total, stage_bytes, limit, p.nslots, p.zstage, p.xch_alias, smem_total);
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
-#define DENO_AN_CASE(GZ, SLABS, EVENW, LABEL)                                                                  \
+  const int mode = !bulk ? 0 : (p.zstage ? (p.nslots == 2 ? 4 : 3) : (p.nslots == 2 ? 2 : 1));
+#define DENO_AN_CASE5(GZ, SLABS, EVENW, MODEV, LABEL)                                                          \
   {                                                                                                            \
-    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW>, (size_t)smem_total, "plane_analysis_tc");  \
+    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW, MODEV>, (size_t)smem_total, "plane_analysis_tc");  \
     if (rc != DENO_OK) return rc;                                                                              \
     prof_before(LABEL, st);                                                                                    \
-    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW, MODEV>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
+  }
+#define DENO_AN_CASE_FWD(SLABS, EVENW)                                                                         \
+  {                                                                                                            \
+    if (mode == 0) DENO_AN_CASE5(false, SLABS, EVENW, 0, "plane_analysis_tc")                                  \
+    else if (mode == 1) DENO_AN_CASE5(false, SLABS, EVENW, 1, "plane_analysis_tc")                             \
+    else DENO_AN_CASE5(false, SLABS, EVENW, 2, "plane_analysis_tc")                                            \
+  }
+#define DENO_AN_CASE_GZ(SLABS, EVENW)                                                                          \
+  {                                                                                                            \
+    if (mode == 0) DENO_AN_CASE5(true, SLABS, EVENW, 0, "plane_analysis_gz_tc")                                \
+    else if (mode == 1) DENO_AN_CASE5(true, SLABS, EVENW, 1, "plane_analysis_gz_tc")                           \
+    else if (mode == 2) DENO_AN_CASE5(true, SLABS, EVENW, 2, "plane_analysis_gz_tc")                           \
+    else if (mode == 3) DENO_AN_CASE5(true, SLABS, EVENW, 3, "plane_analysis_gz_tc")                           \
+    else DENO_AN_CASE5(true, SLABS, EVENW, 4, "plane_analysis_gz_tc")                                          \
   }
   const bool slabs = p.nsub > 1;
   const bool evenw = (s.W % 2) == 0;
-  if (gz && slabs && evenw) DENO_AN_CASE(true, true, true, "plane_analysis_gz_tc")
-  else if (gz && slabs) DENO_AN_CASE(true, true, false, "plane_analysis_gz_tc")
-  else if (gz && evenw) DENO_AN_CASE(true, false, true, "plane_analysis_gz_tc")
-  else if (gz) DENO_AN_CASE(true, false, false, "plane_analysis_gz_tc")
-  else if (slabs && evenw) DENO_AN_CASE(false, true, true, "plane_analysis_tc")
-  else if (slabs) DENO_AN_CASE(false, true, false, "plane_analysis_tc")
-  else if (evenw) DENO_AN_CASE(false, false, true, "plane_analysis_tc")
-  else DENO_AN_CASE(false, false, false, "plane_analysis_tc")
+  if (gz) {
+    if (slabs && evenw) DENO_AN_CASE_GZ(true, true)
+    else if (slabs) DENO_AN_CASE_GZ(true, false)
+    else if (evenw) DENO_AN_CASE_GZ(false, true)
+    else DENO_AN_CASE_GZ(false, false)
+  } else {
+    if (slabs && evenw) DENO_AN_CASE_FWD(true, true)
+    else if (slabs) DENO_AN_CASE_FWD(true, false)
+    else if (evenw) DENO_AN_CASE_FWD(false, true)
+    else DENO_AN_CASE_FWD(false, false)
+  }
+#undef DENO_AN_CASE_GZ
+#undef DENO_AN_CASE_FWD
+#undef DENO_AN_CASE5
+#define DENO_AN_CASE(a, b, c, d)
 #undef DENO_AN_CASE
   return check_launch("plane_analysis_tc", st);
 }

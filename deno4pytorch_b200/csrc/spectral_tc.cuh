@@ -1247,9 +1247,7 @@ struct AnalysisTcParams {
   int xch_alias;            // the exchange buffer lives inside the B2 image (tight fits): one more worker barrier per plane
   int ablate;               // DENO_AN_ABLATE (measurement only, results WRONG): bit 0 no stage-1 MMAs, 1 no stage-2 MMAs, 2 no A-image stores,
                             // 3 no B2 stores, 4 no spectrum stores, 5 no gz stores, 6 no staged-plane loads in the transform
-  int fuse_gz;              // gz = gy * act'(z) formed inside the transform loop (staged act'(z), even widths) instead of a separate pass
   int sync_off;             // byte offset of the barrier words (6 x 8 bytes) inside the dynamic allocation
-  int piece_bytes;          // bulk copies of a slab are issued in pieces of this many bytes (multiple of 16; 0: one copy)
 };
 
 struct AnalysisTcSmem {
@@ -1303,7 +1301,10 @@ constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp 
 // EVEN: the plane width is even, i.e. every row of the staged slab starts 8-byte aligned (64-bit accesses, gz fused into
 // the transform loop).  A template argument: as a run-time branch inside the transform loop it cost the odd-width Pipe
 // planes 2 % of the layer (two code paths live in the hot loop of a latency-bound kernel).
-template <bool FUSE_GZ, bool SLABS, bool EVEN>
+// MODE: how slabs reach shared memory - 0: per-thread cp.async (sizes / offsets not multiples of 16 bytes), 1: one bulk copy,
+// one slot, 2: two-slot ring, 3: one slot with act'(z) staged next to gy, 4: two-slot ring with act'(z) (3, 4: FUSE_GZ only).
+// Template arguments for the same reason as EVEN.
+template <bool FUSE_GZ, bool SLABS, bool EVEN, int MODE>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   // no-swizzle descriptors need 16-byte alignment only; a 1024-byte aligned array would cost the tight fits 1 KB
   extern __shared__ __align__(128) unsigned char an_smem[];
@@ -1334,9 +1335,10 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const int hlast = Hfull - (nsub - 1) * H;              // rows of the last slab
   float* const stage_ring = reinterpret_cast<float*>(smem + p.stage_off);
   const int stage_floats = round_up((nsub == 1 ? Hfull : H) * W, 4);   // one staged slab (u, or act'(z)): the rows that exist
-  const int slot_floats = stage_floats * (1 + p.zstage);
-  const bool two_slots = p.nslots == 2;
-  const bool zstage = FUSE_GZ && p.zstage != 0;
+  constexpr bool bulk = MODE > 0;
+  constexpr bool two_slots = MODE == 2 || MODE == 4;
+  constexpr bool zstage = FUSE_GZ && MODE >= 3;
+  const int slot_floats = stage_floats * (zstage ? 2 : 1);
   auto slot_of = [&](int j) { return two_slots ? (j & 1) : 0; };
 
   const uint32_t tmem_cols = 6 * N1 <= 64 ? 64u : (6 * N1 <= 128 ? 128u : (6 * N1 <= 256 ? 256u : 512u));
@@ -1371,7 +1373,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   const int nmine = nplanes_mine * nsub;                 // items (slabs) of this CTA: item j = slab j % nsub of its plane j / nsub
   // Slabs whose byte size and offsets are multiples of 16 stream in with ONE bulk async copy (cp.async.bulk,
   // completion on an mbarrier) issued by the MMA warp; others fall back to per-thread 4-byte cp.async by the workers.
-  const bool bulk = ((Hfull * W) % 4) == 0 && (HW % 4) == 0 && ((hlast * W) % 4) == 0;
+  // (MODE > 0 requires ((Hfull * W) % 4) == 0 && (HW % 4) == 0 && ((hlast * W) % 4) == 0: checked by the launcher)
   // (the one-slab case takes no integer division here: these run on the MMA warp's issuing lane, the critical path -
   // ten divisions per item cost 18 % at the 3-D turbulence shape with its 151 small planes per CTA)
   constexpr bool one_slab = !SLABS;
@@ -1401,18 +1403,12 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       const uint32_t bar = smem_u32(&bar_stage[slot]);
       float* dst = stage_ring + slot * slot_floats;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(zstage ? 2u * bytes : bytes) : "memory");
-      // One slab goes out as several bulk copies of `piece` bytes: the copy engine works on them concurrently, where a
-      // single 35 KB copy streamed at a few bytes per cycle (the kernel with every arithmetic phase ablated still took
-      // 80 % of its time at the Darcy shape: profiles/round2_s3_analysis_ablation.txt).
-      const uint32_t piece = p.piece_bytes > 0 ? (uint32_t)p.piece_bytes : bytes;
-      for (uint32_t o = 0; o < bytes; o += piece) {
-        const uint32_t nb = min(piece, bytes - o);
+      // (issuing a slab as several smaller bulk copies was measured slower: profiles/round2_ab_analysis_piece_copies.txt)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(dst)), "l"(p.u + base), "r"(bytes), "r"(bar) : "memory");
+      if (zstage)
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst) + o), "l"(reinterpret_cast<const char*>(p.u + base) + o), "r"(nb), "r"(bar) : "memory");
-        if (zstage)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(dst + stage_floats) + o), "l"(reinterpret_cast<const char*>(p.z + base) + o), "r"(nb), "r"(bar) : "memory");
-      }
+                     ::"r"(smem_u32(dst + stage_floats)), "l"(p.z + base), "r"(bytes), "r"(bar) : "memory");
     };
     long long idle = 0;
     auto stage1 = [&](int j) {                         // stage-1 MMAs of plane j once its A images are stored
@@ -1504,7 +1500,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
       // thread that splits a row quad also multiplies it and stores it to gz (a warp's store covers 4 row segments of
       // 128 bytes), so there is no separate pass over the plane, no write-back into the staging buffer and no barrier
       // between the two (that pass + barrier was 1.5 - 2.3 k cycles per plane, profiles/round2_s3_phase_probe.txt).
-      const bool fuse_in_loop = EVEN && zstage && p.fuse_gz != 0;   // odd widths: rows are 4-byte aligned only, the float4 pass below is faster
+      constexpr bool fuse_in_loop = EVEN && zstage;    // odd widths: rows are 4-byte aligned only, the float4 pass below is faster
       if (FUSE_GZ && !fuse_in_loop) {                  // separate pass over the slab, gz kept in staging
         const long long base = item_base(j);
         if (zstage) {                                  // both factors staged: shared memory -> shared memory + global
@@ -1561,7 +1557,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
         const int r0 = warp * 4 + (lane >> 3), r1 = r0 + (kAnWorkers / 32) * 4;     // Hp <= 128: at most two rows per thread
         const float* s0 = stage + r0 * W;
         const float* s1 = stage + r1 * W;
-        const bool fuse = fuse_in_loop;                // multiply by the staged act'(z) and store gz here
+        constexpr bool fuse = fuse_in_loop;            // multiply by the staged act'(z) and store gz here
         const float* zs = stage + stage_floats;
         float* gout = (FUSE_GZ && EVEN) ? p.gz_out + item_base(j) : nullptr;
         constexpr bool even = EVEN;                    // rows start 8-byte aligned: 64-bit shared / global accesses
