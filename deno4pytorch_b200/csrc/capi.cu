@@ -826,12 +826,16 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
   const int grid = p.nplanes < 148 ? p.nplanes : 148;
   int rc;
   const int mode = !bulk ? 0 : (p.zstage ? (p.nslots == 2 ? 4 : 3) : (p.nslots == 2 ? 2 : 1));
-#define DENO_AN_CASE5(GZ, SLABS, EVENW, MODEV, LABEL)                                                          \
+#define DENO_AN_CASE6(GZ, SLABS, EVENW, MODEV, N1V, LABEL)                                                     \
   {                                                                                                            \
-    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW, MODEV>, (size_t)smem_total, "plane_analysis_tc");  \
+    rc = allow_smem(tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW, MODEV, N1V>, (size_t)smem_total, "plane_analysis_tc");  \
     if (rc != DENO_OK) return rc;                                                                              \
     prof_before(LABEL, st);                                                                                    \
-    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW, MODEV>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
+    DENO_LAUNCH((tc::plane_analysis_tc_kernel<GZ, SLABS, EVENW, MODEV, N1V>), dim3(grid), dim3(tc::kAnThreads), (size_t)smem_total, st, p); \
+  }
+#define DENO_AN_CASE5(GZ, SLABS, EVENW, MODEV, LABEL)                                                          \
+  {                                                                                                            \
+    DENO_AN_CASE6(GZ, SLABS, EVENW, MODEV, 0, LABEL)                                                           \
   }
 #define DENO_AN_CASE_FWD(SLABS, EVENW)                                                                         \
   {                                                                                                            \
@@ -863,6 +867,7 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
 #undef DENO_AN_CASE_GZ
 #undef DENO_AN_CASE_FWD
 #undef DENO_AN_CASE5
+#undef DENO_AN_CASE6
 #define DENO_AN_CASE(a, b, c, d)
 #undef DENO_AN_CASE
   return check_launch("plane_analysis_tc", st);
@@ -1411,12 +1416,17 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   const size_t smem = (size_t)tc::synth_tc_smem(CIP, COT, tl.KE, bestR, npass).total;
   const int grid = s.B * s.X * p.tiles * tl.nchunks * nco;
   int rc = DENO_OK;
-#define DENO_TC_CASE4(ACT, CIPV, TILEDV, STAGEA)                                                    \
+#define DENO_TC_CASE5(ACT, CIPV, TILEDV, STAGEA, SQV)                                               \
   {                                                                                                 \
-    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV, STAGEA>, smem, "plane_synthesis_tc");  \
+    rc = allow_smem(tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV, STAGEA, SQV>, smem, "plane_synthesis_tc");  \
     if (rc != DENO_OK) return rc;                                                                   \
     prof_before(label, st);                                                                         \
-    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV, STAGEA>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);       \
+    DENO_LAUNCH((tc::plane_synthesis_tc_kernel<ACT, CIPV, TILEDV, STAGEA, SQV>), dim3(grid), dim3(tc::kSynThreads), smem, st, q);       \
+  }
+#define DENO_TC_CASE4(ACT, CIPV, TILEDV, STAGEA)                                                    \
+  {                                                                                                 \
+    if (COT == CIPV) DENO_TC_CASE5(ACT, CIPV, TILEDV, STAGEA, true)                                 \
+    else DENO_TC_CASE5(ACT, CIPV, TILEDV, STAGEA, false)                                            \
   }
 #define DENO_TC_CASE3(ACT, CIPV, TILEDV)                                                            \
   {                                                                                                 \
@@ -1442,6 +1452,7 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
   }
 #undef DENO_TC_CASE
 #undef DENO_TC_CASE4
+#undef DENO_TC_CASE5
 #undef DENO_TC_CASE3
   return check_launch("plane_synthesis_tc", st);
 }

@@ -539,7 +539,9 @@ constexpr int kSynBarAx = 2;            // A_X images of a row stored (workers a
 // TILED = false (every layer up to 64 channels): one channel tile, one K pass, known at compile time.
 // STAGE_A: the row-axis synthesis runs inside this kernel (1-D layers, callers without the U workspace) instead of
 // arriving as precomputed images; a template argument so that the usual instances do not carry that code path.
-template <int ACT, int CIP, bool TILED, bool STAGE_A>
+// SQ: the CTA's output-channel tile equals the padded input-channel count (every FNO stack: width in = width out), so the
+// GEMM N, the TMEM column offsets and the epilogue's column loops are compile-time constants.
+template <int ACT, int CIP, bool TILED, bool STAGE_A, bool SQ>
 __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthesis_tc_kernel(SynthTcParams q) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint32_t tmem_slot;
@@ -549,7 +551,7 @@ __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthe
   const bool is_mma = warp == 8;             // ninth warp: issues the MMAs, takes no part in the SIMT work
   const int wt = is_mma ? (1 << 28) : tid;     // loop start of the 256 worker threads (beyond every bound for the MMA warp)
   // CO below is the channel tile of THIS CTA (the GEMM N); the layer's output channels are p.CO = q.nco * q.COT
-  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = q.COT;
+  const int H = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW, CI = p.g.C, CO = SQ ? CIP : q.COT;
   const int KH4 = round_up(KH, 4);
   const int KE = q.KE, R = p.R;
   const int npass = TILED ? q.npass : 1;
@@ -1304,7 +1306,9 @@ constexpr int kAnBarB2 = 13;       // B2 image stored (workers arrive, MMA warp 
 // MODE: how slabs reach shared memory - 0: per-thread cp.async (sizes / offsets not multiples of 16 bytes), 1: one bulk copy,
 // one slot, 2: two-slot ring, 3: one slot with act'(z) staged next to gy, 4: two-slot ring with act'(z) (3, 4: FUSE_GZ only).
 // Template arguments for the same reason as EVEN.
-template <bool FUSE_GZ, bool SLABS, bool EVEN, int MODE>
+// N1C: compile-time stage-1 N (0: run-time p.N1).  The launcher always passes 0: fixing N1 = 32 (every demo configuration)
+// was measured SLOWER (3-D layer 1927 -> 1972 us, profiles/round2_ab_analysis_synthesis_specialisations.txt).
+template <bool FUSE_GZ, bool SLABS, bool EVEN, int MODE, int N1C>
 __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(AnalysisTcParams p) {
   // no-swizzle descriptors need 16-byte alignment only; a 1024-byte aligned array would cost the tight fits 1 KB
   extern __shared__ __align__(128) unsigned char an_smem[];
@@ -1329,7 +1333,7 @@ __global__ void __launch_bounds__(kAnThreads, 1) plane_analysis_tc_kernel(Analys
   // current slab (the last one may be shorter).
   const int Hfull = p.g.H, W = p.g.W, KH = p.g.KH, MW = p.g.MW;
   const int nsub = SLABS ? p.nsub : 1, H = p.HS;      // SLABS = false: the one-slab code is the compile-time special case
-  const int N1 = p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
+  const int N1 = N1C > 0 ? N1C : p.N1, Wp = p.Wp, Hp = p.Hp, KS0 = p.KS0, KRp = p.KRp;
   const AnalysisTcSmem so = analysis_tc_smem(H, W, KH, N1, Wp, Hp, KRp, nsub);
   const int HW = H * W;                                  // elements of a full slab
   const int hlast = Hfull - (nsub - 1) * H;              // rows of the last slab
