@@ -868,8 +868,6 @@ int try_launch_analysis_tc(const Shape& s, int channels, const float* u, const f
 #undef DENO_AN_CASE_FWD
 #undef DENO_AN_CASE5
 #undef DENO_AN_CASE6
-#define DENO_AN_CASE(a, b, c, d)
-#undef DENO_AN_CASE
   return check_launch("plane_analysis_tc", st);
 }
 #endif

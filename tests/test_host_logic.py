@@ -87,6 +87,18 @@ def test_twiddle_tables_are_fp64_accurate(built_lib):
     o = ((y & 7) * 16 + (y >> 3) * 128 + ((2 * l) & 3) * 4 + ((2 * l) >> 2) * 2048) // 4
     want = np.cos(2 * np.pi * l * y / 59)
     assert abs(float(hi[o]) + float(lo[o]) - want) < 1e-10
+    # row_synthesis_tc A operand (last region of the table): two 128-row tiles of [hi | lo] images with KP = 48 columns,
+    # column k < 24: cos(2 pi f_k x / H), column 24 + k: sin(...); rows beyond the grid are zero
+    KP, ntm = 48, 2
+    rs = buf[buf.size - ntm * 2 * KP * 128:]
+    for x, k, part in ((5, 3, 0), (100, 17, 1), (128 + 77, 23, 1), (228, 0, 0), (128 + 101, 4, 0)):
+        tm, r, kp = x // 128, x % 128, k + 24 * part
+        o = ((r & 7) * 16 + (r >> 3) * 128 + (kp & 3) * 4 + (kp >> 2) * 2048) // 4
+        hi_t = rs[tm * 2 * KP * 128:tm * 2 * KP * 128 + KP * 128]
+        lo_t = rs[tm * 2 * KP * 128 + KP * 128:(tm + 1) * 2 * KP * 128]
+        assert (hi_t.view(np.uint32) & 0x1FFF).max() == 0
+        want = 0.0 if x >= 229 else (np.sin if part else np.cos)(2 * np.pi * f[k] * x / 229)
+        assert abs(float(hi_t[o]) + float(lo_t[o]) - want) < 1e-10, (x, k, part)
 
 
 @pytest.mark.parametrize("name", golden_names("model"))
