@@ -94,7 +94,10 @@ class EmuLayer:
         self.fwd_launches = lib.deno_spectral_last_launch_count()
         return y
 
-    def backward(self, gy):
+    def backward(self, gy, split_roles=False):
+        """``split_roles``: through deno_spectral_bwd_overlap with an (empty) deno_overlap - the emulation has no streams,
+        but the call then launches the input-gradient and parameter-gradient roles of the mode mix separately, exactly
+        as the two-stream backward does on the GPU."""
         lib, d = self.lib, self.desc
         gy = np.ascontiguousarray(gy, dtype=np.float32)
         gx = np.full(self.x.shape, np.nan, dtype=np.float32)
@@ -105,9 +108,17 @@ class EmuLayer:
         ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
         wptrs = _capi.pointer_array([w.ctypes.data for w in self.w])
         gwptrs = _capi.pointer_array([g.ctypes.data for g in gws])
-        rc = lib.deno_spectral_bwd(C.byref(d), _ptr(gy), _ptr(self.x), _ptr(self.z), _ptr(self.xhat), wptrs,
-                                   _ptr(self.lin_w), _ptr(self.tw), _ptr(gx), gwptrs, _ptr(glw), _ptr(glb), _ptr(ws),
-                                   nws, None)
+        if split_roles:
+            ov = _capi.Overlap()
+            _capi.check(lib, lib.deno_overlap_create(C.byref(ov)), "deno_overlap_create")
+            rc = lib.deno_spectral_bwd_overlap(C.byref(d), _ptr(gy), _ptr(self.x), _ptr(self.z), _ptr(self.xhat), wptrs,
+                                               _ptr(self.lin_w), _ptr(self.tw), _ptr(gx), gwptrs, _ptr(glw), _ptr(glb),
+                                               _ptr(ws), nws, None, C.byref(ov))
+            lib.deno_overlap_destroy(C.byref(ov))
+        else:
+            rc = lib.deno_spectral_bwd(C.byref(d), _ptr(gy), _ptr(self.x), _ptr(self.z), _ptr(self.xhat), wptrs,
+                                       _ptr(self.lin_w), _ptr(self.tw), _ptr(gx), gwptrs, _ptr(glw), _ptr(glb), _ptr(ws),
+                                       nws, None)
         _capi.check(lib, rc, "deno_spectral_bwd")
         self.bwd_launches = lib.deno_spectral_last_launch_count()
         return gx, gws, glw, glb

@@ -148,3 +148,29 @@ def test_emulated_lane_mix_kernel(idx, monkeypatch):
     finally:
         monkeypatch.delenv("DENO_MIX_LANE")
         lib.deno_reload_env()
+
+
+@pytest.mark.parametrize("idx", [0, 2, 5, 8, 11, 13])
+def test_emulated_split_role_backward_equals_fused(idx):
+    """deno_spectral_bwd_overlap launches the mode mix's input-gradient role and its parameter-gradient (+ DC-mode bias)
+    role separately (on the GPU: main stream / side stream).  Same kernels, same summation order: every gradient is
+    bit-identical to the single fused launch of deno_spectral_bwd, and one more kernel is launched."""
+    spatial, modes, B, cin, cout, act = CASES[idx]
+    rng = np.random.default_rng(300 + idx)
+    nd = len(spatial)
+    x = rng.standard_normal((B, cin) + spatial).astype(np.float32)
+    ws = [((rng.standard_normal((cin, cout) + modes) + 1j * rng.standard_normal((cin, cout) + modes)) / cin)
+          .astype(np.complex64) for _ in range(2 ** (nd - 1))]
+    lin_w = (rng.standard_normal((cout, cin) + (1,) * nd) / np.sqrt(cin)).astype(np.float32)
+    lin_b = rng.standard_normal(cout).astype(np.float32)
+    cot = rng.standard_normal((B, cout) + spatial).astype(np.float32)
+    layer = emu_harness.EmuLayer(x, ws, lin_w, lin_b, modes, act)
+    layer.forward(save=True)
+    fused = layer.backward(cot)
+    n_fused = layer.bwd_launches
+    split = layer.backward(cot, split_roles=True)
+    assert layer.bwd_launches == n_fused + 1
+    assert np.array_equal(fused[0], split[0])
+    for a, b in zip(fused[1], split[1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(fused[2], split[2]) and np.array_equal(fused[3], split[3])
