@@ -194,6 +194,58 @@ def make_grid(batch: int, spatial: Sequence[int]) -> torch.Tensor:
     return mesh.unsqueeze(0).expand(batch, *mesh.shape).contiguous()
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# 4-D stand-alone layer / model (not on the CUDA path yet: this restatement + its fixtures
+# pin the oracle first).
+# ----------------------------------------------------------------------------------------------------------------
+def spectral_conv4d(x: torch.Tensor, weights: Sequence[torch.Tensor], modes) -> torch.Tensor:
+    """``SpectralConv4d.forward`` (/root/reference/Demo/Turbulence_3d+t/FNO_HIT.py:31-78): ``rfftn`` over the last four
+    axes, FOUR corner blocks - both signs on the first two axes only, the LOW block ``[:m3]`` on the third axis (its
+    negative frequencies are dropped, unlike the 3-D layer) and ``[:m4]`` on the half-spectrum axis - one complex
+    einsum per block, zero-padded ``irfftn(s=...)``.  No bypass, bias or activation inside the layer.  The reference
+    clamps ``modes4`` to ``min(modes4, 3 // 2 + 1) = 2`` in the constructor (FNO_HIT.py:44): pass the clamped value."""
+    m1, m2, m3, m4 = (int(m) for m in modes)
+    dims = [-4, -3, -2, -1]
+    spatial = tuple(x.shape[2:])
+    x_ft = torch.fft.rfftn(x, dim=dims)
+    cout = weights[0].shape[1]
+    out_ft = torch.zeros((x.shape[0], cout) + spatial[:-1] + (spatial[-1] // 2 + 1,), dtype=x_ft.dtype, device=x.device)
+    low3, low4 = slice(0, m3), slice(0, m4)
+    blocks = [(slice(0, m1), slice(0, m2)), (slice(-m1, None), slice(0, m2)),
+              (slice(0, m1), slice(-m2, None)), (slice(-m1, None), slice(-m2, None))]      # weights1..4 (FNO_HIT.py:63-72)
+    for w, (s1, s2) in zip(weights, blocks):
+        idx = (slice(None), slice(None), s1, s2, low3, low4)
+        out_ft[idx] = torch.einsum("bixyzt,ioxyzt->boxyzt", x_ft[idx], _as_complex(w))
+    return torch.fft.irfftn(out_ft, s=spatial, dim=dims)
+
+
+def make_grid4d(batch: int, spatial: Sequence[int]) -> torch.Tensor:
+    """``FNO4d.get_grid`` (FNO_HIT.py:159-169): linspace(0, 1) coordinates of the four axes, channel-last."""
+    axes = [torch.linspace(0, 1, n, dtype=torch.float32) for n in spatial]
+    mesh = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1)
+    return mesh.unsqueeze(0).expand(batch, *mesh.shape).contiguous()
+
+
+def fno4d_forward(params: Dict[str, torch.Tensor], x: torch.Tensor, modes) -> torch.Tensor:
+    """``FNO4d.forward`` (FNO_HIT.py:118-157): ``cat(x, grid) -> fc0 -> 4 x (SpectralConv4d + 1x1 conv), GELU after the
+    first three only -> fc1 -> GELU -> fc2``; ``x`` is ``(B, X, Y, Z, T, 5)``, the grid adds 4 coordinates (9 features)."""
+    B = x.shape[0]
+    spatial = tuple(x.shape[1:5])
+    h = torch.cat((x, make_grid4d(B, spatial).to(x)), dim=-1)
+    h = F.linear(h, params["fc0.weight"], params["fc0.bias"]).permute(0, 5, 1, 2, 3, 4)
+    width = h.shape[1]
+    for i in range(4):
+        ws = [params[f"conv{i}.weights{j}"] for j in (1, 2, 3, 4)]
+        x1 = spectral_conv4d(h, ws, modes)
+        x2 = F.conv1d(h.reshape(B, width, -1), params[f"w{i}.weight"], params[f"w{i}.bias"]).reshape(B, width, *spatial)
+        h = x1 + x2
+        if i < 3:
+            h = F.gelu(h)
+    h = h.permute(0, 2, 3, 4, 5, 1)
+    h = F.gelu(F.linear(h, params["fc1.weight"], params["fc1.bias"]))
+    return F.linear(h, params["fc2.weight"], params["fc2.bias"])
+
+
 class PortTrainer:
     """fwd + MSE + bwd + Adam on CPU, the way every FNO demo trains
     (/root/reference/Demo/Darcy_2d/run_FNO&UNet.py:43-69,206-209).  Used as the

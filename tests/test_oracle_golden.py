@@ -116,3 +116,49 @@ def test_port_matches_live_reference_darcy_shape():
         params = {k: v.detach() for k, v in ref.state_dict().items()}
     got = fno_port.fno_forward(params, x, grid, ndim=2, modes=(12, 12), depth=4, padding=9)
     assert rel_l2(got, want) < TOL
+
+
+# ---- 4-D stand-alone layer / model (FNO_HIT.py): the oracle is pinned first ----------------
+def test_port_layer4d_matches_reference():
+    g = load_golden("layer4d")
+    m = g["meta"]
+    assert m["kind"] == "layer4d" and m["modes"][3] == 2     # the reference clamps modes4 to 3 // 2 + 1
+    x = g["inputs"]["x"].clone().requires_grad_(True)
+    params = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    y = fno_port.spectral_conv4d(x, [params[f"weights{j}"] for j in (1, 2, 3, 4)], m["modes"])
+    assert rel_l2(y, g["out"]) < TOL
+    (y * g["cot"]).sum().backward()
+    assert rel_l2(x.grad, g["grad_inputs"]["x"]) < TOL
+    for k, p in params.items():
+        assert rel_l2(p.grad, g["grads"][k]) < TOL, k
+
+
+def test_port_layer4d_keeps_only_the_low_block_on_the_third_axis():
+    """Unlike the 3-D layer, SpectralConv4d drops the negative frequencies of its third axis (FNO_HIT.py:63-72 slice
+    ``:modes3`` only): a pure negative-frequency wave along z must come out as zero, a positive one must not."""
+    torch.manual_seed(0)
+    Z = 8
+    z = torch.arange(Z, dtype=torch.float32)
+    w = [torch.ones(1, 1, 1, 1, 3, 1, dtype=torch.complex64) for _ in range(4)]
+    # real input cannot isolate one sign of a NON-last axis unless another axis carries the conjugate: use x-axis phase
+    X = 6
+    xs = torch.arange(X, dtype=torch.float32)
+    pos = torch.cos(2 * torch.pi * (xs[:, None] / X * 0 + 2 * z[None, :] / Z))          # k_z = +-2 (both signs, k_x = 0)
+    field = pos[None, None, :, None, :, None].expand(1, 1, X, 4, Z, 3).contiguous()
+    y = fno_port.spectral_conv4d(field, w, (1, 1, 3, 1))
+    # only the +2 half survives: amplitude halves and the result is complex-analytic in z -> real part cos/2 after C2R
+    assert torch.allclose(y[0, 0, :, 0, :, 0], 0.5 * pos, atol=1e-5)
+
+
+def test_port_fno4d_matches_reference():
+    g = load_golden("fno4d")
+    m = g["meta"]
+    assert m["kind"] == "model4d"
+    x = g["inputs"]["x"].clone().requires_grad_(True)
+    params = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    y = fno_port.fno4d_forward(params, x, m["modes"])
+    assert rel_l2(y, g["out"]) < TOL
+    (y * g["cot"]).sum().backward()
+    assert rel_l2(x.grad, g["grad_inputs"]["x"]) < TOL
+    for k, p in params.items():
+        assert rel_l2(p.grad, g["grads"][k]) < 5 * TOL, k
