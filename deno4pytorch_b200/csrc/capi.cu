@@ -1236,6 +1236,9 @@ int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat,
 }
 
 #ifndef DENO_EMULATE
+// The warp-specialised synthesis variant (24 template instances, slower than the bulk kernel at every measured shape) is
+// compiled only with -DDENO_WITH_SYNTH_WS (DENO_EXTRA_NVCC_FLAGS); without it DENO_SYNTH_WS=1 falls through to the bulk kernel.
+#ifdef DENO_WITH_SYNTH_WS
 // Tensor-core synthesis: returns DENO_OK after launching, or -1 when the shape is outside what the
 // tcgen05 kernel covers (caller falls back to the SIMT kernel).
 int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, cudaStream_t st) {
@@ -1304,6 +1307,8 @@ int try_launch_synthesis_ws(const Shape& s, SynthParams p, const TwPtrs& tw, int
 #undef DENO_TC_CASE2
   return check_launch("plane_synthesis_tc", st);
 }
+
+#endif  // DENO_WITH_SYNTH_WS
 
 // Bulk-synchronous variant (two CTAs per SM, every warp does every phase).  Measured faster than the
 // warp-specialised kernel at the Darcy shape (profiles/r1t_phase_probe.txt), so it is the default;
@@ -1457,7 +1462,9 @@ int try_launch_synthesis_bulk(const Shape& s, SynthParams p, const TwPtrs& tw, i
 
 int try_launch_synthesis_tc(const Shape& s, SynthParams p, const TwPtrs& tw, int act, const char* label, float* urow,
                             cudaStream_t st) {
+#ifdef DENO_WITH_SYNTH_WS
   if (options().synth_ws) return try_launch_synthesis_ws(s, p, tw, act, label, st);
+#endif
   return try_launch_synthesis_bulk(s, p, tw, act, label, urow, st);
 }
 #endif

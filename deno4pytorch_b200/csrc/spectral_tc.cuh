@@ -55,6 +55,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // named barriers: producers arrive without blocking, the consumer warp syncs (count = all participating threads)
 __device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -878,6 +881,7 @@ __global__ void __launch_bounds__(kSynThreads, (CIP <= 32 ? 2 : 1)) plane_synthe
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)q.tmem_cols);
 }
 
+#ifdef DENO_WITH_SYNTH_WS
 // ----------------------------------------------------------------------------------------------
 // plane_synthesis_ws: warp-specialised version of plane_synthesis_tc (same math, same operand images).
 //   warps 0-15  epilogue : TMEM -> registers -> bias + activation (+ derivative) -> coalesced global stores
@@ -908,10 +912,6 @@ __host__ __device__ inline SynthWsSmem synth_ws_smem(int CIP, int CO, int KE, in
   m.bias = off;  off += CO * 4;
   m.total = off;
   return m;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int ACT, int CIP>
@@ -1208,6 +1208,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) plane_synthesis_ws_kernel(Synth
   }
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)q.tmem_cols);
 }
+
+#endif  // DENO_WITH_SYNTH_WS
 
 // ----------------------------------------------------------------------------------------------
 // plane_analysis_tc: same contract as plane_analysis_kernel (spectral_simt.cuh) for planes with
