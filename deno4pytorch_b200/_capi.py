@@ -41,6 +41,32 @@ def make_desc(batch, cin, cout, spatial, modes, act) -> SpectralDesc:
     return d
 
 
+class SpectralDesc4(C.Structure):
+    """struct deno_spectral_desc4 (the 4-D stand-alone layer of Demo/Turbulence_3d+t/FNO_HIT.py)"""
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("cin", C.c_int32),
+        ("cout", C.c_int32),
+        ("spatial", C.c_int32 * 4),
+        ("modes", C.c_int32 * 4),
+        ("act", C.c_int32),
+        ("flags", C.c_int32),
+    ]
+    ndim = 4
+
+
+def make_desc4(batch, cin, cout, spatial, modes, act) -> SpectralDesc4:
+    assert len(spatial) == 4 and len(modes) == 4
+    d = SpectralDesc4()
+    d.batch, d.cin, d.cout = int(batch), int(cin), int(cout)
+    for a in range(4):
+        d.spatial[a] = int(spatial[a])
+        d.modes[a] = int(modes[a])
+    d.act = ACTIVATION_IDS[act] if isinstance(act, str) else int(act)
+    d.flags = 0
+    return d
+
+
 class FnoDesc(C.Structure):
     """struct deno_fno_desc (include/deno_fno.h)"""
     _fields_ = [
@@ -81,6 +107,7 @@ class ProfileRecord(C.Structure):
 
 
 _DESC_P = C.POINTER(SpectralDesc)
+_DESC4_P = C.POINTER(SpectralDesc4)
 _FNO_P = C.POINTER(FnoDesc)
 _V = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -113,6 +140,15 @@ _PROTOTYPES = {
     "deno_spectral_bwd_overlap": (C.c_int, [_DESC_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
                                             C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                             C.c_void_p, C.POINTER(Overlap)]),
+    "deno_spectral4_num_modes": (C.c_size_t, [_DESC4_P]),
+    "deno_spectral4_twiddle_bytes": (C.c_size_t, [_DESC4_P]),
+    "deno_spectral4_twiddle_fill": (C.c_int, [_DESC4_P, C.c_void_p, C.c_size_t]),
+    "deno_spectral4_workspace_bytes": (C.c_size_t, [_DESC4_P, C.c_int]),
+    "deno_spectral4_fwd": (C.c_int, [_DESC4_P, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "deno_spectral4_bwd": (C.c_int, [_DESC4_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p, C.POINTER(Overlap)]),
     "deno_fno_supported": (C.c_int, [_FNO_P]),
     "deno_fno_workspace_bytes": (C.c_size_t, [_FNO_P, C.c_int]),
     "deno_fno_lift_fwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V]),

@@ -58,7 +58,12 @@ struct Shape {
   int Q;              // KH * MW: packed modes of one plane
   int M;              // total packed modes
   int act;
+  // 4-D stand-alone layer (deno_spectral4_*): two outer axes X1, X2 (X = X1 * X2 planes per batch entry, KX = KX1 * KX2),
+  // a ONE-SIDED row axis (KH = mH: the reference keeps [:m3] only) and four weight blocks.  Zero for ndim < 4.
+  int X1, X2, mX1, mX2, KX1, KX2, KX14, KX24;
 };
+
+inline int num_weight_blocks(const Shape& s) { return s.ndim == 4 ? 4 : (1 << (s.ndim - 1)); }
 
 int parse_desc(const deno_spectral_desc* d, Shape& s) {
   if (d == nullptr) return fail(DENO_E_INVALID, "null descriptor");
@@ -96,6 +101,36 @@ int parse_desc(const deno_spectral_desc* d, Shape& s) {
   s.S = (long long)s.X * s.H * s.W;
   s.Q = s.KH * s.MW;
   s.M = s.KX * s.Q;
+  s.X1 = s.X2 = s.mX1 = s.mX2 = s.KX1 = s.KX2 = s.KX14 = s.KX24 = 0;
+  return DENO_OK;
+}
+
+// SpectralConv4d (/root/reference/Demo/Turbulence_3d+t/FNO_HIT.py:31-78): axes (x, y, z, t); both signs of the first two,
+// the low block [:m3] of the third, [:m4] of the half-spectrum axis.  Planes are (z, t), batched over (b, x, y).
+int parse_desc4(const deno_spectral_desc4* d, Shape& s) {
+  if (d == nullptr) return fail(DENO_E_INVALID, "null descriptor");
+  if (d->batch < 1 || d->cin < 1 || d->cout < 1) return fail(DENO_E_INVALID, "batch/cin/cout must be positive");
+  if (d->flags != 0) return fail(DENO_E_INVALID, "flags must be 0");
+  if (d->act < DENO_ACT_IDENTITY || d->act > DENO_ACT_LEAKYRELU) return fail(DENO_E_INVALID, "unknown activation id");
+  for (int a = 0; a < 4; ++a)
+    if (d->spatial[a] < 1 || d->modes[a] < 1) return fail(DENO_E_INVALID, "spatial sizes and modes must be positive");
+  s.ndim = 4;
+  s.B = d->batch; s.CI = d->cin; s.CO = d->cout; s.act = d->act;
+  s.X1 = d->spatial[0]; s.X2 = d->spatial[1]; s.H = d->spatial[2]; s.W = d->spatial[3];
+  s.mX1 = d->modes[0]; s.mX2 = d->modes[1]; s.mH = d->modes[2]; s.mW = d->modes[3];
+  if (s.mW > s.W / 2 + 1)
+    return fail(DENO_E_INVALID, "modes on the last axis exceed the rfft length N/2+1 (the reference fails in einsum)");
+  if (s.mH > s.H) return fail(DENO_E_INVALID, "modes3 exceeds the third axis (the reference fails in einsum)");
+  if (2 * s.mX1 > s.X1 || 2 * s.mX2 > s.X2)
+    return fail(DENO_E_UNSUPPORTED, "2*modes exceeds the grid on a leading axis (overlapping corner blocks)");
+  s.X = s.X1 * s.X2; s.mX = 0;
+  s.KX1 = 2 * s.mX1; s.KX2 = 2 * s.mX2; s.KX = s.KX1 * s.KX2;
+  s.KX14 = round_up(s.KX1, 4); s.KX24 = round_up(s.KX2, 4); s.KX4 = round_up(s.KX, 4);
+  s.KH = s.mH; s.MW = s.mW;
+  s.KH4 = round_up(s.KH, 4); s.MWp = round_up(s.MW, 4);
+  s.S = (long long)s.X * s.H * s.W;
+  s.Q = s.KH * s.MW;
+  s.M = s.KX * s.Q;
   return DENO_OK;
 }
 
@@ -123,9 +158,15 @@ ModeDecode make_decode(const Shape& s) {
   } else if (s.ndim == 2) {
     md.m1 = s.mH; md.m2 = s.mW; md.m3 = 1;
     md.Mblk = s.mH * s.mW;
-  } else {
+  } else if (s.ndim == 3) {
     md.m1 = s.mX; md.m2 = s.mH; md.m3 = s.mW;
     md.Mblk = s.mX * s.mH * s.mW;
+  } else {
+    // 4-D: packed mode = ((k1 * KX2 + k2) * m3 + kz) * m4 + l; the blocks depend on (k1, k2) only and a block is
+    // [m1][m2][m3 * m4] - exactly the 3-D decode with the (z, t) modes merged into its innermost index
+    md.ndim = 3;
+    md.m1 = s.mX1; md.m2 = s.mX2; md.m3 = s.mH * s.mW;
+    md.Mblk = s.mX1 * s.mX2 * s.mH * s.mW;
   }
   md.M = s.M;
   return md;
@@ -135,7 +176,7 @@ ModeDecode make_decode(const Shape& s) {
 // Twiddle tables (host, fp64 -> fp32)
 // ------------------------------------------------------------------------------------------
 struct TwLayout {
-  size_t last, mid, outer, cl, synth_ae, an_e1, an_a2, at_e1, at_a2, total;  // float offsets
+  size_t last, mid, outer, outer2, cl, synth_ae, an_e1, an_a2, at_e1, at_a2, total;  // float offsets
   int nchunks, KE;                               // tensor-core synthesis images: [chunk][hi|lo][KE*128]
   int N1, Wp, Hp, KS0, KRp;                      // tensor-core analysis images: E1 [2*N1 rows: hi, lo][Wp], A2 [slab][hi|lo][KRp*Hp]
   int an_nsub, an_HS;                            // row slabs of the tensor-core analysis (0: shape not covered); Hp = an_HS
@@ -187,7 +228,8 @@ TwLayout tw_layout(const Shape& s) {
   size_t off = 0;
   t.last = off;  off += (size_t)s.W * s.MWp * 2;
   t.mid = off;   off += (size_t)s.H * s.KH4 * 2;
-  t.outer = off; off += (s.ndim == 3) ? (size_t)s.X * s.KX4 * 2 : 0;
+  t.outer = off; off += (s.ndim == 3) ? (size_t)s.X * s.KX4 * 2 : (s.ndim == 4 ? (size_t)s.X1 * s.KX14 * 2 : 0);
+  t.outer2 = off; off += (s.ndim == 4) ? (size_t)s.X2 * s.KX24 * 2 : 0;
   t.cl = off;    off += (size_t)s.MWp;
   t.nchunks = (s.W + 127) / 128;
   t.KE = 2 * s.MWp;
@@ -376,8 +418,8 @@ int wgrad_cfg(const Shape& s, WgradCfg& c) {
 // ------------------------------------------------------------------------------------------
 // Workspace carving
 // ------------------------------------------------------------------------------------------
-struct FwdWs { size_t xhat, yhat, t2, v, urow, total; };
-struct BwdWs { size_t gz, ghat, gxhat, t2, v, partial, urow, total; };
+struct FwdWs { size_t xhat, yhat, t2, v, t3, v3, urow, total; };
+struct BwdWs { size_t gz, ghat, gxhat, t2, v, t3, v3, partial, urow, total; };
 
 // pre-split row-synthesis images for the tensor-core synthesis kernel: [B*X][H][hi|lo][KE * C] floats
 size_t urow_bytes(const Shape& s, int channels) {
@@ -390,8 +432,10 @@ FwdWs fwd_ws(const Shape& s) {
   size_t off = 0;
   w.xhat = off; off += align_up((size_t)s.B * s.CI * s.M * 8);
   w.yhat = off; off += align_up((size_t)s.B * s.CO * s.M * 8);
-  w.t2 = off;   off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
-  w.v = off;    off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
+  w.t2 = off;   off += (s.ndim >= 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.v = off;    off += (s.ndim >= 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
+  w.t3 = off;   off += (s.ndim == 4) ? align_up((size_t)s.B * s.X1 * s.CI * s.KX2 * s.Q * 8) : 0;   // after the first outer pass
+  w.v3 = off;   off += (s.ndim == 4) ? align_up((size_t)s.B * s.X1 * s.CO * s.KX2 * s.Q * 8) : 0;
   w.urow = off; off += urow_bytes(s, s.CO);
   w.total = off;
   return w;
@@ -405,8 +449,10 @@ int bwd_ws(const Shape& s, BwdWs& w) {
   w.gz = off;      off += align_up((size_t)s.B * s.CO * s.S * 4);
   w.ghat = off;    off += align_up((size_t)s.B * s.CO * s.M * 8);
   w.gxhat = off;   off += align_up((size_t)s.B * s.CI * s.M * 8);
-  w.t2 = off;      off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
-  w.v = off;       off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.t2 = off;      off += (s.ndim >= 3) ? align_up((size_t)s.B * s.X * s.CO * s.Q * 8) : 0;
+  w.v = off;       off += (s.ndim >= 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.t3 = off;      off += (s.ndim == 4) ? align_up((size_t)s.B * s.X1 * s.CO * s.KX2 * s.Q * 8) : 0;
+  w.v3 = off;      off += (s.ndim == 4) ? align_up((size_t)s.B * s.X1 * s.CI * s.KX2 * s.Q * 8) : 0;
   const size_t nparts = (size_t)(wc.ncta > kWgradTcMaxCtas ? wc.ncta : kWgradTcMaxCtas);   // either kernel's partial count
   w.partial = off; off += align_up(nparts * ((size_t)s.CO * s.CI + s.CO) * 4);
   w.urow = off;    off += urow_bytes(s, s.CI);
@@ -626,7 +672,7 @@ void fill_analysis_tma_images(float* base, const Shape& s, const TwLayout& t) {
     }
 }
 
-struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float* cl; const float* synth_ae;
+struct TwPtrs { const float2* last; const float2* mid; const float2* outer; const float2* outer2; const float* cl; const float* synth_ae;
                 const float* an_e1; const float* an_a2; const float* at_e1; const float* at_a2; const float* rs_a; };
 
 TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
@@ -636,6 +682,7 @@ TwPtrs tw_ptrs(const Shape& s, const void* twiddles) {
   p.last = reinterpret_cast<const float2*>(base + t.last);
   p.mid = reinterpret_cast<const float2*>(base + t.mid);
   p.outer = reinterpret_cast<const float2*>(base + t.outer);
+  p.outer2 = reinterpret_cast<const float2*>(base + t.outer2);
   p.cl = base + t.cl;
   p.synth_ae = base + t.synth_ae;
   p.an_e1 = base + t.an_e1;
@@ -936,13 +983,15 @@ int launch_analysis(const Shape& s, int channels, const float* u, const float* z
   return check_launch("plane_analysis", st);
 }
 
-int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, float2* out, const TwPtrs& tw,
-                 cudaStream_t st) {
+// One outer-axis pass: analysis  in [Bp][X][C][Q] -> out [Bp][C][KX][Q],  synthesis the other way round.
+int launch_outer_axis(int Bp, int channels, int X, int KX, int Q, const float2* twX, bool analysis, const float2* in,
+                      float2* out, cudaStream_t st) {
   OuterParams p;
-  p.in = in; p.out = out; p.twX = tw.outer;
-  p.B = s.B; p.C = channels; p.X = s.X; p.KX = s.KX; p.Q = s.Q;
-  const long long units = analysis ? (long long)s.B * channels * (s.KX4 / 4) * s.Q
-                                   : (long long)s.B * channels * ((s.X + 3) / 4) * s.Q;
+  p.in = in; p.out = out; p.twX = twX;
+  p.B = Bp; p.C = channels; p.X = X; p.KX = KX; p.Q = Q;
+  const int KX4 = round_up(KX, 4);
+  const long long units = analysis ? (long long)Bp * channels * (KX4 / 4) * Q
+                                   : (long long)Bp * channels * ((X + 3) / 4) * Q;
   long long blocks = (units + 255) / 256;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
   prof_before(analysis ? "outer_analysis" : "outer_synthesis", st);
@@ -952,6 +1001,24 @@ int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, 
     DENO_LAUNCH(outer_synthesis_kernel, dim3((unsigned)blocks), dim3(256), 0, st, p);
   }
   return check_launch(analysis ? "outer_analysis" : "outer_synthesis", st);
+}
+
+int launch_outer(const Shape& s, int channels, bool analysis, const float2* in, float2* out, const TwPtrs& tw,
+                 cudaStream_t st) {
+  return launch_outer_axis(s.B, channels, s.X, s.KX, s.Q, tw.outer, analysis, in, out, st);
+}
+
+// 4-D: the two outer axes, one pass each.  Analysis: plane spectra [B*X1*X2][C][Q] -> (contract y) `mid` [B*X1][C][KX2][Q]
+// -> (contract x; the (ky, q) pair is the inner index) packed [B][C][KX1][KX2*Q].  Synthesis runs the two passes backwards.
+int launch_outer4(const Shape& s, int channels, bool analysis, const float2* in, float2* mid, float2* out, const TwPtrs& tw,
+                  cudaStream_t st) {
+  int rc;
+  if (analysis) {
+    if ((rc = launch_outer_axis(s.B * s.X1, channels, s.X2, s.KX2, s.Q, tw.outer2, true, in, mid, st))) return rc;
+    return launch_outer_axis(s.B, channels, s.X1, s.KX1, s.KX2 * s.Q, tw.outer, true, mid, out, st);
+  }
+  if ((rc = launch_outer_axis(s.B, channels, s.X1, s.KX1, s.KX2 * s.Q, tw.outer, false, in, mid, st))) return rc;
+  return launch_outer_axis(s.B * s.X1, channels, s.X2, s.KX2, s.Q, tw.outer2, false, mid, out, st);
 }
 
 // Tiled per-mode products (mode_mix_tile_kernel / mode_mix_bwd_tile_kernel): picks the modes per block so that the grid
@@ -1003,7 +1070,7 @@ int launch_mix_tc(const Shape& s, bool backward, const float2* in, float2* out, 
   memset(&p, 0, sizeof(p));
   p.in = in; p.out = out;
   p.md = make_decode(s);
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < 4; ++j) p.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
   p.B = s.B;
   if (!backward) {
@@ -1035,7 +1102,7 @@ int launch_mix_wgrad_tc(const Shape& s, const float2* xhat, const float2* ghat, 
   p.xhat = xhat; p.ghat = ghat;
   p.glb = glb_from_dc; p.s_total = (float)s.S;
   p.md = make_decode(s);
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < 4; ++j) p.gw[j] = static_cast<float2*>(gw_blocks[j < nblk ? j : 0]);
   p.B = s.B; p.CI = s.CI; p.CO = s.CO;
   p.Kp = round_up(s.B, 8);
@@ -1061,7 +1128,7 @@ int launch_mix_lane(const Shape& s, bool backward, const float2* in, float2* out
   MixParams p;
   p.in = in; p.out = out;
   p.md = make_decode(s);
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < 4; ++j) p.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
   p.B = s.B;
   if (!backward) {
@@ -1103,7 +1170,7 @@ int launch_mix(const Shape& s, bool backward, const float2* in, float2* out, con
   MixParams p;
   p.in = in; p.out = out;
   p.md = make_decode(s);
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < 4; ++j) p.w[j] = static_cast<const float2*>(w_blocks[j < nblk ? j : 0]);
   p.B = s.B;
   if (!backward) {
@@ -1143,7 +1210,7 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
   MixWgradParams p;
   p.xhat = xhat; p.ghat = ghat;
   p.md = make_decode(s);
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < 4; ++j) p.gw[j] = static_cast<float2*>(gw_blocks[j < nblk ? j : 0]);
   p.B = s.B; p.CI = s.CI; p.CO = s.CO;
   dim3 block(32, 8);
@@ -1157,7 +1224,7 @@ int launch_mix_wgrad(const Shape& s, const float2* xhat, const float2* ghat, voi
 int launch_mix_bwd_fused(const Shape& s, const float2* xhat, const float2* ghat, float2* gxhat, const void* const* w_blocks,
                          void* const* gw_blocks, float* glb_from_dc, cudaStream_t st,
                          const char* label = "mode_mix_bwd_fused") {
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   if (mix_lane_wanted(s) && gxhat != nullptr && w_blocks != nullptr) {   // G^x by the lane kernel, the other roles below
     const int lrc = launch_mix_lane(s, true, ghat, gxhat, w_blocks, st);
     if (lrc != DENO_OK) return lrc;
@@ -1964,20 +2031,21 @@ size_t deno_spectral_twiddle_bytes(const deno_spectral_desc* desc) {
   return tw_layout(s).total * sizeof(float);
 }
 
-int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, size_t bytes) {
-  Shape s;
-  int rc = parse_desc(desc, s);
-  if (rc != DENO_OK) return rc;
+static int twiddle_fill_shape(const Shape& s, void* host_buf, size_t bytes) {
   const TwLayout t = tw_layout(s);
   if (host_buf == nullptr || bytes < t.total * sizeof(float)) return fail(DENO_E_INVALID, "twiddle buffer too small");
   float* base = static_cast<float*>(host_buf);
   fill_axis(base + t.last, s.W, s.MW, s.MWp, s.mW, /*half=*/true);
   if (s.ndim >= 2) {
-    fill_axis(base + t.mid, s.H, s.KH, s.KH4, s.mH, false);
+    fill_axis(base + t.mid, s.H, s.KH, s.KH4, s.mH, /*half=*/s.ndim == 4);   // 4-D: the third axis keeps its low block only
   } else {
     fill_axis(base + t.mid, 1, 1, s.KH4, 0, true);
   }
   if (s.ndim == 3) fill_axis(base + t.outer, s.X, s.KX, s.KX4, s.mX, false);
+  if (s.ndim == 4) {
+    fill_axis(base + t.outer, s.X1, s.KX1, s.KX14, s.mX1, false);
+    fill_axis(base + t.outer2, s.X2, s.KX2, s.KX24, s.mX2, false);
+  }
   fill_synth_ae(base + t.synth_ae, s, t);
   fill_analysis_images(base, s, t);
   memset(base + t.at_e1, 0, (t.total - t.at_e1) * sizeof(float));
@@ -1995,6 +2063,39 @@ int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, s
   return DENO_OK;
 }
 
+int deno_spectral_twiddle_fill(const deno_spectral_desc* desc, void* host_buf, size_t bytes) {
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  return twiddle_fill_shape(s, host_buf, bytes);
+}
+
+// ---- 4-D stand-alone layer: the same queries on a deno_spectral_desc4 ----
+size_t deno_spectral4_num_modes(const deno_spectral_desc4* desc) {
+  Shape s;
+  if (parse_desc4(desc, s) != DENO_OK) return 0;
+  return (size_t)s.M;
+}
+size_t deno_spectral4_twiddle_bytes(const deno_spectral_desc4* desc) {
+  Shape s;
+  if (parse_desc4(desc, s) != DENO_OK) return 0;
+  return tw_layout(s).total * sizeof(float);
+}
+int deno_spectral4_twiddle_fill(const deno_spectral_desc4* desc, void* host_buf, size_t bytes) {
+  Shape s;
+  int rc = parse_desc4(desc, s);
+  if (rc != DENO_OK) return rc;
+  return twiddle_fill_shape(s, host_buf, bytes);
+}
+size_t deno_spectral4_workspace_bytes(const deno_spectral_desc4* desc, int backward) {
+  Shape s;
+  if (parse_desc4(desc, s) != DENO_OK) return 0;
+  if (!backward) return fwd_ws(s).total;
+  BwdWs w;
+  if (bwd_ws(s, w) != DENO_OK) return 0;
+  return w.total;
+}
+
 size_t deno_spectral_workspace_bytes(const deno_spectral_desc* desc, int backward) {
   Shape s;
   if (parse_desc(desc, s) != DENO_OK) return 0;
@@ -2010,16 +2111,13 @@ size_t deno_spectral_xhat_bytes(const deno_spectral_desc* desc) {
   return (size_t)s.B * s.CI * s.M * 8;
 }
 
-int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void* const* w_blocks,
-                      const float* lin_w, const float* lin_b, const void* twiddles, float* y,
-                      float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
-                      void* stream) {
-  g_launches = 0;
-  Shape s;
-  int rc = parse_desc(desc, s);
-  if (rc != DENO_OK) return rc;
+static int spectral_fwd_shape(const Shape& s, const float* x, const void* const* w_blocks,
+                              const float* lin_w, const float* lin_b, const void* twiddles, float* y,
+                              float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  int rc;
   if (!x || !w_blocks || !lin_w || !twiddles || !y || !workspace) return fail(DENO_E_INVALID, "null pointer argument");
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < nblk; ++j)
     if (w_blocks[j] == nullptr) return fail(DENO_E_INVALID, "null weight block");
   const FwdWs ws = fwd_ws(s);
@@ -2030,13 +2128,17 @@ int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void
   float2* xhat = xhat_saved ? static_cast<float2*>(xhat_saved) : reinterpret_cast<float2*>(wsb + ws.xhat);
   float2* yhat = reinterpret_cast<float2*>(wsb + ws.yhat);
 
-  if (s.ndim == 3) {
+  if (s.ndim >= 3) {
     float2* t2 = reinterpret_cast<float2*>(wsb + ws.t2);
     float2* v = reinterpret_cast<float2*>(wsb + ws.v);
     if ((rc = launch_analysis(s, s.CI, x, nullptr, nullptr, t2, tw, 1.0f, 0, st))) return rc;
-    if ((rc = launch_outer(s, s.CI, true, t2, xhat, tw, st))) return rc;
+    if (s.ndim == 4) {
+      if ((rc = launch_outer4(s, s.CI, true, t2, reinterpret_cast<float2*>(wsb + ws.t3), xhat, tw, st))) return rc;
+    } else if ((rc = launch_outer(s, s.CI, true, t2, xhat, tw, st))) return rc;
     if ((rc = launch_mix(s, false, xhat, yhat, w_blocks, st))) return rc;
-    if ((rc = launch_outer(s, s.CO, false, yhat, v, tw, st))) return rc;
+    if (s.ndim == 4) {
+      if ((rc = launch_outer4(s, s.CO, false, yhat, reinterpret_cast<float2*>(wsb + ws.v3), v, tw, st))) return rc;
+    } else if ((rc = launch_outer(s, s.CO, false, yhat, v, tw, st))) return rc;
     return launch_synthesis(s, s.CI, s.CO, v, x, lin_w, s.CI, 1, lin_b, y, z_saved, tw, (float)(1.0 / (double)s.S), 1,
                             s.act, reinterpret_cast<float*>(wsb + ws.urow), st);
   }
@@ -2046,23 +2148,42 @@ int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void
                           s.act, reinterpret_cast<float*>(wsb + ws.urow), st);
 }
 
+int deno_spectral_fwd(const deno_spectral_desc* desc, const float* x, const void* const* w_blocks,
+                      const float* lin_w, const float* lin_b, const void* twiddles, float* y,
+                      float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  return spectral_fwd_shape(s, x, w_blocks, lin_w, lin_b, twiddles, y, z_saved, xhat_saved, workspace, workspace_bytes, stream);
+}
+
+int deno_spectral4_fwd(const deno_spectral_desc4* desc, const float* x, const void* const* w_blocks,
+                       const float* lin_w, const float* lin_b, const void* twiddles, float* y,
+                       float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc4(desc, s);
+  if (rc != DENO_OK) return rc;
+  return spectral_fwd_shape(s, x, w_blocks, lin_w, lin_b, twiddles, y, z_saved, xhat_saved, workspace, workspace_bytes, stream);
+}
+
 // Shared body of deno_spectral_bwd / deno_spectral_bwd_overlap.  With `ov` the kernels that only PRODUCE parameter
 // gradients (gW of the mode mix, the bypass weight / bias gradient and its reduction) go to ov->side_stream right after
 // gz and G^ exist, and the input-gradient chain (G^x -> row synthesis -> plane synthesis) continues on `stream`; the
 // two meet again before the call returns.  Both sides only read gz / G^ / X^ / x and write disjoint outputs and
 // disjoint workspace regions (BwdWs: gxhat, v, urow on the chain; partial on the side).
-static int spectral_bwd_impl(const deno_spectral_desc* desc, const float* gy, const float* x,
+static int spectral_bwd_impl(const Shape& s, const float* gy, const float* x,
                              const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
                              const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
                              float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
                              void* stream, const deno_overlap* ov) {
-  g_launches = 0;
-  Shape s;
-  int rc = parse_desc(desc, s);
-  if (rc != DENO_OK) return rc;
+  int rc;
   if (!gy || !x || !z_saved || !xhat_saved || !w_blocks || !lin_w || !twiddles || !workspace)
     return fail(DENO_E_INVALID, "null pointer argument");
-  const int nblk = 1 << (s.ndim - 1);
+  const int nblk = num_weight_blocks(s);
   for (int j = 0; j < nblk; ++j) {
     if (w_blocks[j] == nullptr) return fail(DENO_E_INVALID, "null weight block");
     if (gw_blocks != nullptr && gw_blocks[j] == nullptr) return fail(DENO_E_INVALID, "null weight-gradient block");
@@ -2080,10 +2201,12 @@ static int spectral_bwd_impl(const deno_spectral_desc* desc, const float* gy, co
   const float inv_s = (float)(1.0 / (double)s.S);
 
   // gz = gy * act'(z);  G^ = (c_l / S) * truncated DFT(gz)
-  if (s.ndim == 3) {
+  if (s.ndim >= 3) {
     float2* t2 = reinterpret_cast<float2*>(wsb + ws.t2);
     if ((rc = launch_analysis(s, s.CO, gy, z_saved, gz, t2, tw, inv_s, 1, st))) return rc;
-    if ((rc = launch_outer(s, s.CO, true, t2, ghat, tw, st))) return rc;
+    if (s.ndim == 4) {
+      if ((rc = launch_outer4(s, s.CO, true, t2, reinterpret_cast<float2*>(wsb + ws.t3), ghat, tw, st))) return rc;
+    } else if ((rc = launch_outer(s, s.CO, true, t2, ghat, tw, st))) return rc;
   } else {
     if ((rc = launch_analysis(s, s.CO, gy, z_saved, gz, ghat, tw, inv_s, 1, st))) return rc;
   }
@@ -2114,9 +2237,11 @@ static int spectral_bwd_impl(const deno_spectral_desc* desc, const float* gy, co
   }
   if (gx != nullptr) {
     const float2* spec = gxhat;
-    if (s.ndim == 3) {
+    if (s.ndim >= 3) {
       float2* v = reinterpret_cast<float2*>(wsb + ws.v);
-      if ((rc = launch_outer(s, s.CI, false, gxhat, v, tw, st))) return rc;
+      if (s.ndim == 4) {
+        if ((rc = launch_outer4(s, s.CI, false, gxhat, reinterpret_cast<float2*>(wsb + ws.v3), v, tw, st))) return rc;
+      } else if ((rc = launch_outer(s, s.CI, false, gxhat, v, tw, st))) return rc;
       spec = v;
     }
     // gx = Re sum G^x e^{+i theta} + W_l^T gz   (channels swap roles: "input" = gz with CO channels)
@@ -2148,7 +2273,11 @@ int deno_spectral_bwd(const deno_spectral_desc* desc, const float* gy, const flo
                       const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
                       float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
                       void* stream) {
-  return spectral_bwd_impl(desc, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  return spectral_bwd_impl(s, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
                            workspace, workspace_bytes, stream, nullptr);
 }
 
@@ -2157,7 +2286,24 @@ int deno_spectral_bwd_overlap(const deno_spectral_desc* desc, const float* gy, c
                               const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
                               float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
                               void* stream, const deno_overlap* ov) {
-  return spectral_bwd_impl(desc, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc(desc, s);
+  if (rc != DENO_OK) return rc;
+  return spectral_bwd_impl(s, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
+                           workspace, workspace_bytes, stream, ov);
+}
+
+int deno_spectral4_bwd(const deno_spectral_desc4* desc, const float* gy, const float* x,
+                       const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                       const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                       float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                       void* stream, const deno_overlap* ov) {
+  g_launches = 0;
+  Shape s;
+  int rc = parse_desc4(desc, s);
+  if (rc != DENO_OK) return rc;
+  return spectral_bwd_impl(s, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
                            workspace, workspace_bytes, stream, ov);
 }
 

@@ -93,17 +93,24 @@ def _desc_key(d: _capi.SpectralDesc):
     return (d.ndim, d.batch, d.cin, d.cout, tuple(d.spatial), tuple(d.modes))
 
 
-def _twiddles(d: _capi.SpectralDesc, device: torch.device) -> torch.Tensor:
+def _fn(L, d, name: str):
+    """Entry point ``name`` for this descriptor: the ``deno_spectral4_*`` family for the 4-D stand-alone layer."""
+    if isinstance(d, _capi.SpectralDesc4):
+        name = name.replace("deno_spectral_", "deno_spectral4_")
+    return getattr(L, name)
+
+
+def _twiddles(d, device: torch.device) -> torch.Tensor:
     """Constant DFT tables: filled on the host in fp64 by the library, uploaded once per shape."""
     key = (device.index, d.ndim, tuple(d.spatial), tuple(d.modes))
     t = _TWIDDLES.get(key)
     if t is None:
         L = lib()
-        nbytes = L.deno_spectral_twiddle_bytes(C.byref(d))
+        nbytes = _fn(L, d, "deno_spectral_twiddle_bytes")(C.byref(d))
         if nbytes == 0:
             raise _capi.DenoError(L.deno_last_error().decode())
         host = np.empty(nbytes // 4, dtype=np.float32)
-        _capi.check(L, L.deno_spectral_twiddle_fill(C.byref(d), host.ctypes.data_as(C.c_void_p), nbytes),
+        _capi.check(L, _fn(L, d, "deno_spectral_twiddle_fill")(C.byref(d), host.ctypes.data_as(C.c_void_p), nbytes),
                     "deno_spectral_twiddle_fill")
         t = torch.from_numpy(host).to(device)
         _TWIDDLES[key] = t
@@ -182,18 +189,20 @@ class _SpectralConvFn(torch.autograd.Function):
         L = lib()
         _check_input(x, "input")
         ndim = x.dim() - 2
-        if ndim not in (1, 2, 3):
-            raise RuntimeError("input must be (B, C, *spatial) with 1-3 spatial dims")
+        if ndim not in (1, 2, 3, 4):
+            raise RuntimeError("input must be (B, C, *spatial) with 1-4 spatial dims")
         B, cin = x.shape[:2]
         spatial = tuple(x.shape[2:])
         cout = lin_w.shape[0]
         if lin_w.shape[1] != cin or lin_w.numel() != cout * cin:
             raise RuntimeError(f"linear.weight {tuple(lin_w.shape)} does not match {cin} input channels")
-        if len(weights) != 2 ** (ndim - 1):
-            raise RuntimeError(f"{ndim}-D layer needs {2 ** (ndim - 1)} weight blocks, got {len(weights)}")
+        nblocks = 4 if ndim == 4 else 2 ** (ndim - 1)      # 4-D (FNO_HIT.py): both signs on the first two axes only
+        if len(weights) != nblocks:
+            raise RuntimeError(f"{ndim}-D layer needs {nblocks} weight blocks, got {len(weights)}")
         for j, w in enumerate(weights):
             _check_weight(w, cin, cout, modes, j)
-        d = _capi.make_desc(B, cin, cout, spatial, modes, act)
+        d = _capi.make_desc4(B, cin, cout, spatial, modes, act) if ndim == 4 else \
+            _capi.make_desc(B, cin, cout, spatial, modes, act)
 
         # ``save`` = grad mode of the CALLER (inside Function.forward it is always off): under torch.no_grad()
         # (validation, roll-out inference) nothing is saved, so act'(z) and the spectrum are neither allocated nor written
@@ -207,13 +216,13 @@ class _SpectralConvFn(torch.autograd.Function):
             tw = _twiddles(d, dev)
             y = torch.empty((B, cout) + spatial, dtype=torch.float32, device=dev)
             z = torch.empty_like(y) if needs_grad else None
-            nmodes = L.deno_spectral_num_modes(C.byref(d))
+            nmodes = _fn(L, d, "deno_spectral_num_modes")(C.byref(d))
             xhat = torch.empty((B, cin, nmodes), dtype=torch.complex64, device=dev) if needs_grad else None
-            nws = L.deno_spectral_workspace_bytes(C.byref(d), 0)
+            nws = _fn(L, d, "deno_spectral_workspace_bytes")(C.byref(d), 0)
             ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
             _poison(ws, y, z, xhat)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = L.deno_spectral_fwd(C.byref(d), xc.data_ptr(), _capi.pointer_array([w.data_ptr() for w in wc]),
+            rc = _fn(L, d, "deno_spectral_fwd")(C.byref(d), xc.data_ptr(), _capi.pointer_array([w.data_ptr() for w in wc]),
                                      lw.data_ptr(), None if lb is None else lb.data_ptr(), tw.data_ptr(),
                                      y.data_ptr(), None if z is None else z.data_ptr(),
                                      None if xhat is None else xhat.data_ptr(), ws.data_ptr(), nws, stream)
@@ -252,13 +261,14 @@ class _SpectralConvFn(torch.autograd.Function):
             glw = (s_lw if s_lw is not None else torch.empty_like(lw)) if need_lw else None
             glb = (s_lb if s_lb is not None else torch.empty(lw.shape[0], dtype=torch.float32, device=dev)) \
                 if (need_lb and ctx.has_bias) else None
-            nws = L.deno_spectral_workspace_bytes(C.byref(d), 1)
+            nws = _fn(L, d, "deno_spectral_workspace_bytes")(C.byref(d), 1)
             ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
             _poison(ws, gx, glw if s_lw is None else None, glb if s_lb is None else None,
                     *([g for g, sk in zip(gws, s_w) if sk is None] if gws is not None else []))
             stream = torch.cuda.current_stream(dev).cuda_stream
             ov = _overlap_handle(dev)
-            rc = L.deno_spectral_bwd_overlap(
+            bwd = L.deno_spectral4_bwd if isinstance(d, _capi.SpectralDesc4) else L.deno_spectral_bwd_overlap
+            rc = bwd(
                 C.byref(d), gy.data_ptr(), xc.data_ptr(), z.data_ptr(), xhat.data_ptr(),
                 _capi.pointer_array([w.data_ptr() for w in wc]), lw.data_ptr(), tw.data_ptr(),
                 None if gx is None else gx.data_ptr(),
@@ -279,7 +289,8 @@ def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor], lin_w: torch
     """``act(irfftn(corner_mix(rfftn(x))) + conv1x1(x) + bias)`` on the CUDA kernels.
 
     ``x`` (B, Cin, *spatial) fp32 CUDA; ``weights`` the reference's 1/2/4 blocks (complex64 or the
-    fp32 ``(..., 2)`` real view); ``lin_w``/``lin_b`` the 1x1 conv parameters; ``activation`` one of
+    fp32 ``(..., 2)`` real view; four spatial dims: the four blocks of ``SpectralConv4d``,
+    /root/reference/Demo/Turbulence_3d+t/FNO_HIT.py:31-78); ``lin_w``/``lin_b`` the 1x1 conv parameters; ``activation`` one of
     identity/gelu/silu/relu/tanh/leakyrelu.  Differentiable w.r.t. x, weights, lin_w, lin_b.
     """
     modes = _normalize_modes(modes, x.dim() - 2)

@@ -142,6 +142,39 @@ int deno_spectral_bwd_overlap(const deno_spectral_desc* desc, const float* gy, c
                               void* stream, const deno_overlap* ov);
 
 /*
+ * The 4-D stand-alone layer of the reference (SpectralConv4d, /root/reference/Demo/Turbulence_3d+t/FNO_HIT.py:31-78, and
+ * the `conv_i(x) + w_i(x)` (+ GELU) steps of FNO4d.forward, :118-150): axes (x, y, z, t); BOTH signs of the retained modes
+ * on the first two axes, the LOW block [:modes3] only on the third, [:modes4] on the half-spectrum axis; FOUR weight
+ * blocks `(Cin, Cout, m1, m2, m3, m4)` complex64 in the reference's order weights1..4 = (+x,+y), (-x,+y), (+x,-y), (-x,-y).
+ * Same call contract as the 1/2/3-D entry points above (bypass weight `lin_w` (Cout, Cin), optional bias, activation id;
+ * pass a zero `lin_w`, no bias and DENO_ACT_IDENTITY for the bare SpectralConv4d).  Planes are (z, t), batched over
+ * (b, x, y); the two leading axes are contracted by two passes of the outer-axis kernels.
+ */
+typedef struct deno_spectral_desc4 {
+  int32_t batch;
+  int32_t cin, cout;
+  int32_t spatial[4]; /* x, y, z, t                         */
+  int32_t modes[4];   /* modes1..4 (modes4 already clamped) */
+  int32_t act;        /* enum deno_activation               */
+  int32_t flags;      /* reserved, must be 0                */
+} deno_spectral_desc4;
+
+size_t deno_spectral4_num_modes(const deno_spectral_desc4* desc);       /* 4 * m1 * m2 * m3 * m4 */
+size_t deno_spectral4_twiddle_bytes(const deno_spectral_desc4* desc);
+int deno_spectral4_twiddle_fill(const deno_spectral_desc4* desc, void* host_buf, size_t bytes);
+size_t deno_spectral4_workspace_bytes(const deno_spectral_desc4* desc, int backward);
+int deno_spectral4_fwd(const deno_spectral_desc4* desc, const float* x, const void* const* w_blocks,
+                       const float* lin_w, const float* lin_b, const void* twiddles, float* y,
+                       float* z_saved, void* xhat_saved, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* `ov` may be NULL (one stream); see deno_spectral_bwd_overlap */
+int deno_spectral4_bwd(const deno_spectral_desc4* desc, const float* gy, const float* x,
+                       const float* z_saved, const void* xhat_saved, const void* const* w_blocks,
+                       const float* lin_w, const void* twiddles, float* gx, void* const* gw_blocks,
+                       float* glin_w, float* glin_b, void* workspace, size_t workspace_bytes,
+                       void* stream, const deno_overlap* ov);
+
+/*
  * One fused Adam step over flat fp32 buffers (all device pointers, `n` elements each), replacing the per-tensor
  * foreach Adam of the reference demos (`torch.optim.Adam(..., betas=(0.7, 0.9), weight_decay=1e-4)`,
  * /root/reference/Demo/Darcy_2d/run_FNO&UNet.py:209).  Same update rule as torch.optim.Adam (no amsgrad); complex

@@ -71,24 +71,28 @@ class EmuLayer:
         spatial = self.x.shape[2:]
         cout = self.lin_w.shape[0]
         modes = (modes,) * len(spatial) if isinstance(modes, int) else tuple(modes)
-        self.desc = _capi.make_desc(B, cin, cout, spatial, modes, act)
+        self.four = len(spatial) == 4          # the 4-D stand-alone layer: deno_spectral4_* on a deno_spectral_desc4
+        self.desc = _capi.make_desc4(B, cin, cout, spatial, modes, act) if self.four else \
+            _capi.make_desc(B, cin, cout, spatial, modes, act)
+        self.fn = (lambda name: getattr(self.lib, name.replace("deno_spectral_", "deno_spectral4_"))) if self.four else \
+            (lambda name: getattr(self.lib, name))
         self.out_shape = (B, cout) + tuple(spatial)
-        nb = self.lib.deno_spectral_twiddle_bytes(C.byref(self.desc))
+        nb = self.fn("deno_spectral_twiddle_bytes")(C.byref(self.desc))
         if nb == 0:
             raise _capi.DenoError(self.lib.deno_last_error().decode())
         self.tw = np.zeros(nb // 4, dtype=np.float32)
-        _capi.check(self.lib, self.lib.deno_spectral_twiddle_fill(C.byref(self.desc), _ptr(self.tw), nb), "twiddle_fill")
-        self.M = self.lib.deno_spectral_num_modes(C.byref(self.desc))
+        _capi.check(self.lib, self.fn("deno_spectral_twiddle_fill")(C.byref(self.desc), _ptr(self.tw), nb), "twiddle_fill")
+        self.M = self.fn("deno_spectral_num_modes")(C.byref(self.desc))
 
     def forward(self, save=True):
         lib, d = self.lib, self.desc
         y = np.full(self.out_shape, np.nan, dtype=np.float32)
         self.z = np.full(self.out_shape, np.nan, dtype=np.float32) if save else None
         self.xhat = np.full((self.x.shape[0], self.x.shape[1], self.M), np.nan, dtype=np.complex64) if save else None
-        nws = lib.deno_spectral_workspace_bytes(C.byref(d), 0)
+        nws = self.fn("deno_spectral_workspace_bytes")(C.byref(d), 0)
         ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
         wptrs = _capi.pointer_array([w.ctypes.data for w in self.w])
-        rc = lib.deno_spectral_fwd(C.byref(d), _ptr(self.x), wptrs, _ptr(self.lin_w), _ptr(self.lin_b), _ptr(self.tw),
+        rc = self.fn("deno_spectral_fwd")(C.byref(d), _ptr(self.x), wptrs, _ptr(self.lin_w), _ptr(self.lin_b), _ptr(self.tw),
                                    _ptr(y), _ptr(self.z), _ptr(self.xhat), _ptr(ws), nws, None)
         _capi.check(lib, rc, "deno_spectral_fwd")
         self.fwd_launches = lib.deno_spectral_last_launch_count()
@@ -104,11 +108,15 @@ class EmuLayer:
         gws = [np.full(w.shape, np.nan, dtype=w.dtype) for w in self.w]
         glw = np.full(self.lin_w.shape, np.nan, dtype=np.float32)
         glb = np.full((self.lin_w.shape[0],), np.nan, dtype=np.float32)
-        nws = lib.deno_spectral_workspace_bytes(C.byref(d), 1)
+        nws = self.fn("deno_spectral_workspace_bytes")(C.byref(d), 1)
         ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
         wptrs = _capi.pointer_array([w.ctypes.data for w in self.w])
         gwptrs = _capi.pointer_array([g.ctypes.data for g in gws])
-        if split_roles:
+        if self.four:
+            rc = lib.deno_spectral4_bwd(C.byref(d), _ptr(gy), _ptr(self.x), _ptr(self.z), _ptr(self.xhat), wptrs,
+                                        _ptr(self.lin_w), _ptr(self.tw), _ptr(gx), gwptrs, _ptr(glw), _ptr(glb), _ptr(ws),
+                                        nws, None, None)
+        elif split_roles:
             ov = _capi.Overlap()
             _capi.check(lib, lib.deno_overlap_create(C.byref(ov)), "deno_overlap_create")
             rc = lib.deno_spectral_bwd_overlap(C.byref(d), _ptr(gy), _ptr(self.x), _ptr(self.z), _ptr(self.xhat), wptrs,

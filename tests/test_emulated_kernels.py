@@ -174,3 +174,70 @@ def test_emulated_split_role_backward_equals_fused(idx):
     for a, b in zip(fused[1], split[1]):
         assert np.array_equal(a, b)
     assert np.array_equal(fused[2], split[2]) and np.array_equal(fused[3], split[3])
+
+
+CASES4 = [
+    # spatial (x, y, z, t), modes, B, cin, cout, act
+    ((6, 7, 5, 3), (2, 3, 2, 2), 2, 3, 2, "gelu"),        # the fixture's geometry: odd sizes, t = 3 as in the reference
+    ((4, 4, 6, 8), (2, 1, 6, 5), 1, 2, 3, "identity"),    # every z mode kept (m3 = Z), Nyquist bin on t, 2 * m1 = X
+    ((5, 6, 4, 6), (1, 2, 3, 2), 3, 4, 4, "tanh"),
+]
+
+
+def _truth4(x, ws, lin_w, lin_b, modes, act, cot):
+    """float64 torch statement of act(SpectralConv4d(x) + conv1x1(x) + b) and its gradients (oracle/fno_port.py)."""
+    import torch
+    from oracle import fno_port
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    wt = [torch.from_numpy(w).to(torch.complex128).requires_grad_(True) for w in ws]
+    lw = torch.from_numpy(lin_w).double().requires_grad_(True)
+    lb = torch.from_numpy(lin_b).double().requires_grad_(True)
+    B, cin = x.shape[:2]
+    spec = fno_port.spectral_conv4d(xt, wt, modes)
+    byp = torch.nn.functional.conv1d(xt.reshape(B, cin, -1), lw.reshape(lw.shape[0], cin, 1), lb).reshape(spec.shape)
+    y = fno_port.activation_fn(act)(spec + byp)
+    (y * torch.from_numpy(cot).double()).sum().backward()
+    return y.detach().numpy(), xt.grad.numpy(), [w.grad.numpy() for w in wt], lw.grad.numpy(), lb.grad.numpy()
+
+
+@pytest.mark.parametrize("idx", range(len(CASES4)))
+def test_emulated_4d_layer_matches_float64_reference_algorithm(idx):
+    """deno_spectral4_fwd / _bwd (planes (z, t) with a one-sided row axis, two outer-axis passes, four weight blocks)
+    against the reference algorithm of Demo/Turbulence_3d+t/FNO_HIT.py:31-78 in float64, forward and every gradient."""
+    spatial, modes, B, cin, cout, act = CASES4[idx]
+    rng = np.random.default_rng(400 + idx)
+    x = rng.standard_normal((B, cin) + spatial).astype(np.float32)
+    ws = [((rng.standard_normal((cin, cout) + modes) + 1j * rng.standard_normal((cin, cout) + modes)) / cin)
+          .astype(np.complex64) for _ in range(4)]
+    lin_w = (rng.standard_normal((cout, cin, 1, 1, 1, 1)) / np.sqrt(cin)).astype(np.float32)
+    lin_b = rng.standard_normal(cout).astype(np.float32)
+    cot = rng.standard_normal((B, cout) + spatial).astype(np.float32)
+    layer = emu_harness.EmuLayer(x, ws, lin_w, lin_b, modes, act)
+    y = layer.forward(save=True)
+    ty, tgx, tgw, tglw, tglb = _truth4(x, ws, lin_w, lin_b, modes, act, cot)
+    assert np.isfinite(y).all()
+    assert rel_l2(y, ty) < TOL
+    gx, gws, glw, glb = layer.backward(cot)
+    assert np.isfinite(gx).all()
+    assert rel_l2(gx, tgx) < TOL
+    for g, t in zip(gws, tgw):
+        assert rel_l2(g, t) < TOL
+    assert rel_l2(glw.reshape(tglw.shape), tglw) < TOL
+    assert rel_l2(glb, tglb) < TOL
+
+
+def test_emulated_4d_layer_matches_reference_fixture():
+    """The bare SpectralConv4d of the reference (zero bypass, identity) against its own fixture (tests/golden/layer4d.npz)."""
+    g = load_golden("layer4d")
+    m = g["meta"]
+    p = g["params"]
+    x = g["inputs"]["x"].numpy()
+    ws = [p[f"weights{j}"].numpy() for j in (1, 2, 3, 4)]
+    cin, cout = ws[0].shape[:2]
+    layer = emu_harness.EmuLayer(x, ws, np.zeros((cout, cin, 1, 1, 1, 1), np.float32), None, tuple(m["modes"]), "identity")
+    y = layer.forward()
+    assert rel_l2(y, g["out"]) < TOL
+    gx, gws, _, _ = layer.backward(g["cot"].numpy())
+    assert rel_l2(gx, g["grad_inputs"]["x"]) < TOL
+    for j, gw in enumerate(gws):
+        assert rel_l2(gw, g["grads"][f"weights{j + 1}"].numpy()) < TOL
