@@ -265,3 +265,54 @@ class PortTrainer:
         loss.backward()
         self.opt.step()
         return loss.item()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Adaptive Fourier layers: AdaptiveFourier1d/2d/3d,
+# /root/reference/Models/fno/spectral_layers.py:341-573.  Pinned by tests/golden/afno{1,2,3}d*.npz
+# (tests/golden/make_golden_afno.py imports the reference classes).
+# ----------------------------------------------------------------------------------------------------------------
+def afno_kept_modes(spatial: Sequence[int], hard_thresholding_fraction: float) -> int:
+    """How many bins of the HALF-SPECTRUM (last) axis the block-diagonal MLP touches.  The reference computes
+    ``total_modes = prod(spatial) // 2 + 1`` (``N // 2 + 1`` in 1-D; spectral_layers.py:394, :470, :547),
+    ``kept = int(total_modes * fraction)`` and slices the LAST axis with ``[..., :kept]`` - so in 2-D / 3-D the default
+    fraction 1 keeps the whole axis and only a small fraction truncates it.  Bins beyond it stay zero."""
+    n = 1
+    for v in spatial:
+        n *= int(v)
+    kept = int((n // 2 + 1) * hard_thresholding_fraction)
+    return max(0, min(kept, int(spatial[-1]) // 2 + 1))
+
+
+def afno_filter(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, *,
+                num_blocks: int, sparsity_threshold: float = 0.01, hard_thresholding_fraction: float = 1.0,
+                activation="gelu") -> torch.Tensor:
+    """``AdaptiveFourier{1,2,3}d.forward`` (spectral_layers.py:383-409, :457-487, :533-565), any of 1-3 spatial axes:
+    ortho ``rfftn`` -> channels split into ``num_blocks`` blocks -> per bin ``act(x W1 + b1) W2 + b2`` with complex
+    block-diagonal weights ``(blocks, block, block)``, the activation applied to real and imaginary parts separately
+    (``view_as_real``) -> soft-shrink of real and imaginary parts -> ortho ``irfftn(s=...)`` -> ``+ x``.  Only
+    ``hidden_size_factor = 1`` runs in the reference (``weights2`` is created ``(blocks, block, block * factor)`` but
+    contracted over its FIRST block axis, :372-374/:381)."""
+    nd = x.dim() - 2
+    dims = list(range(-nd, 0))
+    B, C = x.shape[:2]
+    spatial = tuple(x.shape[2:])
+    act = activation_fn(activation)
+    xf = torch.fft.rfftn(x, dim=dims, norm="ortho")
+    fshape = tuple(xf.shape[2:])
+    bs = C // num_blocks
+    xf = xf.reshape((B, num_blocks, bs) + fshape)
+    kept = afno_kept_modes(spatial, hard_thresholding_fraction)
+    letters = "jkl"[:nd]
+    eq = f"bni{letters},nio->bno{letters}"
+    tail = (None,) * nd
+    cdt = xf.dtype
+    h_in = xf[..., :kept]
+    h = torch.einsum(eq, h_in, w1.to(cdt)) + b1.to(cdt)[(None, slice(None), slice(None)) + tail]
+    h = torch.view_as_complex(act(torch.view_as_real(h)))
+    o = torch.einsum(eq, h, w2.to(cdt)) + b2.to(cdt)[(None, slice(None), slice(None)) + tail]
+    out = torch.zeros_like(xf)
+    out[..., :kept] = o
+    out = torch.view_as_complex(F.softshrink(torch.view_as_real(out), lambd=sparsity_threshold))
+    out = out.reshape((B, C) + fshape)
+    return torch.fft.irfftn(out, s=spatial, dim=dims, norm="ortho") + x

@@ -162,3 +162,36 @@ def test_port_fno4d_matches_reference():
     assert rel_l2(x.grad, g["grad_inputs"]["x"]) < TOL
     for k, p in params.items():
         assert rel_l2(p.grad, g["grads"][k]) < 5 * TOL, k
+
+
+# ---- adaptive Fourier layers (spectral_layers.py:341-573) ------------------------------
+AFNO = golden_names("afno")
+
+
+def test_afno_fixture_inventory():
+    assert {load_golden(n)["meta"]["ndim"] for n in AFNO} == {1, 2, 3} and len(AFNO) >= 5
+
+
+@pytest.mark.parametrize("name", AFNO)
+def test_port_afno_matches_reference(name):
+    g = load_golden(name)
+    m = g["meta"]
+    x = g["inputs"]["x"].clone().requires_grad_(True)
+    p = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    y = fno_port.afno_filter(x, p["weights1"], p["bias1"], p["weights2"], p["bias2"], num_blocks=m["num_blocks"],
+                             sparsity_threshold=m["sparsity_threshold"],
+                             hard_thresholding_fraction=m["hard_thresholding_fraction"], activation=m["activation"])
+    assert rel_l2(y, g["out"]) < TOL
+    (y * g["cot"]).sum().backward()
+    assert rel_l2(x.grad, g["grad_inputs"]["x"]) < TOL
+    for k, v in p.items():
+        assert rel_l2(v.grad, g["grads"][k]) < TOL, k
+
+
+def test_afno_kept_modes_follows_the_reference_slice():
+    # 2-D / 3-D: total_modes counts the whole grid, so fraction 1 keeps the full half-spectrum axis
+    assert fno_port.afno_kept_modes((55, 64), 1) == 33
+    assert fno_port.afno_kept_modes((6, 9), 0.1) == 2          # int(28 * 0.1)
+    assert fno_port.afno_kept_modes((16,), 0.5) == 4            # int(9 * 0.5)
+    assert fno_port.afno_kept_modes((15,), 1) == 8
+    assert fno_port.afno_kept_modes((4, 4), 0.01) == 0
