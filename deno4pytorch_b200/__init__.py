@@ -8,7 +8,8 @@ __version__ = "0.1.0"
 _LAZY = {
     "SpectralConv1d": "spectral_layers", "SpectralConv2d": "spectral_layers", "SpectralConv3d": "spectral_layers",
     "FNO1d": "FNOs", "FNO2d": "FNOs", "FNO3d": "FNOs",
-    "spectral_conv": "functional",
+    "AdaptiveFourier1d": "spectral_layers", "AdaptiveFourier2d": "spectral_layers", "AdaptiveFourier3d": "spectral_layers",
+    "spectral_conv": "functional", "afno_filter": "functional",
 }
 
 

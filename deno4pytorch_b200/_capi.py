@@ -67,6 +67,35 @@ def make_desc4(batch, cin, cout, spatial, modes, act) -> SpectralDesc4:
     return d
 
 
+class AfnoDesc(C.Structure):
+    """struct deno_afno_desc (include/deno_afno.h)"""
+    _fields_ = [
+        ("ndim", C.c_int32),
+        ("batch", C.c_int32),
+        ("channels", C.c_int32),
+        ("num_blocks", C.c_int32),
+        ("spatial", C.c_int32 * 3),
+        ("modes_last", C.c_int32),
+        ("act", C.c_int32),
+        ("sparsity_threshold", C.c_float),
+        ("flags", C.c_int32),
+    ]
+
+
+def make_afno_desc(batch, channels, num_blocks, spatial, modes_last, act, sparsity_threshold) -> AfnoDesc:
+    nd = len(spatial)
+    assert 1 <= nd <= 3
+    d = AfnoDesc()
+    d.ndim, d.batch, d.channels, d.num_blocks = nd, int(batch), int(channels), int(num_blocks)
+    for a in range(3):
+        d.spatial[a] = int(spatial[a]) if a < nd else 0
+    d.modes_last = int(modes_last)
+    d.act = ACTIVATION_IDS[act] if isinstance(act, str) else int(act)
+    d.sparsity_threshold = float(sparsity_threshold)
+    d.flags = 0
+    return d
+
+
 class FnoDesc(C.Structure):
     """struct deno_fno_desc (include/deno_fno.h)"""
     _fields_ = [
@@ -109,6 +138,7 @@ class ProfileRecord(C.Structure):
 _DESC_P = C.POINTER(SpectralDesc)
 _DESC4_P = C.POINTER(SpectralDesc4)
 _FNO_P = C.POINTER(FnoDesc)
+_AFNO_P = C.POINTER(AfnoDesc)
 _V = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
 
@@ -149,6 +179,12 @@ _PROTOTYPES = {
     "deno_spectral4_bwd": (C.c_int, [_DESC4_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _PP, C.c_void_p,
                                      C.c_void_p, C.c_void_p, _PP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p, C.POINTER(Overlap)]),
+    "deno_afno_num_modes": (C.c_size_t, [_AFNO_P]),
+    "deno_afno_twiddle_bytes": (C.c_size_t, [_AFNO_P]),
+    "deno_afno_twiddle_fill": (C.c_int, [_AFNO_P, C.c_void_p, C.c_size_t]),
+    "deno_afno_workspace_bytes": (C.c_size_t, [_AFNO_P, C.c_int]),
+    "deno_afno_fwd": (C.c_int, [_AFNO_P, _V, _V, _V, _V, _V, _V, _V, _V, _V, C.c_size_t, _V]),
+    "deno_afno_bwd": (C.c_int, [_AFNO_P, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V, C.c_size_t, _V]),
     "deno_fno_supported": (C.c_int, [_FNO_P]),
     "deno_fno_workspace_bytes": (C.c_size_t, [_FNO_P, C.c_int]),
     "deno_fno_lift_fwd": (C.c_int, [_FNO_P, _V, _V, _V, _V, _V, _V]),

@@ -25,7 +25,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    deps += [os.path.join(os.path.dirname(HERE), "include", h) for h in ("deno_spectral.h", "deno_fno.h", "deno_dp.h")]
+    deps += [os.path.join(os.path.dirname(HERE), "include", h) for h in ("deno_spectral.h", "deno_fno.h", "deno_dp.h", "deno_afno.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -7,6 +7,7 @@
 #include "../../include/deno_spectral.h"
 #include "../../include/deno_fno.h"
 #include "../../include/deno_dp.h"
+#include "../../include/deno_afno.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -19,6 +20,7 @@
 
 #include "spectral_simt.cuh"
 #include "fno_pointwise.cuh"
+#include "afno_pointwise.cuh"
 #include "dp_fused.cuh"
 #ifndef DENO_EMULATE
 #include "spectral_tc.cuh"
@@ -61,6 +63,9 @@ struct Shape {
   // 4-D stand-alone layer (deno_spectral4_*): two outer axes X1, X2 (X = X1 * X2 planes per batch entry, KX = KX1 * KX2),
   // a ONE-SIDED row axis (KH = mH: the reference keeps [:m3] only) and four weight blocks.  Zero for ndim < 4.
   int X1, X2, mX1, mX2, KX1, KX2, KX14, KX24;
+  // adaptive Fourier layers (deno_afno_*): the SIMT transform kernels only - the tensor-core variants have not been
+  // measured at full-spectrum shapes (KH = H, MW = W / 2 + 1)
+  bool simt_only;
 };
 
 inline int num_weight_blocks(const Shape& s) { return s.ndim == 4 ? 4 : (1 << (s.ndim - 1)); }
@@ -102,6 +107,7 @@ int parse_desc(const deno_spectral_desc* d, Shape& s) {
   s.Q = s.KH * s.MW;
   s.M = s.KX * s.Q;
   s.X1 = s.X2 = s.mX1 = s.mX2 = s.KX1 = s.KX2 = s.KX14 = s.KX24 = 0;
+  s.simt_only = false;
   return DENO_OK;
 }
 
@@ -131,6 +137,7 @@ int parse_desc4(const deno_spectral_desc4* d, Shape& s) {
   s.S = (long long)s.X * s.H * s.W;
   s.Q = s.KH * s.MW;
   s.M = s.KX * s.Q;
+  s.simt_only = false;
   return DENO_OK;
 }
 
@@ -924,7 +931,7 @@ int launch_analysis(const Shape& s, int channels, const float* u, const float* z
                     const TwPtrs& tw, float scale, int herm, cudaStream_t st) {
 #ifndef DENO_EMULATE
   {
-    const PathPref pref = path_pref();
+    const PathPref pref = s.simt_only ? PathPref::Simt : path_pref();
     if (pref != PathPref::Simt) {
       int trc = try_launch_analysis_tma(s, channels, u, z, gz_out, out, tw, scale, herm, st);
       if (trc >= 0) return trc;
@@ -1555,7 +1562,7 @@ int launch_synthesis(const Shape& s, int cin, int cout, const float2* spec, cons
   const int grid = s.B * s.X * c.tiles;
   const char* label = (bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr) ? "plane_synthesis" : "plane_synthesis_bwd";
 #ifndef DENO_EMULATE
-  const PathPref pref = path_pref();
+  const PathPref pref = s.simt_only ? PathPref::Simt : path_pref();
   if (pref != PathPref::Simt) {
     const bool is_fwd = (bias != nullptr || act != DENO_ACT_IDENTITY || z != nullptr);
     rc = try_launch_synthesis_tc(s, p, tw, act, is_fwd ? "plane_synthesis_tc" : "plane_synthesis_bwd_tc", urow, st);
@@ -1799,6 +1806,7 @@ Shape proj_wgrad_shape(const FnoShape& f) {
   s.KX4 = s.KH4 = s.MWp = 4;
   s.S = f.g.nppts;
   s.Q = 1; s.M = 1; s.act = 0;
+  s.simt_only = false;
   return s;
 }
 
@@ -1901,6 +1909,127 @@ int launch_proj_bwd_tc(const tc::ProjTcParams& p, int& nparts, cudaStream_t st) 
     case 64: CALL(64) break;         \
     default: return fail(DENO_E_UNSUPPORTED, "width not built"); \
   }
+
+// ------------------------------------------------------------------------------------------
+// Adaptive Fourier layers (include/deno_afno.h)
+// ------------------------------------------------------------------------------------------
+struct AfnoShape {
+  Shape s;            // transform geometry: CI = CO = C, every frequency of the leading axes, modes_last bins of the last
+  int NB, BS;
+  float lambda;
+};
+
+// AdaptiveFourier{1,2,3}d (/root/reference/Models/fno/spectral_layers.py:341-573).  The leading axes keep ALL their
+// frequencies as a one-sided table f_k = k (KH = H, KX = X: mH = H makes every `k < mH ? k : ...` pick f = k), the last
+// axis its first modes_last half-spectrum bins.
+int parse_afno(const deno_afno_desc* d, AfnoShape& a) {
+  if (d == nullptr) return fail(DENO_E_INVALID, "null descriptor");
+  if (d->ndim < 1 || d->ndim > 3) return fail(DENO_E_INVALID, "ndim must be 1, 2 or 3");
+  if (d->batch < 1 || d->channels < 1 || d->num_blocks < 1) return fail(DENO_E_INVALID, "batch/channels/num_blocks must be positive");
+  if (d->channels % d->num_blocks != 0)
+    return fail(DENO_E_INVALID, "hidden_size should be divisible by num_blocks (the reference asserts, spectral_layers.py:352)");
+  if (d->flags != 0) return fail(DENO_E_INVALID, "flags must be 0");
+  if (d->act < DENO_ACT_IDENTITY || d->act > DENO_ACT_LEAKYRELU) return fail(DENO_E_INVALID, "unknown activation id");
+  if (!(d->sparsity_threshold >= 0.0f)) return fail(DENO_E_INVALID, "sparsity_threshold must be >= 0 (softshrink)");
+  for (int k = 0; k < d->ndim; ++k)
+    if (d->spatial[k] < 1) return fail(DENO_E_INVALID, "spatial sizes must be positive");
+  const int nd = d->ndim;
+  Shape& s = a.s;
+  memset(&s, 0, sizeof(s));
+  s.ndim = nd;
+  s.B = d->batch; s.CI = s.CO = d->channels; s.act = d->act;
+  s.W = d->spatial[nd - 1];
+  s.mW = d->modes_last;
+  if (s.mW < 1 || s.mW > s.W / 2 + 1) return fail(DENO_E_INVALID, "modes_last must be 1 .. spatial[last] / 2 + 1");
+  s.H = nd >= 2 ? d->spatial[nd - 2] : 1;
+  s.X = nd == 3 ? d->spatial[0] : 1;
+  s.mH = nd >= 2 ? s.H : 0;
+  s.mX = nd == 3 ? s.X : 0;
+  s.KH = nd >= 2 ? s.H : 1;
+  s.KX = nd == 3 ? s.X : 1;
+  s.MW = s.mW;
+  s.KH4 = round_up(s.KH, 4);
+  s.KX4 = round_up(s.KX, 4);
+  s.MWp = round_up(s.MW, 4);
+  s.S = (long long)s.X * s.H * s.W;
+  s.Q = s.KH * s.MW;
+  if ((long long)s.KX * s.Q > 0x7fffffffLL) return fail(DENO_E_UNSUPPORTED, "spectrum too large");
+  s.M = s.KX * s.Q;
+  s.simt_only = true;
+  a.NB = d->num_blocks;
+  a.BS = d->channels / d->num_blocks;
+  a.lambda = d->sparsity_threshold;
+  if (a.BS > kAfnoMaxBlock) return fail(DENO_E_UNSUPPORTED, "block size (hidden_size / num_blocks) above 64 is not built");
+  return DENO_OK;
+}
+
+// Launch geometry of the block MLP kernels (pure function of the shape: workspace sizing must agree).
+struct AfnoCfg { int TP, tpb, chunks; size_t smem; };
+int afno_cfg(const AfnoShape& a, bool backward, AfnoCfg& c) {
+  const int threads = backward ? kAfnoBwdThreads : kAfnoFwdThreads;
+  const int ntile_bufs = backward ? 4 : 2;
+  int TP = threads;
+  while (TP > 32 && afno_smem_bytes(a.BS, TP, ntile_bufs) > (size_t)200 * 1024) TP /= 2;
+  while (TP > 32 && TP / 2 >= a.s.M) TP /= 2;                    // tiny spectra: no point in mostly-empty tiles
+  c.TP = TP;
+  c.smem = afno_smem_bytes(a.BS, TP, ntile_bufs);
+  if (c.smem > (size_t)kMaxSmemBytes) return fail(DENO_E_UNSUPPORTED, "afno block MLP does not fit shared memory");
+  c.tpb = (a.s.M + TP - 1) / TP;
+  const long long ntiles = (long long)a.s.B * c.tpb;
+  long long chunks = (148LL * 4 + a.NB - 1) / a.NB;              // about four CTAs per SM over all blocks
+  if (chunks > ntiles) chunks = ntiles;
+  if (chunks < 1) chunks = 1;
+  c.chunks = (int)chunks;
+  return DENO_OK;
+}
+
+struct AfnoWs { size_t xhat, yhat, t2, v, partial, total; };
+int afno_ws(const AfnoShape& a, bool backward, AfnoWs& w) {
+  const Shape& s = a.s;
+  AfnoCfg c;
+  int rc = afno_cfg(a, backward, c);
+  if (rc != DENO_OK) return rc;
+  const size_t spec = align_up((size_t)s.B * s.CI * s.M * 8);
+  size_t off = 0;
+  w.xhat = off; off += spec;                                     // forward: X^ (unless saved by the caller); backward: G^
+  w.yhat = off; off += spec;                                     // forward: filtered spectrum; backward: G^x
+  w.t2 = off;   off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.v = off;    off += (s.ndim == 3) ? align_up((size_t)s.B * s.X * s.CI * s.Q * 8) : 0;
+  w.partial = off; off += backward ? align_up((size_t)c.chunks * afno_partial(a.NB, a.BS).total * 4) : 0;
+  w.total = off;
+  return DENO_OK;
+}
+
+// identity bypass of the residual `+ x`: a C x C unit matrix behind the DFT tables of the transform shape
+size_t afno_eye_offset(const Shape& s) { return (tw_layout(s).total + 63) / 64 * 64; }
+
+int launch_afno_mlp(const AfnoShape& a, bool backward, const float2* xin, const float2* gin, float2* out, const void* w1,
+                    const void* b1, const void* w2, const void* b2, float* partial, cudaStream_t st) {
+  AfnoCfg c;
+  int rc = afno_cfg(a, backward, c);
+  if (rc != DENO_OK) return rc;
+  AfnoParams p;
+  p.xin = xin; p.gin = gin; p.out = out;
+  p.w1 = static_cast<const float2*>(w1); p.b1 = static_cast<const float2*>(b1);
+  p.w2 = static_cast<const float2*>(w2); p.b2 = static_cast<const float2*>(b2);
+  p.partial = partial;
+  p.B = a.s.B; p.C = a.s.CI; p.NB = a.NB; p.BS = a.BS; p.M = a.s.M;
+  p.act = a.s.act; p.lambda = a.lambda;
+  p.TP = c.TP; p.tpb = c.tpb; p.pitch = afno_partial(a.NB, a.BS).total;
+  const dim3 grid((unsigned)c.chunks, (unsigned)a.NB);
+  if (!backward) {
+    rc = allow_smem(afno_mlp_fwd_kernel, c.smem, "afno_mlp_fwd");
+    if (rc != DENO_OK) return rc;
+    prof_before("afno_mlp_fwd", st);
+    DENO_LAUNCH(afno_mlp_fwd_kernel, grid, dim3(kAfnoFwdThreads), c.smem, st, p);
+    return check_launch("afno_mlp_fwd", st);
+  }
+  rc = allow_smem(afno_mlp_bwd_kernel, c.smem, "afno_mlp_bwd");
+  if (rc != DENO_OK) return rc;
+  prof_before("afno_mlp_bwd", st);
+  DENO_LAUNCH(afno_mlp_bwd_kernel, grid, dim3(kAfnoBwdThreads), c.smem, st, p);
+  return check_launch("afno_mlp_bwd", st);
+}
 
 }  // namespace
 
@@ -2305,6 +2434,142 @@ int deno_spectral4_bwd(const deno_spectral_desc4* desc, const float* gy, const f
   if (rc != DENO_OK) return rc;
   return spectral_bwd_impl(s, gy, x, z_saved, xhat_saved, w_blocks, lin_w, twiddles, gx, gw_blocks, glin_w, glin_b,
                            workspace, workspace_bytes, stream, ov);
+}
+
+// ---- adaptive Fourier layers (include/deno_afno.h) ----
+size_t deno_afno_num_modes(const deno_afno_desc* desc) {
+  AfnoShape a;
+  if (parse_afno(desc, a) != DENO_OK) return 0;
+  return (size_t)a.s.M;
+}
+
+size_t deno_afno_twiddle_bytes(const deno_afno_desc* desc) {
+  AfnoShape a;
+  if (parse_afno(desc, a) != DENO_OK) return 0;
+  return (afno_eye_offset(a.s) + (size_t)a.s.CI * a.s.CI) * sizeof(float);
+}
+
+int deno_afno_twiddle_fill(const deno_afno_desc* desc, void* host_buf, size_t bytes) {
+  AfnoShape a;
+  int rc = parse_afno(desc, a);
+  if (rc != DENO_OK) return rc;
+  const size_t eye = afno_eye_offset(a.s), C = (size_t)a.s.CI;
+  if (host_buf == nullptr || bytes < (eye + C * C) * sizeof(float)) return fail(DENO_E_INVALID, "twiddle buffer too small");
+  if ((rc = twiddle_fill_shape(a.s, host_buf, bytes))) return rc;
+  float* base = static_cast<float*>(host_buf);
+  for (size_t k = tw_layout(a.s).total; k < eye; ++k) base[k] = 0.f;
+  for (size_t o = 0; o < C; ++o)
+    for (size_t i = 0; i < C; ++i) base[eye + o * C + i] = (o == i) ? 1.f : 0.f;
+  return DENO_OK;
+}
+
+size_t deno_afno_workspace_bytes(const deno_afno_desc* desc, int backward) {
+  AfnoShape a;
+  if (parse_afno(desc, a) != DENO_OK) return 0;
+  AfnoWs w;
+  if (afno_ws(a, backward != 0, w) != DENO_OK) return 0;
+  return w.total;
+}
+
+int deno_afno_fwd(const deno_afno_desc* desc, const float* x, const void* w1, const void* b1, const void* w2,
+                  const void* b2, const void* twiddles, float* y, void* xhat_saved, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  AfnoShape a;
+  int rc = parse_afno(desc, a);
+  if (rc != DENO_OK) return rc;
+  if (!x || !w1 || !b1 || !w2 || !b2 || !twiddles || !y || !workspace) return fail(DENO_E_INVALID, "deno_afno_fwd: null pointer argument");
+  AfnoWs ws;
+  if ((rc = afno_ws(a, false, ws))) return rc;
+  if (workspace_bytes < ws.total) return fail(DENO_E_WORKSPACE, "workspace too small for deno_afno_fwd");
+  const Shape& s = a.s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* wsb = static_cast<char*>(workspace);
+  const TwPtrs tw = tw_ptrs(s, twiddles);
+  const float* eye = static_cast<const float*>(twiddles) + afno_eye_offset(s);
+  float2* xhat = xhat_saved ? static_cast<float2*>(xhat_saved) : reinterpret_cast<float2*>(wsb + ws.xhat);
+  float2* yhat = reinterpret_cast<float2*>(wsb + ws.yhat);
+  const float ortho = (float)(1.0 / sqrt((double)s.S));
+  // X^ = rfftn(x, norm="ortho"), every frequency of the leading axes
+  if (s.ndim == 3) {
+    float2* t2 = reinterpret_cast<float2*>(wsb + ws.t2);
+    if ((rc = launch_analysis(s, s.CI, x, nullptr, nullptr, t2, tw, ortho, 0, st))) return rc;
+    if ((rc = launch_outer(s, s.CI, true, t2, xhat, tw, st))) return rc;
+  } else if ((rc = launch_analysis(s, s.CI, x, nullptr, nullptr, xhat, tw, ortho, 0, st))) {
+    return rc;
+  }
+  if ((rc = launch_afno_mlp(a, false, xhat, nullptr, yhat, w1, b1, w2, b2, nullptr, st))) return rc;
+  // y = irfftn(., norm="ortho") + x : the residual is the synthesis kernel's bypass with a unit matrix
+  const float2* spec = yhat;
+  if (s.ndim == 3) {
+    float2* v = reinterpret_cast<float2*>(wsb + ws.v);
+    if ((rc = launch_outer(s, s.CO, false, yhat, v, tw, st))) return rc;
+    spec = v;
+  }
+  return launch_synthesis(s, s.CI, s.CO, spec, x, eye, s.CI, 1, nullptr, y, nullptr, tw, ortho, 1, DENO_ACT_IDENTITY,
+                          nullptr, st);
+}
+
+int deno_afno_bwd(const deno_afno_desc* desc, const float* gy, const void* xhat_saved, const void* w1,
+                  const void* b1, const void* w2, const void* b2, const void* twiddles, float* gx, void* gw1,
+                  void* gb1, void* gw2, void* gb2, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  AfnoShape a;
+  int rc = parse_afno(desc, a);
+  if (rc != DENO_OK) return rc;
+  if (!gy || !xhat_saved || !w1 || !b1 || !w2 || !b2 || !twiddles || !workspace)
+    return fail(DENO_E_INVALID, "deno_afno_bwd: null pointer argument");
+  const int nw = (gw1 != nullptr) + (gb1 != nullptr) + (gw2 != nullptr) + (gb2 != nullptr);
+  if (nw != 0 && nw != 4) return fail(DENO_E_INVALID, "deno_afno_bwd: pass all four parameter gradients or none");
+  if (nw == 0 && gx == nullptr) return DENO_OK;
+  AfnoWs ws;
+  if ((rc = afno_ws(a, true, ws))) return rc;
+  if (workspace_bytes < ws.total) return fail(DENO_E_WORKSPACE, "workspace too small for deno_afno_bwd");
+  const Shape& s = a.s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* wsb = static_cast<char*>(workspace);
+  const TwPtrs tw = tw_ptrs(s, twiddles);
+  const float* eye = static_cast<const float*>(twiddles) + afno_eye_offset(s);
+  float2* ghat = reinterpret_cast<float2*>(wsb + ws.xhat);
+  float2* gxhat = reinterpret_cast<float2*>(wsb + ws.yhat);
+  float* partial = reinterpret_cast<float*>(wsb + ws.partial);
+  const float ortho = (float)(1.0 / sqrt((double)s.S));
+  // G^ = (c_l / sqrt(S)) DFT(gy): the adjoint of the ortho C2R synthesis
+  if (s.ndim == 3) {
+    float2* t2 = reinterpret_cast<float2*>(wsb + ws.t2);
+    if ((rc = launch_analysis(s, s.CO, gy, nullptr, nullptr, t2, tw, ortho, 1, st))) return rc;
+    if ((rc = launch_outer(s, s.CO, true, t2, ghat, tw, st))) return rc;
+  } else if ((rc = launch_analysis(s, s.CO, gy, nullptr, nullptr, ghat, tw, ortho, 1, st))) {
+    return rc;
+  }
+  if ((rc = launch_afno_mlp(a, true, static_cast<const float2*>(xhat_saved), ghat, gx != nullptr ? gxhat : nullptr, w1, b1,
+                            w2, b2, nw ? partial : nullptr, st)))
+    return rc;
+  if (nw) {
+    AfnoCfg c;
+    if ((rc = afno_cfg(a, true, c))) return rc;
+    const AfnoPartial pl = afno_partial(a.NB, a.BS);
+    const int nwf = a.NB * a.BS * a.BS * 2, nbf = a.NB * a.BS * 2;
+    if ((rc = launch_reduce(partial + pl.w1, c.chunks, pl.total, nwf + nbf, nwf, static_cast<float*>(gw1),
+                            static_cast<float*>(gb1), "afno_wgrad_reduce", st)))
+      return rc;
+    if ((rc = launch_reduce(partial + pl.w2, c.chunks, pl.total, nwf + nbf, nwf, static_cast<float*>(gw2),
+                            static_cast<float*>(gb2), "afno_wgrad_reduce", st)))
+      return rc;
+  }
+  if (gx != nullptr) {
+    // gx = (1 / sqrt(S)) Re sum G^x e^{+i theta} + gy   (no c_l: adjoint of the R2C analysis; the residual's identity)
+    const float2* spec = gxhat;
+    if (s.ndim == 3) {
+      float2* v = reinterpret_cast<float2*>(wsb + ws.v);
+      if ((rc = launch_outer(s, s.CI, false, gxhat, v, tw, st))) return rc;
+      spec = v;
+    }
+    if ((rc = launch_synthesis(s, s.CO, s.CI, spec, gy, eye, s.CI, 1, nullptr, gx, nullptr, tw, ortho, 0, DENO_ACT_IDENTITY,
+                               nullptr, st)))
+      return rc;
+  }
+  return DENO_OK;
 }
 
 int deno_overlap_create(deno_overlap* out) {

@@ -297,3 +297,123 @@ def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor], lin_w: torch
     if activation not in _capi.ACTIVATION_IDS:
         raise ValueError(f"unknown activation {activation!r}")
     return _SpectralConvFn.apply(x, lin_w, lin_b, modes, activation, torch.is_grad_enabled(), *weights)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Adaptive Fourier layers (include/deno_afno.h)
+# ----------------------------------------------------------------------------------------------------------------
+def afno_kept_modes(spatial: Sequence[int], hard_thresholding_fraction: float) -> int:
+    """Bins of the half-spectrum axis the reference's ``[..., :kept_modes]`` slice leaves
+    (/root/reference/Models/fno/spectral_layers.py:394-395, :470-471, :547-548): ``kept_modes`` is computed from the
+    size of the WHOLE grid but applied to the last axis."""
+    n = 1
+    for v in spatial:
+        n *= int(v)
+    kept = int((n // 2 + 1) * hard_thresholding_fraction)
+    return max(0, min(kept, int(spatial[-1]) // 2 + 1))
+
+
+def _afno_twiddles(d: "_capi.AfnoDesc", device: torch.device) -> torch.Tensor:
+    key = ("afno", device.index, d.ndim, d.channels, tuple(d.spatial), d.modes_last)
+    t = _TWIDDLES.get(key)
+    if t is None:
+        L = lib()
+        nbytes = L.deno_afno_twiddle_bytes(C.byref(d))
+        if nbytes == 0:
+            raise _capi.DenoError(L.deno_last_error().decode())
+        host = np.zeros(nbytes // 4, dtype=np.float32)
+        _capi.check(L, L.deno_afno_twiddle_fill(C.byref(d), host.ctypes.data_as(C.c_void_p), nbytes), "deno_afno_twiddle_fill")
+        t = torch.from_numpy(host).to(device)
+        _TWIDDLES[key] = t
+    return t
+
+
+def _check_afno_param(t: torch.Tensor, shape, name: str):
+    if t.dtype != torch.complex64 or tuple(t.shape) != tuple(shape) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA complex64 tensor {tuple(shape)}, got {t.dtype} {tuple(t.shape)} on {t.device}")
+
+
+class _AfnoFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, num_blocks, modes_last, act, lam, save):
+        L = lib()
+        _check_input(x, "input")
+        ndim = x.dim() - 2
+        if ndim not in (1, 2, 3):
+            raise RuntimeError("input must be (B, C, *spatial) with 1-3 spatial dims")
+        B, Cn = x.shape[:2]
+        if Cn % num_blocks != 0:
+            raise RuntimeError(f"hidden_size {Cn} should be divisble by num_blocks {num_blocks}")
+        bs = Cn // num_blocks
+        _check_afno_param(w1, (num_blocks, bs, bs), "weights1")
+        _check_afno_param(b1, (num_blocks, bs), "bias1")
+        _check_afno_param(w2, (num_blocks, bs, bs), "weights2")
+        _check_afno_param(b2, (num_blocks, bs), "bias2")
+        d = _capi.make_afno_desc(B, Cn, num_blocks, tuple(x.shape[2:]), modes_last, act, lam)
+        needs_grad = bool(save) and any(ctx.needs_input_grad)
+        dev = x.device
+        with torch.cuda.device(dev):
+            xc = x.contiguous()
+            p = [t.detach().contiguous() for t in (w1, b1, w2, b2)]
+            tw = _afno_twiddles(d, dev)
+            y = torch.empty_like(xc)
+            nmodes = L.deno_afno_num_modes(C.byref(d))
+            if nmodes == 0:
+                raise _capi.DenoError(L.deno_last_error().decode())
+            xhat = torch.empty((B, Cn, nmodes), dtype=torch.complex64, device=dev) if needs_grad else None
+            nws = L.deno_afno_workspace_bytes(C.byref(d), 0)
+            if nws == 0:
+                raise _capi.DenoError(L.deno_last_error().decode())
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+            _poison(ws, y, xhat)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = L.deno_afno_fwd(C.byref(d), xc.data_ptr(), p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(),
+                                 p[3].data_ptr(), tw.data_ptr(), y.data_ptr(), None if xhat is None else xhat.data_ptr(),
+                                 ws.data_ptr(), nws, stream)
+            _capi.check(L, rc, "deno_afno_fwd")
+            _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
+        if needs_grad:
+            ctx.save_for_backward(xhat, *p)
+            ctx.desc = d
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        L = lib()
+        xhat, w1, b1, w2, b2 = ctx.saved_tensors
+        d = ctx.desc
+        dev = gy.device
+        need_x = ctx.needs_input_grad[0]
+        need_p = any(ctx.needs_input_grad[1:5])
+        with torch.cuda.device(dev):
+            gy = gy.contiguous()
+            gx = torch.empty_like(gy) if need_x else None
+            gp = [torch.empty_like(t) for t in (w1, b1, w2, b2)] if need_p else [None] * 4
+            nws = L.deno_afno_workspace_bytes(C.byref(d), 1)
+            ws = torch.empty(max(nws, 1), dtype=torch.uint8, device=dev)
+            _poison(ws, gx, *gp)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = L.deno_afno_bwd(C.byref(d), gy.data_ptr(), xhat.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                 b2.data_ptr(), _afno_twiddles(d, dev).data_ptr(), None if gx is None else gx.data_ptr(),
+                                 *[None if g is None else g.data_ptr() for g in gp], ws.data_ptr(), nws, stream)
+            _capi.check(L, rc, "deno_afno_bwd")
+            _LAUNCHES["count"] += L.deno_spectral_last_launch_count()
+        return (gx, gp[0], gp[1], gp[2], gp[3], None, None, None, None, None)
+
+
+def afno_filter(x: torch.Tensor, weights1: torch.Tensor, bias1: torch.Tensor, weights2: torch.Tensor, bias2: torch.Tensor,
+                *, num_blocks: int, sparsity_threshold: float = 0.01, hard_thresholding_fraction: float = 1,
+                activation: str = "gelu") -> torch.Tensor:
+    """``x + irfftn(softshrink(W2^T act(W1^T rfftn(x) + b1) + b2))`` (ortho transforms, block-diagonal complex weights)
+    on the CUDA kernels: one ``AdaptiveFourier{1,2,3}d.forward`` of the reference
+    (/root/reference/Models/fno/spectral_layers.py:383-409, :457-487, :533-565).  ``x`` (B, C, *spatial) fp32 CUDA;
+    weights ``(num_blocks, C/num_blocks, C/num_blocks)`` and biases ``(num_blocks, C/num_blocks)`` complex64.
+    Differentiable w.r.t. x and the four parameters."""
+    if activation not in _capi.ACTIVATION_IDS:
+        raise ValueError(f"unknown activation {activation!r}")
+    _check_input(x, "input")
+    kept = afno_kept_modes(tuple(x.shape[2:]), hard_thresholding_fraction)
+    if kept == 0:
+        return x.clone()          # every bin is masked out: the filter branch is soft-shrink(0) = 0
+    return _AfnoFn.apply(x, weights1, bias1, weights2, bias2, int(num_blocks), kept, activation, float(sparsity_threshold),
+                         torch.is_grad_enabled())

@@ -26,7 +26,7 @@ import torch.nn.functional as F  # noqa: F401
 from torch.nn.parameter import Parameter  # noqa: F401
 
 from .configs import activation_dict, activation_kernel_id, default  # noqa: F401
-from .functional import spectral_conv
+from .functional import afno_filter, spectral_conv
 
 _CONV = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}
 
@@ -144,3 +144,72 @@ class SpectralConv3d(_SpectralConvNd):
     def __init__(self, in_dim, out_dim, modes: tuple, dropout=0.1, norm="ortho", activation="silu",
                  return_freq=False, use_complex=True):
         super().__init__(in_dim, out_dim, modes, dropout, norm, activation, return_freq, use_complex)
+
+
+class _AdaptiveFourierNd(nn.Module):
+    """Adaptive Fourier layer (reference: spectral_layers.py:341-573): ortho ``rfftn`` -> per-bin two-layer complex MLP
+    with block-diagonal weights, activation on real / imaginary parts -> soft-shrink -> ortho ``irfftn`` -> ``+ x``, as
+    ONE fused call (``deno_afno_fwd``, include/deno_afno.h) with a hand-written backward.  Constructor signature,
+    attributes, parameter names / shapes / init as the reference's three classes."""
+    ndim = 0
+
+    def __init__(self, hidden_size, num_blocks, sparsity_threshold, hard_thresholding_fraction, hidden_size_factor,
+                 activation):
+        super().__init__()
+        assert hidden_size % num_blocks == 0, f"hidden_size {hidden_size} should be divisble by num_blocks {num_blocks}"
+        self.hidden_size = hidden_size
+        self.sparsity_threshold = sparsity_threshold
+        self.num_blocks = num_blocks
+        self.block_size = self.hidden_size // self.num_blocks
+        self.hard_thresholding_fraction = hard_thresholding_fraction
+        self.hidden_size_factor = hidden_size_factor
+        self.scale = 0.02
+        self.activation = activation_dict[activation]
+        nb, bs, f = self.num_blocks, self.block_size, self.hidden_size_factor
+        self.weights1 = nn.Parameter(self.scale * torch.rand(nb, bs, bs * f, dtype=torch.cfloat))
+        self.weights2 = nn.Parameter(self.scale * torch.rand(nb, bs, bs * f, dtype=torch.cfloat))
+        self.bias1 = nn.Parameter(self.scale * torch.rand(nb, bs * f, dtype=torch.cfloat))
+        self.bias2 = nn.Parameter(self.scale * torch.rand(nb, bs, dtype=torch.cfloat))
+
+    def forward(self, x):
+        """x: (B, hidden_size, *spatial) fp32 CUDA tensor -> same shape."""
+        if x.dim() != self.ndim + 2:
+            raise RuntimeError(f"expected a (B, C, {self.ndim} spatial dims) input, got {tuple(x.shape)}")
+        if self.hidden_size_factor != 1:
+            # weights2 (blocks, block, block * factor) is contracted over its FIRST block axis with block * factor hidden
+            # channels (spectral_layers.py:372-381): the reference's einsum raises for any factor but 1
+            raise RuntimeError("hidden_size_factor != 1 fails in the reference's second einsum (operand sizes do not match)")
+        act_id = activation_kernel_id(self.activation)
+        if not act_id:
+            raise RuntimeError(f"activation {type(self.activation).__name__} has no fused kernel "
+                               "(identity / gelu / silu / relu / tanh / leakyrelu(0.01))")
+        return afno_filter(x, self.weights1, self.bias1, self.weights2, self.bias2, num_blocks=self.num_blocks,
+                           sparsity_threshold=self.sparsity_threshold,
+                           hard_thresholding_fraction=self.hard_thresholding_fraction, activation=act_id)
+
+
+class AdaptiveFourier1d(_AdaptiveFourierNd):
+    """reference: spectral_layers.py:341-409 (default activation ReLU)."""
+    ndim = 1
+
+    def __init__(self, hidden_size, num_blocks=8, sparsity_threshold=0.01, hard_thresholding_fraction=1,
+                 hidden_size_factor=1, activation="relu"):
+        super().__init__(hidden_size, num_blocks, sparsity_threshold, hard_thresholding_fraction, hidden_size_factor, activation)
+
+
+class AdaptiveFourier2d(_AdaptiveFourierNd):
+    """reference: spectral_layers.py:412-487."""
+    ndim = 2
+
+    def __init__(self, hidden_size, num_blocks=8, sparsity_threshold=0.01, hard_thresholding_fraction=1,
+                 hidden_size_factor=1, activation="gelu"):
+        super().__init__(hidden_size, num_blocks, sparsity_threshold, hard_thresholding_fraction, hidden_size_factor, activation)
+
+
+class AdaptiveFourier3d(_AdaptiveFourierNd):
+    """reference: spectral_layers.py:490-565."""
+    ndim = 3
+
+    def __init__(self, hidden_size, num_blocks=8, sparsity_threshold=0.01, hard_thresholding_fraction=1,
+                 hidden_size_factor=1, activation="gelu"):
+        super().__init__(hidden_size, num_blocks, sparsity_threshold, hard_thresholding_fraction, hidden_size_factor, activation)

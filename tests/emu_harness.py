@@ -26,7 +26,7 @@ def _stale():
     t = os.path.getmtime(OUT)
     deps = [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".cu", ".cuh"))]
     deps += [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(ROOT, "include", "deno_spectral.h"),
-             os.path.join(ROOT, "include", "deno_fno.h")]
+             os.path.join(ROOT, "include", "deno_fno.h"), os.path.join(ROOT, "include", "deno_afno.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -130,6 +130,49 @@ class EmuLayer:
         _capi.check(lib, rc, "deno_spectral_bwd")
         self.bwd_launches = lib.deno_spectral_last_launch_count()
         return gx, gws, glw, glb
+
+
+class EmuAfno:
+    """One adaptive Fourier layer call (include/deno_afno.h) through the emulated C ABI; numpy in, numpy out."""
+
+    def __init__(self, x, w1, b1, w2, b2, num_blocks, modes_last, act, sparsity_threshold):
+        self.lib = load()
+        self.x = np.ascontiguousarray(x, dtype=np.float32)
+        self.p = [np.ascontiguousarray(np.asarray(a).astype(np.complex64)) for a in (w1, b1, w2, b2)]
+        B, Cn = self.x.shape[:2]
+        self.desc = _capi.make_afno_desc(B, Cn, num_blocks, self.x.shape[2:], modes_last, act, sparsity_threshold)
+        nb = self.lib.deno_afno_twiddle_bytes(C.byref(self.desc))
+        if nb == 0:
+            raise _capi.DenoError(self.lib.deno_last_error().decode())
+        self.tw = np.zeros(nb // 4, dtype=np.float32)
+        _capi.check(self.lib, self.lib.deno_afno_twiddle_fill(C.byref(self.desc), _ptr(self.tw), nb), "deno_afno_twiddle_fill")
+        assert np.array_equal(self.tw[-Cn * Cn:].reshape(Cn, Cn), np.eye(Cn, dtype=np.float32))   # the residual's bypass
+        self.M = self.lib.deno_afno_num_modes(C.byref(self.desc))
+
+    def forward(self, save=True):
+        lib, d = self.lib, self.desc
+        y = np.full(self.x.shape, np.nan, dtype=np.float32)
+        self.xhat = np.full(self.x.shape[:2] + (self.M,), np.nan, dtype=np.complex64) if save else None
+        nws = lib.deno_afno_workspace_bytes(C.byref(d), 0)
+        ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
+        rc = lib.deno_afno_fwd(C.byref(d), _ptr(self.x), *[_ptr(a) for a in self.p], _ptr(self.tw), _ptr(y),
+                               _ptr(self.xhat), _ptr(ws), nws, None)
+        _capi.check(lib, rc, "deno_afno_fwd")
+        self.fwd_launches = lib.deno_spectral_last_launch_count()
+        return y
+
+    def backward(self, gy, want_gx=True, want_params=True):
+        lib, d = self.lib, self.desc
+        gy = np.ascontiguousarray(gy, dtype=np.float32)
+        gx = np.full(self.x.shape, np.nan, dtype=np.float32) if want_gx else None
+        gp = [np.full(a.shape, np.nan, dtype=np.complex64) if want_params else None for a in self.p]
+        nws = lib.deno_afno_workspace_bytes(C.byref(d), 1)
+        ws = np.full(max(nws, 1), 0xFF, dtype=np.uint8)
+        rc = lib.deno_afno_bwd(C.byref(d), _ptr(gy), _ptr(self.xhat), *[_ptr(a) for a in self.p], _ptr(self.tw), _ptr(gx),
+                               *[_ptr(g) for g in gp], _ptr(ws), nws, None)
+        _capi.check(lib, rc, "deno_afno_bwd")
+        self.bwd_launches = lib.deno_spectral_last_launch_count()
+        return gx, gp
 
 
 class EmuEnds:

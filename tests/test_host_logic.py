@@ -21,7 +21,7 @@ def built_lib():
 
 
 def _header_functions():
-    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("deno_spectral.h", "deno_fno.h", "deno_dp.h"))
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("deno_spectral.h", "deno_fno.h", "deno_dp.h", "deno_afno.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(deno_[a-z_0-9]+)\s*\(", text)))
 
