@@ -60,7 +60,10 @@ def _reference_f64(x, p, num_blocks, lam, frac, act, cot):
     ((2, 10, 24), 5, 0.05, 0.6, "tanh"),
     ((1, 4, 3, 5, 12), 2, 0.01, 1, "leakyrelu"),
     ((3, 8, 5, 6), 8, 0.0, 1, "identity"),
-], ids=["2d_tiles", "1d_block12", "1d_frac", "3d_odd", "2d_bs1"])
+    # the largest blocks: 64 (every pair slot of the backward's 17 per thread in use, 64-bin tiles) and 32
+    ((2, 64, 6, 40), 1, 0.01, 1, "gelu"),
+    ((1, 64, 150), 2, 0.01, 1, "silu"),
+], ids=["2d_tiles", "1d_block12", "1d_frac", "3d_odd", "2d_bs1", "2d_block64", "1d_block32"])
 def test_emulated_afno_matches_float64_reference_algorithm(case):
     shape, nb, lam, frac, act = case
     rng = np.random.default_rng(11)
@@ -96,3 +99,36 @@ def test_emulated_afno_rejects_what_the_reference_rejects():
     z2, z1 = np.zeros((2, 3, 3), np.complex64), np.zeros((2, 3), np.complex64)
     with pytest.raises(_capi.DenoError, match="modes_last"):
         emu_harness.EmuAfno(x, z2, z1, z2, z1, 2, 6, "relu", 0.01)
+
+
+def test_emulated_afno_limits_fail_loudly():
+    """Outside what the kernels cover the call returns an error - never a silent fallback."""
+    from deno4pytorch_b200 import _capi
+    z = lambda *s: np.zeros(s, np.complex64)
+    with pytest.raises(_capi.DenoError, match="above 64"):                  # block size 128
+        emu_harness.EmuAfno(np.zeros((1, 128, 8), np.float32), z(1, 128, 128), z(1, 128), z(1, 128, 128), z(1, 128), 1, 5, "gelu", 0.01)
+    layer = emu_harness.EmuAfno(np.zeros((1, 4, 8, 260), np.float32), z(1, 4, 4), z(1, 4), z(1, 4, 4), z(1, 4), 1, 131, "gelu", 0.01)
+    with pytest.raises(_capi.DenoError, match="last axis"):                 # 131 bins: beyond the plane kernel's thread layout
+        layer.forward()
+
+
+def test_afno_host_queries_through_the_built_library():
+    """The shape bookkeeping entry points of include/deno_afno.h are pure host code: check them on the nvcc-built .so."""
+    import ctypes as C
+    from deno4pytorch_b200 import _capi, build
+    lib = _capi.bind(C.CDLL(build.build()))
+    d = _capi.make_afno_desc(10, 64, 4, (55, 64), 33, "gelu", 0.01)
+    assert lib.deno_afno_num_modes(C.byref(d)) == 55 * 33                    # every row frequency, 33 half-spectrum bins
+    nb = lib.deno_afno_twiddle_bytes(C.byref(d))
+    tw = np.zeros(nb // 4, np.float32)
+    assert lib.deno_afno_twiddle_fill(C.byref(d), tw.ctypes.data_as(C.c_void_p), nb) == 0
+    assert np.array_equal(tw[-64 * 64:].reshape(64, 64), np.eye(64, dtype=np.float32))
+    spec = 10 * 64 * 55 * 33 * 8
+    assert lib.deno_afno_workspace_bytes(C.byref(d), 0) >= 2 * spec
+    assert lib.deno_afno_workspace_bytes(C.byref(d), 1) >= 2 * spec
+    d3 = _capi.make_afno_desc(2, 8, 2, (5, 4, 6), 4, "relu", 0.0)
+    assert lib.deno_afno_num_modes(C.byref(d3)) == 5 * 4 * 4
+    bad = _capi.make_afno_desc(1, 6, 4, (8,), 5, "relu", 0.01)
+    assert lib.deno_afno_twiddle_bytes(C.byref(bad)) == 0 and b"divisible" in lib.deno_last_error()
+    bad = _capi.make_afno_desc(1, 8, 4, (8,), 5, "relu", -1.0)
+    assert lib.deno_afno_num_modes(C.byref(bad)) == 0 and b"sparsity_threshold" in lib.deno_last_error()
