@@ -232,3 +232,50 @@ def test_flat_gradient_spans_and_direct_write_registration():
     assert float(fg.flat[16:30:2].sum()) == 14.0                # complex gradients live in the flat buffer as (re, im)
     fg.direct_writes(False)
     assert grad_sink(a) is None
+
+
+# ---- §8f rank 4: the adaptive Fourier layers and the 4-D stand-alone model as drop-ins (host side only) --------------------
+@pytest.mark.parametrize("name", golden_names("afno"))
+def test_afno_dropin_state_dict_and_attributes_match_reference(name):
+    import deno4pytorch_b200 as d4
+    g = load_golden(name)
+    m = g["meta"]
+    cls = {1: d4.AdaptiveFourier1d, 2: d4.AdaptiveFourier2d, 3: d4.AdaptiveFourier3d}[m["ndim"]]
+    layer = cls(m["hidden_size"], num_blocks=m["num_blocks"], sparsity_threshold=m["sparsity_threshold"],
+                hard_thresholding_fraction=m["hard_thresholding_fraction"], activation=m["activation"])
+    sd = layer.state_dict()
+    assert list(sd.keys()) == list(g["params"].keys()) == ["weights1", "weights2", "bias1", "bias2"]
+    for k, v in sd.items():
+        assert v.shape == g["params"][k].shape and v.dtype == g["params"][k].dtype == torch.complex64, k
+    layer.load_state_dict(g["params"], strict=True)
+    assert (layer.hidden_size, layer.num_blocks, layer.block_size, layer.hidden_size_factor, layer.scale) == \
+        (m["hidden_size"], m["num_blocks"], m["hidden_size"] // m["num_blocks"], 1, 0.02)
+
+
+def test_afno_defaults_and_init_distribution():
+    import deno4pytorch_b200 as d4
+    torch.manual_seed(0)
+    l1, l2, l3 = d4.AdaptiveFourier1d(64), d4.AdaptiveFourier2d(64), d4.AdaptiveFourier3d(64, num_blocks=4)
+    assert isinstance(l1.activation, torch.nn.ReLU) and isinstance(l2.activation, torch.nn.GELU) \
+        and isinstance(l3.activation, torch.nn.GELU)                      # spectral_layers.py:350, :426, :504
+    assert (l2.num_blocks, l2.sparsity_threshold, l2.hard_thresholding_fraction) == (8, 0.01, 1)
+    assert l3.weights1.shape == (4, 16, 16) and l3.bias2.shape == (4, 16)
+    w = torch.view_as_real(l2.weights1.detach())
+    assert w.min() >= 0 and w.max() < 0.02 and abs(w.mean().item() - 0.01) < 1e-3      # 0.02 * U[0, 1) on re and im
+    with pytest.raises(AssertionError, match="divisble"):
+        d4.AdaptiveFourier2d(10, num_blocks=4)
+    from deno4pytorch_b200.functional import afno_kept_modes
+    assert afno_kept_modes((55, 64), 1) == 33 and afno_kept_modes((16,), 0.5) == 4 and afno_kept_modes((4, 4), 0.01) == 0
+
+
+def test_fno4d_dropin_state_dict_matches_reference():
+    from deno4pytorch_b200.FNO_HIT import FNO4d, SpectralConv4d
+    g = load_golden("fno4d")
+    m = g["meta"]
+    model = FNO4d(*m["modes"][:3], 4, m["width"])
+    assert list(model.state_dict().keys()) == list(g["params"].keys())
+    model.load_state_dict(g["params"], strict=True)
+    gl = load_golden("layer4d")
+    layer = SpectralConv4d(gl["meta"]["in_dim"], gl["meta"]["out_dim"], *gl["meta"]["modes"])
+    layer.load_state_dict(gl["params"], strict=True)
+    assert layer.modes4 == 2 and SpectralConv4d(2, 2, 4, 4, 4, 9).modes4 == 2      # clamped like FNO_HIT.py:44
