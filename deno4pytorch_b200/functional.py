@@ -414,6 +414,9 @@ def afno_filter(x: torch.Tensor, weights1: torch.Tensor, bias1: torch.Tensor, we
     _check_input(x, "input")
     kept = afno_kept_modes(tuple(x.shape[2:]), hard_thresholding_fraction)
     if kept == 0:
-        return x.clone()          # every bin is masked out: the filter branch is soft-shrink(0) = 0
+        # every bin is masked out: the filter branch is soft-shrink(0) = 0.  The reference still runs its einsums on
+        # empty slices, so the four parameters receive ZERO gradients there (not None): keep them in the graph
+        zero = sum(torch.view_as_real(p)[..., :0].sum() for p in (weights1, bias1, weights2, bias2))
+        return x + zero
     return _AfnoFn.apply(x, weights1, bias1, weights2, bias2, int(num_blocks), kept, activation, float(sparsity_threshold),
                          torch.is_grad_enabled())
