@@ -117,3 +117,47 @@ def test_fuzz_adaptive_fourier_layers(seed):
         assert _close(gx, xr.grad), tag
         for a, b in zip(gp, pr):
             assert _close(a, b.grad, 1e-7 if b.grad.abs().max() == 0 else 0.0), tag     # fully shrunk: exact zeros
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_fuzz_lift_and_projection(seed):
+    """include/deno_fno.h over random grids (1 .. 300 points per axis, any padding, every built width, 1 .. 4 outputs) against
+    the torch-op formulation of FNOs.py:136-152 in float64."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(seed)
+    f32 = lambda t: t.detach().numpy().astype(np.float32)
+    for _ in range(40):
+        nd = int(rng.integers(1, 4))
+        spatial = [(int(rng.integers(1, 300)),), (int(rng.integers(1, 24)), int(rng.integers(1, 24))),
+                   (int(rng.integers(1, 7)), int(rng.integers(1, 7)), int(rng.integers(1, 9)))][nd - 1]
+        pad = int(rng.choice([0, 0, 1, 2, 5, 9]))
+        Cw, Hd = int(rng.choice([8, 12, 16, 20, 24, 32, 40, 48, 64])), int(rng.choice([4, 16, 24, 32, 128]))
+        Kx, O, B = int(rng.integers(1, 17 - nd)), int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        e = emu_harness.EmuEnds(B, Cw, Hd, Kx, nd, O, spatial, pad)
+        assert e.supported()
+        dd = torch.float64
+        g = torch.Generator().manual_seed(int(rng.integers(0, 1 << 30)))
+        rn = lambda *s: torch.randn(*s, generator=g, dtype=dd)
+        x = rn((B,) + spatial + (Kx,)).requires_grad_(True)
+        grid = torch.rand((B,) + spatial + (nd,), generator=g, dtype=dd)
+        w0, b0 = (rn(Cw, Kx + nd) * 0.5).requires_grad_(True), (rn(Cw) * 0.1).requires_grad_(True)
+        w1, b1 = (rn(Hd, Cw) / Cw ** 0.5).requires_grad_(True), (rn(Hd) * 0.1).requires_grad_(True)
+        w2, b2 = (rn(O, Hd) / Hd ** 0.5).requires_grad_(True), (rn(O) * 0.1).requires_grad_(True)
+        h = F.linear(torch.cat((x, grid), -1), w0, b0).movedim(-1, 1)
+        if pad:
+            h = F.pad(h, [0, pad] * nd)
+        gh = rn(h.shape)
+        h.backward(gh)
+        tag = (B, Cw, Hd, Kx, O, spatial, pad)
+        assert _close(e.lift(f32(x), f32(grid), f32(w0), f32(b0)), h.detach()), tag
+        gx, gw0, gb0 = e.lift_bwd(f32(gh), f32(x), f32(grid), f32(w0))
+        assert _close(gx, x.grad) and _close(gw0, w0.grad) and _close(gb0, b0.grad, 2e-6 * gh.abs().sum().item()), tag
+        hp = rn((B, Cw) + tuple(s + pad for s in spatial)).requires_grad_(True)
+        crop = hp[(slice(None), slice(None)) + tuple(slice(0, s) for s in spatial)]
+        y = F.linear(F.gelu(F.linear(crop.movedim(1, -1), w1, b1)), w2, b2)
+        gy = rn(y.shape)
+        y.backward(gy)
+        assert _close(e.proj(f32(hp), f32(w1), f32(b1), f32(w2), f32(b2)), y.detach()), tag
+        ghp, gw1, gb1, gw2, gb2 = e.proj_bwd(f32(gy), f32(hp), f32(w1), f32(b1), f32(w2))
+        assert _close(ghp, hp.grad) and _close(gw1, w1.grad) and _close(gb1, b1.grad) and _close(gw2, w2.grad), tag
+        assert _close(gb2, b2.grad, 2e-6 * gy.abs().sum().item()), tag        # one output: a plain sum that may cancel
